@@ -1,0 +1,125 @@
+/* rapiddoc_b200 — C-ABI of the B200-native OCR hot path that drops in under RapidDoc.
+ *
+ * RapidDoc (the reference) is pure Python and has no FFI of its own; the seam it already
+ * swaps engines at is the `InferSession.__call__(np.ndarray) -> np.ndarray` protocol
+ * (rapidocr InferSession, replaced by rapid_doc/model/ocr/ocr_patch.py:95-105 with
+ * rapid_doc/model/ocr/torch.py:33-200).  Every entry point below names the reference
+ * interface (file:line under /root/reference) it replaces.  INTEGRATION.md shows the
+ * ctypes binding a RapidDoc maintainer would add.
+ *
+ * Conventions: plain pointers + sizes, no torch types.  Every data pointer may be a HOST
+ * pointer (pageable or pinned) or a DEVICE pointer on the engine's GPU; the library
+ * detects which (cudaPointerGetAttributes).  With host pointers the call copies in,
+ * computes, copies out and returns after the results are in host memory.  With device
+ * pointers the work is enqueued on `stream` (a cudaStream_t, may be NULL = legacy default
+ * stream) and the call returns without synchronising.  Handles are not thread-safe;
+ * distinct handles are independent.  All functions return RDB_OK (0) or a negative code;
+ * rdb_last_error() gives the message of the calling thread's last failure.
+ */
+#ifndef RAPIDDOC_B200_H_
+#define RAPIDDOC_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RDB_OK 0
+#define RDB_ERR_INVALID (-1)
+#define RDB_ERR_CUDA (-2)
+#define RDB_ERR_NO_DEVICE (-3)
+
+/* arithmetic mode of the pointwise-conv / linear engine */
+#define RDB_PREC_FP32 0 /* fp32 storage + fp32 SIMT math: the exact-parity mode            */
+#define RDB_PREC_FP16 1 /* fp16 NHWC storage, tcgen05 (fp16 x fp16 -> fp32 TMEM) GEMMs      */
+
+typedef struct rdb_det rdb_det_t; /* PP-OCRv6-small DBNet detector on one GPU  */
+typedef struct rdb_rec rdb_rec_t; /* PP-OCRv6-small LightSVTR/CTC recogniser   */
+
+int rdb_version(void);
+const char* rdb_last_error(void);
+int rdb_device_count(void);
+/* pinned host memory for the callers' page / crop buffers */
+int rdb_pinned_alloc(size_t nbytes, void** out);
+int rdb_pinned_free(void* p);
+
+/* ---- text detection -------------------------------------------------------------------
+ * weights: "RDW1" blob (rapiddoc_b200/weights.py), BN folded.  Replaces building
+ * BaseModel + load_state_dict + .to(device): rapid_doc/model/ocr/torch.py:78-89,156-168. */
+int rdb_det_create(const void* weights, size_t nbytes, int device, int precision, rdb_det_t** out);
+void rdb_det_destroy(rdb_det_t* h);
+
+/* InferSession seam for det.  x [n,3,h,w] f32 (h,w multiples of 32) -> prob [n,1,h,w] f32.
+ * Replaces TorchInferSession.__call__ for "maps": rapid_doc/model/ocr/torch.py:171-184
+ * (network: backbones/rec_lcnetv4.py:283-305, necks/db_fpn.py:366-415,
+ * heads/det_db_head.py:103-147). */
+int rdb_det_infer_f32(rdb_det_t* h, const float* x, int n, int hgt, int wid, float* prob, void* stream);
+
+/* Facade seam for det: uint8 BGR HWC pages (already resized to h,w multiples of 32) ->
+ * prob map + DB bitmap.  Fuses DetPreProcess' normalisation ((v/255-mean)/std, rapidocr
+ * ch_ppocr_det/utils.py as pinned by ocr_patch.py:33-40, rapid_ocr.py:59-62), the forward
+ * above, and DBPostProcess' binarise + 2x2 dilate (ocr_patch.py:223-235).
+ * prob may be NULL (bitmap only) and bitmap may be NULL. */
+int rdb_det_infer_u8(rdb_det_t* h, const uint8_t* pages, int n, int hgt, int wid, const float mean[3],
+                     const float stdv[3], float thresh, int use_dilation, float* prob, uint8_t* bitmap,
+                     void* stream);
+
+/* DBPostProcess binarise (+ optional cv2.dilate 2x2) on an existing prob map [n,h,w]:
+ * rapid_doc/model/ocr/ocr_patch.py:228-235. */
+int rdb_db_bitmap(int device, const float* prob, int n, int hgt, int wid, float thresh, int use_dilation,
+                  uint8_t* bitmap, void* stream);
+
+/* DBPostProcess.unclip for one quad (host-only, integer Clipper offset JT_ROUND /
+ * ET_CLOSEDPOLYGON): rapid_doc/model/ocr/ocr_patch.py:161-172 (pyclipper).  box: 4 (x,y)
+ * pairs; distance = area*ratio/perimeter is computed by the caller.  Writes up to
+ * max_pts points to out_xy, returns the count (or a negative error). */
+int rdb_clipper_offset(const double* box_xy, int n_pts, double distance, int64_t* out_xy, int max_pts);
+
+/* ---- text recognition ----------------------------------------------------------------- */
+int rdb_rec_create(const void* weights, size_t nbytes, int device, int precision, rdb_rec_t** out);
+void rdb_rec_destroy(rdb_rec_t* h);
+int rdb_rec_vocab(rdb_rec_t* h); /* 18710 */
+/* T (CTC steps) the network produces for an input of width wid: stem1 s2, stem3 s2,
+ * avg_pool [3,2] (backbones/rec_lcnetv4.py:151,154,311); wid = int(48*max_wh_ratio) is
+ * arbitrary (rapid_ocr.py:425-438), T = wid/8 for multiples of 8. */
+int rdb_rec_tokens(int wid);
+
+/* InferSession seam for rec.  x [n,3,48,w] f32 (w multiple of 8), T = w/8.
+ * Replaces TorchInferSession.__call__ + softmax (rapid_doc/model/ocr/torch.py:171-192;
+ * network backbones/rec_lcnetv4.py:26-43,306-311, necks/rnn.py:321-379,
+ * heads/rec_multi_head.py:66-77) AND CTCLabelDecode's argmax/max (rapidocr
+ * ch_ppocr_rec/utils.py, called rapid_ocr.py:443-449) fused in the head GEMM epilogue:
+ *   ids   [n,T] int32  argmax token per step          (may be NULL)
+ *   probs [n,T] f32    softmax probability of that token (may be NULL)
+ *   text_ids [n,T] int32 CTC-collapsed ids, -1 padded; text_len [n]; conf [n] mean kept prob
+ *   softmax [n,T,V] f32 full probability tensor (may be NULL; the compat output the
+ *   reference engine returns — 3 MB per 48x320 crop, avoid on the fast path). */
+int rdb_rec_infer_f32(rdb_rec_t* h, const float* x, int n, int wid, int32_t* ids, float* probs,
+                      int32_t* text_ids, int32_t* text_len, float* conf, float* softmax, void* stream);
+
+/* Facade seam for rec: uint8 BGR crops already resized to height 48, packed [n,48,w,3] with
+ * valid_w[i] real columns (right part zero-padded AFTER normalisation, as
+ * TextRecognizer.resize_norm_img does; called rapid_ocr.py:438).  Fuses (v/255-0.5)/0.5. */
+int rdb_rec_infer_u8(rdb_rec_t* h, const uint8_t* crops, const int32_t* valid_w, int n, int wid, int32_t* ids,
+                     float* probs, int32_t* text_ids, int32_t* text_len, float* conf, void* stream);
+
+/* stats of the last infer call on a handle: number of kernel launches it enqueued */
+long long rdb_det_last_launches(rdb_det_t* h);
+long long rdb_rec_last_launches(rdb_rec_t* h);
+
+/* per-kernel device timing (CUDA events on the launching stream around every launch of
+ * subsequent infer calls; process-wide).  dump writes a JSON object
+ * {"kernel": [total_ms, launches], ...} and returns the bytes needed. */
+int rdb_profile_enable(int on);
+int rdb_profile_reset(void);
+int rdb_profile_dump(char* buf, size_t cap);
+
+/* scheduling knobs: pixels (det) / crops (rec) processed per internal chunk */
+int rdb_det_set_chunk_pixels(rdb_det_t* h, long long pixels);
+int rdb_rec_set_chunk_crops(rdb_rec_t* h, int crops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAPIDDOC_B200_H_ */

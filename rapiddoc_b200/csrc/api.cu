@@ -1,0 +1,276 @@
+// C-ABI of librapiddoc_b200.so (see include/rapiddoc_b200.h for the contract and the
+// reference interfaces each entry point replaces).
+#include "../../include/rapiddoc_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "det.h"
+#include "rec.h"
+
+struct rdb_det { rdb::DetEngine* e; };
+struct rdb_rec { rdb::RecEngine* e; };
+
+namespace {
+thread_local std::string g_err;
+
+template <typename F>
+int guarded(F&& f) {
+  try {
+    f();
+    return RDB_OK;
+  } catch (const rdb::Error& e) {
+    g_err = e.what();
+    return g_err.find("cuda") != std::string::npos ? RDB_ERR_CUDA : RDB_ERR_INVALID;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return RDB_ERR_INVALID;
+  }
+}
+
+// Clipper 6.4.2 ClipperOffset for ONE closed polygon, JT_ROUND, ET_CLOSEDPOLYGON, delta>0
+// (published algorithm: AddPath / FixOrientations / DoOffset / OffsetPoint / DoRound with
+// arc tolerance 0.25; Round() = half away from zero).  Replaces the pyclipper call at
+// rapid_doc/model/ocr/ocr_patch.py:166-171.  The trailing clean-up union is omitted: it
+// does not change the vertex set of the convex quads DB feeds it, and the consumer
+// (cv2.minAreaRect) only sees the convex hull.
+inline long long cround(double v) { return v < 0 ? (long long)(v - 0.5) : (long long)(v + 0.5); }
+
+int clipper_offset(const double* xy, int n_in, double delta, int64_t* out, int max_pts) {
+  struct P { long long x, y; };
+  std::vector<P> pts;
+  for (int i = 0; i < n_in; ++i) pts.push_back({(long long)xy[2 * i], (long long)xy[2 * i + 1]});  // pyclipper truncates
+  int hi = n_in - 1;
+  if (hi < 0) return 0;
+  while (hi > 0 && pts[0].x == pts[hi].x && pts[0].y == pts[hi].y) --hi;
+  std::vector<P> src{pts[0]};
+  for (int i = 1; i <= hi; ++i)
+    if (src.back().x != pts[i].x || src.back().y != pts[i].y) src.push_back(pts[i]);
+  const int n = (int)src.size();
+  if (n < 3) return 0;
+  double a = 0;
+  for (int i = 0, j = n - 1; i < n; j = i++) a += ((double)src[j].x + src[i].x) * ((double)src[j].y - src[i].y);
+  if (-a * 0.5 < 0) std::reverse(src.begin(), src.end());
+  std::vector<P> dst;
+  if (std::fabs(delta) < 1e-20) dst = src;
+  else {
+    const double pi = 3.141592653589793238;
+    double y = 0.25;
+    if (y > std::fabs(delta) * 0.25) y = std::fabs(delta) * 0.25;
+    double steps = pi / std::acos(1 - y / std::fabs(delta));
+    if (steps > std::fabs(delta) * pi) steps = std::fabs(delta) * pi;
+    double m_sin = std::sin(2 * pi / steps), m_cos = std::cos(2 * pi / steps);
+    const double steps_per_rad = steps / (2 * pi);
+    if (delta < 0) m_sin = -m_sin;
+    std::vector<double> nx(n), ny(n);
+    for (int i = 0; i < n; ++i) {
+      const P& p1 = src[i];
+      const P& p2 = src[(i + 1) % n];
+      double dx = (double)(p2.x - p1.x), dy = (double)(p2.y - p1.y);
+      double f = 1.0 / std::sqrt(dx * dx + dy * dy);
+      nx[i] = dy * f;
+      ny[i] = -dx * f;
+    }
+    int k = n - 1;
+    for (int j = 0; j < n; ++j) {
+      double sin_a = nx[k] * ny[j] - nx[j] * ny[k];
+      bool done = false;
+      if (std::fabs(sin_a * delta) < 1.0) {
+        double cos_a = nx[k] * nx[j] + ny[j] * ny[k];
+        if (cos_a > 0) {
+          dst.push_back({cround(src[j].x + nx[k] * delta), cround(src[j].y + ny[k] * delta)});
+          done = true;
+        }
+      } else if (sin_a > 1.0) sin_a = 1.0;
+      else if (sin_a < -1.0) sin_a = -1.0;
+      if (!done) {
+        if (sin_a * delta < 0) {
+          dst.push_back({cround(src[j].x + nx[k] * delta), cround(src[j].y + ny[k] * delta)});
+          dst.push_back(src[j]);
+          dst.push_back({cround(src[j].x + nx[j] * delta), cround(src[j].y + ny[j] * delta)});
+        } else {
+          double ang = std::atan2(sin_a, nx[k] * nx[j] + ny[k] * ny[j]);
+          long long st = cround(steps_per_rad * std::fabs(ang));
+          if (st < 1) st = 1;
+          double X = nx[k], Y = ny[k];
+          for (long long i = 0; i < st; ++i) {
+            dst.push_back({cround(src[j].x + X * delta), cround(src[j].y + Y * delta)});
+            double X2 = X;
+            X = X * m_cos - m_sin * Y;
+            Y = X2 * m_sin + Y * m_cos;
+          }
+          dst.push_back({cround(src[j].x + nx[j] * delta), cround(src[j].y + ny[j] * delta)});
+        }
+      }
+      k = j;
+    }
+  }
+  int cnt = (int)dst.size();
+  if (cnt > max_pts) throw rdb::Error("clipper_offset: output buffer too small");
+  for (int i = 0; i < cnt; ++i) { out[2 * i] = dst[i].x; out[2 * i + 1] = dst[i].y; }
+  return cnt;
+}
+}  // namespace
+
+extern "C" {
+
+int rdb_version(void) { return 100; }
+const char* rdb_last_error(void) { return g_err.c_str(); }
+
+int rdb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int rdb_pinned_alloc(size_t nbytes, void** out) {
+  return guarded([&] { RDB_CHECK(out != nullptr, "null out"); RDB_CUDA(cudaHostAlloc(out, nbytes, cudaHostAllocDefault)); });
+}
+int rdb_pinned_free(void* p) {
+  return guarded([&] { RDB_CUDA(cudaFreeHost(p)); });
+}
+
+static void require_device(int device) {
+  int n = rdb_device_count();
+  if (n <= 0) throw rdb::Error("cuda: no CUDA device visible — rapiddoc_b200 has no CPU fallback");
+  if (device < 0 || device >= n) throw rdb::Error("invalid device index");
+  cudaDeviceProp p;
+  RDB_CUDA(cudaGetDeviceProperties(&p, device));
+  if (p.major != 10) throw rdb::Error(std::string("cuda: device is sm_") + std::to_string(p.major * 10 + p.minor) + ", this library is built for sm_100a only");
+}
+
+int rdb_det_create(const void* weights, size_t nbytes, int device, int precision, rdb_det_t** out) {
+  int rc = guarded([&] {
+    RDB_CHECK(weights && out, "null argument");
+    RDB_CHECK(precision == RDB_PREC_FP32 || precision == RDB_PREC_FP16, "bad precision");
+    require_device(device);
+    *out = new rdb_det{new rdb::DetEngine(weights, nbytes, device, precision)};
+  });
+  if (rc == RDB_ERR_CUDA && g_err.find("no CUDA device") != std::string::npos) rc = RDB_ERR_NO_DEVICE;
+  return rc;
+}
+void rdb_det_destroy(rdb_det_t* h) {
+  if (h) { delete h->e; delete h; }
+}
+
+int rdb_det_infer_f32(rdb_det_t* h, const float* x, int n, int hgt, int wid, float* prob, void* stream) {
+  return guarded([&] {
+    RDB_CHECK(h && x && prob, "null argument");
+    rdb::DetInput in;
+    in.f32 = x;
+    h->e->infer(in, n, hgt, wid, 0.3f, false, prob, nullptr, (cudaStream_t)stream);
+  });
+}
+
+int rdb_det_infer_u8(rdb_det_t* h, const uint8_t* pages, int n, int hgt, int wid, const float mean[3], const float stdv[3],
+                     float thresh, int use_dilation, float* prob, uint8_t* bitmap, void* stream) {
+  return guarded([&] {
+    RDB_CHECK(h && pages && mean && stdv && (prob || bitmap), "null argument");
+    rdb::DetInput in;
+    in.u8 = pages;
+    for (int i = 0; i < 3; ++i) { in.mean[i] = mean[i]; in.stdv[i] = stdv[i]; }
+    h->e->infer(in, n, hgt, wid, thresh, use_dilation != 0, prob, bitmap, (cudaStream_t)stream);
+  });
+}
+
+int rdb_db_bitmap(int device, const float* prob, int n, int hgt, int wid, float thresh, int use_dilation, uint8_t* bitmap,
+                  void* stream) {
+  return guarded([&] {
+    RDB_CHECK(prob && bitmap && n > 0, "null argument");
+    require_device(device);
+    rdb::db_bitmap(device, prob, n, hgt, wid, thresh, use_dilation != 0, bitmap, (cudaStream_t)stream);
+  });
+}
+
+int rdb_clipper_offset(const double* box_xy, int n_pts, double distance, int64_t* out_xy, int max_pts) {
+  int cnt = 0;
+  int rc = guarded([&] {
+    RDB_CHECK(box_xy && out_xy && n_pts >= 0, "null argument");
+    cnt = clipper_offset(box_xy, n_pts, distance, out_xy, max_pts);
+  });
+  return rc == RDB_OK ? cnt : rc;
+}
+
+int rdb_rec_create(const void* weights, size_t nbytes, int device, int precision, rdb_rec_t** out) {
+  int rc = guarded([&] {
+    RDB_CHECK(weights && out, "null argument");
+    RDB_CHECK(precision == RDB_PREC_FP32 || precision == RDB_PREC_FP16, "bad precision");
+    require_device(device);
+    *out = new rdb_rec{new rdb::RecEngine(weights, nbytes, device, precision)};
+  });
+  if (rc == RDB_ERR_CUDA && g_err.find("no CUDA device") != std::string::npos) rc = RDB_ERR_NO_DEVICE;
+  return rc;
+}
+void rdb_rec_destroy(rdb_rec_t* h) {
+  if (h) { delete h->e; delete h; }
+}
+int rdb_rec_vocab(rdb_rec_t* h) { return h ? h->e->vocab() : RDB_ERR_INVALID; }
+int rdb_rec_tokens(int wid) { return rdb::RecEngine::tokens_for_width(wid); }
+
+int rdb_rec_infer_f32(rdb_rec_t* h, const float* x, int n, int wid, int32_t* ids, float* probs, int32_t* text_ids,
+                      int32_t* text_len, float* conf, float* softmax, void* stream) {
+  return guarded([&] {
+    RDB_CHECK(h && x, "null argument");
+    rdb::RecInput in;
+    in.f32 = x;
+    rdb::RecOutput o;
+    o.ids = ids; o.probs = probs; o.text_ids = text_ids; o.text_len = text_len; o.conf = conf; o.softmax = softmax;
+    h->e->infer(in, n, wid, o, (cudaStream_t)stream);
+  });
+}
+
+int rdb_rec_infer_u8(rdb_rec_t* h, const uint8_t* crops, const int32_t* valid_w, int n, int wid, int32_t* ids, float* probs,
+                     int32_t* text_ids, int32_t* text_len, float* conf, void* stream) {
+  return guarded([&] {
+    RDB_CHECK(h && crops, "null argument");
+    rdb::RecInput in;
+    in.u8 = crops;
+    in.valid_w = valid_w;
+    rdb::RecOutput o;
+    o.ids = ids; o.probs = probs; o.text_ids = text_ids; o.text_len = text_len; o.conf = conf;
+    h->e->infer(in, n, wid, o, (cudaStream_t)stream);
+  });
+}
+
+long long rdb_det_last_launches(rdb_det_t* h) { return h ? h->e->last_launches() : -1; }
+long long rdb_rec_last_launches(rdb_rec_t* h) { return h ? h->e->last_launches() : -1; }
+
+int rdb_profile_enable(int on) {
+  rdb::Profiler::global().on = (on != 0);
+  return RDB_OK;
+}
+int rdb_profile_reset(void) {
+  rdb::Profiler::global().acc.clear();
+  return RDB_OK;
+}
+// JSON object {"kernel name": [total_ms, launches], ...}; returns bytes needed (incl. NUL)
+int rdb_profile_dump(char* buf, size_t cap) {
+  std::string s = "{";
+  bool first = true;
+  for (auto& kv : rdb::Profiler::global().acc) {
+    if (!first) s += ", ";
+    first = false;
+    s += "\"" + kv.first + "\": [" + std::to_string(kv.second.first) + ", " + std::to_string(kv.second.second) + "]";
+  }
+  s += "}";
+  if (buf && cap > 0) {
+    size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+    std::memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return (int)s.size() + 1;
+}
+
+int rdb_det_set_chunk_pixels(rdb_det_t* h, long long px) {
+  if (!h || px <= 0) return RDB_ERR_INVALID;
+  h->e->set_chunk_pixels(px);
+  return RDB_OK;
+}
+int rdb_rec_set_chunk_crops(rdb_rec_t* h, int crops) {
+  if (!h || crops <= 0) return RDB_ERR_INVALID;
+  h->e->set_chunk_crops(crops);
+  return RDB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+// Shared helpers for the rapiddoc_b200 CUDA kernels (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <stdexcept>
+#include <string>
+
+namespace rdb {
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define RDB_CUDA(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      throw rdb::Error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + \
+                       ":" + std::to_string(__LINE__));                                      \
+  } while (0)
+
+#define RDB_CHECK(cond, msg)                                                           \
+  do {                                                                                 \
+    if (!(cond)) throw rdb::Error(std::string("check failed: ") + #cond + " — " + msg); \
+  } while (0)
+
+#define RDB_LAUNCH_CHECK() RDB_CUDA(cudaGetLastError())
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SILU = 3, ACT_SIGMOID = 4 };
+
+template <int ACT>
+__device__ __forceinline__ float apply_act(float x) {
+  if (ACT == ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));  // exact erf GELU
+  if (ACT == ACT_SILU) return x / (1.f + __expf(-x));
+  if (ACT == ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
+  return x;
+}
+
+__device__ __forceinline__ float apply_act_rt(float x, int act) {
+  switch (act) {
+    case ACT_RELU: return apply_act<ACT_RELU>(x);
+    case ACT_GELU: return apply_act<ACT_GELU>(x);
+    case ACT_SILU: return apply_act<ACT_SILU>(x);
+    case ACT_SIGMOID: return apply_act<ACT_SIGMOID>(x);
+    default: return x;
+  }
+}
+
+// ---- 8-channel vector access, fp32 math, storage T in {float, __half} -----------------
+template <typename T>
+struct Vec8;
+
+template <>
+struct Vec8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    float4 a = *reinterpret_cast<const float4*>(p);
+    float4 b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+
+template <>
+struct Vec8<__half> {
+  static __device__ __forceinline__ void load(const __half* p, float (&v)[8]) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __half22float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void store(__half* p, const float (&v)[8]) {
+    uint4 u;
+    __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace rdb

@@ -1,0 +1,205 @@
+// PP-OCRv6-small DBNet text detector forward + DB binarise/dilate on one B200.
+// Reference network: rapid_doc/model/ocr/ppocrv6_pytorch/modeling/backbones/rec_lcnetv4.py:7-23,
+// necks/db_fpn.py:366-415, heads/det_db_head.py:103-147; engine seam rapid_doc/model/ocr/torch.py:171-184.
+#include "det.h"
+
+namespace rdb {
+
+static const BlockCfg kDetBlocks[4][5] = {
+    {{48, 48, 1, 1, 1}, {48, 48, 1, 1, 0}},
+    {{48, 96, 2, 2, 0}, {96, 96, 1, 1, 1}, {96, 96, 1, 1, 0}},
+    {{96, 192, 2, 2, 0}, {192, 192, 1, 1, 1}, {192, 192, 1, 1, 0}, {192, 192, 1, 1, 1}, {192, 192, 1, 1, 0}},
+    {{192, 384, 2, 2, 0}, {384, 384, 1, 1, 1}, {384, 384, 1, 1, 0}},
+};
+static const int kDetBlockCount[4] = {2, 3, 5, 3};
+
+DetEngine::DetEngine(const void* blob, size_t nbytes, int device, int precision) : device_(device), precision_(precision) {
+  RDB_CUDA(cudaSetDevice(device));
+  weights_.reset(new Weights(blob, nbytes));
+  RDB_CHECK(weights_->has("head.final.w") && weights_->has("neck.lk3.pw.w"), "blob is not a det model");
+}
+
+DetEngine::~DetEngine() {
+  cudaSetDevice(device_);
+  pool_.release_all();
+}
+
+template <typename T>
+void DetEngine::forward_chunk(Ctx& cx, const DetInput& in, int n, int H, int W, float thresh, bool dilate, float* prob,
+                              uint8_t* bitmap) {
+  using O = Ops<T>;
+  using Act = typename O::Act;
+  const Weights& w = *weights_;
+  const int H1 = H / 2, W1 = W / 2;
+  // ---- stem1
+  Act e1 = O::make(cx, n, H1, W1, 24);
+  {
+    long long total = e1.pixels();
+    cx.begin("stem1");
+    if (in.f32 != nullptr) {
+      InF32NCHW src{in.f32, H, W};
+      stem1_kernel<T, InF32NCHW, 24><<<cdiv(total, 128), 128, 0, cx.st>>>(src, n, w.get("stem1.w").d, w.get("stem1.b").d, e1.p, H1, W1);
+    } else {
+      InU8HWC src{in.u8, H, W, 0, {in.mean[0], in.mean[1], in.mean[2]}, {in.stdv[0], in.stdv[1], in.stdv[2]}, nullptr};
+      stem1_kernel<T, InU8HWC, 24><<<cdiv(total, 128), 128, 0, cx.st>>>(src, n, w.get("stem1.w").d, w.get("stem1.b").d, e1.p, H1, W1);
+    }
+    cx.end();
+  }
+  Act x = Backbone<T>::template stem_rest<24>(cx, w, e1);
+  // ---- stages
+  Act feats[4];
+  for (int s = 0; s < 4; ++s) {
+    for (int b = 0; b < kDetBlockCount[s]; ++b) {
+      bool keep = (b == 0 && s > 0);  // the previous stage output also feeds the neck
+      std::string name = "s" + std::to_string(s) + ".b" + std::to_string(b) + ".";
+      Act y = Backbone<T>::block(cx, w, name, kDetBlocks[s][b], x, keep);
+      x = y;
+    }
+    feats[s] = x;
+  }
+  // ---- RepLKFPN
+  Act f[4];
+  for (int i = 0; i < 4; ++i) {
+    std::string p = "neck.in" + std::to_string(i) + ".";
+    f[i] = O::make(cx, n, feats[i].h, feats[i].w, 96);
+    O::pw(cx, feats[i], w.get(p + "w"), nullptr, ACT_NONE, nullptr, f[i]);
+    O::release(cx, feats[i]);
+    float* gate = O::se_gate(cx, f[i], w.get(p + "se.w1"), w.get(p + "se.b1"), w.get(p + "se.w2"), w.get(p + "se.b2"), 1);
+    O::scale(cx, f[i], gate);  // x + x*g = x*(1+g)
+    cx.pool->free(gate);
+  }
+  for (int i = 2; i >= 0; --i) {
+    long long total = f[i].pixels() * 12;
+    cx.begin("neck_upadd");
+    upsample2_add_kernel<T><<<cdiv(total, kThreads), kThreads, 0, cx.st>>>(f[i].p, f[i + 1].p, n, f[i].h, f[i].w, 96);
+    cx.end();
+  }
+  Act pq[4];
+  NeckSrc<T> ns;
+  float* gates[4];
+  for (int i = 0; i < 4; ++i) {
+    std::string p = "neck.lk" + std::to_string(i) + ".";
+    Act d = O::make(cx, n, f[i].h, f[i].w, 96);
+    O::template dwconv<7, 7, ACT_NONE, false>(cx, f[i], 1, 1, w.get(p + "dw.w"), w.get(p + "dw.b"), d);
+    O::release(cx, f[i]);
+    pq[i] = O::make(cx, n, d.h, d.w, 24);
+    O::pw(cx, d, w.get(p + "pw.w"), nullptr, ACT_NONE, nullptr, pq[i]);
+    O::release(cx, d);
+    gates[i] = O::se_gate(cx, pq[i], w.get(p + "se.w1"), w.get(p + "se.b1"), w.get(p + "se.w2"), w.get(p + "se.b2"), 1);
+    ns.f[i] = pq[i].p;
+    ns.gate[i] = gates[i];
+  }
+  Act neck = O::make(cx, n, pq[0].h, pq[0].w, 96);
+  {
+    long long total = neck.pixels() * 12;
+    cx.begin("neck_concat");
+    neck_concat_kernel<T><<<cdiv(total, kThreads), kThreads, 0, cx.st>>>(ns, n, neck.h, neck.w, neck.p);
+    cx.end();
+  }
+  for (int i = 0; i < 4; ++i) { O::release(cx, pq[i]); cx.pool->free(gates[i]); }
+  // ---- DBHead
+  Act hd = O::make(cx, n, neck.h, neck.w, 24);
+  {
+    auto k = conv_direct_kernel<T, 3, 3, 1, 1, 96, 24, 24, ACT_RELU>;
+    size_t sm = (size_t)(9 * 96 * 24 + 24) * sizeof(float);
+    set_smem(k, sm);
+    cx.begin("head_conv3x3");
+    k<<<dim3(cdiv(hd.pixels(), 128), 1), 128, sm, cx.st>>>(neck.p, n, neck.h, neck.w, 1, 1, w.get("head.down.w").d,
+                                                          w.get("head.down.b").d, hd.p, hd.h, hd.w, 24, 0);
+    cx.end();
+  }
+  O::release(cx, neck);
+  uint8_t* seg = nullptr;
+  if (bitmap != nullptr) seg = dilate ? cx.pool->alloc_t<uint8_t>((size_t)n * H * W) : bitmap;
+  {
+    long long total = (long long)n * (2 * hd.h) * (2 * hd.w);
+    cx.begin("head_tail");
+    head_tail_kernel<T><<<cdiv(total, 128), 128, 0, cx.st>>>(hd.p, n, hd.h, hd.w, w.get("head.up.w").d, w.get("head.up.b").d,
+                                                            w.get("head.final.w").d, w.get("head.final.b").d, thresh, prob, seg);
+    cx.end();
+  }
+  O::release(cx, hd);
+  if (bitmap != nullptr && dilate) {
+    long long total = (long long)n * H * (W / 4);
+    cx.begin("db_dilate");
+    dilate2x2_kernel<<<cdiv(total, kThreads), kThreads, 0, cx.st>>>(seg, n, H, W, bitmap);
+    cx.end();
+    cx.pool->free(seg);
+  }
+}
+
+void DetEngine::infer(const DetInput& in_host_or_dev, int n, int H, int W, float thresh, bool dilate, float* prob, uint8_t* bitmap,
+                      cudaStream_t st) {
+  RDB_CUDA(cudaSetDevice(device_));
+  RDB_CHECK(n > 0 && H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0, "det: h and w must be positive multiples of 32");
+  RDB_CHECK((in_host_or_dev.f32 != nullptr) != (in_host_or_dev.u8 != nullptr), "det: exactly one input");
+  Ctx cx;
+  cx.st = st; cx.pool = &pool_; cx.precision = precision_;
+  const void* src = in_host_or_dev.f32 ? (const void*)in_host_or_dev.f32 : (const void*)in_host_or_dev.u8;
+  const size_t in_elem = in_host_or_dev.f32 ? sizeof(float) : 1;
+  const size_t page_in = (size_t)3 * H * W * in_elem;
+  const size_t page_px = (size_t)H * W;
+  const bool in_dev = is_device_ptr(src);
+  const bool prob_dev = prob ? is_device_ptr(prob) : true;
+  const bool bm_dev = bitmap ? is_device_ptr(bitmap) : true;
+  // chunk so that one chunk's activations stay a bounded working set
+  long long px_budget = chunk_pixels_;
+  int chunk = (int)(px_budget / (long long)(H * (long long)W));
+  if (chunk < 1) chunk = 1;
+  if (chunk > n) chunk = n;
+  void* d_in = in_dev ? nullptr : pool_.alloc(page_in * chunk);
+  float* d_prob = (prob_dev && prob) ? nullptr : pool_.alloc_t<float>(page_px * chunk);
+  uint8_t* d_bm = (bm_dev || !bitmap) ? nullptr : pool_.alloc_t<uint8_t>(page_px * chunk);
+  for (int i0 = 0; i0 < n; i0 += chunk) {
+    int m = (n - i0 < chunk) ? (n - i0) : chunk;
+    const uint8_t* src_i = static_cast<const uint8_t*>(src) + (size_t)i0 * page_in;
+    DetInput in = in_host_or_dev;
+    const void* dsrc = src_i;
+    if (!in_dev) {
+      RDB_CUDA(cudaMemcpyAsync(d_in, src_i, page_in * m, cudaMemcpyHostToDevice, st));
+      dsrc = d_in;
+    }
+    if (in.f32) in.f32 = static_cast<const float*>(dsrc); else in.u8 = static_cast<const uint8_t*>(dsrc);
+    float* p_out = (prob_dev && prob) ? prob + (size_t)i0 * page_px : d_prob;
+    uint8_t* b_out = bitmap ? (bm_dev ? bitmap + (size_t)i0 * page_px : d_bm) : nullptr;
+    if (precision_ == 0) forward_chunk<float>(cx, in, m, H, W, thresh, dilate, p_out, b_out);
+    else forward_chunk<__half>(cx, in, m, H, W, thresh, dilate, p_out, b_out);
+    if (prob && !prob_dev) RDB_CUDA(cudaMemcpyAsync(prob + (size_t)i0 * page_px, d_prob, page_px * m * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (bitmap && !bm_dev) RDB_CUDA(cudaMemcpyAsync(bitmap + (size_t)i0 * page_px, d_bm, page_px * m, cudaMemcpyDeviceToHost, st));
+  }
+  if (d_in) pool_.free(d_in);
+  if (d_prob) pool_.free(d_prob);
+  if (d_bm) pool_.free(d_bm);
+  const bool any_host = !in_dev || (prob && !prob_dev) || (bitmap && !bm_dev);
+  if (any_host) RDB_CUDA(cudaStreamSynchronize(st));
+  cx.finish();
+  last_launches_ = cx.launches;
+}
+
+void db_bitmap(int device, const float* prob, int n, int H, int W, float thresh, bool dilate, uint8_t* bitmap, cudaStream_t st) {
+  RDB_CUDA(cudaSetDevice(device));
+  RDB_CHECK(W % 4 == 0, "db_bitmap: width must be a multiple of 4");
+  const size_t px = (size_t)n * H * W;
+  const bool p_dev = is_device_ptr(prob), b_dev = is_device_ptr(bitmap);
+  float* dp = const_cast<float*>(prob);
+  uint8_t* db = bitmap;
+  uint8_t* seg = nullptr;
+  if (!p_dev) { RDB_CUDA(cudaMalloc(&dp, px * 4)); RDB_CUDA(cudaMemcpyAsync(dp, prob, px * 4, cudaMemcpyHostToDevice, st)); }
+  if (!b_dev) RDB_CUDA(cudaMalloc(&db, px));
+  if (dilate) RDB_CUDA(cudaMalloc(&seg, px));
+  threshold_kernel<<<cdiv((long long)(px + 3) / 4, 256), 256, 0, st>>>(dp, thresh, dilate ? seg : db, (long long)px);
+  RDB_LAUNCH_CHECK();
+  if (dilate) {
+    dilate2x2_kernel<<<cdiv((long long)n * H * (W / 4), 256), 256, 0, st>>>(seg, n, H, W, db);
+    RDB_LAUNCH_CHECK();
+  }
+  if (!b_dev) RDB_CUDA(cudaMemcpyAsync(bitmap, db, px, cudaMemcpyDeviceToHost, st));
+  if (!p_dev || !b_dev || dilate) {
+    RDB_CUDA(cudaStreamSynchronize(st));
+    if (!p_dev) cudaFree(dp);
+    if (!b_dev) cudaFree(db);
+    if (seg) cudaFree(seg);
+  }
+}
+
+}  // namespace rdb

@@ -1,0 +1,36 @@
+#pragma once
+#include <memory>
+
+#include "engine.cuh"
+
+namespace rdb {
+
+struct DetInput {
+  const float* f32 = nullptr;    // [n,3,H,W] fp32 NCHW (InferSession seam)
+  const uint8_t* u8 = nullptr;   // [n,H,W,3] uint8 BGR (facade seam)
+  float mean[3] = {0, 0, 0}, stdv[3] = {1, 1, 1};
+};
+
+class DetEngine {
+ public:
+  DetEngine(const void* blob, size_t nbytes, int device, int precision);
+  ~DetEngine();
+  // prob [n,H,W] f32 / bitmap [n,H,W] u8: host or device pointers, may be null.
+  void infer(const DetInput& in, int n, int H, int W, float thresh, bool dilate, float* prob, uint8_t* bitmap, cudaStream_t st);
+  long long last_launches() const { return last_launches_; }
+  int device() const { return device_; }
+  void set_chunk_pixels(long long px) { chunk_pixels_ = px; }
+
+ private:
+  template <typename T>
+  void forward_chunk(Ctx& cx, const DetInput& in, int n, int H, int W, float thresh, bool dilate, float* prob, uint8_t* bitmap);
+  int device_, precision_;
+  std::unique_ptr<Weights> weights_;
+  Pool pool_;
+  long long last_launches_ = 0;
+  long long chunk_pixels_ = 8ll * 1024 * 1024;  // pages per internal chunk = chunk_pixels / (H*W)
+};
+
+void db_bitmap(int device, const float* prob, int n, int H, int W, float thresh, bool dilate, uint8_t* bitmap, cudaStream_t st);
+
+}  // namespace rdb

@@ -1,0 +1,343 @@
+// Host-side runtime shared by the det / rec engines: weight blob, device buffer pool,
+// launch helpers.  One engine = one (GPU, model); all work of a call goes to one stream.
+#pragma once
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "kernels.cuh"
+
+namespace rdb {
+
+// ---------------------------------------------------------------- weights ("RDW1" blob)
+struct Tensor {
+  const float* d = nullptr;  // device
+  int ndim = 0;
+  int shape[4] = {1, 1, 1, 1};
+  size_t numel = 0;
+};
+
+class Weights {
+ public:
+  Weights(const void* blob, size_t nbytes) {
+    RDB_CHECK(nbytes >= 8 && std::memcmp(blob, "RDW1", 4) == 0, "not an RDW1 weight blob");
+    const uint8_t* p = static_cast<const uint8_t*>(blob);
+    uint32_t n;
+    std::memcpy(&n, p + 4, 4);
+    RDB_CHECK(8 + (size_t)n * 100 <= nbytes, "truncated RDW1 header");
+    RDB_CUDA(cudaMalloc(&dev_, nbytes));
+    RDB_CUDA(cudaMemcpy(dev_, blob, nbytes, cudaMemcpyHostToDevice));
+    for (uint32_t i = 0; i < n; ++i) {
+      const uint8_t* e = p + 8 + (size_t)i * 100;
+      char name[65];
+      std::memcpy(name, e, 64);
+      name[64] = 0;
+      Tensor t;
+      uint32_t nd, shp[4];
+      uint64_t off, numel;
+      std::memcpy(&nd, e + 64, 4);
+      std::memcpy(shp, e + 68, 16);
+      std::memcpy(&off, e + 84, 8);
+      std::memcpy(&numel, e + 92, 8);
+      RDB_CHECK(off + numel * 4 <= nbytes, "RDW1 entry out of bounds");
+      t.ndim = nd;
+      for (int k = 0; k < 4; ++k) t.shape[k] = shp[k];
+      t.numel = numel;
+      t.d = reinterpret_cast<const float*>(static_cast<uint8_t*>(dev_) + off);
+      map_[name] = t;
+    }
+  }
+  ~Weights() { if (dev_) cudaFree(dev_); }
+  const Tensor& get(const std::string& name) const {
+    auto it = map_.find(name);
+    if (it == map_.end()) throw Error("weight tensor missing: " + name);
+    return it->second;
+  }
+  bool has(const std::string& name) const { return map_.count(name) != 0; }
+
+ private:
+  void* dev_ = nullptr;
+  std::unordered_map<std::string, Tensor> map_;
+};
+
+// ---------------------------------------------------------------- device buffer pool
+// Size-keyed caching allocator.  Every alloc/free of one engine call happens in program
+// order on ONE stream, so a block may be handed out again as soon as it is freed.
+class Pool {
+ public:
+  ~Pool() { release_all(); }
+  void* alloc(size_t bytes) {
+    bytes = (bytes + 511) / 512 * 512;
+    if (bytes == 0) bytes = 512;
+    auto it = free_.find(bytes);
+    if (it != free_.end() && !it->second.empty()) {
+      void* p = it->second.back();
+      it->second.pop_back();
+      live_[p] = bytes;
+      return p;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+      trim();
+      RDB_CUDA(cudaMalloc(&p, bytes));
+    }
+    total_ += bytes;
+    live_[p] = bytes;
+    return p;
+  }
+  template <typename T>
+  T* alloc_t(size_t n) { return static_cast<T*>(alloc(n * sizeof(T))); }
+  void free(void* p) {
+    if (!p) return;
+    auto it = live_.find(p);
+    RDB_CHECK(it != live_.end(), "pool: free of unknown pointer");
+    free_[it->second].push_back(p);
+    live_.erase(it);
+  }
+  void trim() {  // give cached blocks back to the driver
+    cudaDeviceSynchronize();
+    for (auto& kv : free_)
+      for (void* p : kv.second) { cudaFree(p); total_ -= kv.first; }
+    free_.clear();
+  }
+  void release_all() {
+    trim();
+    for (auto& kv : live_) cudaFree(kv.first);
+    live_.clear();
+  }
+  size_t total_bytes() const { return total_; }
+
+ private:
+  std::map<size_t, std::vector<void*>> free_;
+  std::unordered_map<void*, size_t> live_;
+  size_t total_ = 0;
+};
+
+inline bool is_device_ptr(const void* p) {
+  if (p == nullptr) return false;
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// ---------------------------------------------------------------- launch context
+// Optional per-kernel timing (rdb_profile_*): CUDA events recorded on the launching stream
+// around every launch, resolved after the call's final synchronise.  Off by default.
+struct Profiler {
+  bool on = false;
+  struct Rec { std::string name; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> spare;
+  std::map<std::string, std::pair<double, long long>> acc;  // name -> (ms, launches)
+  cudaEvent_t get() {
+    if (!spare.empty()) { cudaEvent_t e = spare.back(); spare.pop_back(); return e; }
+    cudaEvent_t e; RDB_CUDA(cudaEventCreate(&e)); return e;
+  }
+  void resolve() {
+    for (auto& r : recs) {
+      RDB_CUDA(cudaEventSynchronize(r.b));
+      float ms = 0.f;
+      RDB_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+      auto& p = acc[r.name]; p.first += ms; p.second += 1;
+      spare.push_back(r.a); spare.push_back(r.b);
+    }
+    recs.clear();
+  }
+  static Profiler& global() { static Profiler p; return p; }
+};
+
+struct Ctx {
+  cudaStream_t st = nullptr;
+  Pool* pool = nullptr;
+  long long launches = 0;
+  int precision = 0;
+  // bracket ONE kernel launch:  cx.begin("name"); kernel<<<...>>>(...); cx.end();
+  void begin(const std::string& name) {
+    Profiler& p = Profiler::global();
+    if (!p.on) return;
+    Profiler::Rec r{name, p.get(), p.get()};
+    RDB_CUDA(cudaEventRecord(r.a, st));
+    p.recs.push_back(r);
+  }
+  void end() {
+    RDB_LAUNCH_CHECK();
+    launches++;
+    Profiler& p = Profiler::global();
+    if (p.on) RDB_CUDA(cudaEventRecord(p.recs.back().b, st));
+  }
+  void finish() {  // after the work of a call is enqueued; resolves timings if profiling
+    Profiler& p = Profiler::global();
+    if (p.on) { RDB_CUDA(cudaStreamSynchronize(st)); p.resolve(); }
+  }
+};
+
+constexpr int kThreads = 256;
+
+// ---------------------------------------------------------------- typed launch helpers
+template <typename T>
+struct Ops {
+  // NHWC activation handle
+  struct Act {
+    T* p = nullptr; int n = 0, h = 0, w = 0, c = 0;
+    long long pixels() const { return (long long)n * h * w; }
+    long long numel() const { return pixels() * c; }
+  };
+  static Act make(Ctx& cx, int n, int h, int w, int c) {
+    Act a; a.n = n; a.h = h; a.w = w; a.c = c;
+    a.p = cx.pool->alloc_t<T>((size_t)a.numel());
+    return a;
+  }
+  static void release(Ctx& cx, Act& a) { cx.pool->free(a.p); a.p = nullptr; }
+
+  // pointwise conv / linear: out[M,N] = act(A W^T + b) (+res)
+  static void gemm(Ctx& cx, const T* A, int lda, long long M, int K, const Tensor& W, const Tensor* bias, int act,
+                   const T* res, int ldr, T* out, int ldc, int c_off) {
+    int N = W.shape[0];
+    RDB_CHECK(W.shape[1] == K, "gemm: weight K mismatch");
+    GemmArgs g{};
+    g.A = A; g.lda = lda; g.W = W.d; g.bias = bias ? bias->d : nullptr; g.res = res; g.ldr = ldr;
+    g.out = out; g.ldc = ldc; g.c_off = c_off; g.M = (int)M; g.N = N; g.K = K; g.act = act;
+    RDB_CHECK(M < (1ll << 31), "gemm: M too large");
+    cx.begin("gemm_simt[M=" + std::to_string(M) + ",K=" + std::to_string(K) + ",N=" + std::to_string(N) + ",res=" + (res ? "1" : "0") + "]");
+    launch_gemm_simt<T, T>(g, cx.st);
+    cx.end();
+  }
+  static void pw(Ctx& cx, const Act& in, const Tensor& W, const Tensor* bias, int act, const T* res, Act& out) {
+    gemm(cx, in.p, in.c, in.pixels(), in.c, W, bias, act, res, out.c, out.p, out.c, 0);
+  }
+
+  template <int KH, int KW, int ACT, bool ADD_IN>
+  static void dwconv(Ctx& cx, const Act& in, int sh, int sw, const Tensor& w, const Tensor& b, Act& out) {
+    long long total = out.pixels() * (in.c / 8);
+    cx.begin("dwconv" + std::to_string(KH) + "x" + std::to_string(KW) + "[P=" + std::to_string(out.pixels()) + ",C=" + std::to_string(in.c) + ",s=" + std::to_string(sh * sw) + "]");
+    dwconv_kernel<T, KH, KW, ACT, ADD_IN><<<cdiv(total, kThreads), kThreads, 0, cx.st>>>(
+        in.p, in.n, in.h, in.w, in.c, sh, sw, w.d, b.d, out.p, out.h, out.w);
+    cx.end();
+  }
+
+  // SE gate (mode 0: hardsigmoid; mode 1: 1+clip(.2z+.5)) -> float gate[n][C] from pool
+  static float* se_gate(Ctx& cx, const Act& x, const Tensor& w1, const Tensor& b1, const Tensor& w2, const Tensor& b2, int mode) {
+    int HW = x.h * x.w, C = x.c, Cr = w1.shape[0];
+    int G = C / 8;
+    int threads = 256;
+    int P = threads / G;
+    RDB_CHECK(P >= 1, "se: too many channels");
+    int chunks = HW / (P * 16);
+    if (chunks < 1) chunks = 1;
+    if (chunks > 148) chunks = 148;
+    float* partial = cx.pool->alloc_t<float>((size_t)x.n * chunks * C);
+    float* gate = cx.pool->alloc_t<float>((size_t)x.n * C);
+    cx.begin("se_pool[P=" + std::to_string(x.pixels()) + ",C=" + std::to_string(C) + "]");
+    pool_partial_kernel<T><<<dim3(chunks, x.n), threads, (size_t)P * C * sizeof(float), cx.st>>>(x.p, HW, C, partial, chunks);
+    cx.end();
+    cx.begin("se_fc");
+    se_fc_kernel<<<x.n, 128, (size_t)(C + Cr) * sizeof(float), cx.st>>>(partial, chunks, HW, C, Cr, w1.d, b1.d, w2.d, b2.d, mode, gate);
+    cx.end();
+    cx.pool->free(partial);
+    return gate;
+  }
+  static void scale(Ctx& cx, Act& x, const float* gate) {
+    long long total8 = x.numel() / 8;
+    cx.begin("se_scale[P=" + std::to_string(x.pixels()) + ",C=" + std::to_string(x.c) + "]");
+    scale_channels_kernel<T><<<cdiv(total8, kThreads), kThreads, 0, cx.st>>>(x.p, (long long)x.h * x.w, x.c, gate, total8);
+    cx.end();
+  }
+};
+
+template <typename K>
+inline void set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) RDB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+// PPLCNetV4 block table (cin, cout, stride_h, stride_w, se) — rec_lcnetv4.py:7-43
+struct BlockCfg { int cin, cout, sh, sw, se; };
+
+// stem + 4 stages, shared by det and rec.  x: stem1 output already computed by caller.
+template <typename T>
+struct Backbone {
+  using O = Ops<T>;
+  using Act = typename O::Act;
+
+  // stem2a..stem4 (rec_lcnetv4.py:160-169).  C1 = stem1 channels (24 det / 48 rec).
+  template <int C1>
+  static Act stem_rest(Ctx& cx, const Weights& w, Act& e1) {
+    constexpr int CH = C1 / 2, C2 = 2 * C1;
+    const int n = e1.n, H1 = e1.h, W1 = e1.w;
+    Act a = O::make(cx, n, H1, W1, CH);
+    {
+      auto k = conv_direct_kernel<T, 2, 2, 1, 1, C1, CH, CH, ACT_RELU>;
+      size_t sm = (size_t)(4 * C1 * CH + CH) * sizeof(float);
+      set_smem(k, sm);
+      cx.begin("stem2a");
+      k<<<dim3(cdiv(a.pixels(), 128), 1), 128, sm, cx.st>>>(e1.p, n, H1, W1, 0, 0, w.get("stem2a.w").d, w.get("stem2a.b").d,
+                                                            a.p, H1, W1, CH, 0);
+      cx.end();
+    }
+    Act cat = O::make(cx, n, H1, W1, C2);
+    {
+      auto k = conv_direct_kernel<T, 2, 2, 1, 1, CH, C1, C1 / 2, ACT_RELU>;
+      size_t sm = (size_t)(4 * CH * C1 + C1) * sizeof(float);
+      set_smem(k, sm);
+      cx.begin("stem2b");
+      k<<<dim3(cdiv(a.pixels(), 128), 2), 128, sm, cx.st>>>(a.p, n, H1, W1, 0, 0, w.get("stem2b.w").d, w.get("stem2b.b").d,
+                                                            cat.p, H1, W1, C2, C1);
+      cx.end();
+    }
+    {
+      long long total = e1.pixels() * (C1 / 8);
+      cx.begin("stem_pool");
+      pool2x2_concat_kernel<T><<<cdiv(total, kThreads), kThreads, 0, cx.st>>>(e1.p, n, H1, W1, C1, cat.p, C2);
+      cx.end();
+    }
+    O::release(cx, a);
+    O::release(cx, e1);
+    const int H2 = (H1 - 1) / 2 + 1, W2 = (W1 - 1) / 2 + 1;
+    Act s3 = O::make(cx, n, H2, W2, C1);
+    {
+      auto k = conv_direct_kernel<T, 3, 3, 2, 2, C2, C1, C1 / 2, ACT_RELU>;
+      size_t sm = (size_t)(9 * C2 * C1 + C1) * sizeof(float);
+      set_smem(k, sm);
+      cx.begin("stem3");
+      k<<<dim3(cdiv(s3.pixels(), 128), 2), 128, sm, cx.st>>>(cat.p, n, H1, W1, 1, 1, w.get("stem3.w").d, w.get("stem3.b").d,
+                                                             s3.p, H2, W2, C1, 0);
+      cx.end();
+    }
+    O::release(cx, cat);
+    Act x = O::make(cx, n, H2, W2, C2);
+    // stem4 weight is stored [C2][1][1][C1] == [C2][C1]
+    Tensor w4 = w.get("stem4.w");
+    w4.shape[1] = C1;
+    O::pw(cx, s3, w4, &w.get("stem4.b"), ACT_RELU, nullptr, x);
+    O::release(cx, s3);
+    return x;
+  }
+
+  // one PPLCNetV4 block (rec_lcnetv4.py:226-236).  Consumes x unless keep_in.
+  static Act block(Ctx& cx, const Weights& w, const std::string& name, const BlockCfg& c, Act& x, bool keep_in) {
+    const int OH = (x.h + 2 - 3) / c.sh + 1, OW = (x.w + 2 - 3) / c.sw + 1;
+    Act t = O::make(cx, x.n, OH, OW, c.cin);
+    O::template dwconv<3, 3, ACT_NONE, false>(cx, x, c.sh, c.sw, w.get(name + "dw.w"), w.get(name + "dw.b"), t);
+    if (!keep_in) O::release(cx, x);
+    if (c.se) {
+      float* gate = O::se_gate(cx, t, w.get(name + "se.w1"), w.get(name + "se.b1"), w.get(name + "se.w2"), w.get(name + "se.b2"), 0);
+      O::scale(cx, t, gate);
+      cx.pool->free(gate);
+    }
+    Act u = O::make(cx, x.n, OH, OW, 2 * c.cin);
+    O::pw(cx, t, w.get(name + "pw1.w"), &w.get(name + "pw1.b"), ACT_GELU, nullptr, u);
+    Act y = O::make(cx, x.n, OH, OW, c.cout);
+    const bool rep = (c.sh == 1 && c.sw == 1 && c.cin == c.cout);
+    O::pw(cx, u, w.get(name + "pw2.w"), &w.get(name + "pw2.b"), ACT_NONE, rep ? t.p : nullptr, y);
+    O::release(cx, u);
+    O::release(cx, t);
+    return y;
+  }
+};
+
+}  // namespace rdb

@@ -1,0 +1,631 @@
+// HBM-bound SIMT kernels of the PP-OCRv6 det/rec forward passes (NHWC activations,
+// fp32 math, storage type T in {float, __half}).  Each kernel cites the reference op it
+// implements (paths relative to rapid_doc/model/ocr/ppocrv6_pytorch/modeling/).
+#pragma once
+#include "common.cuh"
+
+namespace rdb {
+
+// =====================================================================================
+// stem1: conv3x3 s2 p1, Cin=3 -> C1, +bias(BN folded) + ReLU.   rec_lcnetv4.py:151,160
+// Input variants: fp32 NCHW (InferSession seam) or uint8 HWC + fused normalisation
+// (facade seam; DetPreProcess / resize_norm_img arithmetic).
+// =====================================================================================
+struct InF32NCHW {
+  const float* x; int H, W;
+  __device__ __forceinline__ float get(int n, int y, int xx, int c) const {
+    return x[(((long long)n * 3 + c) * H + y) * W + xx];
+  }
+};
+// norm_mode 0: (v*(1/255) - mean)/std   (DetPreProcess)
+// norm_mode 1: (v/255 - 0.5)/0.5        (resize_norm_img); pixels with xx >= valid_w[n] are 0 (right pad)
+struct InU8HWC {
+  const uint8_t* x; int H, W; int norm_mode; float mean[3], stdv[3]; const int* valid_w;
+  __device__ __forceinline__ float get(int n, int y, int xx, int c) const {
+    float v = (float)x[(((long long)n * H + y) * W + xx) * 3 + c];
+    if (norm_mode == 0) return __fdiv_rn(__fsub_rn(__fmul_rn(v, 1.0f / 255.0f), mean[c]), stdv[c]);
+    if (valid_w != nullptr && xx >= valid_w[n]) return 0.f;
+    return __fdiv_rn(__fsub_rn(__fdiv_rn(v, 255.0f), 0.5f), 0.5f);
+  }
+};
+
+template <typename T, typename IN, int C1>
+__global__ void __launch_bounds__(128) stem1_kernel(IN in, int N, const float* __restrict__ w /*[C1][3][3][3]*/,
+                                                    const float* __restrict__ b, T* __restrict__ out, int OH, int OW) {
+  __shared__ float sw[27 * C1];
+  __shared__ float sb[C1];
+  for (int i = threadIdx.x; i < 27 * C1; i += blockDim.x) {
+    int co = i / 27, r = i % 27;  // r = (ky*3+kx)*3+ci
+    sw[r * C1 + co] = w[i];
+  }
+  for (int i = threadIdx.x; i < C1; i += blockDim.x) sb[i] = b[i];
+  __syncthreads();
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)N * OH * OW;
+  if (idx >= total) return;
+  int ox = idx % OW; int oy = (idx / OW) % OH; int n = idx / ((long long)OW * OH);
+  float acc[C1];
+#pragma unroll
+  for (int c = 0; c < C1; ++c) acc[c] = sb[c];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    int iy = oy * 2 - 1 + ky;
+    if (iy < 0 || iy >= in.H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      int ix = ox * 2 - 1 + kx;
+      if (ix < 0 || ix >= in.W) continue;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        float v = in.get(n, iy, ix, ci);
+        const float* wp = &sw[((ky * 3 + kx) * 3 + ci) * C1];
+#pragma unroll
+        for (int c = 0; c < C1; c += 4) {
+          float4 w4 = *reinterpret_cast<const float4*>(wp + c);
+          acc[c] = fmaf(v, w4.x, acc[c]); acc[c + 1] = fmaf(v, w4.y, acc[c + 1]);
+          acc[c + 2] = fmaf(v, w4.z, acc[c + 2]); acc[c + 3] = fmaf(v, w4.w, acc[c + 3]);
+        }
+      }
+    }
+  }
+  T* op = out + idx * C1;
+#pragma unroll
+  for (int c = 0; c < C1; c += 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(acc[c + j], 0.f);
+    Vec8<T>::store(op + c, v);
+  }
+}
+
+// =====================================================================================
+// Generic small dense conv, NHWC -> NHWC, zero outside [0,H)x[0,W) (covers both the
+// symmetric conv padding and the F.pad(0,1,0,1) of the stem, rec_lcnetv4.py:161-164).
+// thread = one output pixel x CO_T output channels; weights staged in smem as
+// [tap][ci][COUT] so a warp reads them as broadcast float4.
+// =====================================================================================
+template <typename T, int KH, int KW, int SH, int SW, int CIN, int COUT, int CO_T, int ACT>
+__global__ void __launch_bounds__(128) conv_direct_kernel(const T* __restrict__ in, int N, int H, int W, int pt, int pl,
+                                                          const float* __restrict__ w /*[COUT][KH][KW][CIN]*/,
+                                                          const float* __restrict__ b, T* __restrict__ out, int OH, int OW,
+                                                          int ld_out, int co_off) {
+  extern __shared__ float smem[];
+  float* sw = smem;                       // [KH*KW*CIN][COUT]
+  float* sb = smem + KH * KW * CIN * COUT;
+  constexpr int TAPS = KH * KW * CIN;
+  for (int i = threadIdx.x; i < TAPS * COUT; i += blockDim.x) {
+    int co = i / TAPS, r = i % TAPS;
+    sw[r * COUT + co] = w[i];
+  }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = b[i];
+  __syncthreads();
+  constexpr int GROUPS = COUT / CO_T;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)N * OH * OW;
+  if (idx >= total) return;
+  const int g = blockIdx.y;  // output-channel group (warp-uniform)
+  int ox = idx % OW; int oy = (idx / OW) % OH; int n = idx / ((long long)OW * OH);
+  float acc[CO_T];
+#pragma unroll
+  for (int c = 0; c < CO_T; ++c) acc[c] = sb[g * CO_T + c];
+#pragma unroll
+  for (int ky = 0; ky < KH; ++ky) {
+    int iy = oy * SH - pt + ky;
+    if (iy < 0 || iy >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < KW; ++kx) {
+      int ix = ox * SW - pl + kx;
+      if (ix < 0 || ix >= W) continue;
+      const T* ip = in + (((long long)n * H + iy) * W + ix) * CIN;
+      const float* wt = sw + (ky * KW + kx) * CIN * COUT + g * CO_T;
+#pragma unroll 1
+      for (int c8 = 0; c8 < CIN; c8 += 8) {
+        float v[8];
+        if (CIN % 8 == 0) {
+          Vec8<T>::load(ip + c8, v);
+        } else {  // CIN % 4 == 0 (12-channel stem2a output)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = (c8 + j < CIN) ? to_f32<T>(ip[c8 + j]) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (c8 + j < CIN) {
+            const float* wp = wt + (c8 + j) * COUT;
+#pragma unroll
+            for (int c = 0; c < CO_T; c += 4) {
+              float4 w4 = *reinterpret_cast<const float4*>(wp + c);
+              acc[c] = fmaf(v[j], w4.x, acc[c]); acc[c + 1] = fmaf(v[j], w4.y, acc[c + 1]);
+              acc[c + 2] = fmaf(v[j], w4.z, acc[c + 2]); acc[c + 3] = fmaf(v[j], w4.w, acc[c + 3]);
+            }
+          }
+        }
+      }
+    }
+  }
+  T* op = out + idx * ld_out + co_off + g * CO_T;
+#pragma unroll
+  for (int c = 0; c < CO_T; c += 4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) op[c + j] = from_f32<T>(apply_act<ACT>(acc[c + j]));
+  }
+}
+
+// =====================================================================================
+// stem max-pool 2x2 s1 over the zero-padded (bottom/right) stem1 output, written into the
+// first C channels of the concat buffer.  rec_lcnetv4.py:156,165-166
+// =====================================================================================
+template <typename T>
+__global__ void pool2x2_concat_kernel(const T* __restrict__ in, int N, int H, int W, int C, T* __restrict__ out, int ld_out) {
+  int G = C / 8;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)N * H * W * G;
+  if (idx >= total) return;
+  int g = idx % G; long long p = idx / G;
+  int x = p % W; int y = (p / W) % H; int n = p / ((long long)W * H);
+  float m[8];
+  Vec8<T>::load(in + (((long long)n * H + y) * W + x) * C + g * 8, m);
+#pragma unroll
+  for (int d = 1; d < 4; ++d) {
+    int yy = y + (d >> 1), xx = x + (d & 1);
+    float v[8];
+    if (yy < H && xx < W) {
+      Vec8<T>::load(in + (((long long)n * H + yy) * W + xx) * C + g * 8, v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;  // F.pad zeros take part in the max
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+  }
+  Vec8<T>::store(out + p * ld_out + g * 8, m);
+}
+
+// =====================================================================================
+// Depthwise conv KHxKW, stride (sh,sw), pad (KH/2,KW/2), +bias, optional act, optional
+// "+ centre input" (LightSVTR h + dw(h), necks/rnn.py:367).  thread = pixel x 8 channels.
+// rec_lcnetv4.py:187-206 (token_conv), db_fpn.py:317-325 (7x7), rnn.py:352 (1x7)
+// =====================================================================================
+template <typename T, int KH, int KW, int ACT, bool ADD_IN>
+__global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ in, int N, int H, int W, int C, int sh, int sw,
+                                                     const float* __restrict__ w /*[KH][KW][C]*/, const float* __restrict__ b,
+                                                     T* __restrict__ out, int OH, int OW) {
+  int G = C / 8;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)N * OH * OW * G;
+  if (idx >= total) return;
+  int g = idx % G; long long p = idx / G;
+  int ox = p % OW; int oy = (p / OW) % OH; int n = p / ((long long)OW * OH);
+  float acc[8];
+  {
+    float4 b0 = __ldg(reinterpret_cast<const float4*>(b + g * 8));
+    float4 b1 = __ldg(reinterpret_cast<const float4*>(b + g * 8 + 4));
+    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+  }
+#pragma unroll
+  for (int ky = 0; ky < KH; ++ky) {
+    int iy = oy * sh - KH / 2 + ky;
+    if (iy < 0 || iy >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < KW; ++kx) {
+      int ix = ox * sw - KW / 2 + kx;
+      if (ix < 0 || ix >= W) continue;
+      float v[8];
+      Vec8<T>::load(in + (((long long)n * H + iy) * W + ix) * C + g * 8, v);
+      const float* wp = w + (ky * KW + kx) * C + g * 8;
+      float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
+      float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+      acc[0] = fmaf(v[0], w0.x, acc[0]); acc[1] = fmaf(v[1], w0.y, acc[1]);
+      acc[2] = fmaf(v[2], w0.z, acc[2]); acc[3] = fmaf(v[3], w0.w, acc[3]);
+      acc[4] = fmaf(v[4], w1.x, acc[4]); acc[5] = fmaf(v[5], w1.y, acc[5]);
+      acc[6] = fmaf(v[6], w1.z, acc[6]); acc[7] = fmaf(v[7], w1.w, acc[7]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = apply_act<ACT>(acc[j]);
+  if (ADD_IN) {
+    float v[8];
+    Vec8<T>::load(in + (((long long)n * H + oy) * W + ox) * C + g * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+  }
+  Vec8<T>::store(out + p * C + g * 8, acc);
+}
+
+// =====================================================================================
+// Squeeze-excitation: deterministic two-stage global average pool, the two tiny FCs and
+// the gate.  rec_lcnetv4.py:120-142 (gate = clip(x/6+.5,0,1)), db_fpn.py:288-308
+// (gate = clip(.2x+.5,0,1), used as x + x*gate -> we emit 1+gate).
+// =====================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) pool_partial_kernel(const T* __restrict__ in, int HW, int C, float* __restrict__ partial,
+                                                           int chunks) {
+  extern __shared__ float red[];  // [P][C]
+  int G = C / 8;
+  int P = blockDim.x / G;
+  int n = blockIdx.y, chunk = blockIdx.x;
+  int g = threadIdx.x % G, p = threadIdx.x / G;
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  if (p < P) {
+    const T* base = in + (long long)n * HW * C + g * 8;
+    for (long long px = (long long)chunk * P + p; px < HW; px += (long long)chunks * P) {
+      float v[8];
+      Vec8<T>::load(base + px * C, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[p * C + g * 8 + j] = s[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+    for (int q = 0; q < P; ++q) t += red[q * C + c];
+    partial[((long long)n * chunks + chunk) * C + c] = t;
+  }
+}
+
+// mode 0: gate = hardsigmoid(z) = clip(z/6+.5,0,1);  mode 1: gate = 1 + clip(.2z+.5,0,1)
+static __global__ void se_fc_kernel(const float* __restrict__ partial, int chunks, int HW, int C, int Cr, const float* __restrict__ w1,
+                             const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                             int mode, float* __restrict__ gate) {
+  extern __shared__ float sm[];  // mean[C] + hid[Cr]
+  float* mean = sm;
+  float* hid = sm + C;
+  int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+    for (int k = 0; k < chunks; ++k) t += partial[((long long)n * chunks + k) * C + c];
+    mean[c] = t / (float)HW;
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < Cr; r += blockDim.x) {
+    float t = b1[r];
+    for (int c = 0; c < C; ++c) t = fmaf(w1[r * C + c], mean[c], t);
+    hid[r] = fmaxf(t, 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = b2[c];
+    for (int r = 0; r < Cr; ++r) t = fmaf(w2[c * Cr + r], hid[r], t);
+    float gt;
+    if (mode == 0) gt = fminf(fmaxf(t / 6.f + 0.5f, 0.f), 1.f);
+    else gt = 1.f + fminf(fmaxf(0.2f * t + 0.5f, 0.f), 1.f);
+    gate[(long long)n * C + c] = gt;
+  }
+}
+
+template <typename T>
+__global__ void scale_channels_kernel(T* __restrict__ x, long long HW, int C, const float* __restrict__ gate, long long total8) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total8) return;
+  int G = C / 8;
+  int g = idx % G; long long p = idx / G;
+  int n = p / HW;
+  float v[8];
+  Vec8<T>::load(x + p * C + g * 8, v);
+  const float* gp = gate + (long long)n * C + g * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] *= gp[j];
+  Vec8<T>::store(x + p * C + g * 8, v);
+}
+
+// =====================================================================================
+// RepLKFPN top-down: dst += nearest_up2(src).   db_fpn.py:394-399
+// =====================================================================================
+template <typename T>
+__global__ void upsample2_add_kernel(T* __restrict__ dst, const T* __restrict__ src, int N, int H, int W, int C) {
+  int G = C / 8;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)N * H * W * G;
+  if (idx >= total) return;
+  int g = idx % G; long long p = idx / G;
+  int x = p % W; int y = (p / W) % H; int n = p / ((long long)W * H);
+  float a[8], b[8];
+  Vec8<T>::load(dst + p * C + g * 8, a);
+  Vec8<T>::load(src + (((long long)n * (H / 2) + (y >> 1)) * (W / 2) + (x >> 1)) * C + g * 8, b);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] += b[j];
+  Vec8<T>::store(dst + p * C + g * 8, a);
+}
+
+// RepLKFPN output: nearest upsample x1/2/4/8 of the four 24-channel maps (each scaled by
+// its SE gate 1+g), concatenated coarse->fine.   db_fpn.py:401-415
+template <typename T>
+struct NeckSrc { const T* f[4]; const float* gate[4]; };
+
+template <typename T>
+__global__ void neck_concat_kernel(NeckSrc<T> s, int N, int H, int W, T* __restrict__ out) {
+  // out [N,H,W,96]; channel group j (24 ch) comes from level 3-j (level L has size H>>L)
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)N * H * W * 12;
+  if (idx >= total) return;
+  int g = idx % 12; long long p = idx / 12;
+  int x = p % W; int y = (p / W) % H; int n = p / ((long long)W * H);
+  int j = g / 3, c8 = (g % 3) * 8;
+  int L = 3 - j;
+  int h = H >> L, w = W >> L;
+  float v[8];
+  Vec8<T>::load(s.f[L] + (((long long)n * h + (y >> L)) * w + (x >> L)) * 24 + c8, v);
+  const float* gp = s.gate[L] + n * 24 + c8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] *= gp[k];
+  Vec8<T>::store(out + p * 96 + g * 8, v);
+}
+
+// =====================================================================================
+// DBHead tail: ConvT2x2s2(24->24)+BN+ReLU -> ConvT2x2s2(24->1)+bias -> sigmoid ->
+// nan_to_num, fused; also emits the pre-dilation segmentation byte (prob > thresh).
+// det_db_head.py:117-147; threshold: ocr_patch.py:229.
+// thread = one pixel of the intermediate 2H x 2W grid -> 2x2 output probabilities.
+// =====================================================================================
+template <typename T>
+__global__ void __launch_bounds__(128) head_tail_kernel(const T* __restrict__ in /*[N,H,W,24]*/, int N, int H, int W,
+                                                        const float* __restrict__ w_up /*[2][2][24][24]*/,
+                                                        const float* __restrict__ b_up, const float* __restrict__ w_fin /*[2][2][24]*/,
+                                                        const float* __restrict__ b_fin, float thresh, float* __restrict__ prob,
+                                                        uint8_t* __restrict__ seg) {
+  __shared__ float s_up[4 * 24 * 24];
+  __shared__ float s_bu[24];
+  __shared__ float s_fin[4 * 24];
+  for (int i = threadIdx.x; i < 4 * 24 * 24; i += blockDim.x) {
+    // store as [q][ci][co] for broadcast float4 reads over co
+    int q = i / 576, r = i % 576, co = r / 24, ci = r % 24;
+    s_up[q * 576 + ci * 24 + co] = w_up[i];
+  }
+  for (int i = threadIdx.x; i < 24; i += blockDim.x) s_bu[i] = b_up[i];
+  for (int i = threadIdx.x; i < 96; i += blockDim.x) s_fin[i] = w_fin[i];
+  __syncthreads();
+  const int H2 = 2 * H, W2 = 2 * W;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)N * H2 * W2;
+  if (idx >= total) return;
+  int x2 = idx % W2; int y2 = (idx / W2) % H2; int n = idx / ((long long)W2 * H2);
+  int q = (y2 & 1) * 2 + (x2 & 1);
+  const T* ip = in + (((long long)n * H + (y2 >> 1)) * W + (x2 >> 1)) * 24;
+  float hid[24];
+#pragma unroll
+  for (int c = 0; c < 24; ++c) hid[c] = s_bu[c];
+#pragma unroll
+  for (int c8 = 0; c8 < 24; c8 += 8) {
+    float v[8];
+    Vec8<T>::load(ip + c8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float* wp = &s_up[q * 576 + (c8 + j) * 24];
+#pragma unroll
+      for (int c = 0; c < 24; c += 4) {
+        float4 w4 = *reinterpret_cast<const float4*>(wp + c);
+        hid[c] = fmaf(v[j], w4.x, hid[c]); hid[c + 1] = fmaf(v[j], w4.y, hid[c + 1]);
+        hid[c + 2] = fmaf(v[j], w4.z, hid[c + 2]); hid[c + 3] = fmaf(v[j], w4.w, hid[c + 3]);
+      }
+    }
+  }
+  const float bf = b_fin[0];
+  float o[4] = {bf, bf, bf, bf};
+#pragma unroll
+  for (int c = 0; c < 24; ++c) {
+    float hv = fmaxf(hid[c], 0.f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = fmaf(hv, s_fin[k * 24 + c], o[k]);
+  }
+  const int W4 = 2 * W2;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float pz = 1.f / (1.f + expf(-o[k]));
+    if (pz != pz) pz = 0.f;  // nan_to_num
+    o[k] = pz;
+  }
+  long long base = ((long long)n * (2 * H2) + 2 * y2) * W4 + 2 * x2;
+  *reinterpret_cast<float2*>(prob + base) = make_float2(o[0], o[1]);
+  *reinterpret_cast<float2*>(prob + base + W4) = make_float2(o[2], o[3]);
+  if (seg != nullptr) {
+    *reinterpret_cast<uchar2*>(seg + base) = make_uchar2(o[0] > thresh, o[1] > thresh);
+    *reinterpret_cast<uchar2*>(seg + base + W4) = make_uchar2(o[2] > thresh, o[3] > thresh);
+  }
+}
+
+// prob -> seg byte (used when the prob map came from elsewhere, e.g. the DB C-ABI entry)
+static __global__ void threshold_kernel(const float* __restrict__ prob, float thresh, uint8_t* __restrict__ seg, long long total) {
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < total) {
+    float4 p = *reinterpret_cast<const float4*>(prob + i);
+    *reinterpret_cast<uchar4*>(seg + i) = make_uchar4(p.x > thresh, p.y > thresh, p.z > thresh, p.w > thresh);
+  } else {
+    for (; i < total; ++i) seg[i] = prob[i] > thresh;
+  }
+}
+
+// cv2.dilate(seg, ones(2,2)) : anchor (1,1) -> out[y,x] = OR seg[y-1..y, x-1..x]
+// (ocr_patch.py:232-235; border pixels outside the image are ignored).
+static __global__ void dilate2x2_kernel(const uint8_t* __restrict__ seg, int N, int H, int W, uint8_t* __restrict__ out) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // 4 pixels per thread along x
+  int W4 = W / 4;
+  long long total = (long long)N * H * W4;
+  if (idx >= total) return;
+  int xq = idx % W4; int y = (idx / W4) % H; int n = idx / ((long long)W4 * H);
+  const uint8_t* row = seg + ((long long)n * H + y) * W + xq * 4;
+  uchar4 c = *reinterpret_cast<const uchar4*>(row);
+  uint8_t cl = (xq > 0) ? row[-1] : 0;
+  uchar4 u = make_uchar4(0, 0, 0, 0);
+  uint8_t ul = 0;
+  if (y > 0) {
+    u = *reinterpret_cast<const uchar4*>(row - W);
+    ul = (xq > 0) ? row[-W - 1] : 0;
+  }
+  uchar4 o;
+  o.x = c.x | cl | u.x | ul;
+  o.y = c.y | c.x | u.y | u.x;
+  o.z = c.z | c.y | u.z | u.y;
+  o.w = c.w | c.z | u.w | u.z;
+  *reinterpret_cast<uchar4*>(out + ((long long)n * H + y) * W + xq * 4) = o;
+}
+
+// =====================================================================================
+// rec: avg_pool2d([3,2]) on [N,3,W,C] -> [N,1,W/2,C].   rec_lcnetv4.py:311
+// =====================================================================================
+template <typename T>
+__global__ void avgpool3x2_kernel(const T* __restrict__ in, int N, int W, int C, T* __restrict__ out) {
+  int G = C / 8, OW = W / 2;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)N * OW * G;
+  if (idx >= total) return;
+  int g = idx % G; long long p = idx / G;
+  int ox = p % OW; int n = p / OW;
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  for (int y = 0; y < 3; ++y)
+    for (int dx = 0; dx < 2; ++dx) {
+      float v[8];
+      Vec8<T>::load(in + (((long long)n * 3 + y) * W + ox * 2 + dx) * C + g * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += v[j];
+    }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] *= (1.f / 6.f);
+  Vec8<T>::store(out + p * C + g * 8, s);
+}
+
+// LayerNorm over the last dim (C <= 1024), one warp per row; optional residual add
+// (out = ln(x)*g+b [+ res]).   necks/rnn.py:301-318,376-379
+template <typename T>
+__global__ void layernorm_kernel(const T* __restrict__ x, long long rows, int C, const float* __restrict__ g,
+                                 const float* __restrict__ b, float eps, const T* __restrict__ res, T* __restrict__ out) {
+  long long row = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const T* xp = x + row * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += to_f32<T>(xp[c]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffff, s, o);
+  float mean = s / C;
+  float v = 0.f;
+  for (int c = lane; c < C; c += 32) { float d = to_f32<T>(xp[c]) - mean; v += d * d; }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffff, v, o);
+  float rstd = rsqrtf(v / C + eps);
+  for (int c = lane; c < C; c += 32) {
+    float y = (to_f32<T>(xp[c]) - mean) * rstd * g[c] + b[c];
+    if (res != nullptr) y += to_f32<T>(res[row * C + c]);
+    out[row * C + c] = from_f32<T>(y);
+  }
+}
+
+// LightSVTR self-attention: qkv [N,T,3,heads,hd] -> out [N,T,heads*hd].  One block per
+// (n, head); K,V of the head staged in smem; one thread per query with online softmax.
+// necks/rnn.py:253-265 (scale = hd^-0.5)
+template <typename T, int HD>
+__global__ void attention_kernel(const T* __restrict__ qkv, int Tn, int heads, float scale, T* __restrict__ out) {
+  extern __shared__ float kv[];  // K[T][HD], V[T][HD]
+  float* K = kv;
+  float* V = kv + Tn * HD;
+  int n = blockIdx.x / heads, h = blockIdx.x % heads;
+  int C = heads * HD;
+  const T* base = qkv + (long long)n * Tn * 3 * C;
+  for (int i = threadIdx.x; i < Tn * HD; i += blockDim.x) {
+    int t = i / HD, d = i % HD;
+    K[i] = to_f32<T>(base[(long long)t * 3 * C + C + h * HD + d]);
+    V[i] = to_f32<T>(base[(long long)t * 3 * C + 2 * C + h * HD + d]);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < Tn; t += blockDim.x) {
+    float q[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) q[d] = to_f32<T>(base[(long long)t * 3 * C + h * HD + d]) * scale;
+    float m = -INFINITY, l = 0.f, acc[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+    for (int j = 0; j < Tn; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) s = fmaf(q[d], K[j * HD + d], s);
+      float mn = fmaxf(m, s);
+      float corr = __expf(m - mn), pj = __expf(s - mn);
+      l = l * corr + pj;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) acc[d] = acc[d] * corr + pj * V[j * HD + d];
+      m = mn;
+    }
+    float inv = 1.f / l;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) out[((long long)n * Tn + t) * C + h * HD + d] = from_f32<T>(acc[d] * inv);
+  }
+}
+
+// =====================================================================================
+// CTC greedy decode.  Stage 1 (fused in the head GEMM epilogue) leaves per-row, per-N-tile
+// partials (max, argmax, sum exp(x-max)); this kernel merges them into (id, prob) where
+// prob = softmax max = 1/sum exp(x - max)   (torch.py:186-187 + CTCLabelDecode argmax/max).
+// Ties resolve to the lowest index, as numpy argmax does.
+// =====================================================================================
+static __global__ void ctc_merge_kernel(const float* __restrict__ pmax, const int* __restrict__ pidx, const float* __restrict__ psum,
+                                 int rows, int tiles, int* __restrict__ ids, float* __restrict__ probs) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float m = -INFINITY; int id = 0;
+  for (int t = 0; t < tiles; ++t) {
+    float v = pmax[(long long)r * tiles + t];
+    if (v > m) { m = v; id = pidx[(long long)r * tiles + t]; }
+  }
+  float s = 0.f;
+  for (int t = 0; t < tiles; ++t) s += psum[(long long)r * tiles + t] * __expf(pmax[(long long)r * tiles + t] - m);
+  ids[r] = id;
+  probs[r] = 1.f / s;
+}
+
+// CTC collapse: keep t where id != blank(0) and id != id[t-1]; one warp per text line.
+// out_ids [N,T] (compacted, -1 padded), out_len [N], conf [N] = mean kept prob (0 if none).
+static __global__ void ctc_collapse_kernel(const int* __restrict__ ids, const float* __restrict__ probs, int N, int T,
+                                    int* __restrict__ out_ids, int* __restrict__ out_len, float* __restrict__ conf) {
+  int n = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  int count = 0; float sum = 0.f;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    int t = t0 + lane;
+    int id = (t < T) ? ids[(long long)n * T + t] : 0;
+    int prev = (t > 0 && t < T) ? ids[(long long)n * T + t - 1] : -1;
+    bool keep = (t < T) && id != 0 && id != prev;
+    unsigned mask = __ballot_sync(0xffffffff, keep);
+    int pos = count + __popc(mask & ((1u << lane) - 1));
+    if (keep) out_ids[(long long)n * T + pos] = id;
+    float pv = keep ? probs[(long long)n * T + t] : 0.f;
+    // sequential-order sum (lane 0..31) for run-to-run determinism
+    for (int l = 0; l < 32; ++l) { float x = __shfl_sync(0xffffffff, pv, l); sum += x; }
+    count += __popc(mask);
+  }
+  for (int t = count + lane; t < T; t += 32) out_ids[(long long)n * T + t] = -1;
+  if (lane == 0) { out_len[n] = count; conf[n] = count ? sum / count : 0.f; }
+}
+
+// row-wise softmax over V (compat path for the InferSession seam that must return the
+// full [N,T,V] probability tensor, torch.py:186-192); one block per row.
+static __global__ void softmax_rows_kernel(const float* __restrict__ logits, int V, float* __restrict__ out) {
+  __shared__ float red[32];
+  const float* x = logits + (long long)blockIdx.x * V;
+  float* o = out + (long long)blockIdx.x * V;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) m = fmaxf(m, x[i]);
+#pragma unroll
+  for (int k = 16; k; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffff, m, k));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float s = 0.f;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) s += expf(x[i] - m);
+#pragma unroll
+  for (int k = 16; k; k >>= 1) s += __shfl_xor_sync(0xffffffff, s, k);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+  float inv = 1.f / s;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) o[i] = expf(x[i] - m) * inv;
+}
+
+}  // namespace rdb
