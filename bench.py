@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's config, one process per GPU.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
+  python bench.py --impl reference ...                     (reference CPU arm, rank 0 only)
+
+Workload (config.workload): `det_dbnet_b64_1024` = BASELINE.json configs[1], "RapidOCR DBNet
+text-detection, batch=64 1024x1024 synthetic pages": one STEP = one pass of the hot path
+(fused normalise -> PP-OCRv6-small DBNet forward -> DB binarise + 2x2 dilate) over one batch
+of 64 synthetic uint8 BGR pages per GPU.  `--workload rec` runs configs[2] (512 48x320 crops,
+forward + fused CTC greedy decode) with the same contract.
+
+value = whole-job pages/s (crops/s) with the batch resident in HBM, timed with CUDA events
+        on the stream the kernels are launched on, barrier + synchronize on both sides,
+        max over ranks.
+e2e   = the same metric through the C-ABI with HOST (pinned) buffers: H2D of the uint8
+        pages and D2H of prob map + bitmap (det) / ids+probs+text (rec) inside the timed
+        region.
+roofline = the dominant kernel of the step (largest share of device time in a profiled
+        pass taken right after the timed region, CUDA events around every launch on the
+        launching stream): algorithmic bytes per launch / average launch duration against
+        the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+cpu_baseline = the CPU oracle port of the same path (oracle/nets.py + oracle/ocr_post.py,
+        torch CPU fp32, all host cores) on a bounded sample, rank 0 at N=1 only.
+"""
+import argparse
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "det": dict(name="det_dbnet_b64_1024x1024", batch=64, h=1024, w=1024, unit="pages/s", metric="pages/sec (DBNet text-detection hot path)"),
+    "rec": dict(name="rec_svtr_ctc_b512_48x320", batch=512, h=48, w=320, unit="crops/s", metric="SVTR text-line crops/sec"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("RDB_BENCH_WORKLOAD", "det"), choices=list(WORKLOADS))
+    ap.add_argument("--precision", default=os.environ.get("RDB_BENCH_PRECISION", "fp16"), choices=["fp16", "fp32"])
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debug only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk-pixels", type=int, default=0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[2:6]):
+                if v == "Active":
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------- roofline model
+def _kv(name):
+    m = re.match(r"([^\[]+)(?:\[(.*)\])?", name)
+    kind, args = m.group(1), {}
+    if m.group(2):
+        for item in m.group(2).split(","):
+            k, v = item.split("=")
+            args[k] = int(v)
+    return kind, args
+
+
+def algorithmic_bytes(name, esz, wl, n_chunk):
+    """Minimum HBM bytes one launch of this kernel must move: every input
+    element read once, every output written once, at the storage size of the precision mode."""
+    kind, a = _kv(name)
+    H, W = wl["h"], wl["w"]
+    if kind.startswith("gemm"):
+        return a["M"] * (a["K"] + a["N"] + (a["N"] if a.get("res") else 0)) * esz + a["N"] * a["K"] * 4
+    if kind.startswith("dwconv"):
+        return a["P"] * a["C"] * esz * (1 + a.get("s", 1))       # stride-s input is s x the output
+    if kind == "se_pool":
+        return a["P"] * a["C"] * esz
+    if kind == "se_scale":
+        return 2 * a["P"] * a["C"] * esz
+    px = n_chunk * H * W
+    table = {
+        "stem1": px * 3 * 1 + px // 4 * 24 * esz, "stem2a": px // 4 * (24 + 12) * esz, "stem2b": px // 4 * (12 + 24) * esz,
+        "stem_pool": px // 4 * 48 * esz, "stem3": px // 4 * 48 * esz + px // 16 * 24 * esz,
+        "head_conv3x3": px // 16 * (96 + 24) * esz, "head_tail": px // 16 * 24 * esz + px * 5,
+        "db_dilate": px * 2, "neck_concat": px // 16 * 96 * esz * 2, "neck_upadd": 0,
+    }
+    return table.get(kind)
+
+
+def algorithmic_flops(name):
+    kind, a = _kv(name)
+    if kind.startswith("gemm"):
+        return 2 * a["M"] * a["K"] * a["N"]
+    return None
+
+
+# ------------------------------------------------------------------------------- CPU oracle arm
+def cpu_step_det(pages):
+    from oracle import nets, ocr_post as P
+    x = np.concatenate([P.det_preprocess(p, limit_side_len=max(p.shape[:2])) for p in pages])
+    prob = nets.det_forward(x)
+    return [P.db_bitmap(prob[i, 0], 0.3, True) for i in range(len(pages))]
+
+
+def cpu_step_rec(crops):
+    from oracle import nets, ocr_post as P
+    x, _ = P.rec_batch_tensor(list(crops))
+    probs = nets.rec_forward(x)
+    return P.ctc_decode(probs, nets.load_characters())
+
+
+def time_cpu(wl_key, data, sample, reps=1):
+    import torch
+    torch.set_num_threads(os.cpu_count())
+    fn = cpu_step_det if wl_key == "det" else cpu_step_rec
+    fn(data[: min(2, sample)])  # warm
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn(data[:sample])
+    dt = (time.perf_counter() - t0) / reps
+    return sample / dt, dt
+
+
+# ------------------------------------------------------------------------------- main arms
+def run_reference(args, wl_key, wl):
+    """Reference arm: the reference's own CPU implementation of the path.  RapidDoc is pure
+    Python and cannot travel to the GPU box (its engines onnxruntime/rapidocr are absent even
+    here), so this times the CPU oracle port (bit-identical to the reference's torch nets,
+    tests/test_oracle.py) on all host cores, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from rapiddoc_b200 import synth
+    sample = 4 if wl_key == "det" else 64
+    data = synth.det_pages(sample, wl["h"], wl["w"], seed=1) if wl_key == "det" else synth.rec_crops(sample, wl["h"], wl["w"], seed=2)
+    fn = cpu_step_det if wl_key == "det" else cpu_step_rec
+    import torch
+    torch.set_num_threads(os.cpu_count())
+    for _ in range(args.warmup):
+        fn(data)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn(data)
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    line = {"impl": "reference", "metric": wl["metric"], "value": v, "unit": wl["unit"], "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "sample": f"{sample} of the {wl['batch']} per step", "engine": "torch CPU fp32 (oracle port of the reference nets)"},
+            "cpu_baseline": {"value": v, "unit": wl["unit"], "cores": os.cpu_count(), "kind": "port", "sample": f"{sample} {wl['unit'].split('/')[0]} per step x {args.steps} steps"},
+            "e2e": {"value": v, "unit": wl["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    wl_key = args.workload
+    wl = dict(WORKLOADS[wl_key])
+    if args.batch:
+        wl["batch"] = args.batch
+    if args.impl == "reference":
+        return run_reference(args, wl_key, wl)
+
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from rapiddoc_b200 import _lib, PREC_FP16, PREC_FP32, synth, weights as W
+    from rapiddoc_b200.engine import DetEngine, RecEngine
+    from rapiddoc_b200.parallel import broadcast_blob, shard_range
+    prec = PREC_FP16 if args.precision == "fp16" else PREC_FP32
+    esz = 2 if prec == PREC_FP16 else 4
+    # weights: rank 0 packs, NCCL broadcast over NVLink at init (the only collective on the path)
+    blob = broadcast_blob((W.det_blob() if wl_key == "det" else W.rec_blob()) if rank == 0 else None, local)
+    B, H, Wd = wl["batch"], wl["h"], wl["w"]
+    # every rank generates ITS shard of the global synthetic batch (weak scaling: B per GPU)
+    lo, hi = shard_range(world * B, world, rank)
+    if wl_key == "det":
+        uniq = min(B, 8)
+        base = synth.det_pages(uniq, H, Wd, seed=1 + rank)
+        host = torch.empty((B, H, Wd, 3), dtype=torch.uint8).pin_memory()
+        for i in range(B):  # distinct pages: roll the unique ones by a per-page offset
+            host[i] = torch.from_numpy(np.roll(base[i % uniq], shift=(7 * (i // uniq), 13 * (i // uniq)), axis=(0, 1)))
+        eng = DetEngine(device=local, precision=prec, blob=blob)
+        if args.chunk_pixels:
+            eng.set_chunk_pixels(args.chunk_pixels)
+        dev_in = host.cuda()
+        d_prob = torch.empty((B, H, Wd), dtype=torch.float32, device="cuda")
+        d_bm = torch.empty((B, H, Wd), dtype=torch.uint8, device="cuda")
+        h_prob = torch.empty((B, H, Wd), dtype=torch.float32).pin_memory()
+        h_bm = torch.empty((B, H, Wd), dtype=torch.uint8).pin_memory()
+        host_np, h_prob_np, h_bm_np = host.numpy(), h_prob.numpy(), h_bm.numpy()
+
+        def step_dev():
+            eng.infer_u8(dev_in, prob=d_prob, bitmap=d_bm, stream=torch.cuda.current_stream())
+
+        def step_host():
+            eng.infer_u8(host_np, prob=h_prob_np, bitmap=h_bm_np)
+        h2d, d2h = host.numel(), h_prob.numel() * 4 + h_bm.numel()
+    else:
+        base = synth.rec_crops(B, H, Wd, seed=2 + rank)
+        host = torch.from_numpy(base).pin_memory()
+        vw = np.full(B, Wd, np.int32)
+        eng = RecEngine(device=local, precision=prec, blob=blob)
+        dev_in = host.cuda()
+        d_vw = torch.from_numpy(vw).cuda()
+        T = eng.tokens(Wd)
+        d_out = eng._outs(B, T, dev_in, False)
+        h_out = {k: (v.cpu().pin_memory().numpy() if v is not None else None) for k, v in d_out.items()}
+        host_np = host.numpy()
+
+        def step_dev():
+            eng.infer_u8(dev_in, d_vw, stream=torch.cuda.current_stream(), outs=d_out)
+
+        def step_host():
+            eng.infer_u8(host_np, vw, outs=h_out)
+        h2d, d2h = host.numel() + B * 4, B * T * 12 + B * 8
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: device-resident, CUDA events on the launching (torch current) stream
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    e0.record()
+    for _ in range(args.steps):
+        step_dev()
+        launches += eng.last_launches
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    value = world * B * args.steps / (ms / 1e3)
+    # ---- e2e: host pinned buffers through the C-ABI, copies inside the timed region
+    for _ in range(2):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e = world * B * args.steps / dt
+    # ---- roofline of the dominant kernel: profiled pass (events around every launch)
+    roofline = None
+    if rank == 0:
+        _lib.profile(True)
+        _lib.profile_reset()
+        for _ in range(2):
+            step_dev()
+        torch.cuda.synchronize()
+        prof = _lib.profile_dump()
+        _lib.profile(False)
+        total = sum(v[0] for v in prof.values())
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        name, (kms, kn) = max(prof.items(), key=lambda kv: kv[1][0])
+        n_chunk = max(1, min(B, (args.chunk_pixels or 8 * 1024 * 1024) // (H * Wd))) if wl_key == "det" else B
+        ab = algorithmic_bytes(name, esz, wl, n_chunk)
+        avg_s = kms / kn / 1e3
+        ach = (ab / avg_s / 1e9) if ab else None
+        roofline = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": (ach / hbm) if ach else None,
+                    "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                    "algorithmic_bytes_per_launch": ab, "avg_launch_us": avg_s * 1e6, "share_of_step": kms / total,
+                    "top5": [{"kernel": k, "share": v[0] / total, "avg_us": v[0] / v[1] * 1e3} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:5]]}
+        fl = algorithmic_flops(name)
+        if fl:
+            roofline["achieved_tflops"] = fl / avg_s / 1e12
+    # ---- CPU baseline (oracle port) on a bounded sample, rank 0 at N=1 only
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample = 8 if wl_key == "det" else 128
+        data = host_np[:sample]
+        v, dt_cpu = time_cpu(wl_key, data, sample, reps=2 if wl_key == "det" else 3)
+        cpu = {"value": v, "unit": wl["unit"], "cores": os.cpu_count(), "kind": "port",
+               "sample": f"{sample} {wl['unit'].split('/')[0]} of this step's batch, torch CPU fp32 oracle incl. normalise + DB bitmap / CTC decode, {dt_cpu:.1f}s per pass"}
+    if rank == 0:
+        line = {"metric": wl["metric"], "value": value, "unit": wl["unit"], "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f16" if prec == PREC_FP16 else "f32", "data": "synthetic",
+                "config": {"workload": wl["name"], "batch_per_gpu": B, "h": H, "w": Wd, "precision": args.precision, "input": "uint8 BGR HWC",
+                           "l2": f"inputs {host.numel() / 1e6:.0f} MB + activations per step exceed the 126 MB L2 (no explicit flush)",
+                           "parallelism": f"page-parallel replicas x{world}, NCCL weight broadcast at init only"},
+                "clocks": clocks, "e2e": {"value": e2e, "unit": wl["unit"], "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

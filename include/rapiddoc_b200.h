@@ -108,6 +108,13 @@ int rdb_rec_infer_u8(rdb_rec_t* h, const uint8_t* crops, const int32_t* valid_w,
 long long rdb_det_last_launches(rdb_det_t* h);
 long long rdb_rec_last_launches(rdb_rec_t* h);
 
+/* Diagnostic: one GEMM out[M,N] = act(A[M,K] W[N,K]^T + bias) (+res) through the fp16
+ * pointwise-conv engines (use_tc=1 tcgen05 kernel, 0 SIMT kernel); host fp32 in/out, inputs
+ * rounded to fp16 as the engines store them.  mode 1: fused CTC epilogue, out = [M,2]
+ * (argmax id, softmax max prob).  Used by the kernel unit tests. */
+int rdb_debug_gemm(int device, int use_tc, int mode, const float* A, const float* W, const float* bias,
+                   const float* res, int M, int N, int K, int act, float* out);
+
 /* per-kernel device timing (CUDA events on the launching stream around every launch of
  * subsequent infer calls; process-wide).  dump writes a JSON object
  * {"kernel": [total_ms, launches], ...} and returns the bytes needed. */

@@ -236,6 +236,76 @@ int rdb_rec_infer_u8(rdb_rec_t* h, const uint8_t* crops, const int32_t* valid_w,
 long long rdb_det_last_launches(rdb_det_t* h) { return h ? h->e->last_launches() : -1; }
 long long rdb_rec_last_launches(rdb_rec_t* h) { return h ? h->e->last_launches() : -1; }
 
+// Diagnostic entry: one GEMM through the fp16 engines (use_tc=1: tcgen05 kernel, 0: SIMT kernel on
+// fp16 storage).  Host fp32 in/out; inputs are rounded to fp16 on the device exactly as the
+// engines store them.  out[M,N] = act(A W^T + bias) (+res).  mode 1 = CTC partial epilogue:
+// out receives [M,2] = (argmax id, softmax max prob).
+static __global__ void f2h_kernel(const float* in, __half* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2half_rn(in[i]);
+}
+static __global__ void h2f_kernel(const __half* in, float* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __half2float(in[i]);
+}
+int rdb_debug_gemm(int device, int use_tc, int mode, const float* A, const float* W, const float* bias, const float* res, int M,
+                   int N, int K, int act, float* out) {
+  return guarded([&] {
+    require_device(device);
+    RDB_CUDA(cudaSetDevice(device));
+    rdb::Pool pool;
+    rdb::Ctx cx;
+    cx.pool = &pool; cx.st = nullptr; cx.use_tc = use_tc != 0;
+    RDB_CUDA(cudaDeviceGetAttribute(&cx.num_sms, cudaDevAttrMultiProcessorCount, device));
+    auto up = [&](const float* h, size_t n, float** df, __half** dh) {
+      *df = pool.alloc_t<float>(n);
+      *dh = pool.alloc_t<__half>(n);
+      RDB_CUDA(cudaMemcpy(*df, h, n * 4, cudaMemcpyHostToDevice));
+      f2h_kernel<<<(unsigned)((n + 255) / 256), 256>>>(*df, *dh, n);
+    };
+    float *dAf, *dWf, *dRf = nullptr, *dB = nullptr; __half *dAh, *dWh, *dRh = nullptr;
+    up(A, (size_t)M * K, &dAf, &dAh);
+    up(W, (size_t)N * K, &dWf, &dWh);
+    if (res) up(res, (size_t)M * N, &dRf, &dRh);
+    if (bias) { dB = pool.alloc_t<float>(N); RDB_CUDA(cudaMemcpy(dB, bias, (size_t)N * 4, cudaMemcpyHostToDevice)); }
+    if (mode == 0) {
+      __half* dO = pool.alloc_t<__half>((size_t)M * N);
+      float* dOf = pool.alloc_t<float>((size_t)M * N);
+      if (use_tc) {
+        rdb::launch_gemm_tc(cx, dAh, K, M, K, dWh, N, dB, act, dRh, N, dO, N, 0);
+      } else {
+        rdb::GemmArgs g{};
+        g.A = dAh; g.lda = K; g.W = dWf; g.bias = dB; g.res = dRh; g.ldr = N; g.out = dO; g.ldc = N; g.M = M; g.N = N; g.K = K; g.act = act;
+        rdb::launch_gemm_simt<__half, __half>(g, nullptr);
+      }
+      h2f_kernel<<<(unsigned)(((size_t)M * N + 255) / 256), 256>>>(dO, dOf, (size_t)M * N);
+      RDB_CUDA(cudaMemcpy(out, dOf, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
+    } else {
+      int tiles = rdb::cdiv(N, rdb::SG_BN);
+      if (tiles < 80) tiles = 80;
+      float* pmax = pool.alloc_t<float>((size_t)M * tiles);
+      float* psum = pool.alloc_t<float>((size_t)M * tiles);
+      int* pidx = pool.alloc_t<int>((size_t)M * tiles);
+      int* ids = pool.alloc_t<int>(M);
+      float* pr = pool.alloc_t<float>(M);
+      if (use_tc) {
+        rdb::launch_gemm_tc_ctc(cx, dAh, K, M, K, dWh, N, dB, pmax, pidx, psum, &tiles);
+      } else {
+        rdb::GemmArgs g{};
+        g.A = dAh; g.lda = K; g.W = dWf; g.bias = dB; g.M = M; g.N = N; g.K = K; g.pmax = pmax; g.pidx = pidx; g.psum = psum;
+        tiles = rdb::cdiv(N, rdb::SG_BN);
+        rdb::launch_gemm_simt_ctc<__half>(g, nullptr);
+      }
+      rdb::ctc_merge_kernel<<<rdb::cdiv(M, 128), 128>>>(pmax, pidx, psum, M, tiles, ids, pr);
+      std::vector<int> hi(M); std::vector<float> hp(M);
+      RDB_CUDA(cudaMemcpy(hi.data(), ids, (size_t)M * 4, cudaMemcpyDeviceToHost));
+      RDB_CUDA(cudaMemcpy(hp.data(), pr, (size_t)M * 4, cudaMemcpyDeviceToHost));
+      for (int i = 0; i < M; ++i) { out[2 * i] = (float)hi[i]; out[2 * i + 1] = hp[i]; }
+    }
+    RDB_CUDA(cudaDeviceSynchronize());
+  });
+}
+
 int rdb_profile_enable(int on) {
   rdb::Profiler::global().on = (on != 0);
   return RDB_OK;

@@ -17,6 +17,7 @@ DetEngine::DetEngine(const void* blob, size_t nbytes, int device, int precision)
   RDB_CUDA(cudaSetDevice(device));
   weights_.reset(new Weights(blob, nbytes));
   RDB_CHECK(weights_->has("head.final.w") && weights_->has("neck.lk3.pw.w"), "blob is not a det model");
+  RDB_CUDA(cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, device));
 }
 
 DetEngine::~DetEngine() {
@@ -135,6 +136,8 @@ void DetEngine::infer(const DetInput& in_host_or_dev, int n, int H, int W, float
   RDB_CHECK((in_host_or_dev.f32 != nullptr) != (in_host_or_dev.u8 != nullptr), "det: exactly one input");
   Ctx cx;
   cx.st = st; cx.pool = &pool_; cx.precision = precision_;
+  cx.use_tc = (precision_ == 1) && !env_gemm_simt();
+  cx.num_sms = num_sms_;
   const void* src = in_host_or_dev.f32 ? (const void*)in_host_or_dev.f32 : (const void*)in_host_or_dev.u8;
   const size_t in_elem = in_host_or_dev.f32 ? sizeof(float) : 1;
   const size_t page_in = (size_t)3 * H * W * in_elem;

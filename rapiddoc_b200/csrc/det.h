@@ -28,6 +28,7 @@ class DetEngine {
   std::unique_ptr<Weights> weights_;
   Pool pool_;
   long long last_launches_ = 0;
+  int num_sms_ = 148;
   long long chunk_pixels_ = 8ll * 1024 * 1024;  // pages per internal chunk = chunk_pixels / (H*W)
 };
 

@@ -1,7 +1,9 @@
 // Host-side runtime shared by the det / rec engines: weight blob, device buffer pool,
 // launch helpers.  One engine = one (GPU, model); all work of a call goes to one stream.
 #pragma once
+#include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <map>
 #include <string>
 #include <unordered_map>
@@ -9,17 +11,24 @@
 
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "kernels.cuh"
 
 namespace rdb {
 
 // ---------------------------------------------------------------- weights ("RDW1" blob)
 struct Tensor {
-  const float* d = nullptr;  // device
+  const float* d = nullptr;  // device fp32
+  const __half* h = nullptr; // device fp16 copy (same layout), used by the tcgen05 GEMMs
   int ndim = 0;
   int shape[4] = {1, 1, 1, 1};
   size_t numel = 0;
 };
+
+static __global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2half_rn(in[i]);
+}
 
 class Weights {
  public:
@@ -50,8 +59,15 @@ class Weights {
       t.d = reinterpret_cast<const float*>(static_cast<uint8_t*>(dev_) + off);
       map_[name] = t;
     }
+    // fp16 mirror of the whole blob (element i of the fp32 payload <-> element i of the mirror)
+    const size_t nfl = nbytes / 4;
+    RDB_CUDA(cudaMalloc(&half_, nfl * 2));
+    f32_to_f16_kernel<<<(unsigned)((nfl + 255) / 256), 256>>>(reinterpret_cast<const float*>(dev_), half_, nfl);
+    RDB_CUDA(cudaGetLastError());
+    RDB_CUDA(cudaDeviceSynchronize());
+    for (auto& kv : map_) kv.second.h = half_ + (kv.second.d - reinterpret_cast<const float*>(dev_));
   }
-  ~Weights() { if (dev_) cudaFree(dev_); }
+  ~Weights() { if (dev_) cudaFree(dev_); if (half_) cudaFree(half_); }
   const Tensor& get(const std::string& name) const {
     auto it = map_.find(name);
     if (it == map_.end()) throw Error("weight tensor missing: " + name);
@@ -61,6 +77,7 @@ class Weights {
 
  private:
   void* dev_ = nullptr;
+  __half* half_ = nullptr;
   std::unordered_map<std::string, Tensor> map_;
 };
 
@@ -157,6 +174,8 @@ struct Ctx {
   Pool* pool = nullptr;
   long long launches = 0;
   int precision = 0;
+  bool use_tc = false;   // fp16 mode: tcgen05 GEMMs (default) vs SIMT GEMMs on fp16 storage (RDB_GEMM=simt)
+  int num_sms = 148;
   // bracket ONE kernel launch:  cx.begin("name"); kernel<<<...>>>(...); cx.end();
   void begin(const std::string& name) {
     Profiler& p = Profiler::global();
@@ -178,6 +197,43 @@ struct Ctx {
 };
 
 constexpr int kThreads = 256;
+
+inline bool env_gemm_simt() {
+  const char* e = std::getenv("RDB_GEMM");
+  return e != nullptr && std::strcmp(e, "simt") == 0;
+}
+
+// tcgen05 GEMM launch: out[M,N] = act(A[M,K] W^T + b) (+res), everything fp16 in HBM.
+inline void launch_gemm_tc(Ctx& cx, const __half* A, int lda, long long M, int K, const __half* Wh, int N, const float* bias, int act,
+                           const __half* res, int ldr, __half* out, int ldc, int c_off) {
+  tc::Plan p = tc::make_plan(M, N, K, cx.num_sms);
+  tc::Args& a = p.a;
+  a.bias = bias; a.res = res; a.ldr = ldr; a.out = out; a.ldc = ldc; a.c_off = c_off; a.act = act;
+  CUtensorMap mA = tc::make_map(A, M, K, lda, a.AW, 128);
+  CUtensorMap mB = tc::make_map(Wh, N, K, K, a.AW, a.BN);
+  auto k = tc::gemm_tc_kernel<tc::EPI_STORE>;
+  static bool attr_done = false;
+  if (!attr_done) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
+  cx.begin("gemm_tc[M=" + std::to_string(M) + ",K=" + std::to_string(K) + ",N=" + std::to_string(N) + ",res=" + (res ? "1" : "0") + "]");
+  k<<<p.grid, tc::kThreadsTc, p.smem, cx.st>>>(mA, mB, a);
+  cx.end();
+}
+
+inline void launch_gemm_tc_ctc(Ctx& cx, const __half* A, int lda, long long M, int K, const __half* Wh, int N, const float* bias,
+                               float* pmax, int* pidx, float* psum, int* tiles_out) {
+  tc::Plan p = tc::make_plan(M, N, K, cx.num_sms);
+  tc::Args& a = p.a;
+  a.bias = bias; a.pmax = pmax; a.pidx = pidx; a.psum = psum;
+  *tiles_out = a.tiles_n;
+  CUtensorMap mA = tc::make_map(A, M, K, lda, a.AW, 128);
+  CUtensorMap mB = tc::make_map(Wh, N, K, K, a.AW, a.BN);
+  auto k = tc::gemm_tc_kernel<tc::EPI_CTC>;
+  static bool attr_done = false;
+  if (!attr_done) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
+  cx.begin("gemm_tc_ctc[M=" + std::to_string(M) + ",K=" + std::to_string(K) + ",N=" + std::to_string(N) + "]");
+  k<<<p.grid, tc::kThreadsTc, p.smem, cx.st>>>(mA, mB, a);
+  cx.end();
+}
 
 // ---------------------------------------------------------------- typed launch helpers
 template <typename T>
@@ -204,6 +260,12 @@ struct Ops {
     g.A = A; g.lda = lda; g.W = W.d; g.bias = bias ? bias->d : nullptr; g.res = res; g.ldr = ldr;
     g.out = out; g.ldc = ldc; g.c_off = c_off; g.M = (int)M; g.N = N; g.K = K; g.act = act;
     RDB_CHECK(M < (1ll << 31), "gemm: M too large");
+    if constexpr (std::is_same<T, __half>::value) {
+      if (cx.use_tc) {
+        launch_gemm_tc(cx, A, lda, M, K, W.h, N, bias ? bias->d : nullptr, act, res, ldr, out, ldc, c_off);
+        return;
+      }
+    }
     cx.begin("gemm_simt[M=" + std::to_string(M) + ",K=" + std::to_string(K) + ",N=" + std::to_string(N) + ",res=" + (res ? "1" : "0") + "]");
     launch_gemm_simt<T, T>(g, cx.st);
     cx.end();

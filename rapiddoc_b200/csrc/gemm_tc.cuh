@@ -1,0 +1,376 @@
+// tcgen05 tensor-core GEMM for the pointwise convs / linears (precision mode fp16):
+//   out[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ res)          A, W, out: fp16; accumulate fp32
+// A is the NHWC activation tensor viewed as a K-major [M,K] matrix, W the K-major weight.
+//
+// Blackwell structure (sm_100a only; nothing here compiles for another arch):
+//   * TMA (cp.async.bulk.tensor.2d, hardware 32/64/128-byte swizzle) stages A/B k-blocks into a
+//     multi-stage shared-memory ring guarded by full/empty mbarriers,
+//   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (UMMA M=128, N<=256, K=16)
+//     with the fp32 accumulator in TMEM; tcgen05.commit releases smem stages / publishes the
+//     accumulator,
+//   * two TMEM accumulator stages: the epilogue warps drain tile i (tcgen05.ld -> bias/act/
+//     residual -> fp16 global stores, or the fused CTC argmax/sum-exp) while the tensor core
+//     already works on tile i+1,
+//   * persistent CTAs (grid = #SMs) walk the (m-tile, n-tile) list.
+// K is tiny on this path (24..768): the k-block is ONE swizzle atom wide (16/32/64 halves, the
+// largest that divides K) so any channel count that is a multiple of 16 maps without padding
+// HBM traffic; ragged K/N/M edges are zero-filled by TMA out-of-bounds handling.
+// Reference ops covered: channel_conv1/2 (backbones/rec_lcnetv4.py:210-224), RepLKFPN 1x1s
+// (necks/db_fpn.py:326-331,350-356), LightSVTR convs/linears (necks/rnn.py:238-290), CTC head
+// (heads/rec_multi_head.py:45,70).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace rdb {
+namespace tc {
+
+// ------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) { printf("rdb gemm_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major operand in a hardware-swizzled tile whose rows are one
+// swizzle span (32/64/128 B) wide: 8-row groups are SBO = 8*span bytes apart.
+// (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor — start>>4 [0,14), LBO>>4 [16,30),
+//  SBO>>4 [32,46), version=1 [46,48), layout_type [61,64): 2=128B, 4=64B, 6=32B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t span_bytes) {
+  uint64_t lt = span_bytes == 128 ? 2ull : (span_bytes == 64 ? 4ull : 6ull);
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8u * span_bytes) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= lt << 61;
+  return d;
+}
+
+// ------------------------------------------------------------------------ kernel
+struct Args {
+  int M, N, K;
+  int BN;          // n-tile (UMMA N), multiple of 16, <= 256
+  int tiles_m, tiles_n;
+  int k_blocks;    // ceil(K / AW)
+  int AW;          // k-block width in halves: 16, 32 or 64 (= one swizzle span)
+  int stages;
+  int tmem_cols;   // power of two >= 2*BN
+  uint32_t idesc;
+  const float* bias;
+  const __half* res; int ldr;
+  __half* out; int ldc; int c_off;
+  int act;
+  float* pmax; int* pidx; float* psum;  // EPI_CTC partials [M, tiles_n]
+};
+
+constexpr int kThreadsTc = 192;  // warp0: TMA, warp1: MMA + TMEM alloc, warps 2-5: epilogue
+enum { EPI_STORE = 0, EPI_CTC = 1 };
+
+template <int EPI>
+__global__ void __launch_bounds__(kThreadsTc, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t span = (uint32_t)g.AW * 2u;
+  const uint32_t a_bytes = 128u * span;
+  const uint32_t b_bytes = ((uint32_t)g.BN * span + 1023u) & ~1023u;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)g.stages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + g.stages;
+  uint64_t* tfull_bar = bars + 2 * g.stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < g.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)g.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total_tiles = g.tiles_m * g.tiles_n;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int tm = t / g.tiles_n, tn = t % g.tiles_n;
+        for (int kb = 0; kb < g.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          mbar_expect_tx(&full_bar[s], a_bytes + (uint32_t)g.BN * span);
+          tma_load_2d(sa, &tmA, &full_bar[s], kb * g.AW, tm * 128);
+          tma_load_2d(sa + a_bytes, &tmB, &full_bar[s], kb * g.AW, tn * g.BN);
+          if (++s == g.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (single thread) =================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * g.BN);
+        for (int kb = 0; kb < g.k_blocks; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint64_t da = make_smem_desc(sa, span);
+          const uint64_t db = make_smem_desc(sa + a_bytes, span);
+          const int ksteps = g.AW / 16;
+          for (int kk = 0; kk < ksteps; ++kk) {
+            // advancing K by 16 halves = 32 bytes inside the swizzle span: +2 in the (addr>>4) field
+            umma_f16(d_tmem, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), g.idesc, (kb | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (kb == g.k_blocks - 1) umma_commit(&tfull_bar[as]);
+          if (++s == g.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ================= epilogue warps (TMEM -> registers -> global) =================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int tm = t / g.tiles_n, tn = t % g.tiles_n;
+      const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const long long row = (long long)tm * 128 + q * 32 + lane;
+      const int n0 = tn * g.BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * g.BN);
+      float cmax = -INFINITY, csum = 0.f; int cidx = 0x7fffffff;
+      for (int c0 = 0; c0 < g.BN; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (n0 + c0 >= g.N) continue;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          int c = n0 + c0 + j;
+          float b = (g.bias != nullptr && c < g.N) ? __ldg(g.bias + c) : 0.f;
+          v[j] = __uint_as_float(r[j]) + b;
+        }
+        if (EPI == EPI_STORE) {
+          if (row < g.M) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = apply_act_rt(v[j], g.act);
+            const bool full = (n0 + c0 + 16 <= g.N);
+            if (g.res != nullptr) {
+              const __half* rp = g.res + row * g.ldr + n0 + c0;
+              if (full) {
+                float a[8], b2[8];
+                Vec8<__half>::load(rp, a);
+                Vec8<__half>::load(rp + 8, b2);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { v[j] += a[j]; v[8 + j] += b2[j]; }
+              } else {
+                for (int j = 0; j < 16; ++j) if (n0 + c0 + j < g.N) v[j] += __half2float(rp[j]);
+              }
+            }
+            __half* op = g.out + row * g.ldc + g.c_off + n0 + c0;
+            if (full) {
+              float a[8], b2[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { a[j] = v[j]; b2[j] = v[8 + j]; }
+              Vec8<__half>::store(op, a);
+              Vec8<__half>::store(op + 8, b2);
+            } else {
+              for (int j = 0; j < 16; ++j) if (n0 + c0 + j < g.N) op[j] = __float2half_rn(v[j]);
+            }
+          }
+        } else {
+          // fused greedy-decode partials: running (max, argmax, sum exp(x - max)) over this row
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            int c = n0 + c0 + j;
+            if (c < g.N) {
+              float x = v[j];
+              if (x > cmax) { csum = csum * __expf(cmax - x) + 1.f; cmax = x; cidx = c; }
+              else csum += __expf(x - cmax);
+            }
+          }
+        }
+      }
+      if (EPI == EPI_CTC && row < g.M) {
+        g.pmax[row * g.tiles_n + tn] = cmax;
+        g.pidx[row * g.tiles_n + tn] = cidx;
+        g.psum[row * g.tiles_n + tn] = csum;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    RDB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    RDB_CHECK(p != nullptr && q == cudaDriverEntryPointSuccess, "cuda: cuTensorMapEncodeTiled unavailable");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp16 row-major [rows, cols] with row pitch ld (elements); box = [box_rows, aw] k-major
+inline CUtensorMap make_map(const void* base, long long rows, int cols, int ld, int aw, int box_rows) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)aw, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUtensorMapSwizzle sw = aw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (aw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  RDB_CHECK(((uintptr_t)base & 15) == 0 && (ld * 2) % 16 == 0, "tma: base/pitch must be 16-byte aligned");
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error("cuda: cuTensorMapEncodeTiled failed, code " + std::to_string((int)r));
+  return m;
+}
+
+struct Plan {
+  Args a;
+  size_t smem;
+  int grid;
+};
+
+inline int pick_aw(int K) { return (K % 64 == 0) ? 64 : ((K % 32 == 0) ? 32 : ((K % 16 == 0) ? 16 : ((K > 32) ? 64 : 32))); }
+
+inline int pick_bn(int N) {
+  if (N <= 256) return (N + 15) / 16 * 16;
+  // fewest tiles, then least padding
+  int best = 256, best_tiles = (N + 255) / 256, best_pad = best_tiles * 256 - N;
+  for (int bn = 240; bn >= 128; bn -= 16) {
+    int tiles = (N + bn - 1) / bn, pad = tiles * bn - N;
+    if (tiles < best_tiles || (tiles == best_tiles && pad < best_pad)) { best = bn; best_tiles = tiles; best_pad = pad; }
+  }
+  return best;
+}
+
+inline Plan make_plan(long long M, int N, int K, int num_sms) {
+  Plan p{};
+  Args& a = p.a;
+  a.M = (int)M; a.N = N; a.K = K;
+  a.AW = pick_aw(K);
+  a.k_blocks = (K + a.AW - 1) / a.AW;
+  a.BN = pick_bn(N);
+  a.tiles_m = (int)((M + 127) / 128);
+  a.tiles_n = (N + a.BN - 1) / a.BN;
+  int cols = 32;
+  while (cols < 2 * a.BN) cols *= 2;
+  a.tmem_cols = cols;
+  // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c=F32 [4,6)=1, a/b = F16 (0),
+  // a_major/b_major = K (0), n>>3 at [17,23), m>>4 at [24,29)
+  a.idesc = (1u << 4) | ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const size_t span = (size_t)a.AW * 2;
+  const size_t stage = 128 * span + (((size_t)a.BN * span + 1023) & ~(size_t)1023);
+  int stages = (int)((200 * 1024) / stage);
+  if (stages > 8) stages = 8;
+  int want = a.k_blocks * 3;  // up to three tiles in flight
+  if (stages > want) stages = want;
+  if (stages < 2) stages = 2;
+  a.stages = stages;
+  p.smem = 1024 + stages * stage + (2 * stages + 4) * 8 + 16;
+  long long tiles = (long long)a.tiles_m * a.tiles_n;
+  p.grid = (int)(tiles < num_sms ? tiles : num_sms);
+  return p;
+}
+
+}  // namespace tc
+}  // namespace rdb

@@ -19,6 +19,7 @@ RecEngine::RecEngine(const void* blob, size_t nbytes, int device, int precision)
   weights_.reset(new Weights(blob, nbytes));
   RDB_CHECK(weights_->has("ctc.w") && weights_->has("svtr.norm.g"), "blob is not a rec model");
   vocab_ = weights_->get("ctc.w").shape[0];
+  RDB_CUDA(cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, device));
 }
 
 RecEngine::~RecEngine() {
@@ -130,16 +131,25 @@ void RecEngine::forward_chunk(Ctx& cx, const RecInput& in, int n, int W, int32_t
     cx.pool->free(logits);
   }
   {
-    const int tiles = cdiv(V, SG_BN);
+    int tiles = cdiv(V, SG_BN);
     float* pmax = cx.pool->alloc_t<float>((size_t)M * tiles);
     float* psum = cx.pool->alloc_t<float>((size_t)M * tiles);
     int* pidx = cx.pool->alloc_t<int>((size_t)M * tiles);
-    GemmArgs g{};
-    g.A = seq.p; g.lda = 120; g.W = cw.d; g.bias = cb.d; g.M = (int)M; g.N = V; g.K = 120;
-    g.pmax = pmax; g.pidx = pidx; g.psum = psum;
-    cx.begin("ctc_head_gemm_argmax");
-    launch_gemm_simt_ctc<T>(g, cx.st);
-    cx.end();
+    bool done = false;
+    if constexpr (std::is_same<T, __half>::value) {
+      if (cx.use_tc) {
+        launch_gemm_tc_ctc(cx, seq.p, 120, M, 120, cw.h, V, cb.d, pmax, pidx, psum, &tiles);
+        done = true;
+      }
+    }
+    if (!done) {
+      GemmArgs g{};
+      g.A = seq.p; g.lda = 120; g.W = cw.d; g.bias = cb.d; g.M = (int)M; g.N = V; g.K = 120;
+      g.pmax = pmax; g.pidx = pidx; g.psum = psum;
+      cx.begin("ctc_head_gemm_argmax");
+      launch_gemm_simt_ctc<T>(g, cx.st);
+      cx.end();
+    }
     cx.begin("ctc_merge");
     ctc_merge_kernel<<<cdiv(M, 128), 128, 0, cx.st>>>(pmax, pidx, psum, (int)M, tiles, ids, probs);
     cx.end();
@@ -157,6 +167,8 @@ void RecEngine::infer(const RecInput& in0, int n, int W, const RecOutput& out, c
   RDB_CHECK((in0.f32 != nullptr) != (in0.u8 != nullptr), "rec: exactly one input");
   Ctx cx;
   cx.st = st; cx.pool = &pool_; cx.precision = precision_;
+  cx.use_tc = (precision_ == 1) && !env_gemm_simt();
+  cx.num_sms = num_sms_;
   const int Tn = tokens_for_width(W);
   const void* src = in0.f32 ? (const void*)in0.f32 : (const void*)in0.u8;
   const size_t crop_in = (size_t)3 * 48 * W * (in0.f32 ? sizeof(float) : 1);

@@ -37,6 +37,7 @@ class RecEngine {
   std::unique_ptr<Weights> weights_;
   Pool pool_;
   long long last_launches_ = 0;
+  int num_sms_ = 148;
   int chunk_crops_ = 512;
 };
 

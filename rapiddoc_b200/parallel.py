@@ -1,0 +1,60 @@
+"""Multi-GPU plumbing: one process per GPU, page-/crop-parallel replicas.
+
+The hot path shards by independent units (pages, text-line crops):
+there is NO data-path collective.  The only collective is the init-time broadcast of the
+packed weight blob from rank 0 (NCCL over NVLink/NVSwitch on GPUs, gloo in CPU tests);
+results are small per-unit structs that stay on the rank that produced them or are
+gathered by the Python driver.
+"""
+import numpy as np
+
+
+def shard_range(total: int, world: int, rank: int):
+    """Contiguous balanced [lo, hi) of `total` units for `rank` (first `total % world` ranks get one extra)."""
+    base, extra = divmod(int(total), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def round_robin(total: int, world: int, rank: int):
+    """Indices rank handles when units are dealt round-robin (pages of a window)."""
+    return list(range(rank, int(total), int(world)))
+
+
+def deal_sorted_by_width(ratios, world: int):
+    """Crops sorted by aspect ratio (rapid_doc/model/ocr/rapid_ocr.py:411-414) are dealt in
+    contiguous runs round-robin so every rank sees a similar width mix.  Returns a list of
+    index arrays, one per rank; the union is a permutation of range(len(ratios))."""
+    order = np.argsort(np.asarray(ratios, dtype=np.float64), kind="stable")
+    return [order[r::world] for r in range(world)]
+
+
+def broadcast_blob(blob, device_index=0):
+    """rank 0 passes the packed weight bytes, every rank returns them.  No-op when
+    torch.distributed is not initialised (single GPU)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        assert blob is not None
+        return blob
+    rank = dist.get_rank()
+    cuda = dist.get_backend() == "nccl"
+    dev = torch.device("cuda", device_index) if cuda else torch.device("cpu")
+    n = torch.tensor([len(blob) if rank == 0 else 0], dtype=torch.int64, device=dev)
+    dist.broadcast(n, src=0)
+    if rank == 0:
+        t = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+    else:
+        t = torch.empty(int(n.item()), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=0)
+    return t.cpu().numpy().tobytes()
+
+
+def gather_objects(obj):
+    """Gather small per-rank Python result structs on every rank (host side, not on the data path)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [obj]
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, obj)
+    return out

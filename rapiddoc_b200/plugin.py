@@ -1,0 +1,93 @@
+"""Drop-in hooks: put the B200 engines under RapidDoc's unchanged orchestration.
+
+Three nested seams, all provided here:
+
+1. `CustomBaseModel.batch_predict(image_list, **kw) -> list[str]`
+   (rapid_doc/model/custom/__init__.py:4-20; dispatched by
+   rapid_doc/backend/pipeline/model_init.py:96-120 on isinstance).  `B200OcrCustomModel`
+   is the block-level OCR plugin: each layout block image -> its text lines joined by "\n"
+   (the mode `_run_custom_ocr` expects, rapid_doc/backend/pipeline/batch_analyze.py:286-333).
+2. The `rapid_doc/model/*` class API: `install()` rebinds
+   `rapid_doc.backend.pipeline.model_init.ocr_model_init` (model_init.py:45-54) so that
+   AtomModelSingleton builds `B200OcrModel` instead of `RapidOcrModel` (seal models keep the
+   reference implementation).  Nothing in the reference tree is edited.
+3. The engine protocol `InferSession.__call__(np.ndarray) -> np.ndarray`:
+   `install_engine()` swaps rapidocr's torch session class the same way
+   rapid_doc/model/ocr/ocr_patch.py:95-105 does, with `B200DetSession` / `B200RecSession`
+   picked by the model file name.
+"""
+from abc import ABC, abstractmethod
+
+import numpy as np
+
+try:  # the reference's ABC when RapidDoc is installed, an identical stand-in otherwise
+    from rapid_doc.model.custom import CustomBaseModel
+except Exception:  # pragma: no cover - exercised on boxes without RapidDoc
+    class CustomBaseModel(ABC):
+        @abstractmethod
+        def batch_predict(self, image_list, **kwargs):
+            ...
+
+
+class B200OcrCustomModel(CustomBaseModel):
+    """Block-level OCR plugin (seam 1): BGR block images -> multi-line text."""
+
+    def __init__(self, device=0, precision=None, box_thresh=0.3, unclip_ratio=1.8):
+        from .ocr import B200OcrModel
+        self.model = B200OcrModel(det_db_box_thresh=box_thresh, det_db_unclip_ratio=unclip_ratio, device=device, precision=precision)
+
+    def batch_predict(self, image_list, **kwargs):
+        out = []
+        for img in image_list:
+            boxes, res = self.model(np.ascontiguousarray(img))
+            out.append("\n".join(t for t, _ in res) if res else "")
+        return out
+
+
+def make_ocr_model_init(device=0, precision=None, fallback=None):
+    """Factory with the signature of model_init.ocr_model_init (model_init.py:45-54)."""
+    def ocr_model_init(det_db_box_thresh=0.5, lang=None, ocr_config=None, det_db_unclip_ratio=1.8, enable_merge_det_boxes=True,
+                       is_seal=False):
+        if is_seal:
+            if fallback is None:
+                raise NotImplementedError("seal OCR is outside the B200 hot path")
+            return fallback(det_db_box_thresh, lang, ocr_config, det_db_unclip_ratio, enable_merge_det_boxes, is_seal)
+        from .ocr import B200OcrModel
+        return B200OcrModel(det_db_box_thresh=det_db_box_thresh, lang=lang, ocr_config=ocr_config, use_dilation=True,
+                            det_db_unclip_ratio=det_db_unclip_ratio, enable_merge_det_boxes=enable_merge_det_boxes, device=device,
+                            precision=precision)
+    return ocr_model_init
+
+
+def install(device=0, precision=None):
+    """Seam 2: rebind RapidDoc's OCR model factory.  Returns the original factory."""
+    from rapid_doc.backend.pipeline import model_init as mi
+    orig = mi.ocr_model_init
+    mi.ocr_model_init = make_ocr_model_init(device, precision, fallback=orig)
+    mi.AtomModelSingleton._models.clear()
+    return orig
+
+
+def session_for(cfg):
+    """Seam 3: pick the B200 session from the configured model file (det vs rec)."""
+    from .engine import B200DetSession, B200RecSession
+    path = str(cfg.get("model_path", "") if hasattr(cfg, "get") else "")
+    return B200RecSession(cfg) if "rec" in path.lower() else B200DetSession(cfg)
+
+
+def install_engine():
+    """Seam 3: replace rapidocr's TorchInferSession (what ocr_patch.patch_torch_ocr does,
+    rapid_doc/model/ocr/ocr_patch.py:95-105) with the B200 sessions."""
+    try:
+        from rapidocr.inference_engine.pytorch import main as rt
+        import rapidocr.inference_engine.pytorch as rt_pkg
+    except Exception:
+        from rapidocr.inference_engine import torch as rt
+        rt_pkg = None
+
+    class _B200Session:
+        def __new__(cls, cfg):
+            return session_for(cfg)
+    rt.TorchInferSession = _B200Session
+    if rt_pkg is not None:
+        rt_pkg.TorchInferSession = _B200Session

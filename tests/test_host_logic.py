@@ -1,0 +1,48 @@
+"""CPU tests of the product's host-side logic (rapiddoc_b200/ocr.py) against the oracle
+restatement: DB post-process on a golden prob map, rec crop packing, box sorting."""
+import os
+
+import numpy as np
+
+from oracle import ocr_post as P
+from rapiddoc_b200 import ocr as O
+
+
+def test_db_postprocess_host_matches_oracle(golden_dir):
+    g = np.load(os.path.join(golden_dir, "det_page_img5.npz"))
+    prob = g["prob"][0, 0]
+    shape = tuple(int(v) for v in g["shape"])
+    for box_thresh, ratio, dil in [(0.3, 1.8, True), (0.5, 1.6, True), (0.3, 1.8, False)]:
+        bitmap = P.db_bitmap(prob, 0.3, dil)
+        post = O.DBPostProcess(0.3, box_thresh, 1000, ratio, dil)
+        boxes, scores = post(prob, bitmap, shape)
+        want_b, want_s = P.db_postprocess(g["prob"], shape, 0.3, box_thresh, ratio, dil)
+        assert np.array_equal(np.asarray(boxes), np.asarray(want_b))
+        assert np.allclose(scores, want_s, rtol=0, atol=0)
+        assert [b.tolist() for b in O.sorted_boxes(boxes)] == [b.tolist() for b in P.sorted_boxes(want_b)]
+    assert len(boxes) >= 10
+
+
+def test_rec_pack_equals_resize_norm_img(golden_dir):
+    g = np.load(os.path.join(golden_dir, "rec_real_6lines.npz"))
+    crops = [g[f"crop{i}"] for i in range(6)]
+    rec = O.B200TextRecognizer.__new__(O.B200TextRecognizer)
+    rec.rec_image_shape = [3, 48, 320]
+    ratio = max([320 / 48] + [c.shape[1] / c.shape[0] for c in crops])
+    buf, vw = rec._pack(crops, ratio)
+    x = ((buf.astype(np.float32) / 255 - 0.5) / 0.5).transpose(0, 3, 1, 2)
+    for i in range(6):
+        x[i, :, :, vw[i]:] = 0
+    want, r2 = P.rec_batch_tensor(crops)
+    assert r2 == ratio and x.shape == want.shape
+    assert np.array_equal(x, want)
+
+
+def test_rotate_crop_shapes():
+    img = (np.random.default_rng(0).random((200, 300, 3)) * 255).astype(np.uint8)
+    quad = np.float32([[10, 20], [110, 22], [109, 52], [9, 50]])
+    c = O.get_rotate_crop_image(img, quad)
+    assert c.shape[0] in (29, 30, 31) and c.shape[1] in (99, 100, 101)
+    tall = np.float32([[10, 10], [30, 10], [30, 150], [10, 150]])
+    c = O.get_rotate_crop_image(img, tall)
+    assert c.shape[1] > c.shape[0]          # rotated by 90 degrees (h/w >= 2)

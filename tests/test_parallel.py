@@ -1,0 +1,52 @@
+"""CPU tests of the N>1 host logic with the gloo backend, world_size 2."""
+import os
+import socket
+
+import numpy as np
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from rapiddoc_b200 import parallel as PL
+
+
+def test_shard_range_partitions():
+    for total in (0, 1, 7, 64, 1200):
+        for world in (1, 2, 3, 8):
+            spans = [PL.shard_range(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_deal_sorted_by_width_is_a_permutation():
+    r = np.random.default_rng(0).uniform(1, 30, 101)
+    parts = PL.deal_sorted_by_width(r, 4)
+    allidx = np.sort(np.concatenate(parts))
+    assert np.array_equal(allidx, np.arange(101))
+    means = [r[p].mean() for p in parts]
+    assert max(means) - min(means) < 1.5
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from rapiddoc_b200 import weights as W
+    blob = W.pack({"a.w": np.arange(24, dtype=np.float32).reshape(2, 3, 4), "b": np.ones(5, np.float32)}) if rank == 0 else None
+    got = PL.broadcast_blob(blob)
+    lo, hi = PL.shard_range(11, world, rank)
+    res = PL.gather_objects({"rank": rank, "units": list(range(lo, hi))})
+    q.put((rank, len(got), got[:4], sum(len(r["units"]) for r in res), sorted(sum((r["units"] for r in res), []))))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_broadcast_and_gather():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    out = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(30) for p in ps]
+    assert out[0][1] == out[1][1] > 0 and out[0][2] == out[1][2] == b"RDW1"
+    assert out[0][3] == out[1][3] == 11 and out[0][4] == list(range(11))
