@@ -282,7 +282,7 @@ int rdb_debug_gemm(int device, int use_tc, int mode, const float* A, const float
       RDB_CUDA(cudaMemcpy(out, dOf, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
     } else {
       int tiles = rdb::cdiv(N, rdb::SG_BN);
-      if (tiles < 80) tiles = 80;
+      if (tiles < 320) tiles = 320;
       float* pmax = pool.alloc_t<float>((size_t)M * tiles);
       float* psum = pool.alloc_t<float>((size_t)M * tiles);
       int* pidx = pool.alloc_t<int>((size_t)M * tiles);

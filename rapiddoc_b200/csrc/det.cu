@@ -100,7 +100,15 @@ void DetEngine::forward_chunk(Ctx& cx, const DetInput& in, int n, int H, int W, 
   for (int i = 0; i < 4; ++i) { O::release(cx, pq[i]); cx.pool->free(gates[i]); }
   // ---- DBHead
   Act hd = O::make(cx, n, neck.h, neck.w, 24);
-  {
+  bool head_tc = false;
+  if constexpr (std::is_same<T, __half>::value) {
+    if (cx.use_tc && !env_is("RDB_CONV", "simt")) {
+      launch_conv_tc(cx, "head_conv3x3", neck.p, n, neck.h, neck.w, 96, w.get("head.down.w").h, 24, w.get("head.down.b").d, ACT_RELU, 3, 3, 1, 1,
+                     1, 1, hd.p, hd.h, hd.w, 24, 0);
+      head_tc = true;
+    }
+  }
+  if (!head_tc) {
     auto k = conv_direct_kernel<T, 3, 3, 1, 1, 96, 24, 24, ACT_RELU>;
     size_t sm = (size_t)(9 * 96 * 24 + 24) * sizeof(float);
     set_smem(k, sm);

@@ -198,9 +198,36 @@ struct Ctx {
 
 constexpr int kThreads = 256;
 
+template <typename K>
+inline void set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) RDB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+inline bool env_is(const char* name, const char* val) {
+  const char* e = std::getenv(name);
+  return e != nullptr && std::strcmp(e, val) == 0;
+}
+
 inline bool env_gemm_simt() {
   const char* e = std::getenv("RDB_GEMM");
   return e != nullptr && std::strcmp(e, "simt") == 0;
+}
+
+template <int ACT>
+inline void launch_tc_store_act(const tc::Plan& p, const CUtensorMap& mA, const CUtensorMap& mB, cudaStream_t st) {
+  auto k = tc::gemm_tc_kernel<tc::EPI_STORE, ACT>;
+  static bool attr_done = false;
+  if (!attr_done) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
+  k<<<p.grid, tc::kThreadsTc, p.smem, st>>>(mA, mB, p.a);
+}
+inline void launch_tc_store(const tc::Plan& p, const CUtensorMap& mA, const CUtensorMap& mB, int act, cudaStream_t st) {
+  switch (act) {
+    case ACT_NONE: launch_tc_store_act<ACT_NONE>(p, mA, mB, st); break;
+    case ACT_RELU: launch_tc_store_act<ACT_RELU>(p, mA, mB, st); break;
+    case ACT_GELU: launch_tc_store_act<ACT_GELU>(p, mA, mB, st); break;
+    case ACT_SILU: launch_tc_store_act<ACT_SILU>(p, mA, mB, st); break;
+    default: throw Error("gemm_tc: bad act");
+  }
 }
 
 // tcgen05 GEMM launch: out[M,N] = act(A[M,K] W^T + b) (+res), everything fp16 in HBM.
@@ -211,11 +238,22 @@ inline void launch_gemm_tc(Ctx& cx, const __half* A, int lda, long long M, int K
   a.bias = bias; a.res = res; a.ldr = ldr; a.out = out; a.ldc = ldc; a.c_off = c_off; a.act = act;
   CUtensorMap mA = tc::make_map(A, M, K, lda, a.AW, 128);
   CUtensorMap mB = tc::make_map(Wh, N, K, K, a.AW, a.BN);
-  auto k = tc::gemm_tc_kernel<tc::EPI_STORE>;
-  static bool attr_done = false;
-  if (!attr_done) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
   cx.begin("gemm_tc[M=" + std::to_string(M) + ",K=" + std::to_string(K) + ",N=" + std::to_string(N) + ",res=" + (res ? "1" : "0") + "]");
-  k<<<p.grid, tc::kThreadsTc, p.smem, cx.st>>>(mA, mB, a);
+  launch_tc_store(p, mA, mB, act, cx.st);
+  cx.end();
+}
+
+// tcgen05 implicit-GEMM convolution (dense KHxKW conv, NHWC fp16): the stem 2x2 / 3x3-s2 convs and the
+// DBHead 3x3 conv (rec_lcnetv4.py:152-154, det_db_head.py:104-109) on the tensor cores.
+inline void launch_conv_tc(Ctx& cx, const char* name, const __half* in, int n, int H, int W, int C, const __half* Wh, int N, const float* bias,
+                           int act, int KH, int KW, int sh, int sw, int pt, int pl, __half* out, int OH, int OW, int ldc, int c_off) {
+  tc::Plan p = tc::make_conv_plan(n, H, W, C, N, KH, KW, sh, sw, pt, pl, OH, OW, cx.num_sms);
+  tc::Args& a = p.a;
+  a.bias = bias; a.res = nullptr; a.ldr = 0; a.out = out; a.ldc = ldc; a.c_off = c_off; a.act = act;
+  CUtensorMap mA = tc::make_map_nhwc(in, n, H, W, C, a.AW, a.TH, a.TW, sh, sw);
+  CUtensorMap mB = tc::make_map(Wh, N, KH * KW * C, KH * KW * C, a.AW, a.BN);
+  cx.begin(std::string(name) + "_tc[P=" + std::to_string((long long)n * OH * OW) + ",C=" + std::to_string(C) + ",N=" + std::to_string(N) + "]");
+  launch_tc_store(p, mA, mB, act, cx.st);
   cx.end();
 }
 
@@ -224,10 +262,10 @@ inline void launch_gemm_tc_ctc(Ctx& cx, const __half* A, int lda, long long M, i
   tc::Plan p = tc::make_plan(M, N, K, cx.num_sms);
   tc::Args& a = p.a;
   a.bias = bias; a.pmax = pmax; a.pidx = pidx; a.psum = psum;
-  *tiles_out = a.tiles_n;
+  *tiles_out = a.tiles_n * tc::kEpiSubs;
   CUtensorMap mA = tc::make_map(A, M, K, lda, a.AW, 128);
   CUtensorMap mB = tc::make_map(Wh, N, K, K, a.AW, a.BN);
-  auto k = tc::gemm_tc_kernel<tc::EPI_CTC>;
+  auto k = tc::gemm_tc_kernel<tc::EPI_CTC, ACT_NONE>;
   static bool attr_done = false;
   if (!attr_done) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
   cx.begin("gemm_tc_ctc[M=" + std::to_string(M) + ",K=" + std::to_string(K) + ",N=" + std::to_string(N) + "]");
@@ -276,6 +314,19 @@ struct Ops {
 
   template <int KH, int KW, int ACT, bool ADD_IN>
   static void dwconv(Ctx& cx, const Act& in, int sh, int sw, const Tensor& w, const Tensor& b, Act& out) {
+    if constexpr (std::is_same<T, __half>::value && KH == 7 && KW == 7 && ACT == ACT_NONE && !ADD_IN) {
+      if (sh == 1 && sw == 1 && in.c % 32 == 0 && !env_is("RDB_DW", "simple")) {
+        constexpr int TH = 8, TW = 32, G = 4;
+        auto k = dwconv_tiled_kernel<T, 7, G, TH, TW>;
+        const size_t sm = (size_t)(TH + 6) * (TW + 6) * (16 * G + 16) + 49 * 8 * G * sizeof(float);
+        set_smem(k, sm);
+        dim3 grid(cdiv(in.w, TW), cdiv(in.h, TH), in.n * (in.c / (8 * G)));
+        cx.begin("dwconv7x7_tiled[P=" + std::to_string(out.pixels()) + ",C=" + std::to_string(in.c) + ",s=1]");
+        k<<<grid, G * (TW / 4) * TH, sm, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.d, b.d, out.p);
+        cx.end();
+        return;
+      }
+    }
     long long total = out.pixels() * (in.c / 8);
     cx.begin("dwconv" + std::to_string(KH) + "x" + std::to_string(KW) + "[P=" + std::to_string(out.pixels()) + ",C=" + std::to_string(in.c) + ",s=" + std::to_string(sh * sw) + "]");
     dwconv_kernel<T, KH, KW, ACT, ADD_IN><<<cdiv(total, kThreads), kThreads, 0, cx.st>>>(
@@ -312,10 +363,6 @@ struct Ops {
   }
 };
 
-template <typename K>
-inline void set_smem(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024) RDB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-}
 
 // PPLCNetV4 block table (cin, cout, stride_h, stride_w, se) — rec_lcnetv4.py:7-43
 struct BlockCfg { int cin, cout, sh, sw, se; };
@@ -330,26 +377,44 @@ struct Backbone {
   template <int C1>
   static Act stem_rest(Ctx& cx, const Weights& w, Act& e1) {
     constexpr int CH = C1 / 2, C2 = 2 * C1;
+    constexpr int CHP = (CH + 7) / 8 * 8;   // stem2a output channels padded to a 16-byte pixel pitch (TMA)
     const int n = e1.n, H1 = e1.h, W1 = e1.w;
-    Act a = O::make(cx, n, H1, W1, CH);
-    {
-      auto k = conv_direct_kernel<T, 2, 2, 1, 1, C1, CH, CH, ACT_RELU>;
-      size_t sm = (size_t)(4 * C1 * CH + CH) * sizeof(float);
-      set_smem(k, sm);
-      cx.begin("stem2a");
-      k<<<dim3(cdiv(a.pixels(), 128), 1), 128, sm, cx.st>>>(e1.p, n, H1, W1, 0, 0, w.get("stem2a.w").d, w.get("stem2a.b").d,
-                                                            a.p, H1, W1, CH, 0);
-      cx.end();
-    }
+    const int H2 = (H1 - 1) / 2 + 1, W2 = (W1 - 1) / 2 + 1;
+    bool tc_path = false;
+    if constexpr (std::is_same<T, __half>::value) tc_path = cx.use_tc && !env_is("RDB_CONV", "simt");
     Act cat = O::make(cx, n, H1, W1, C2);
-    {
-      auto k = conv_direct_kernel<T, 2, 2, 1, 1, CH, C1, C1 / 2, ACT_RELU>;
-      size_t sm = (size_t)(4 * CH * C1 + C1) * sizeof(float);
-      set_smem(k, sm);
-      cx.begin("stem2b");
-      k<<<dim3(cdiv(a.pixels(), 128), 2), 128, sm, cx.st>>>(a.p, n, H1, W1, 0, 0, w.get("stem2b.w").d, w.get("stem2b.b").d,
-                                                            cat.p, H1, W1, C2, C1);
-      cx.end();
+    Act s3 = O::make(cx, n, H2, W2, C1);
+    if (tc_path) {
+      if constexpr (std::is_same<T, __half>::value) {
+        Act a = O::make(cx, n, H1, W1, CHP);
+        // F.pad(0,1,0,1) + conv2x2 == conv with pt=pl=0 and zero fill past the bottom/right edge
+        launch_conv_tc(cx, "stem2a", e1.p, n, H1, W1, C1, w.get("stem2a.wp").h, CHP, w.get("stem2a.bp").d, ACT_RELU, 2, 2, 1, 1, 0, 0,
+                       a.p, H1, W1, CHP, 0);
+        launch_conv_tc(cx, "stem2b", a.p, n, H1, W1, CHP, w.get("stem2b.wp").h, C1, w.get("stem2b.b").d, ACT_RELU, 2, 2, 1, 1, 0, 0,
+                       cat.p, H1, W1, C2, C1);
+        O::release(cx, a);
+      }
+    } else {
+      Act a = O::make(cx, n, H1, W1, CH);
+      {
+        auto k = conv_direct_kernel<T, 2, 2, 1, 1, C1, CH, CH, ACT_RELU>;
+        size_t sm = (size_t)(4 * C1 * CH + CH) * sizeof(float);
+        set_smem(k, sm);
+        cx.begin("stem2a");
+        k<<<dim3(cdiv(a.pixels(), 128), 1), 128, sm, cx.st>>>(e1.p, n, H1, W1, 0, 0, w.get("stem2a.w").d, w.get("stem2a.b").d,
+                                                              a.p, H1, W1, CH, 0);
+        cx.end();
+      }
+      {
+        auto k = conv_direct_kernel<T, 2, 2, 1, 1, CH, C1, C1 / 2, ACT_RELU>;
+        size_t sm = (size_t)(4 * CH * C1 + C1) * sizeof(float);
+        set_smem(k, sm);
+        cx.begin("stem2b");
+        k<<<dim3(cdiv(a.pixels(), 128), 2), 128, sm, cx.st>>>(a.p, n, H1, W1, 0, 0, w.get("stem2b.w").d, w.get("stem2b.b").d,
+                                                              cat.p, H1, W1, C2, C1);
+        cx.end();
+      }
+      O::release(cx, a);
     }
     {
       long long total = e1.pixels() * (C1 / 8);
@@ -357,11 +422,12 @@ struct Backbone {
       pool2x2_concat_kernel<T><<<cdiv(total, kThreads), kThreads, 0, cx.st>>>(e1.p, n, H1, W1, C1, cat.p, C2);
       cx.end();
     }
-    O::release(cx, a);
     O::release(cx, e1);
-    const int H2 = (H1 - 1) / 2 + 1, W2 = (W1 - 1) / 2 + 1;
-    Act s3 = O::make(cx, n, H2, W2, C1);
-    {
+    if (tc_path) {
+      if constexpr (std::is_same<T, __half>::value)
+        launch_conv_tc(cx, "stem3", cat.p, n, H1, W1, C2, w.get("stem3.w").h, C1, w.get("stem3.b").d, ACT_RELU, 3, 3, 2, 2, 1, 1, s3.p, H2, W2,
+                       C1, 0);
+    } else {
       auto k = conv_direct_kernel<T, 3, 3, 2, 2, C2, C1, C1 / 2, ACT_RELU>;
       size_t sm = (size_t)(9 * C2 * C1 + C1) * sizeof(float);
       set_smem(k, sm);

@@ -64,6 +64,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
                "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -128,13 +134,21 @@ struct Args {
   const __half* res; int ldr;
   __half* out; int ldc; int c_off;
   int act;
-  float* pmax; int* pidx; float* psum;  // EPI_CTC partials [M, tiles_n]
+  float* pmax; int* pidx; float* psum;  // EPI_CTC partials [M, tiles_n * kEpiSubs]
+  // implicit-GEMM conv mode (conv != 0): A is the NHWC input behind a 4-D tensor map
+  // {C, W, H, n}; an m-tile is a TH x TW patch of output pixels (TH*TW = 128) of one image and
+  // k-block kb = (tap, channel chunk) is the same patch shifted by the tap — TMA out-of-bounds
+  // zero fill provides the conv padding.
+  int conv;
+  int OH, OW, TH, TW, tiles_y, tiles_x;
+  int KW, sh, sw, pt, pl, cchunks, C;
 };
 
-constexpr int kThreadsTc = 192;  // warp0: TMA, warp1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int kEpiSubs = 4;                        // epilogue warps per TMEM lane quarter
+constexpr int kThreadsTc = 64 + 128 * kEpiSubs;    // warp0: TMA, warp1: MMA + TMEM alloc, warps 2..: epilogue
 enum { EPI_STORE = 0, EPI_CTC = 1 };
 
-template <int EPI>
+template <int EPI, int ACT>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -155,7 +169,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < g.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4 * kEpiSubs); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)g.tmem_cols);
@@ -175,8 +189,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           mbar_expect_tx(&full_bar[s], a_bytes + (uint32_t)g.BN * span);
-          tma_load_2d(sa, &tmA, &full_bar[s], kb * g.AW, tm * 128);
-          tma_load_2d(sa + a_bytes, &tmB, &full_bar[s], kb * g.AW, tn * g.BN);
+          if (g.conv == 0) {
+            tma_load_2d(sa, &tmA, &full_bar[s], kb * g.AW, tm * 128);
+            tma_load_2d(sa + a_bytes, &tmB, &full_bar[s], kb * g.AW, tn * g.BN);
+          } else {
+            const int tx = tm % g.tiles_x, ty = (tm / g.tiles_x) % g.tiles_y, n = tm / (g.tiles_x * g.tiles_y);
+            const int tap = kb / g.cchunks, cc = kb % g.cchunks;
+            const int ky = tap / g.KW, kx = tap % g.KW;
+            tma_load_4d(sa, &tmA, &full_bar[s], cc * g.AW, tx * g.TW * g.sw - g.pl + kx, ty * g.TH * g.sh - g.pt + ky, n);
+            tma_load_2d(sa + a_bytes, &tmB, &full_bar[s], tap * g.C + cc * g.AW, tn * g.BN);
+          }
           if (++s == g.stages) { s = 0; ph ^= 1; }
         }
       }
@@ -210,34 +232,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ================= epilogue warps (TMEM -> registers -> global) =================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // 16 warps: warp w may only touch TMEM lanes [32*(w%4), +32) (hardware rule), so the four warps
+    // sharing a lane quarter split the tile's 16-column chunks between them (sub = 0..3).
+    const int q = warp & 3;
+    const int sub = (warp - 2) >> 2;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int tm = t / g.tiles_n, tn = t % g.tiles_n;
       const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
-      const long long row = (long long)tm * 128 + q * 32 + lane;
+      long long row = (long long)tm * 128 + q * 32 + lane;   // GEMM: output row; conv: output pixel index
+      bool row_ok = row < g.M;
+      if (g.conv != 0) {
+        const int tx = tm % g.tiles_x, ty = (tm / g.tiles_x) % g.tiles_y, n = tm / (g.tiles_x * g.tiles_y);
+        const int r = q * 32 + lane;
+        const int oy = ty * g.TH + r / g.TW, ox = tx * g.TW + r % g.TW;
+        row_ok = (oy < g.OH) && (ox < g.OW);
+        row = ((long long)n * g.OH + oy) * g.OW + ox;
+      }
       const int n0 = tn * g.BN;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * g.BN);
       float cmax = -INFINITY, csum = 0.f; int cidx = 0x7fffffff;
-      for (int c0 = 0; c0 < g.BN; c0 += 16) {
+      for (int c0 = sub * 16; c0 < g.BN; c0 += 16 * kEpiSubs) {
+        if (n0 + c0 >= g.N) break;                 // warp-uniform: the rest of this n-tile is padding
         uint32_t r[16];
         tmem_ld16(taddr + (uint32_t)c0, r);
-        tmem_ld_wait();
-        if (n0 + c0 >= g.N) continue;
+        const bool full = (n0 + c0 + 16 <= g.N);
         float v[16];
+        if (g.bias != nullptr) {
+          if (full) {
+            const float4* bp = reinterpret_cast<const float4*>(g.bias + n0 + c0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          int c = n0 + c0 + j;
-          float b = (g.bias != nullptr && c < g.N) ? __ldg(g.bias + c) : 0.f;
-          v[j] = __uint_as_float(r[j]) + b;
+            for (int j = 0; j < 4; ++j) { float4 b4 = __ldg(bp + j); v[4 * j] = b4.x; v[4 * j + 1] = b4.y; v[4 * j + 2] = b4.z; v[4 * j + 3] = b4.w; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = (n0 + c0 + j < g.N) ? __ldg(g.bias + n0 + c0 + j) : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
         }
-        if (EPI == EPI_STORE) {
-          if (row < g.M) {
+        tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = apply_act_rt(v[j], g.act);
-            const bool full = (n0 + c0 + 16 <= g.N);
+        for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r[j]);
+        if (EPI == EPI_STORE) {
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = apply_act<ACT>(v[j]);
             if (g.res != nullptr) {
               const __half* rp = g.res + row * g.ldr + n0 + c0;
               if (full) {
@@ -274,10 +316,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
-      if (EPI == EPI_CTC && row < g.M) {
-        g.pmax[row * g.tiles_n + tn] = cmax;
-        g.pidx[row * g.tiles_n + tn] = cidx;
-        g.psum[row * g.tiles_n + tn] = csum;
+      if (EPI == EPI_CTC && row_ok) {
+        const long long pi = row * ((long long)g.tiles_n * kEpiSubs) + tn * kEpiSubs + sub;
+        g.pmax[pi] = cmax;
+        g.pidx[pi] = cidx;
+        g.psum[pi] = csum;
       }
       tc_fence_before();
       __syncwarp();
@@ -324,13 +367,36 @@ inline CUtensorMap make_map(const void* base, long long rows, int cols, int ld, 
   return m;
 }
 
+// 4-D fp16 NHWC tensor {C, W, H, n}; box {aw, TW*sw, TH*sh, 1} traversed with element strides {1, sw, sh, 1}
+inline CUtensorMap make_map_nhwc(const void* base, int n, int H, int W, int C, int aw, int TH, int TW, int sh, int sw) {
+  CUtensorMap m;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)aw, (cuuint32_t)(TW * sw), (cuuint32_t)(TH * sh), 1};
+  cuuint32_t es[4] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1};
+  CUtensorMapSwizzle swz = aw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (aw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  RDB_CHECK(((uintptr_t)base & 15) == 0 && (C * 2) % 16 == 0, "tma: NHWC base/channel pitch must be 16-byte aligned");
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error("cuda: cuTensorMapEncodeTiled(4d) failed, code " + std::to_string((int)r));
+  return m;
+}
+
 struct Plan {
   Args a;
   size_t smem;
   int grid;
 };
 
-inline int pick_aw(int K) { return (K % 64 == 0) ? 64 : ((K % 32 == 0) ? 32 : ((K % 16 == 0) ? 16 : ((K > 32) ? 64 : 32))); }
+// k-block width (one swizzle span): prefer few wide TMA boxes; a ragged last block is zero-filled by
+// TMA (no HBM traffic for the out-of-bounds part), e.g. K=48 -> one 64-wide block with 16 zero columns.
+inline int pick_aw(int K) {
+  if (K % 64 == 0) return 64;
+  if (K % 32 == 0) return 32;
+  if (K <= 16) return 16;
+  if (K <= 32) return 32;
+  return 64;
+}
 
 inline int pick_bn(int N) {
   if (N <= 256) return (N + 15) / 16 * 16;
@@ -364,6 +430,40 @@ inline Plan make_plan(long long M, int N, int K, int num_sms) {
   if (stages > 8) stages = 8;
   int want = a.k_blocks * 3;  // up to three tiles in flight
   if (stages > want) stages = want;
+  if (stages < 2) stages = 2;
+  a.stages = stages;
+  p.smem = 1024 + stages * stage + (2 * stages + 4) * 8 + 16;
+  long long tiles = (long long)a.tiles_m * a.tiles_n;
+  p.grid = (int)(tiles < num_sms ? tiles : num_sms);
+  return p;
+}
+
+// conv plan: out[n,OH,OW,N] = act(conv(in[n,H,W,C], w[N][KH][KW][C]) + bias)
+inline Plan make_conv_plan(int n, int H, int W, int C, int N, int KH, int KW, int sh, int sw, int pt, int pl, int OH, int OW, int num_sms) {
+  Plan p{};
+  Args& a = p.a;
+  a.conv = 1;
+  a.N = N; a.K = KH * KW * C; a.C = C;
+  a.AW = pick_aw(C);
+  a.cchunks = (C + a.AW - 1) / a.AW;
+  a.k_blocks = KH * KW * a.cchunks;
+  a.BN = pick_bn(N);
+  a.OH = OH; a.OW = OW; a.KW = KW; a.sh = sh; a.sw = sw; a.pt = pt; a.pl = pl;
+  a.TW = OW >= 16 ? 16 : (OW >= 8 ? 8 : 4);
+  a.TH = 128 / a.TW;
+  a.tiles_x = (OW + a.TW - 1) / a.TW;
+  a.tiles_y = (OH + a.TH - 1) / a.TH;
+  a.tiles_m = n * a.tiles_x * a.tiles_y;
+  a.tiles_n = (N + a.BN - 1) / a.BN;
+  a.M = n * OH * OW;
+  int cols = 32;
+  while (cols < 2 * a.BN) cols *= 2;
+  a.tmem_cols = cols;
+  a.idesc = (1u << 4) | ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const size_t span = (size_t)a.AW * 2;
+  const size_t stage = 128 * span + (((size_t)a.BN * span + 1023) & ~(size_t)1023);
+  int stages = (int)((200 * 1024) / stage);
+  if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   a.stages = stages;
   p.smem = 1024 + stages * stage + (2 * stages + 4) * 8 + 16;

@@ -231,6 +231,86 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ in, i
   Vec8<T>::store(out + p * C + g * 8, acc);
 }
 
+// Shared-memory tiled depthwise conv, stride 1, for the large kernels (RepLKFPN 7x7,
+// db_fpn.py:317-325): a block owns TH x TW output pixels x 8*G channels, stages the halo tile
+// once in smem (pixel pitch 16*G+16 bytes => the 4-pixel strips of a quarter-warp land on
+// distinct banks) and every thread produces a strip of 4 consecutive outputs x 8 channels so
+// each staged input vector is reused K times in registers.
+template <typename T, int K, int G, int TH, int TW>
+__global__ void __launch_bounds__(G * (TW / 4) * TH)
+dwconv_tiled_kernel(const T* __restrict__ in, int N, int H, int W, int C, const float* __restrict__ w /*[K][K][C]*/,
+                    const float* __restrict__ b, T* __restrict__ out) {
+  constexpr int HH = TH + K - 1, HW = TW + K - 1;
+  constexpr int PITCH = 16 * G + 16;                 // bytes per staged pixel
+  constexpr int XS = TW / 4;
+  extern __shared__ __align__(16) uint8_t dsm[];
+  uint8_t* tile = dsm;                                // [HH][HW][PITCH]
+  float* sw = reinterpret_cast<float*>(dsm + HH * HW * PITCH);  // [K*K][8*G]
+  const int cblocks = C / (8 * G);
+  const int cb = blockIdx.z % cblocks, n = blockIdx.z / cblocks;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  const int c0 = cb * 8 * G;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < K * K * 8 * G; i += blockDim.x) sw[i] = w[(i / (8 * G)) * C + c0 + i % (8 * G)];
+  for (int i = tid; i < HH * HW * G; i += blockDim.x) {
+    const int g = i % G, p = i / G;
+    const int hx = p % HW, hy = p / HW;
+    const int iy = y0 + hy - K / 2, ix = x0 + hx - K / 2;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      if (sizeof(T) == 2) {
+        v = *reinterpret_cast<const uint4*>(in + (((long long)n * H + iy) * W + ix) * C + c0 + g * 8);
+      } else {
+        float f[8];
+        Vec8<T>::load(in + (((long long)n * H + iy) * W + ix) * C + c0 + g * 8, f);
+        __half2* hp = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hp[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+      }
+    }
+    *reinterpret_cast<uint4*>(tile + (hy * HW + hx) * PITCH + g * 16) = v;
+  }
+  __syncthreads();
+  const int g = tid % G, xs = (tid / G) % XS, ty = tid / (G * XS);
+  float acc[4][8];
+  {
+    float4 b0 = __ldg(reinterpret_cast<const float4*>(b + c0 + g * 8));
+    float4 b1 = __ldg(reinterpret_cast<const float4*>(b + c0 + g * 8 + 4));
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      acc[o][0] = b0.x; acc[o][1] = b0.y; acc[o][2] = b0.z; acc[o][3] = b0.w;
+      acc[o][4] = b1.x; acc[o][5] = b1.y; acc[o][6] = b1.z; acc[o][7] = b1.w;
+    }
+  }
+#pragma unroll 1
+  for (int ky = 0; ky < K; ++ky) {
+    uint4 iv[K + 3];
+#pragma unroll
+    for (int i = 0; i < K + 3; ++i) iv[i] = *reinterpret_cast<const uint4*>(tile + ((ty + ky) * HW + xs * 4 + i) * PITCH + g * 16);
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) {
+      const float4 w0 = *reinterpret_cast<const float4*>(sw + (ky * K + kx) * 8 * G + g * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(sw + (ky * K + kx) * 8 * G + g * 8 + 4);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const __half2* hp = reinterpret_cast<const __half2*>(&iv[o + kx]);
+        float2 f0 = __half22float2(hp[0]), f1 = __half22float2(hp[1]), f2 = __half22float2(hp[2]), f3 = __half22float2(hp[3]);
+        acc[o][0] = fmaf(f0.x, w0.x, acc[o][0]); acc[o][1] = fmaf(f0.y, w0.y, acc[o][1]);
+        acc[o][2] = fmaf(f1.x, w0.z, acc[o][2]); acc[o][3] = fmaf(f1.y, w0.w, acc[o][3]);
+        acc[o][4] = fmaf(f2.x, w1.x, acc[o][4]); acc[o][5] = fmaf(f2.y, w1.y, acc[o][5]);
+        acc[o][6] = fmaf(f3.x, w1.z, acc[o][6]); acc[o][7] = fmaf(f3.y, w1.w, acc[o][7]);
+      }
+    }
+  }
+  const int oy = y0 + ty;
+  if (oy >= H) return;
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    const int ox = x0 + xs * 4 + o;
+    if (ox < W) Vec8<T>::store(out + (((long long)n * H + oy) * W + ox) * C + c0 + g * 8, acc[o]);
+  }
+}
+
 // =====================================================================================
 // Squeeze-excitation: deterministic two-stage global average pool, the two tiny FCs and
 // the gate.  rec_lcnetv4.py:120-142 (gate = clip(x/6+.5,0,1)), db_fpn.py:288-308

@@ -132,9 +132,10 @@ void RecEngine::forward_chunk(Ctx& cx, const RecInput& in, int n, int W, int32_t
   }
   {
     int tiles = cdiv(V, SG_BN);
-    float* pmax = cx.pool->alloc_t<float>((size_t)M * tiles);
-    float* psum = cx.pool->alloc_t<float>((size_t)M * tiles);
-    int* pidx = cx.pool->alloc_t<int>((size_t)M * tiles);
+    const int cap = tiles < 320 ? 320 : tiles;  // room for the tcgen05 kernel's (n-tile x sub-warp) partials
+    float* pmax = cx.pool->alloc_t<float>((size_t)M * cap);
+    float* psum = cx.pool->alloc_t<float>((size_t)M * cap);
+    int* pidx = cx.pool->alloc_t<int>((size_t)M * cap);
     bool done = false;
     if constexpr (std::is_same<T, __half>::value) {
       if (cx.use_tc) {

@@ -77,6 +77,14 @@ def _backbone(sd, blocks, out):
         w, b = _fold(sd[p + name + ".convolution.weight"], p + name + ".normalization", sd)
         out[name + ".w"] = _dense(w)
         out[name + ".b"] = b
+    # stem2a/2b with the intermediate channel count padded to a multiple of 8 (16-byte NHWC pixel pitch
+    # for TMA): padded output channels have zero weight + zero bias (relu(0) = 0), padded inputs zero weight
+    ch = out["stem2a.w"].shape[0]
+    chp = (ch + 7) // 8 * 8
+    wa = np.zeros((chp,) + out["stem2a.w"].shape[1:]); wa[:ch] = out["stem2a.w"]
+    ba = np.zeros(chp); ba[:ch] = out["stem2a.b"]
+    wb = np.zeros(out["stem2b.w"].shape[:3] + (chp,)); wb[..., :ch] = out["stem2b.w"]
+    out["stem2a.wp"], out["stem2a.bp"], out["stem2b.wp"] = wa, ba, wb
     for si, stage in enumerate(blocks):
         for bi, (cin, cout, sh, sw, se) in enumerate(stage):
             q = f"backbone.encoder.blocks.{si}.blocks.{bi}."

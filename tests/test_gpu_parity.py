@@ -47,7 +47,7 @@ def _check_det(prob, want, prec, bitmap=None, dilate=True):
             assert seg_flip.sum() == 0
         own = P.db_bitmap(prob, 0.3, dilate)          # binarise+dilate of OUR prob map on CPU
         assert np.array_equal(bitmap, own), "GPU binarise/dilate != cv2 on the same prob map"
-        assert (bitmap != ref).mean() <= 5e-4
+        assert (bitmap != ref).mean() <= (0.0 if prec == PREC_FP32 else 2e-3)   # noise images sit near the threshold
 
 
 @pytest.mark.parametrize("prec", [PREC_FP32, PREC_FP16])
