@@ -22,7 +22,23 @@ DetEngine::DetEngine(const void* blob, size_t nbytes, int device, int precision)
 
 DetEngine::~DetEngine() {
   cudaSetDevice(device_);
+  cudaDeviceSynchronize();
   pool_.release_all();
+  if (copy_in_) {
+    cudaStreamDestroy(copy_in_); cudaStreamDestroy(copy_out_);
+    for (int s = 0; s < 2; ++s) { cudaEventDestroy(ev_in_[s]); cudaEventDestroy(ev_out_[s]); cudaEventDestroy(ev_compute_[s]); }
+  }
+}
+
+void DetEngine::ensure_copy_streams() {
+  if (copy_in_) return;
+  RDB_CUDA(cudaStreamCreateWithFlags(&copy_in_, cudaStreamNonBlocking));
+  RDB_CUDA(cudaStreamCreateWithFlags(&copy_out_, cudaStreamNonBlocking));
+  for (int s = 0; s < 2; ++s) {
+    RDB_CUDA(cudaEventCreateWithFlags(&ev_in_[s], cudaEventDisableTiming));
+    RDB_CUDA(cudaEventCreateWithFlags(&ev_out_[s], cudaEventDisableTiming));
+    RDB_CUDA(cudaEventCreateWithFlags(&ev_compute_[s], cudaEventDisableTiming));
+  }
 }
 
 template <typename T>
@@ -120,7 +136,15 @@ void DetEngine::forward_chunk(Ctx& cx, const DetInput& in, int n, int H, int W, 
   O::release(cx, neck);
   uint8_t* seg = nullptr;
   if (bitmap != nullptr) seg = dilate ? cx.pool->alloc_t<uint8_t>((size_t)n * H * W) : bitmap;
-  {
+  bool tail_tc = false;
+  if constexpr (std::is_same<T, __half>::value) {
+    if (cx.use_tc && !env_is("RDB_HEAD", "simt")) {
+      launch_head_tail_tc(cx, hd.p, n, hd.h, hd.w, w.get("head.up.w").h, w.get("head.up.b").d, w.get("head.final.w").d,
+                          w.get("head.final.b").d, thresh, prob, seg);
+      tail_tc = true;
+    }
+  }
+  if (!tail_tc) {
     long long total = (long long)n * (2 * hd.h) * (2 * hd.w);
     cx.begin("head_tail");
     head_tail_kernel<T><<<cdiv(total, 128), 128, 0, cx.st>>>(hd.p, n, hd.h, hd.w, w.get("head.up.w").d, w.get("head.up.b").d,
@@ -158,31 +182,56 @@ void DetEngine::infer(const DetInput& in_host_or_dev, int n, int H, int W, float
   int chunk = (int)(px_budget / (long long)(H * (long long)W));
   if (chunk < 1) chunk = 1;
   if (chunk > n) chunk = n;
-  void* d_in = in_dev ? nullptr : pool_.alloc(page_in * chunk);
-  float* d_prob = (prob_dev && prob) ? nullptr : pool_.alloc_t<float>(page_px * chunk);
-  uint8_t* d_bm = (bm_dev || !bitmap) ? nullptr : pool_.alloc_t<uint8_t>(page_px * chunk);
-  for (int i0 = 0; i0 < n; i0 += chunk) {
+  // Host buffers: 2-slot software pipeline — H2D of chunk i+1 and D2H of chunk i-1 overlap the compute
+  // of chunk i (dedicated copy streams + events); device buffers: everything on `st`, no synchronise.
+  const bool any_host = !in_dev || (prob && !prob_dev) || (bitmap && !bm_dev);
+  const int slots = any_host ? 2 : 1;
+  void* d_in[2] = {nullptr, nullptr};
+  float* d_prob[2] = {nullptr, nullptr};
+  uint8_t* d_bm[2] = {nullptr, nullptr};
+  for (int s = 0; s < slots; ++s) {
+    if (!in_dev) d_in[s] = pool_.alloc(page_in * chunk);
+    if (!(prob_dev && prob)) d_prob[s] = pool_.alloc_t<float>(page_px * chunk);
+    if (bitmap && !bm_dev) d_bm[s] = pool_.alloc_t<uint8_t>(page_px * chunk);
+  }
+  if (any_host) ensure_copy_streams();
+  int it = 0;
+  for (int i0 = 0; i0 < n; i0 += chunk, ++it) {
+    const int s = it % slots;
     int m = (n - i0 < chunk) ? (n - i0) : chunk;
     const uint8_t* src_i = static_cast<const uint8_t*>(src) + (size_t)i0 * page_in;
     DetInput in = in_host_or_dev;
     const void* dsrc = src_i;
     if (!in_dev) {
-      RDB_CUDA(cudaMemcpyAsync(d_in, src_i, page_in * m, cudaMemcpyHostToDevice, st));
-      dsrc = d_in;
+      if (it >= slots) RDB_CUDA(cudaStreamWaitEvent(copy_in_, ev_compute_[s], 0));   // slot's previous reader done
+      RDB_CUDA(cudaMemcpyAsync(d_in[s], src_i, page_in * m, cudaMemcpyHostToDevice, copy_in_));
+      RDB_CUDA(cudaEventRecord(ev_in_[s], copy_in_));
+      RDB_CUDA(cudaStreamWaitEvent(st, ev_in_[s], 0));
+      dsrc = d_in[s];
     }
+    if (any_host && it >= slots) RDB_CUDA(cudaStreamWaitEvent(st, ev_out_[s], 0));     // slot's previous D2H done
     if (in.f32) in.f32 = static_cast<const float*>(dsrc); else in.u8 = static_cast<const uint8_t*>(dsrc);
-    float* p_out = (prob_dev && prob) ? prob + (size_t)i0 * page_px : d_prob;
-    uint8_t* b_out = bitmap ? (bm_dev ? bitmap + (size_t)i0 * page_px : d_bm) : nullptr;
+    float* p_out = (prob_dev && prob) ? prob + (size_t)i0 * page_px : d_prob[s];
+    uint8_t* b_out = bitmap ? (bm_dev ? bitmap + (size_t)i0 * page_px : d_bm[s]) : nullptr;
     if (precision_ == 0) forward_chunk<float>(cx, in, m, H, W, thresh, dilate, p_out, b_out);
     else forward_chunk<__half>(cx, in, m, H, W, thresh, dilate, p_out, b_out);
-    if (prob && !prob_dev) RDB_CUDA(cudaMemcpyAsync(prob + (size_t)i0 * page_px, d_prob, page_px * m * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (bitmap && !bm_dev) RDB_CUDA(cudaMemcpyAsync(bitmap + (size_t)i0 * page_px, d_bm, page_px * m, cudaMemcpyDeviceToHost, st));
+    if (any_host) {
+      RDB_CUDA(cudaEventRecord(ev_compute_[s], st));
+      RDB_CUDA(cudaStreamWaitEvent(copy_out_, ev_compute_[s], 0));
+      if (prob && !prob_dev) RDB_CUDA(cudaMemcpyAsync(prob + (size_t)i0 * page_px, d_prob[s], page_px * m * sizeof(float), cudaMemcpyDeviceToHost, copy_out_));
+      if (bitmap && !bm_dev) RDB_CUDA(cudaMemcpyAsync(bitmap + (size_t)i0 * page_px, d_bm[s], page_px * m, cudaMemcpyDeviceToHost, copy_out_));
+      RDB_CUDA(cudaEventRecord(ev_out_[s], copy_out_));
+    }
   }
-  if (d_in) pool_.free(d_in);
-  if (d_prob) pool_.free(d_prob);
-  if (d_bm) pool_.free(d_bm);
-  const bool any_host = !in_dev || (prob && !prob_dev) || (bitmap && !bm_dev);
-  if (any_host) RDB_CUDA(cudaStreamSynchronize(st));
+  if (any_host) {
+    RDB_CUDA(cudaStreamSynchronize(copy_out_));
+    RDB_CUDA(cudaStreamSynchronize(st));
+  }
+  for (int s = 0; s < slots; ++s) {
+    if (d_in[s]) pool_.free(d_in[s]);
+    if (d_prob[s]) pool_.free(d_prob[s]);
+    if (d_bm[s]) pool_.free(d_bm[s]);
+  }
   cx.finish();
   last_launches_ = cx.launches;
 }

@@ -24,7 +24,10 @@ class DetEngine {
  private:
   template <typename T>
   void forward_chunk(Ctx& cx, const DetInput& in, int n, int H, int W, float thresh, bool dilate, float* prob, uint8_t* bitmap);
+  void ensure_copy_streams();
   int device_, precision_;
+  cudaStream_t copy_in_ = nullptr, copy_out_ = nullptr;
+  cudaEvent_t ev_in_[2] = {nullptr, nullptr}, ev_out_[2] = {nullptr, nullptr}, ev_compute_[2] = {nullptr, nullptr};
   std::unique_ptr<Weights> weights_;
   Pool pool_;
   long long last_launches_ = 0;

@@ -257,6 +257,25 @@ inline void launch_conv_tc(Ctx& cx, const char* name, const __half* in, int n, i
   cx.end();
 }
 
+// DBHead tail on the tensor cores: ConvT2x2(24->24)+BN+ReLU as one [P,24]x[24,96] tcgen05 GEMM whose epilogue
+// applies the final ConvT2x2(24->1), sigmoid, nan_to_num and the DB threshold (det_db_head.py:117-147).
+inline void launch_head_tail_tc(Ctx& cx, const __half* hd, int n, int H, int W, const __half* w_up_h /*[96][24]*/, const float* b_up,
+                                const float* w_fin, const float* b_fin, float thresh, float* prob, uint8_t* seg) {
+  const long long M = (long long)n * H * W;
+  tc::Plan p = tc::make_plan(M, 96, 24, cx.num_sms);
+  tc::Args& a = p.a;
+  a.epi_subs = 4;  // EPI_HEAD: sub-warp = ConvT tap, all four always active
+  a.bias = b_up; a.hH = H; a.hW = W; a.w_fin = w_fin; a.b_fin = b_fin; a.thresh = thresh; a.prob = prob; a.seg = seg;
+  CUtensorMap mA = tc::make_map(hd, M, 24, 24, a.AW, 128);
+  CUtensorMap mB = tc::make_map(w_up_h, 96, 24, 24, a.AW, a.BN);
+  auto k = tc::gemm_tc_kernel<tc::EPI_HEAD, ACT_NONE>;
+  static bool attr_done = false;
+  if (!attr_done) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
+  cx.begin("head_tail_tc[P=" + std::to_string(M) + "]");
+  k<<<p.grid, tc::kThreadsTc, p.smem, cx.st>>>(mA, mB, a);
+  cx.end();
+}
+
 inline void launch_gemm_tc_ctc(Ctx& cx, const __half* A, int lda, long long M, int K, const __half* Wh, int N, const float* bias,
                                float* pmax, int* pidx, float* psum, int* tiles_out) {
   tc::Plan p = tc::make_plan(M, N, K, cx.num_sms);
@@ -327,6 +346,21 @@ struct Ops {
         return;
       }
     }
+    if constexpr (std::is_same<T, __half>::value && KH == 3 && KW == 3 && ACT == ACT_NONE && !ADD_IN) {
+      if (sh == 1 && sw == 1 && in.c % 16 == 0 && !env_is("RDB_DW", "simple")) {
+        const bool g4 = (in.c % 32 == 0), tall = in.h >= 8;
+        const int G = g4 ? 4 : 2, TH = tall ? 8 : 4, TW = 32;
+        const size_t sm = (size_t)(TH + 2) * (TW + 2) * (16 * G + 16) + 9 * 8 * G * sizeof(float);
+        dim3 grid(cdiv(in.w, TW), cdiv(in.h, TH), in.n * (in.c / (8 * G)));
+        cx.begin("dwconv3x3_tiled[P=" + std::to_string(out.pixels()) + ",C=" + std::to_string(in.c) + ",s=1]");
+        if (g4 && tall) dwconv_tiled_kernel<T, 3, 4, 8, 32><<<grid, 4 * 8 * 8, sm, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.d, b.d, out.p);
+        else if (g4) dwconv_tiled_kernel<T, 3, 4, 4, 32><<<grid, 4 * 8 * 4, sm, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.d, b.d, out.p);
+        else if (tall) dwconv_tiled_kernel<T, 3, 2, 8, 32><<<grid, 2 * 8 * 8, sm, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.d, b.d, out.p);
+        else dwconv_tiled_kernel<T, 3, 2, 4, 32><<<grid, 2 * 8 * 4, sm, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.d, b.d, out.p);
+        cx.end();
+        return;
+      }
+    }
     long long total = out.pixels() * (in.c / 8);
     cx.begin("dwconv" + std::to_string(KH) + "x" + std::to_string(KW) + "[P=" + std::to_string(out.pixels()) + ",C=" + std::to_string(in.c) + ",s=" + std::to_string(sh * sw) + "]");
     dwconv_kernel<T, KH, KW, ACT, ADD_IN><<<cdiv(total, kThreads), kThreads, 0, cx.st>>>(
@@ -343,14 +377,14 @@ struct Ops {
     RDB_CHECK(P >= 1, "se: too many channels");
     int chunks = HW / (P * 16);
     if (chunks < 1) chunks = 1;
-    if (chunks > 148) chunks = 148;
+    if (chunks > 32) chunks = 32;
     float* partial = cx.pool->alloc_t<float>((size_t)x.n * chunks * C);
     float* gate = cx.pool->alloc_t<float>((size_t)x.n * C);
     cx.begin("se_pool[P=" + std::to_string(x.pixels()) + ",C=" + std::to_string(C) + "]");
     pool_partial_kernel<T><<<dim3(chunks, x.n), threads, (size_t)P * C * sizeof(float), cx.st>>>(x.p, HW, C, partial, chunks);
     cx.end();
     cx.begin("se_fc");
-    se_fc_kernel<<<x.n, 128, (size_t)(C + Cr) * sizeof(float), cx.st>>>(partial, chunks, HW, C, Cr, w1.d, b1.d, w2.d, b2.d, mode, gate);
+    se_fc_kernel<<<x.n, 256, (size_t)(C + Cr) * sizeof(float), cx.st>>>(partial, chunks, HW, C, Cr, w1.d, b1.d, w2.d, b2.d, mode, gate);
     cx.end();
     cx.pool->free(partial);
     return gate;

@@ -39,13 +39,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  // suspend-time hint: the warp sleeps in hardware until the phase flips (or the hint expires) instead of
+  // hammering the mbarrier unit — 16 spinning epilogue warps otherwise starve the TMA / tcgen05.commit arrivals
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
 }
@@ -53,7 +55,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) { printf("rdb gemm_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    if (++spins > (1u << 22)) { printf("rdb gemm_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -103,6 +105,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major operand in a hardware-swizzled tile whose rows are one
@@ -128,6 +135,11 @@ struct Args {
   int k_blocks;    // ceil(K / AW)
   int AW;          // k-block width in halves: 16, 32 or 64 (= one swizzle span)
   int stages;
+  int resident;    // 1: the CTA keeps its n-tile of B (all k-blocks) in smem for its whole life; stages hold A only
+  int ctas_per_n;  // resident: CTAs per n-tile, each walks m-tiles tm = blockIdx.x / tiles_n + i * ctas_per_n
+  int walk_dm, walk_dn;          // per-iteration tile step of one CTA: tm += walk_dm, tn += walk_dn (with carry)
+  int walk_sx, walk_sy, walk_sn; // conv: walk_dm decomposed into (x, y, image) tile steps
+  int epi_subs;                  // epilogue sub-warps per lane quarter that own at least one 16-column chunk
   int tmem_cols;   // power of two >= 2*BN
   uint32_t idesc;
   const float* bias;
@@ -135,18 +147,26 @@ struct Args {
   __half* out; int ldc; int c_off;
   int act;
   float* pmax; int* pidx; float* psum;  // EPI_CTC partials [M, tiles_n * kEpiSubs]
+  // EPI_HEAD (fused DBHead tail): rows are pixels of an [n, hH, hW] map, N = 4*24 ConvT outputs; the
+  // epilogue applies ReLU, the final ConvT(24->1, 2x2 s2), sigmoid and the DB threshold.
+  int hH, hW;
+  const float* w_fin; const float* b_fin; float thresh;
+  float* prob; uint8_t* seg;
   // implicit-GEMM conv mode (conv != 0): A is the NHWC input behind a 4-D tensor map
   // {C, W, H, n}; an m-tile is a TH x TW patch of output pixels (TH*TW = 128) of one image and
   // k-block kb = (tap, channel chunk) is the same patch shifted by the tap — TMA out-of-bounds
   // zero fill provides the conv padding.
   int conv;
   int OH, OW, TH, TW, tiles_y, tiles_x;
-  int KW, sh, sw, pt, pl, cchunks, C;
+  int KW, sh, sw, pt, pl, cchunks, C, tw_shift;
 };
 
 constexpr int kEpiSubs = 4;                        // epilogue warps per TMEM lane quarter
-constexpr int kThreadsTc = 64 + 128 * kEpiSubs;    // warp0: TMA, warp1: MMA + TMEM alloc, warps 2..: epilogue
-enum { EPI_STORE = 0, EPI_CTC = 1 };
+constexpr int kThreadsTc = 64 + 128 * kEpiSubs;    // warps 0..15: epilogue, warp 16: TMA producer, warp 17: MMA + TMEM alloc
+constexpr int kWarpTma = 4 * kEpiSubs, kWarpMma = 4 * kEpiSubs + 1;
+// (the SM's warp arbiter favours HIGH warp ids: the two single-thread critical roles sit above the 16 epilogue warps so
+//  their instruction streams are never starved by epilogue warps waking up to poll their barriers)
+enum { EPI_STORE = 0, EPI_CTC = 1, EPI_HEAD = 2 };
 
 template <int EPI, int ACT>
 __global__ void __launch_bounds__(kThreadsTc, 1)
@@ -155,60 +175,107 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t span = (uint32_t)g.AW * 2u;
   const uint32_t a_bytes = 128u * span;
   const uint32_t b_bytes = ((uint32_t)g.BN * span + 1023u) & ~1023u;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t stage_bytes = g.resident ? a_bytes : a_bytes + b_bytes;
+  uint8_t* smem_al = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem_al;                                                         // resident B: [k_blocks][b_bytes]
+  uint8_t* smem = smem_al + (g.resident ? (size_t)g.k_blocks * b_bytes : 0);          // stage ring
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)g.stages * stage_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + g.stages;
   uint64_t* tfull_bar = bars + 2 * g.stages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* bfull_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
+  if (warp == kWarpTma && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < g.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4 * kEpiSubs); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4 * g.epi_subs); }
+    mbar_init(bfull_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)g.tmem_cols);
+  if (warp == kWarpMma) tmem_alloc(tmem_slot, (uint32_t)g.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int total_tiles = g.tiles_m * g.tiles_n;
-
-  if (warp == 0) {
+  const uint32_t tx_bytes = g.resident ? a_bytes : a_bytes + (uint32_t)g.BN * span;
+  // Tile walk shared by the three roles.  Divisions happen ONCE per CTA; every further tile is reached by
+  // adds + carries (16 epilogue warps x a few runtime divisions per tile used to cost more issue slots than
+  // the tile's actual work).
+  struct Walk {
+    int tm, tn, tx, ty, n;
+    __device__ __forceinline__ void init(const Args& g) {
+      if (g.resident) { tn = blockIdx.x % g.tiles_n; tm = blockIdx.x / g.tiles_n; }
+      else { tm = blockIdx.x / g.tiles_n; tn = blockIdx.x % g.tiles_n; }
+      tx = ty = n = 0;
+      if (g.conv != 0) { tx = tm % g.tiles_x; ty = (tm / g.tiles_x) % g.tiles_y; n = tm / (g.tiles_x * g.tiles_y); }
+    }
+    __device__ __forceinline__ bool valid(const Args& g) const { return tm < g.tiles_m; }
+    __device__ __forceinline__ void next(const Args& g) {
+      tm += g.walk_dm; tn += g.walk_dn;
+      if (tn >= g.tiles_n) { tn -= g.tiles_n; ++tm; }
+      if (g.conv != 0) {
+        tx += g.walk_sx; ty += g.walk_sy; n += g.walk_sn;
+        if (tx >= g.tiles_x) { tx -= g.tiles_x; ++ty; }
+        if (ty >= g.tiles_y) { ty -= g.tiles_y; ++n; }
+      }
+    }
+  };
+  if (warp == kWarpTma) {
     // ================= TMA producer =================
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int tm = t / g.tiles_n, tn = t % g.tiles_n;
+      Walk wk; wk.init(g);
+      if (g.resident && wk.valid(g)) {
+        const int tn = wk.tn;
+        // one-time load of this CTA's B n-tile: every k-block, laid out exactly like a stage's B buffer
+        mbar_expect_tx(bfull_bar, (uint32_t)g.k_blocks * (uint32_t)g.BN * span);
+        int kx = 0, cc = 0, bk = 0;
+        for (int kb = 0; kb < g.k_blocks; ++kb) {
+          const int kcoord = g.conv == 0 ? kb * g.AW : bk + cc * g.AW;
+          tma_load_2d(smem_b + (size_t)kb * b_bytes, &tmB, bfull_bar, kcoord, tn * g.BN);
+          if (g.conv != 0 && ++cc == g.cchunks) { cc = 0; bk += g.C; ++kx; }
+        }
+      }
+      for (; wk.valid(g); wk.next(g)) {
+        const int tm = wk.tm, tn = wk.tn;
+        // per-tile coordinates hoisted out of the k loop: this single thread is the latency-critical
+        // instruction stream of the CTA, so the k loop must stay free of integer divisions
+        const int cn = wk.n;
+        const int cx0 = wk.tx * g.TW * g.sw - g.pl;
+        const int cy0 = wk.ty * g.TH * g.sh - g.pt;
+        const int m_row = tm * 128, n_row = tn * g.BN;
+        int kx = 0, ky = 0, cc = 0, bk = 0;   // conv: tap (ky,kx), channel chunk cc, B k-offset of the tap
         for (int kb = 0; kb < g.k_blocks; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + (size_t)s * stage_bytes;
-          mbar_expect_tx(&full_bar[s], a_bytes + (uint32_t)g.BN * span);
+          mbar_expect_tx(&full_bar[s], tx_bytes);
           if (g.conv == 0) {
-            tma_load_2d(sa, &tmA, &full_bar[s], kb * g.AW, tm * 128);
-            tma_load_2d(sa + a_bytes, &tmB, &full_bar[s], kb * g.AW, tn * g.BN);
+            tma_load_2d(sa, &tmA, &full_bar[s], kb * g.AW, m_row);
+            if (!g.resident) tma_load_2d(sa + a_bytes, &tmB, &full_bar[s], kb * g.AW, n_row);
           } else {
-            const int tx = tm % g.tiles_x, ty = (tm / g.tiles_x) % g.tiles_y, n = tm / (g.tiles_x * g.tiles_y);
-            const int tap = kb / g.cchunks, cc = kb % g.cchunks;
-            const int ky = tap / g.KW, kx = tap % g.KW;
-            tma_load_4d(sa, &tmA, &full_bar[s], cc * g.AW, tx * g.TW * g.sw - g.pl + kx, ty * g.TH * g.sh - g.pt + ky, n);
-            tma_load_2d(sa + a_bytes, &tmB, &full_bar[s], tap * g.C + cc * g.AW, tn * g.BN);
+            tma_load_4d(sa, &tmA, &full_bar[s], cc * g.AW, cx0 + kx, cy0 + ky, cn);
+            if (!g.resident) tma_load_2d(sa + a_bytes, &tmB, &full_bar[s], bk + cc * g.AW, n_row);
+            if (++cc == g.cchunks) {
+              cc = 0; bk += g.C;
+              if (++kx == g.KW) { kx = 0; ++ky; }
+            }
           }
           if (++s == g.stages) { s = 0; ph ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kWarpMma) {
     // ================= MMA issuer (single thread) =================
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      Walk wk; wk.init(g);
+      if (g.resident && wk.valid(g)) mbar_wait(bfull_bar, 0);
+      for (int it = 0; wk.valid(g); wk.next(g), ++it) {
         const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after();
@@ -218,7 +285,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           const uint64_t da = make_smem_desc(sa, span);
-          const uint64_t db = make_smem_desc(sa + a_bytes, span);
+          const uint64_t db = make_smem_desc(g.resident ? smem_u32(smem_b + (size_t)kb * b_bytes) : sa + a_bytes, span);
           const int ksteps = g.AW / 16;
           for (int kk = 0; kk < ksteps; ++kk) {
             // advancing K by 16 halves = 32 bytes inside the swizzle span: +2 in the (addr>>4) field
@@ -235,24 +302,65 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // 16 warps: warp w may only touch TMEM lanes [32*(w%4), +32) (hardware rule), so the four warps
     // sharing a lane quarter split the tile's 16-column chunks between them (sub = 0..3).
     const int q = warp & 3;
-    const int sub = (warp - 2) >> 2;
-    int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const int tm = t / g.tiles_n, tn = t % g.tiles_n;
+    const int sub = warp >> 2;
+    Walk wk; wk.init(g);
+    for (int it = 0; sub < g.epi_subs && wk.valid(g); wk.next(g), ++it) {
+      const int tm = wk.tm, tn = wk.tn;
       const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       long long row = (long long)tm * 128 + q * 32 + lane;   // GEMM: output row; conv: output pixel index
       bool row_ok = row < g.M;
       if (g.conv != 0) {
-        const int tx = tm % g.tiles_x, ty = (tm / g.tiles_x) % g.tiles_y, n = tm / (g.tiles_x * g.tiles_y);
         const int r = q * 32 + lane;
-        const int oy = ty * g.TH + r / g.TW, ox = tx * g.TW + r % g.TW;
+        const int oy = wk.ty * g.TH + (r >> g.tw_shift), ox = wk.tx * g.TW + (r & (g.TW - 1));
         row_ok = (oy < g.OH) && (ox < g.OW);
-        row = ((long long)n * g.OH + oy) * g.OW + ox;
+        row = ((long long)wk.n * g.OH + oy) * g.OW + ox;
       }
       const int n0 = tn * g.BN;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * g.BN);
+      if (EPI == EPI_HEAD) {
+        // sub = ConvT tap (dy,dx) of the first up-conv; this thread owns its 24 hidden channels of one pixel
+        uint32_t r16[16], r8[8];
+        tmem_ld16(taddr + (uint32_t)(24 * sub), r16);
+        tmem_ld8(taddr + (uint32_t)(24 * sub + 16), r8);
+        float o[4];
+        {
+          const float bf = __ldg(g.b_fin);
+          o[0] = bf; o[1] = bf; o[2] = bf; o[3] = bf;
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 24; ++c) {
+          const float acc = __uint_as_float(c < 16 ? r16[c < 16 ? c : 0] : r8[c >= 16 ? c - 16 : 0]);
+          const float hv = fmaxf(acc + __ldg(g.bias + c), 0.f);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) o[k] = fmaf(hv, __ldg(g.w_fin + k * 24 + c), o[k]);
+        }
+        if (row_ok) {
+          const int hw = g.hH * g.hW;
+          const int n = (int)(row / hw), rem = (int)(row % hw);
+          const int y = rem / g.hW, x = rem % g.hW;
+          const int W4 = 4 * g.hW;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float pz = 1.f / (1.f + expf(-o[k]));
+            if (pz != pz) pz = 0.f;
+            o[k] = pz;
+          }
+          const long long base = ((long long)n * (4 * g.hH) + 4 * y + 2 * (sub >> 1)) * W4 + 4 * x + 2 * (sub & 1);
+          *reinterpret_cast<float2*>(g.prob + base) = make_float2(o[0], o[1]);
+          *reinterpret_cast<float2*>(g.prob + base + W4) = make_float2(o[2], o[3]);
+          if (g.seg != nullptr) {
+            *reinterpret_cast<uchar2*>(g.seg + base) = make_uchar2(o[0] > g.thresh, o[1] > g.thresh);
+            *reinterpret_cast<uchar2*>(g.seg + base + W4) = make_uchar2(o[2] > g.thresh, o[3] > g.thresh);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        continue;
+      }
       float cmax = -INFINITY, csum = 0.f; int cidx = 0x7fffffff;
       for (int c0 = sub * 16; c0 < g.BN; c0 += 16 * kEpiSubs) {
         if (n0 + c0 >= g.N) break;                 // warp-uniform: the rest of this n-tile is padding
@@ -329,7 +437,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kWarpMma) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
   }
@@ -409,6 +517,56 @@ inline int pick_bn(int N) {
   return best;
 }
 
+// stage count / residency / grid, common to GEMM and conv plans
+inline void finish_plan(Plan& p, int num_sms) {
+  Args& a = p.a;
+  const size_t span = (size_t)a.AW * 2;
+  const size_t a_bytes = 128 * span;
+  const size_t b_bytes = ((size_t)a.BN * span + 1023) & ~(size_t)1023;
+  const size_t budget = 200 * 1024;
+  const size_t b_res = (size_t)a.k_blocks * b_bytes;
+  const char* e = std::getenv("RDB_TC_RESIDENT");
+  const bool allow = !(e != nullptr && e[0] == '0');
+  int min_stages = a.k_blocks < 3 ? a.k_blocks + 2 : 4;
+  if (allow && a.tiles_n <= num_sms && b_res + (size_t)min_stages * a_bytes <= budget) {
+    a.resident = 1;
+    int stages = (int)((budget - b_res) / a_bytes);
+    if (stages > 12) stages = 12;
+    int want = a.k_blocks * 3;
+    if (stages > want) stages = want;
+    if (stages < 2) stages = 2;
+    a.stages = stages;
+    a.ctas_per_n = num_sms / a.tiles_n;
+    if (a.ctas_per_n > a.tiles_m) a.ctas_per_n = a.tiles_m;
+    if (a.ctas_per_n < 1) a.ctas_per_n = 1;
+    p.grid = a.ctas_per_n * a.tiles_n;
+    p.smem = 1024 + b_res + stages * a_bytes + (2 * stages + 8) * 8 + 16;
+    a.walk_dm = a.ctas_per_n; a.walk_dn = 0;
+  } else {
+    a.resident = 0;
+    const size_t stage = a_bytes + b_bytes;
+    int stages = (int)(budget / stage);
+    if (stages > 8) stages = 8;
+    int want = a.k_blocks * 3;
+    if (stages > want) stages = want;
+    if (stages < 2) stages = 2;
+    a.stages = stages;
+    p.smem = 1024 + stages * stage + (2 * stages + 8) * 8 + 16;
+    long long tiles = (long long)a.tiles_m * a.tiles_n;
+    p.grid = (int)(tiles < num_sms ? tiles : num_sms);
+    a.walk_dm = p.grid / a.tiles_n; a.walk_dn = p.grid % a.tiles_n;
+  }
+  if (a.conv) {
+    a.walk_sx = a.walk_dm % a.tiles_x;
+    a.walk_sy = (a.walk_dm / a.tiles_x) % a.tiles_y;
+    a.walk_sn = a.walk_dm / (a.tiles_x * a.tiles_y);
+  }
+  if (a.epi_subs == 0) {   // sub-warps that own >= 1 chunk (EPI_HEAD overrides to 4)
+    const int chunks = a.BN / 16;
+    a.epi_subs = chunks < kEpiSubs ? chunks : kEpiSubs;
+  }
+}
+
 inline Plan make_plan(long long M, int N, int K, int num_sms) {
   Plan p{};
   Args& a = p.a;
@@ -424,17 +582,7 @@ inline Plan make_plan(long long M, int N, int K, int num_sms) {
   // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c=F32 [4,6)=1, a/b = F16 (0),
   // a_major/b_major = K (0), n>>3 at [17,23), m>>4 at [24,29)
   a.idesc = (1u << 4) | ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  const size_t span = (size_t)a.AW * 2;
-  const size_t stage = 128 * span + (((size_t)a.BN * span + 1023) & ~(size_t)1023);
-  int stages = (int)((200 * 1024) / stage);
-  if (stages > 8) stages = 8;
-  int want = a.k_blocks * 3;  // up to three tiles in flight
-  if (stages > want) stages = want;
-  if (stages < 2) stages = 2;
-  a.stages = stages;
-  p.smem = 1024 + stages * stage + (2 * stages + 4) * 8 + 16;
-  long long tiles = (long long)a.tiles_m * a.tiles_n;
-  p.grid = (int)(tiles < num_sms ? tiles : num_sms);
+  finish_plan(p, num_sms);
   return p;
 }
 
@@ -451,6 +599,7 @@ inline Plan make_conv_plan(int n, int H, int W, int C, int N, int KH, int KW, in
   a.OH = OH; a.OW = OW; a.KW = KW; a.sh = sh; a.sw = sw; a.pt = pt; a.pl = pl;
   a.TW = OW >= 16 ? 16 : (OW >= 8 ? 8 : 4);
   a.TH = 128 / a.TW;
+  a.tw_shift = a.TW == 16 ? 4 : (a.TW == 8 ? 3 : 2);
   a.tiles_x = (OW + a.TW - 1) / a.TW;
   a.tiles_y = (OH + a.TH - 1) / a.TH;
   a.tiles_m = n * a.tiles_x * a.tiles_y;
@@ -460,15 +609,7 @@ inline Plan make_conv_plan(int n, int H, int W, int C, int N, int KH, int KW, in
   while (cols < 2 * a.BN) cols *= 2;
   a.tmem_cols = cols;
   a.idesc = (1u << 4) | ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  const size_t span = (size_t)a.AW * 2;
-  const size_t stage = 128 * span + (((size_t)a.BN * span + 1023) & ~(size_t)1023);
-  int stages = (int)((200 * 1024) / stage);
-  if (stages > 8) stages = 8;
-  if (stages < 2) stages = 2;
-  a.stages = stages;
-  p.smem = 1024 + stages * stage + (2 * stages + 4) * 8 + 16;
-  long long tiles = (long long)a.tiles_m * a.tiles_n;
-  p.grid = (int)(tiles < num_sms ? tiles : num_sms);
+  finish_plan(p, num_sms);
   return p;
 }
 

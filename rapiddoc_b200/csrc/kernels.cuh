@@ -347,23 +347,34 @@ __global__ void __launch_bounds__(256) pool_partial_kernel(const T* __restrict__
 }
 
 // mode 0: gate = hardsigmoid(z) = clip(z/6+.5,0,1);  mode 1: gate = 1 + clip(.2z+.5,0,1)
-static __global__ void se_fc_kernel(const float* __restrict__ partial, int chunks, int HW, int C, int Cr, const float* __restrict__ w1,
-                             const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
-                             int mode, float* __restrict__ gate) {
+static __global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ partial, int chunks, int HW, int C, int Cr,
+                                                         const float* __restrict__ w1, const float* __restrict__ b1,
+                                                         const float* __restrict__ w2, const float* __restrict__ b2, int mode,
+                                                         float* __restrict__ gate) {
   extern __shared__ float sm[];  // mean[C] + hid[Cr]
   float* mean = sm;
   float* hid = sm + C;
-  int n = blockIdx.x;
+  const int n = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  // fixed-order (deterministic) sum of the per-chunk partials, 4 independent chains per thread
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float t = 0.f;
-    for (int k = 0; k < chunks; ++k) t += partial[((long long)n * chunks + k) * C + c];
-    mean[c] = t / (float)HW;
+    const float* pp = partial + (long long)n * chunks * C + c;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    int k = 0;
+    for (; k + 3 < chunks; k += 4) {
+      t0 += pp[(long long)k * C]; t1 += pp[(long long)(k + 1) * C]; t2 += pp[(long long)(k + 2) * C]; t3 += pp[(long long)(k + 3) * C];
+    }
+    for (; k < chunks; ++k) t0 += pp[(long long)k * C];
+    mean[c] = ((t0 + t1) + (t2 + t3)) / (float)HW;
   }
   __syncthreads();
-  for (int r = threadIdx.x; r < Cr; r += blockDim.x) {
-    float t = b1[r];
-    for (int c = 0; c < C; ++c) t = fmaf(w1[r * C + c], mean[c], t);
-    hid[r] = fmaxf(t, 0.f);
+  // hidden = relu(W1 mean + b1): one warp per output, lanes stride the C inputs
+  for (int r = warp; r < Cr; r += nwarps) {
+    float t = 0.f;
+    for (int c = lane; c < C; c += 32) t = fmaf(w1[r * C + c], mean[c], t);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffff, t, o);
+    if (lane == 0) hid[r] = fmaxf(t + b1[r], 0.f);
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
