@@ -23,21 +23,29 @@ DetEngine::DetEngine(const void* blob, size_t nbytes, int device, int precision)
 DetEngine::~DetEngine() {
   cudaSetDevice(device_);
   cudaDeviceSynchronize();
-  pool_.release_all();
+  pools_[0].release_all();
+  pools_[1].release_all();
   if (copy_in_) {
     cudaStreamDestroy(copy_in_); cudaStreamDestroy(copy_out_);
-    for (int s = 0; s < 2; ++s) { cudaEventDestroy(ev_in_[s]); cudaEventDestroy(ev_out_[s]); cudaEventDestroy(ev_compute_[s]); }
+    cudaEventDestroy(ev_fork_);
+    for (int s = 0; s < 2; ++s) {
+      cudaStreamDestroy(lane_[s]);
+      cudaEventDestroy(ev_in_[s]); cudaEventDestroy(ev_out_[s]); cudaEventDestroy(ev_compute_[s]); cudaEventDestroy(ev_join_[s]);
+    }
   }
 }
 
-void DetEngine::ensure_copy_streams() {
+void DetEngine::ensure_streams() {
   if (copy_in_) return;
   RDB_CUDA(cudaStreamCreateWithFlags(&copy_in_, cudaStreamNonBlocking));
   RDB_CUDA(cudaStreamCreateWithFlags(&copy_out_, cudaStreamNonBlocking));
+  RDB_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
   for (int s = 0; s < 2; ++s) {
+    RDB_CUDA(cudaStreamCreateWithFlags(&lane_[s], cudaStreamNonBlocking));
     RDB_CUDA(cudaEventCreateWithFlags(&ev_in_[s], cudaEventDisableTiming));
     RDB_CUDA(cudaEventCreateWithFlags(&ev_out_[s], cudaEventDisableTiming));
     RDB_CUDA(cudaEventCreateWithFlags(&ev_compute_[s], cudaEventDisableTiming));
+    RDB_CUDA(cudaEventCreateWithFlags(&ev_join_[s], cudaEventDisableTiming));
   }
 }
 
@@ -167,7 +175,7 @@ void DetEngine::infer(const DetInput& in_host_or_dev, int n, int H, int W, float
   RDB_CHECK(n > 0 && H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0, "det: h and w must be positive multiples of 32");
   RDB_CHECK((in_host_or_dev.f32 != nullptr) != (in_host_or_dev.u8 != nullptr), "det: exactly one input");
   Ctx cx;
-  cx.st = st; cx.pool = &pool_; cx.precision = precision_;
+  cx.st = st; cx.pool = &pools_[0]; cx.precision = precision_;
   cx.use_tc = (precision_ == 1) && !env_gemm_simt();
   cx.num_sms = num_sms_;
   const void* src = in_host_or_dev.f32 ? (const void*)in_host_or_dev.f32 : (const void*)in_host_or_dev.u8;
@@ -182,58 +190,75 @@ void DetEngine::infer(const DetInput& in_host_or_dev, int n, int H, int W, float
   int chunk = (int)(px_budget / (long long)(H * (long long)W));
   if (chunk < 1) chunk = 1;
   if (chunk > n) chunk = n;
-  // Host buffers: 2-slot software pipeline — H2D of chunk i+1 and D2H of chunk i-1 overlap the compute
-  // of chunk i (dedicated copy streams + events); device buffers: everything on `st`, no synchronise.
+  // Two compute LANES (stream + buffer pool each): consecutive chunks alternate lanes so the many tiny
+  // kernels of one chunk (SE FCs, stage-4 layers) overlap the other chunk's work, and — with host buffers —
+  // the H2D of chunk i+1 and the D2H of chunk i-1 (dedicated copy streams) overlap the compute of chunk i.
+  // With device buffers the call stays asynchronous: lanes fork from `st` and join back into it by events.
   const bool any_host = !in_dev || (prob && !prob_dev) || (bitmap && !bm_dev);
-  const int slots = any_host ? 2 : 1;
+  const int n_chunks = (n + chunk - 1) / chunk;
+  const int lanes = (n_chunks >= 2 && !env_is("RDB_LANES", "1")) ? 2 : 1;
+  ensure_streams();
+  Ctx cxs[2];
   void* d_in[2] = {nullptr, nullptr};
   float* d_prob[2] = {nullptr, nullptr};
   uint8_t* d_bm[2] = {nullptr, nullptr};
-  for (int s = 0; s < slots; ++s) {
-    if (!in_dev) d_in[s] = pool_.alloc(page_in * chunk);
-    if (!(prob_dev && prob)) d_prob[s] = pool_.alloc_t<float>(page_px * chunk);
-    if (bitmap && !bm_dev) d_bm[s] = pool_.alloc_t<uint8_t>(page_px * chunk);
+  RDB_CUDA(cudaEventRecord(ev_fork_, st));
+  for (int l = 0; l < lanes; ++l) {
+    cxs[l] = cx;
+    cxs[l].st = lane_[l];
+    cxs[l].pool = &pools_[l];
+    cxs[l].launches = 0;
+    RDB_CUDA(cudaStreamWaitEvent(lane_[l], ev_fork_, 0));
+    if (!in_dev) d_in[l] = pools_[l].alloc(page_in * chunk);
+    if (!(prob_dev && prob)) d_prob[l] = pools_[l].alloc_t<float>(page_px * chunk);
+    if (bitmap && !bm_dev) d_bm[l] = pools_[l].alloc_t<uint8_t>(page_px * chunk);
   }
-  if (any_host) ensure_copy_streams();
   int it = 0;
   for (int i0 = 0; i0 < n; i0 += chunk, ++it) {
-    const int s = it % slots;
+    const int l = it % lanes;
+    cudaStream_t ls = lane_[l];
     int m = (n - i0 < chunk) ? (n - i0) : chunk;
     const uint8_t* src_i = static_cast<const uint8_t*>(src) + (size_t)i0 * page_in;
     DetInput in = in_host_or_dev;
     const void* dsrc = src_i;
     if (!in_dev) {
-      if (it >= slots) RDB_CUDA(cudaStreamWaitEvent(copy_in_, ev_compute_[s], 0));   // slot's previous reader done
-      RDB_CUDA(cudaMemcpyAsync(d_in[s], src_i, page_in * m, cudaMemcpyHostToDevice, copy_in_));
-      RDB_CUDA(cudaEventRecord(ev_in_[s], copy_in_));
-      RDB_CUDA(cudaStreamWaitEvent(st, ev_in_[s], 0));
-      dsrc = d_in[s];
+      if (it >= lanes) RDB_CUDA(cudaStreamWaitEvent(copy_in_, ev_compute_[l], 0));   // lane's previous reader done
+      RDB_CUDA(cudaMemcpyAsync(d_in[l], src_i, page_in * m, cudaMemcpyHostToDevice, copy_in_));
+      RDB_CUDA(cudaEventRecord(ev_in_[l], copy_in_));
+      RDB_CUDA(cudaStreamWaitEvent(ls, ev_in_[l], 0));
+      dsrc = d_in[l];
     }
-    if (any_host && it >= slots) RDB_CUDA(cudaStreamWaitEvent(st, ev_out_[s], 0));     // slot's previous D2H done
+    if (any_host && it >= lanes) RDB_CUDA(cudaStreamWaitEvent(ls, ev_out_[l], 0));     // lane's previous D2H done
     if (in.f32) in.f32 = static_cast<const float*>(dsrc); else in.u8 = static_cast<const uint8_t*>(dsrc);
-    float* p_out = (prob_dev && prob) ? prob + (size_t)i0 * page_px : d_prob[s];
-    uint8_t* b_out = bitmap ? (bm_dev ? bitmap + (size_t)i0 * page_px : d_bm[s]) : nullptr;
-    if (precision_ == 0) forward_chunk<float>(cx, in, m, H, W, thresh, dilate, p_out, b_out);
-    else forward_chunk<__half>(cx, in, m, H, W, thresh, dilate, p_out, b_out);
+    float* p_out = (prob_dev && prob) ? prob + (size_t)i0 * page_px : d_prob[l];
+    uint8_t* b_out = bitmap ? (bm_dev ? bitmap + (size_t)i0 * page_px : d_bm[l]) : nullptr;
+    if (precision_ == 0) forward_chunk<float>(cxs[l], in, m, H, W, thresh, dilate, p_out, b_out);
+    else forward_chunk<__half>(cxs[l], in, m, H, W, thresh, dilate, p_out, b_out);
     if (any_host) {
-      RDB_CUDA(cudaEventRecord(ev_compute_[s], st));
-      RDB_CUDA(cudaStreamWaitEvent(copy_out_, ev_compute_[s], 0));
-      if (prob && !prob_dev) RDB_CUDA(cudaMemcpyAsync(prob + (size_t)i0 * page_px, d_prob[s], page_px * m * sizeof(float), cudaMemcpyDeviceToHost, copy_out_));
-      if (bitmap && !bm_dev) RDB_CUDA(cudaMemcpyAsync(bitmap + (size_t)i0 * page_px, d_bm[s], page_px * m, cudaMemcpyDeviceToHost, copy_out_));
-      RDB_CUDA(cudaEventRecord(ev_out_[s], copy_out_));
+      RDB_CUDA(cudaEventRecord(ev_compute_[l], ls));
+      RDB_CUDA(cudaStreamWaitEvent(copy_out_, ev_compute_[l], 0));
+      if (prob && !prob_dev) RDB_CUDA(cudaMemcpyAsync(prob + (size_t)i0 * page_px, d_prob[l], page_px * m * sizeof(float), cudaMemcpyDeviceToHost, copy_out_));
+      if (bitmap && !bm_dev) RDB_CUDA(cudaMemcpyAsync(bitmap + (size_t)i0 * page_px, d_bm[l], page_px * m, cudaMemcpyDeviceToHost, copy_out_));
+      RDB_CUDA(cudaEventRecord(ev_out_[l], copy_out_));
     }
+  }
+  long long launches = 0;
+  for (int l = 0; l < lanes; ++l) {
+    RDB_CUDA(cudaEventRecord(ev_join_[l], lane_[l]));
+    RDB_CUDA(cudaStreamWaitEvent(st, ev_join_[l], 0));
+    launches += cxs[l].launches;
   }
   if (any_host) {
     RDB_CUDA(cudaStreamSynchronize(copy_out_));
     RDB_CUDA(cudaStreamSynchronize(st));
   }
-  for (int s = 0; s < slots; ++s) {
-    if (d_in[s]) pool_.free(d_in[s]);
-    if (d_prob[s]) pool_.free(d_prob[s]);
-    if (d_bm[s]) pool_.free(d_bm[s]);
+  for (int l = 0; l < lanes; ++l) {
+    if (d_in[l]) pools_[l].free(d_in[l]);
+    if (d_prob[l]) pools_[l].free(d_prob[l]);
+    if (d_bm[l]) pools_[l].free(d_bm[l]);
   }
-  cx.finish();
-  last_launches_ = cx.launches;
+  if (Profiler::global().on) { RDB_CUDA(cudaDeviceSynchronize()); Profiler::global().resolve(); }
+  last_launches_ = launches;
 }
 
 void db_bitmap(int device, const float* prob, int n, int H, int W, float thresh, bool dilate, uint8_t* bitmap, cudaStream_t st) {

@@ -24,12 +24,13 @@ class DetEngine {
  private:
   template <typename T>
   void forward_chunk(Ctx& cx, const DetInput& in, int n, int H, int W, float thresh, bool dilate, float* prob, uint8_t* bitmap);
-  void ensure_copy_streams();
+  void ensure_streams();
   int device_, precision_;
-  cudaStream_t copy_in_ = nullptr, copy_out_ = nullptr;
+  cudaStream_t copy_in_ = nullptr, copy_out_ = nullptr, lane_[2] = {nullptr, nullptr};
   cudaEvent_t ev_in_[2] = {nullptr, nullptr}, ev_out_[2] = {nullptr, nullptr}, ev_compute_[2] = {nullptr, nullptr};
+  cudaEvent_t ev_join_[2] = {nullptr, nullptr}, ev_fork_ = nullptr;
   std::unique_ptr<Weights> weights_;
-  Pool pool_;
+  Pool pools_[2];   // one per compute lane
   long long last_launches_ = 0;
   int num_sms_ = 148;
   long long chunk_pixels_ = 8ll * 1024 * 1024;  // pages per internal chunk = chunk_pixels / (H*W)

@@ -12,20 +12,28 @@ namespace rdb {
 // (facade seam; DetPreProcess / resize_norm_img arithmetic).
 // =====================================================================================
 struct InF32NCHW {
+  static constexpr bool kU8 = false;
   const float* x; int H, W;
   __device__ __forceinline__ float get(int n, int y, int xx, int c) const {
     return x[(((long long)n * 3 + c) * H + y) * W + xx];
   }
+  __device__ __forceinline__ float norm(int, int) const { return 0.f; }
+  __device__ __forceinline__ float look(const float*, int n, int y, int xx, int c) const { return get(n, y, xx, c); }
 };
 // norm_mode 0: (v*(1/255) - mean)/std   (DetPreProcess)
 // norm_mode 1: (v/255 - 0.5)/0.5        (resize_norm_img); pixels with xx >= valid_w[n] are 0 (right pad)
 struct InU8HWC {
+  static constexpr bool kU8 = true;
   const uint8_t* x; int H, W; int norm_mode; float mean[3], stdv[3]; const int* valid_w;
-  __device__ __forceinline__ float get(int n, int y, int xx, int c) const {
-    float v = (float)x[(((long long)n * H + y) * W + xx) * 3 + c];
+  // the reference's float32 op order, evaluated once per (channel, byte value) into a 768-entry table
+  __device__ __forceinline__ float norm(int c, int v8) const {
+    const float v = (float)v8;
     if (norm_mode == 0) return __fdiv_rn(__fsub_rn(__fmul_rn(v, 1.0f / 255.0f), mean[c]), stdv[c]);
-    if (valid_w != nullptr && xx >= valid_w[n]) return 0.f;
     return __fdiv_rn(__fsub_rn(__fdiv_rn(v, 255.0f), 0.5f), 0.5f);
+  }
+  __device__ __forceinline__ float look(const float* lut, int n, int y, int xx, int c) const {
+    if (norm_mode != 0 && valid_w != nullptr && xx >= valid_w[n]) return 0.f;
+    return lut[c * 256 + x[(((long long)n * H + y) * W + xx) * 3 + c]];
   }
 };
 
@@ -34,11 +42,14 @@ __global__ void __launch_bounds__(128) stem1_kernel(IN in, int N, const float* _
                                                     const float* __restrict__ b, T* __restrict__ out, int OH, int OW) {
   __shared__ float sw[27 * C1];
   __shared__ float sb[C1];
+  __shared__ float lut[IN::kU8 ? 768 : 1];
   for (int i = threadIdx.x; i < 27 * C1; i += blockDim.x) {
     int co = i / 27, r = i % 27;  // r = (ky*3+kx)*3+ci
     sw[r * C1 + co] = w[i];
   }
   for (int i = threadIdx.x; i < C1; i += blockDim.x) sb[i] = b[i];
+  if (IN::kU8)
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) lut[i] = in.norm(i >> 8, i & 255);
   __syncthreads();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)N * OH * OW;
@@ -57,7 +68,7 @@ __global__ void __launch_bounds__(128) stem1_kernel(IN in, int N, const float* _
       if (ix < 0 || ix >= in.W) continue;
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci) {
-        float v = in.get(n, iy, ix, ci);
+        float v = in.look(lut, n, iy, ix, ci);
         const float* wp = &sw[((ky * 3 + kx) * 3 + ci) * C1];
 #pragma unroll
         for (int c = 0; c < C1; c += 4) {

@@ -24,7 +24,13 @@ RecEngine::RecEngine(const void* blob, size_t nbytes, int device, int precision)
 
 RecEngine::~RecEngine() {
   cudaSetDevice(device_);
-  pool_.release_all();
+  cudaDeviceSynchronize();
+  pools_[0].release_all();
+  pools_[1].release_all();
+  if (ev_fork_) {
+    cudaEventDestroy(ev_fork_);
+    for (int s = 0; s < 2; ++s) { cudaStreamDestroy(lane_[s]); cudaEventDestroy(ev_join_[s]); }
+  }
 }
 
 template <typename T>
@@ -167,7 +173,7 @@ void RecEngine::infer(const RecInput& in0, int n, int W, const RecOutput& out, c
   RDB_CHECK(n > 0 && W >= 16, "rec: width must be >= 16");
   RDB_CHECK((in0.f32 != nullptr) != (in0.u8 != nullptr), "rec: exactly one input");
   Ctx cx;
-  cx.st = st; cx.pool = &pool_; cx.precision = precision_;
+  cx.st = st; cx.pool = &pools_[0]; cx.precision = precision_;
   cx.use_tc = (precision_ == 1) && !env_gemm_simt();
   cx.num_sms = num_sms_;
   const int Tn = tokens_for_width(W);
@@ -176,57 +182,89 @@ void RecEngine::infer(const RecInput& in0, int n, int W, const RecOutput& out, c
   const bool in_dev = is_device_ptr(src);
   int chunk = chunk_crops_;
   if (chunk > n) chunk = n;
-  void* d_in = in_dev ? nullptr : pool_.alloc(crop_in * chunk);
+  // two compute lanes (stream + pool each), chunks alternate (see DetEngine::infer)
+  const int n_chunks = (n + chunk - 1) / chunk;
+  const int lanes = (n_chunks >= 2 && !env_is("RDB_LANES", "1")) ? 2 : 1;
+  ensure_streams();
   int32_t* d_vw = nullptr;
   if (in0.valid_w) {
     if (is_device_ptr(in0.valid_w)) d_vw = const_cast<int32_t*>(in0.valid_w);
     else {
-      d_vw = pool_.alloc_t<int32_t>(n);
+      d_vw = pools_[0].alloc_t<int32_t>(n);
       RDB_CUDA(cudaMemcpyAsync(d_vw, in0.valid_w, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     }
   }
-  // device-side result buffers for one chunk
-  int32_t* d_ids = pool_.alloc_t<int32_t>((size_t)chunk * Tn);
-  float* d_probs = pool_.alloc_t<float>((size_t)chunk * Tn);
-  int32_t* d_tids = pool_.alloc_t<int32_t>((size_t)chunk * Tn);
-  int32_t* d_tlen = pool_.alloc_t<int32_t>(chunk);
-  float* d_conf = pool_.alloc_t<float>(chunk);
+  RDB_CUDA(cudaEventRecord(ev_fork_, st));
+  Ctx cxs[2];
+  void* d_in[2] = {nullptr, nullptr};
+  int32_t *d_ids[2], *d_tids[2], *d_tlen[2];
+  float *d_probs[2], *d_conf[2], *d_sm[2] = {nullptr, nullptr};
   const bool sm_dev = out.softmax ? is_device_ptr(out.softmax) : true;
-  float* d_sm = (out.softmax && !sm_dev) ? pool_.alloc_t<float>((size_t)chunk * Tn * vocab_) : nullptr;
+  for (int l = 0; l < lanes; ++l) {
+    cxs[l] = cx; cxs[l].st = lane_[l]; cxs[l].pool = &pools_[l]; cxs[l].launches = 0;
+    RDB_CUDA(cudaStreamWaitEvent(lane_[l], ev_fork_, 0));
+    if (!in_dev) d_in[l] = pools_[l].alloc(crop_in * chunk);
+    d_ids[l] = pools_[l].alloc_t<int32_t>((size_t)chunk * Tn);
+    d_probs[l] = pools_[l].alloc_t<float>((size_t)chunk * Tn);
+    d_tids[l] = pools_[l].alloc_t<int32_t>((size_t)chunk * Tn);
+    d_tlen[l] = pools_[l].alloc_t<int32_t>(chunk);
+    d_conf[l] = pools_[l].alloc_t<float>(chunk);
+    if (out.softmax && !sm_dev) d_sm[l] = pools_[l].alloc_t<float>((size_t)chunk * Tn * vocab_);
+  }
   bool any_host = !in_dev;
-  auto emit = [&](void* dst, const void* dsrc, size_t bytes) {
-    if (!dst) return;
-    if (is_device_ptr(dst)) RDB_CUDA(cudaMemcpyAsync(dst, dsrc, bytes, cudaMemcpyDeviceToDevice, st));
-    else { RDB_CUDA(cudaMemcpyAsync(dst, dsrc, bytes, cudaMemcpyDeviceToHost, st)); any_host = true; }
-  };
-  for (int i0 = 0; i0 < n; i0 += chunk) {
+  int it = 0;
+  for (int i0 = 0; i0 < n; i0 += chunk, ++it) {
+    const int l = it % lanes;
+    cudaStream_t ls = lane_[l];
     int m = (n - i0 < chunk) ? (n - i0) : chunk;
     const uint8_t* src_i = static_cast<const uint8_t*>(src) + (size_t)i0 * crop_in;
     const void* dsrc = src_i;
     if (!in_dev) {
-      RDB_CUDA(cudaMemcpyAsync(d_in, src_i, crop_in * m, cudaMemcpyHostToDevice, st));
-      dsrc = d_in;
+      RDB_CUDA(cudaMemcpyAsync(d_in[l], src_i, crop_in * m, cudaMemcpyHostToDevice, ls));
+      dsrc = d_in[l];
     }
     RecInput in = in0;
     if (in.f32) in.f32 = static_cast<const float*>(dsrc); else in.u8 = static_cast<const uint8_t*>(dsrc);
     in.valid_w = d_vw ? d_vw + i0 : nullptr;
-    float* smx = out.softmax ? (sm_dev ? out.softmax + (size_t)i0 * Tn * vocab_ : d_sm) : nullptr;
-    if (precision_ == 0) forward_chunk<float>(cx, in, m, W, d_ids, d_probs, d_tids, d_tlen, d_conf, smx);
-    else forward_chunk<__half>(cx, in, m, W, d_ids, d_probs, d_tids, d_tlen, d_conf, smx);
-    emit(out.ids ? out.ids + (size_t)i0 * Tn : nullptr, d_ids, (size_t)m * Tn * 4);
-    emit(out.probs ? out.probs + (size_t)i0 * Tn : nullptr, d_probs, (size_t)m * Tn * 4);
-    emit(out.text_ids ? out.text_ids + (size_t)i0 * Tn : nullptr, d_tids, (size_t)m * Tn * 4);
-    emit(out.text_len ? out.text_len + i0 : nullptr, d_tlen, (size_t)m * 4);
-    emit(out.conf ? out.conf + i0 : nullptr, d_conf, (size_t)m * 4);
-    if (out.softmax && !sm_dev) emit(out.softmax + (size_t)i0 * Tn * vocab_, d_sm, (size_t)m * Tn * vocab_ * 4);
+    float* smx = out.softmax ? (sm_dev ? out.softmax + (size_t)i0 * Tn * vocab_ : d_sm[l]) : nullptr;
+    if (precision_ == 0) forward_chunk<float>(cxs[l], in, m, W, d_ids[l], d_probs[l], d_tids[l], d_tlen[l], d_conf[l], smx);
+    else forward_chunk<__half>(cxs[l], in, m, W, d_ids[l], d_probs[l], d_tids[l], d_tlen[l], d_conf[l], smx);
+    auto emit = [&](void* dst, const void* dsrc2, size_t bytes) {
+      if (!dst) return;
+      if (is_device_ptr(dst)) RDB_CUDA(cudaMemcpyAsync(dst, dsrc2, bytes, cudaMemcpyDeviceToDevice, ls));
+      else { RDB_CUDA(cudaMemcpyAsync(dst, dsrc2, bytes, cudaMemcpyDeviceToHost, ls)); any_host = true; }
+    };
+    emit(out.ids ? out.ids + (size_t)i0 * Tn : nullptr, d_ids[l], (size_t)m * Tn * 4);
+    emit(out.probs ? out.probs + (size_t)i0 * Tn : nullptr, d_probs[l], (size_t)m * Tn * 4);
+    emit(out.text_ids ? out.text_ids + (size_t)i0 * Tn : nullptr, d_tids[l], (size_t)m * Tn * 4);
+    emit(out.text_len ? out.text_len + i0 : nullptr, d_tlen[l], (size_t)m * 4);
+    emit(out.conf ? out.conf + i0 : nullptr, d_conf[l], (size_t)m * 4);
+    if (out.softmax && !sm_dev) emit(out.softmax + (size_t)i0 * Tn * vocab_, d_sm[l], (size_t)m * Tn * vocab_ * 4);
   }
-  if (d_in) pool_.free(d_in);
-  if (d_vw && d_vw != in0.valid_w) pool_.free(d_vw);
-  pool_.free(d_ids); pool_.free(d_probs); pool_.free(d_tids); pool_.free(d_tlen); pool_.free(d_conf);
-  if (d_sm) pool_.free(d_sm);
+  long long launches = 0;
+  for (int l = 0; l < lanes; ++l) {
+    RDB_CUDA(cudaEventRecord(ev_join_[l], lane_[l]));
+    RDB_CUDA(cudaStreamWaitEvent(st, ev_join_[l], 0));
+    launches += cxs[l].launches;
+  }
   if (any_host) RDB_CUDA(cudaStreamSynchronize(st));
-  cx.finish();
-  last_launches_ = cx.launches;
+  for (int l = 0; l < lanes; ++l) {
+    if (d_in[l]) pools_[l].free(d_in[l]);
+    pools_[l].free(d_ids[l]); pools_[l].free(d_probs[l]); pools_[l].free(d_tids[l]); pools_[l].free(d_tlen[l]); pools_[l].free(d_conf[l]);
+    if (d_sm[l]) pools_[l].free(d_sm[l]);
+  }
+  if (d_vw && d_vw != in0.valid_w) pools_[0].free(d_vw);
+  if (Profiler::global().on) { RDB_CUDA(cudaDeviceSynchronize()); Profiler::global().resolve(); }
+  last_launches_ = launches;
+}
+
+void RecEngine::ensure_streams() {
+  if (ev_fork_) return;
+  RDB_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+  for (int s = 0; s < 2; ++s) {
+    RDB_CUDA(cudaStreamCreateWithFlags(&lane_[s], cudaStreamNonBlocking));
+    RDB_CUDA(cudaEventCreateWithFlags(&ev_join_[s], cudaEventDisableTiming));
+  }
 }
 
 }  // namespace rdb

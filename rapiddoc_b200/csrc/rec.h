@@ -35,10 +35,13 @@ class RecEngine {
                      float* conf, float* softmax);
   int device_, precision_, vocab_ = 0;
   std::unique_ptr<Weights> weights_;
-  Pool pool_;
+  void ensure_streams();
+  Pool pools_[2];
+  cudaStream_t lane_[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork_ = nullptr, ev_join_[2] = {nullptr, nullptr};
   long long last_launches_ = 0;
   int num_sms_ = 148;
-  int chunk_crops_ = 512;
+  int chunk_crops_ = 256;
 };
 
 }  // namespace rdb
