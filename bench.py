@@ -117,26 +117,35 @@ def _kv(name):
 
 
 def algorithmic_bytes(name, esz, wl, n_chunk):
-    """Minimum HBM bytes one launch of this kernel must move (DESIGN.md section 5): every input
+    """Minimum HBM bytes one launch of this kernel must move (DESIGN.md section 4): every input
     element read once, every output written once, at the storage size of the precision mode."""
     kind, a = _kv(name)
     H, W = wl["h"], wl["w"]
-    if kind.startswith("gemm"):
-        return a["M"] * (a["K"] + a["N"] + (a["N"] if a.get("res") else 0)) * esz + a["N"] * a["K"] * 4
-    if kind.startswith("dwconv"):
+    base = kind.replace("_tcp", "").replace("_tc", "").replace("_tiled", "")
+    if base.startswith("gemm") and "ctc" in base:
+        return a["M"] * a["K"] * esz + a["N"] * a["K"] * 2 + a["M"] * 12 * ((a["N"] + 255) // 256) * 4
+    if base.startswith("gemm"):
+        return a["M"] * (a["K"] + a["N"] + (a["N"] if a.get("res") else 0)) * esz + a["N"] * a["K"] * esz
+    if base.startswith("dwconv"):
         return a["P"] * a["C"] * esz * (1 + a.get("s", 1))       # stride-s input is s x the output
-    if kind == "se_pool":
+    if base in ("stem2a", "stem2b", "head_conv3x3"):
+        return a["P"] * (a["C"] + a["N"]) * esz                    # stride-1 dense convs: in + out once
+    if base == "stem3":
+        return (4 * a["P"] * a["C"] + a["P"] * a["N"]) * esz       # 3x3 stride 2
+    if base == "head_tail" and "P" in a:
+        return a["P"] * 24 * esz + a["P"] * 16 * 5                 # 24-ch map in, 4x4 prob f32 + seg u8 out per pixel
+    if base == "se_pool":
         return a["P"] * a["C"] * esz
-    if kind == "se_scale":
+    if base == "se_scale":
         return 2 * a["P"] * a["C"] * esz
     px = n_chunk * H * W
     table = {
-        "stem1": px * 3 * 1 + px // 4 * 24 * esz, "stem2a": px // 4 * (24 + 12) * esz, "stem2b": px // 4 * (12 + 24) * esz,
+        "stem1": px * 3 * 1 + px // 4 * (24 if wl["h"] > 48 else 48) * esz, "stem2a": px // 4 * (24 + 12) * esz, "stem2b": px // 4 * (12 + 24) * esz,
         "stem_pool": px // 4 * 48 * esz, "stem3": px // 4 * 48 * esz + px // 16 * 24 * esz,
         "head_conv3x3": px // 16 * (96 + 24) * esz, "head_tail": px // 16 * 24 * esz + px * 5,
-        "db_dilate": px * 2, "neck_concat": px // 16 * 96 * esz * 2, "neck_upadd": 0,
+        "db_dilate": px * 2, "neck_concat": px // 16 * 96 * esz * 2,
     }
-    return table.get(kind)
+    return table.get(base)
 
 
 def algorithmic_flops(name):
@@ -335,6 +344,7 @@ def main():
     # ---- roofline of the dominant kernel: profiled pass (events around every launch)
     roofline = None
     if rank == 0:
+        os.environ["RDB_LANES"] = "1"     # one compute lane: kernels run back to back, so event pairs time ONE kernel each
         _lib.profile(True)
         _lib.profile_reset()
         for _ in range(2):
@@ -342,6 +352,7 @@ def main():
         torch.cuda.synchronize()
         prof = _lib.profile_dump()
         _lib.profile(False)
+        os.environ.pop("RDB_LANES", None)
         total = sum(v[0] for v in prof.values())
         if args.profile_out:
             rows = [{"kernel": k, "total_ms": v[0], "launches": v[1], "avg_us": v[0] / v[1] * 1e3, "share": v[0] / total,
@@ -358,13 +369,20 @@ def main():
         except Exception:
             pass
         hbm = peaks.get("hbm_gbs", 6650.0)
+        n_chunk = max(1, min(B, (args.chunk_pixels or 8 * 1024 * 1024) // (H * Wd))) if wl_key == "det" else min(B, 256)
         name, (kms, kn) = max(prof.items(), key=lambda kv: kv[1][0])
-        n_chunk = max(1, min(B, (args.chunk_pixels or 8 * 1024 * 1024) // (H * Wd))) if wl_key == "det" else B
         ab = algorithmic_bytes(name, esz, wl, n_chunk)
         avg_s = kms / kn / 1e3
         ach = (ab / avg_s / 1e9) if ab else None
+        traffic = None
+        try:   # dram__bytes_read+write per launch of this kernel from the committed ncu --set full capture, if one exists
+            for row in json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))):
+                if row["kernel"] == name:
+                    traffic = row["dram_bytes"]
+        except Exception:
+            pass
         roofline = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": (ach / hbm) if ach else None,
-                    "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                    "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                     "algorithmic_bytes_per_launch": ab, "avg_launch_us": avg_s * 1e6, "share_of_step": kms / total,
                     "top5": [{"kernel": k, "share": v[0] / total, "avg_us": v[0] / v[1] * 1e3} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:5]]}
         fl = algorithmic_flops(name)

@@ -250,9 +250,9 @@ inline void launch_conv_tc(Ctx& cx, const char* name, const __half* in, int n, i
   tc::Plan p = tc::make_conv_plan(n, H, W, C, N, KH, KW, sh, sw, pt, pl, OH, OW, cx.num_sms);
   tc::Args& a = p.a;
   a.bias = bias; a.res = nullptr; a.ldr = 0; a.out = out; a.ldc = ldc; a.c_off = c_off; a.act = act;
-  CUtensorMap mA = tc::make_map_nhwc(in, n, H, W, C, a.AW, a.TH, a.TW, sh, sw);
+  CUtensorMap mA = tc::make_map_nhwc(in, n, H, W, C, a.AW, a.patch ? a.TH + a.KH - 1 : a.TH, a.TW, sh, sw);
   CUtensorMap mB = tc::make_map(Wh, N, KH * KW * C, KH * KW * C, a.AW, a.BN);
-  cx.begin(std::string(name) + "_tc[P=" + std::to_string((long long)n * OH * OW) + ",C=" + std::to_string(C) + ",N=" + std::to_string(N) + "]");
+  cx.begin(std::string(name) + (a.patch ? "_tcp[P=" : "_tc[P=") + std::to_string((long long)n * OH * OW) + ",C=" + std::to_string(C) + ",N=" + std::to_string(N) + "]");
   launch_tc_store(p, mA, mB, act, cx.st);
   cx.end();
 }

@@ -159,6 +159,9 @@ struct Args {
   int conv;
   int OH, OW, TH, TW, tiles_y, tiles_x;
   int KW, sh, sw, pt, pl, cchunks, C, tw_shift;
+  // patch mode (stride-1 convs, B resident): one TMA box per (kx, channel chunk) holds TH+KH-1 input rows x 8 columns; the
+  // KH vertical taps are the SAME smem box read at +8-row (= one swizzle atom) descriptor offsets -> KH x fewer loads/bytes
+  int patch, KH, b_blocks;   // b_blocks: resident B k-blocks (= KH*KW*cchunks in conv modes, k_blocks otherwise)
 };
 
 constexpr int kEpiSubs = 4;                        // epilogue warps per TMEM lane quarter
@@ -173,12 +176,13 @@ __global__ void __launch_bounds__(kThreadsTc, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t span = (uint32_t)g.AW * 2u;
-  const uint32_t a_bytes = 128u * span;
+  const uint32_t a_bytes = g.patch ? (((uint32_t)(g.TH + g.KH - 1) * 8u * span + 1023u) & ~1023u) : 128u * span;
+  const uint32_t a_tx = g.patch ? (uint32_t)(g.TH + g.KH - 1) * 8u * span : a_bytes;
   const uint32_t b_bytes = ((uint32_t)g.BN * span + 1023u) & ~1023u;
   const uint32_t stage_bytes = g.resident ? a_bytes : a_bytes + b_bytes;
   uint8_t* smem_al = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_b = smem_al;                                                         // resident B: [k_blocks][b_bytes]
-  uint8_t* smem = smem_al + (g.resident ? (size_t)g.k_blocks * b_bytes : 0);          // stage ring
+  uint8_t* smem = smem_al + (g.resident ? (size_t)g.b_blocks * b_bytes : 0);          // stage ring
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)g.stages * stage_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + g.stages;
@@ -202,7 +206,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int total_tiles = g.tiles_m * g.tiles_n;
-  const uint32_t tx_bytes = g.resident ? a_bytes : a_bytes + (uint32_t)g.BN * span;
+  const uint32_t tx_bytes = g.resident ? a_tx : a_bytes + (uint32_t)g.BN * span;
   // Tile walk shared by the three roles.  Divisions happen ONCE per CTA; every further tile is reached by
   // adds + carries (16 epilogue warps x a few runtime divisions per tile used to cost more issue slots than
   // the tile's actual work).
@@ -233,9 +237,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (g.resident && wk.valid(g)) {
         const int tn = wk.tn;
         // one-time load of this CTA's B n-tile: every k-block, laid out exactly like a stage's B buffer
-        mbar_expect_tx(bfull_bar, (uint32_t)g.k_blocks * (uint32_t)g.BN * span);
+        mbar_expect_tx(bfull_bar, (uint32_t)g.b_blocks * (uint32_t)g.BN * span);
         int kx = 0, cc = 0, bk = 0;
-        for (int kb = 0; kb < g.k_blocks; ++kb) {
+        for (int kb = 0; kb < g.b_blocks; ++kb) {
           const int kcoord = g.conv == 0 ? kb * g.AW : bk + cc * g.AW;
           tma_load_2d(smem_b + (size_t)kb * b_bytes, &tmB, bfull_bar, kcoord, tn * g.BN);
           if (g.conv != 0 && ++cc == g.cchunks) { cc = 0; bk += g.C; ++kx; }
@@ -262,7 +266,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (!g.resident) tma_load_2d(sa + a_bytes, &tmB, &full_bar[s], bk + cc * g.AW, n_row);
             if (++cc == g.cchunks) {
               cc = 0; bk += g.C;
-              if (++kx == g.KW) { kx = 0; ++ky; }
+              if (g.patch) ++kx;                       // patch mode walks (kx, cc); ky lives in the MMA loop
+              else if (++kx == g.KW) { kx = 0; ++ky; }
             }
           }
           if (++s == g.stages) { s = 0; ph ^= 1; }
@@ -280,16 +285,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * g.BN);
+        int pkx = 0, pcc = 0;   // patch mode: (kx, channel chunk) of the stage being consumed
         for (int kb = 0; kb < g.k_blocks; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint64_t da = make_smem_desc(sa, span);
-          const uint64_t db = make_smem_desc(g.resident ? smem_u32(smem_b + (size_t)kb * b_bytes) : sa + a_bytes, span);
           const int ksteps = g.AW / 16;
-          for (int kk = 0; kk < ksteps; ++kk) {
-            // advancing K by 16 halves = 32 bytes inside the swizzle span: +2 in the (addr>>4) field
-            umma_f16(d_tmem, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), g.idesc, (kb | kk) != 0 ? 1u : 0u);
+          if (!g.patch) {
+            const uint64_t da = make_smem_desc(sa, span);
+            const uint64_t db = make_smem_desc(g.resident ? smem_u32(smem_b + (size_t)kb * b_bytes) : sa + a_bytes, span);
+            for (int kk = 0; kk < ksteps; ++kk) {
+              // advancing K by 16 halves = 32 bytes inside the swizzle span: +2 in the (addr>>4) field
+              umma_f16(d_tmem, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), g.idesc, (kb | kk) != 0 ? 1u : 0u);
+            }
+          } else {
+            for (int ky = 0; ky < g.KH; ++ky) {
+              // vertical tap ky = the same box, 8 rows (one 8-row swizzle atom, 8*span bytes) further down
+              const uint64_t da = make_smem_desc(sa + (uint32_t)ky * 8u * span, span);
+              const int bidx = (ky * g.KW + pkx) * g.cchunks + pcc;
+              const uint64_t db = make_smem_desc(smem_u32(smem_b + (size_t)bidx * b_bytes), span);
+              for (int kk = 0; kk < ksteps; ++kk)
+                umma_f16(d_tmem, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), g.idesc, (kb | ky | kk) != 0 ? 1u : 0u);
+            }
+            if (++pcc == g.cchunks) { pcc = 0; ++pkx; }
           }
           umma_commit(&empty_bar[s]);
           if (kb == g.k_blocks - 1) umma_commit(&tfull_bar[as]);
@@ -521,10 +539,11 @@ inline int pick_bn(int N) {
 inline void finish_plan(Plan& p, int num_sms) {
   Args& a = p.a;
   const size_t span = (size_t)a.AW * 2;
-  const size_t a_bytes = 128 * span;
+  const size_t a_bytes = a.patch ? (((size_t)(a.TH + a.KH - 1) * 8 * span + 1023) & ~(size_t)1023) : 128 * span;
   const size_t b_bytes = ((size_t)a.BN * span + 1023) & ~(size_t)1023;
   const size_t budget = 200 * 1024;
-  const size_t b_res = (size_t)a.k_blocks * b_bytes;
+  if (a.b_blocks == 0) a.b_blocks = a.k_blocks;
+  const size_t b_res = (size_t)a.b_blocks * b_bytes;
   const char* e = std::getenv("RDB_TC_RESIDENT");
   const bool allow = !(e != nullptr && e[0] == '0');
   int min_stages = a.k_blocks < 3 ? a.k_blocks + 2 : 4;
@@ -587,17 +606,21 @@ inline Plan make_plan(long long M, int N, int K, int num_sms) {
 }
 
 // conv plan: out[n,OH,OW,N] = act(conv(in[n,H,W,C], w[N][KH][KW][C]) + bias)
-inline Plan make_conv_plan(int n, int H, int W, int C, int N, int KH, int KW, int sh, int sw, int pt, int pl, int OH, int OW, int num_sms) {
+inline Plan make_conv_plan_mode(int n, int H, int W, int C, int N, int KH, int KW, int sh, int sw, int pt, int pl, int OH, int OW, int num_sms,
+                                bool patch) {
   Plan p{};
   Args& a = p.a;
   a.conv = 1;
   a.N = N; a.K = KH * KW * C; a.C = C;
   a.AW = pick_aw(C);
   a.cchunks = (C + a.AW - 1) / a.AW;
-  a.k_blocks = KH * KW * a.cchunks;
+  a.KH = KH;
+  a.b_blocks = KH * KW * a.cchunks;
+  a.patch = patch ? 1 : 0;
+  a.k_blocks = patch ? KW * a.cchunks : KH * KW * a.cchunks;   // smem stages consumed per tile
   a.BN = pick_bn(N);
   a.OH = OH; a.OW = OW; a.KW = KW; a.sh = sh; a.sw = sw; a.pt = pt; a.pl = pl;
-  a.TW = OW >= 16 ? 16 : (OW >= 8 ? 8 : 4);
+  a.TW = patch ? 8 : (OW >= 16 ? 16 : (OW >= 8 ? 8 : 4));
   a.TH = 128 / a.TW;
   a.tw_shift = a.TW == 16 ? 4 : (a.TW == 8 ? 3 : 2);
   a.tiles_x = (OW + a.TW - 1) / a.TW;
@@ -611,6 +634,16 @@ inline Plan make_conv_plan(int n, int H, int W, int C, int N, int KH, int KW, in
   a.idesc = (1u << 4) | ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   finish_plan(p, num_sms);
   return p;
+}
+
+inline Plan make_conv_plan(int n, int H, int W, int C, int N, int KH, int KW, int sh, int sw, int pt, int pl, int OH, int OW, int num_sms) {
+  const char* e = std::getenv("RDB_TC_PATCH");
+  const bool allow = !(e != nullptr && e[0] == '0');
+  if (allow && sh == 1 && sw == 1 && OW >= 8) {
+    Plan p = make_conv_plan_mode(n, H, W, C, N, KH, KW, sh, sw, pt, pl, OH, OW, num_sms, true);
+    if (p.a.resident) return p;   // patch mode needs the weights resident (B is indexed by tap inside the MMA loop)
+  }
+  return make_conv_plan_mode(n, H, W, C, N, KH, KW, sh, sw, pt, pl, OH, OW, num_sms, false);
 }
 
 }  // namespace tc
