@@ -128,9 +128,9 @@ def algorithmic_bytes(name, esz, wl, n_chunk):
         return a["M"] * (a["K"] + a["N"] + (a["N"] if a.get("res") else 0)) * esz + a["N"] * a["K"] * esz
     if base.startswith("dwconv"):
         return a["P"] * a["C"] * esz * (1 + a.get("s", 1))       # stride-s input is s x the output
-    if base in ("stem2a", "stem2b", "head_conv3x3"):
+    if base in ("stem2a", "stem2b", "head_conv3x3") and "P" in a:
         return a["P"] * (a["C"] + a["N"]) * esz                    # stride-1 dense convs: in + out once
-    if base == "stem3":
+    if base == "stem3" and "P" in a:
         return (4 * a["P"] * a["C"] + a["P"] * a["N"]) * esz       # 3x3 stride 2
     if base == "head_tail" and "P" in a:
         return a["P"] * 24 * esz + a["P"] * 16 * 5                 # 24-ch map in, 4x4 prob f32 + seg u8 out per pixel

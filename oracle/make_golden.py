@@ -77,3 +77,34 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def make_e2e_golden():
+    """tests/golden/page_img5_e2e.npz: the demo page (PNG bytes), the reference-net boxes and the texts the
+    reference flow produces on them (crop -> sort by ratio -> batches of 6 -> rec -> CTC decode)."""
+    from oracle import nets
+    img = cv2.imread(f"{R.REF}/demo/images/img_5.png")
+    g = np.load(os.path.join(OUT, "det_page_img5.npz"))
+    crops = []
+    for b in g["boxes"]:
+        pts = np.array(b, np.float32)
+        w = int(max(np.linalg.norm(pts[0] - pts[1]), np.linalg.norm(pts[2] - pts[3])))
+        h = int(max(np.linalg.norm(pts[0] - pts[3]), np.linalg.norm(pts[1] - pts[2])))
+        M = cv2.getPerspectiveTransform(pts, np.float32([[0, 0], [w, 0], [w, h], [0, h]]))
+        c = cv2.warpPerspective(img, M, (w, h), borderMode=cv2.BORDER_REPLICATE, flags=cv2.INTER_CUBIC)
+        crops.append(np.rot90(c) if c.shape[0] * 1.0 / c.shape[1] >= 2 else c)
+    order = np.argsort([c.shape[1] / c.shape[0] for c in crops])
+    res = [None] * len(crops)
+    for b0 in range(0, len(crops), 6):
+        idx = order[b0:b0 + 6]
+        xb, _ = P.rec_batch_tensor([crops[i] for i in idx])
+        out = P.ctc_decode(nets.rec_forward(xb), nets.load_characters())
+        for j, i in enumerate(idx):
+            res[i] = out[j]
+    ok, enc = cv2.imencode(".png", img)
+    np.savez_compressed(os.path.join(OUT, "page_img5_e2e.npz"), png=enc, texts=np.array([t for t, _ in res]),
+                        conf=np.array([c for _, c in res]), boxes=g["boxes"])
+
+
+if __name__ == "__main__" and "--e2e" in sys.argv:
+    make_e2e_golden()

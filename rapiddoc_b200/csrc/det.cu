@@ -84,20 +84,41 @@ void DetEngine::forward_chunk(Ctx& cx, const DetInput& in, int n, int H, int W, 
   }
   // ---- RepLKFPN
   Act f[4];
-  for (int i = 0; i < 4; ++i) {
-    std::string p = "neck.in" + std::to_string(i) + ".";
-    f[i] = O::make(cx, n, feats[i].h, feats[i].w, 96);
-    O::pw(cx, feats[i], w.get(p + "w"), nullptr, ACT_NONE, nullptr, f[i]);
-    O::release(cx, feats[i]);
-    float* gate = O::se_gate(cx, f[i], w.get(p + "se.w1"), w.get(p + "se.b1"), w.get(p + "se.w2"), w.get(p + "se.b2"), 1);
-    O::scale(cx, f[i], gate);  // x + x*g = x*(1+g)
-    cx.pool->free(gate);
+  bool neck_fused = false;
+  if constexpr (std::is_same<T, __half>::value) {
+    if (cx.use_tc && !env_is("RDB_NECK", "unfused")) {
+      // fused input stage: the SE gate comes from the pooled backbone feature (mean(conv(x)) = W mean(x)), and ONE
+      // tcgen05 GEMM per level applies the 1x1 conv, the (1+gate) column scale and the top-down nearest-up add.
+      neck_fused = true;
+      for (int i = 3; i >= 0; --i) {
+        std::string p = "neck.in" + std::to_string(i) + ".";
+        float* gate = O::se_gate(cx, feats[i], w.get(p + "se.w1"), w.get(p + "se.b1"), w.get(p + "se.w2"), w.get(p + "se.b2"), 1, &w.get(p + "w"));
+        f[i] = O::make(cx, n, feats[i].h, feats[i].w, 96);
+        TcFuse fu;
+        fu.colscale = gate; fu.rows_per_img = feats[i].h * feats[i].w;
+        if (i < 3) { fu.up_res = f[i + 1].p; fu.up_H = feats[i].h; fu.up_W = feats[i].w; }
+        launch_gemm_tc(cx, feats[i].p, feats[i].c, feats[i].pixels(), feats[i].c, w.get(p + "w").h, 96, nullptr, ACT_NONE, nullptr, 96, f[i].p, 96, 0, &fu);
+        O::release(cx, feats[i]);
+        cx.pool->free(gate);
+      }
+    }
   }
-  for (int i = 2; i >= 0; --i) {
-    long long total = f[i].pixels() * 12;
-    cx.begin("neck_upadd");
-    upsample2_add_kernel<T><<<cdiv(total, kThreads), kThreads, 0, cx.st>>>(f[i].p, f[i + 1].p, n, f[i].h, f[i].w, 96);
-    cx.end();
+  if (!neck_fused) {
+    for (int i = 0; i < 4; ++i) {
+      std::string p = "neck.in" + std::to_string(i) + ".";
+      f[i] = O::make(cx, n, feats[i].h, feats[i].w, 96);
+      O::pw(cx, feats[i], w.get(p + "w"), nullptr, ACT_NONE, nullptr, f[i]);
+      O::release(cx, feats[i]);
+      float* gate = O::se_gate(cx, f[i], w.get(p + "se.w1"), w.get(p + "se.b1"), w.get(p + "se.w2"), w.get(p + "se.b2"), 1);
+      O::scale(cx, f[i], gate);  // x + x*g = x*(1+g)
+      cx.pool->free(gate);
+    }
+    for (int i = 2; i >= 0; --i) {
+      long long total = f[i].pixels() * 12;
+      cx.begin("neck_upadd");
+      upsample2_add_kernel<T><<<cdiv(total, kThreads), kThreads, 0, cx.st>>>(f[i].p, f[i + 1].p, n, f[i].h, f[i].w, 96);
+      cx.end();
+    }
   }
   Act pq[4];
   NeckSrc<T> ns;

@@ -231,14 +231,20 @@ inline void launch_tc_store(const tc::Plan& p, const CUtensorMap& mA, const CUte
 }
 
 // tcgen05 GEMM launch: out[M,N] = act(A[M,K] W^T + b) (+res), everything fp16 in HBM.
+struct TcFuse {   // optional fused RepLKFPN input stage: out = acc*colscale[img][col] + nearest_up2(up_res)
+  const float* colscale = nullptr; int rows_per_img = 0;
+  const __half* up_res = nullptr; int up_H = 0, up_W = 0;
+};
+
 inline void launch_gemm_tc(Ctx& cx, const __half* A, int lda, long long M, int K, const __half* Wh, int N, const float* bias, int act,
-                           const __half* res, int ldr, __half* out, int ldc, int c_off) {
+                           const __half* res, int ldr, __half* out, int ldc, int c_off, const TcFuse* fuse = nullptr) {
   tc::Plan p = tc::make_plan(M, N, K, cx.num_sms);
   tc::Args& a = p.a;
   a.bias = bias; a.res = res; a.ldr = ldr; a.out = out; a.ldc = ldc; a.c_off = c_off; a.act = act;
+  if (fuse) { a.colscale = fuse->colscale; a.rows_per_img = fuse->rows_per_img; a.up_res = fuse->up_res; a.up_H = fuse->up_H; a.up_W = fuse->up_W; }
   CUtensorMap mA = tc::make_map(A, M, K, lda, a.AW, 128);
   CUtensorMap mB = tc::make_map(Wh, N, K, K, a.AW, a.BN);
-  cx.begin("gemm_tc[M=" + std::to_string(M) + ",K=" + std::to_string(K) + ",N=" + std::to_string(N) + ",res=" + (res ? "1" : "0") + "]");
+  cx.begin("gemm_tc[M=" + std::to_string(M) + ",K=" + std::to_string(K) + ",N=" + std::to_string(N) + ",res=" + ((res || (fuse && fuse->up_res)) ? "1" : "0") + "]");
   launch_tc_store(p, mA, mB, act, cx.st);
   cx.end();
 }
@@ -368,23 +374,27 @@ struct Ops {
     cx.end();
   }
 
-  // SE gate (mode 0: hardsigmoid; mode 1: 1+clip(.2z+.5)) -> float gate[n][C] from pool
-  static float* se_gate(Ctx& cx, const Act& x, const Tensor& w1, const Tensor& b1, const Tensor& w2, const Tensor& b2, int mode) {
-    int HW = x.h * x.w, C = x.c, Cr = w1.shape[0];
-    int G = C / 8;
+  // SE gate (mode 0: hardsigmoid; mode 1: 1+clip(.2z+.5)) -> float gate[n][C] from pool.
+  // pre != null: x is the input of the bias-free 1x1 conv `pre` [C][x.c] and the SE acts on the conv OUTPUT (C channels).
+  static float* se_gate(Ctx& cx, const Act& x, const Tensor& w1, const Tensor& b1, const Tensor& w2, const Tensor& b2, int mode,
+                        const Tensor* pre = nullptr) {
+    int HW = x.h * x.w, Cp = x.c, Cr = w1.shape[0];
+    const int C = pre ? pre->shape[0] : Cp;
+    int G = Cp / 8;
     int threads = 256;
     int P = threads / G;
     RDB_CHECK(P >= 1, "se: too many channels");
     int chunks = HW / (P * 16);
     if (chunks < 1) chunks = 1;
     if (chunks > 32) chunks = 32;
-    float* partial = cx.pool->alloc_t<float>((size_t)x.n * chunks * C);
+    float* partial = cx.pool->alloc_t<float>((size_t)x.n * chunks * Cp);
     float* gate = cx.pool->alloc_t<float>((size_t)x.n * C);
-    cx.begin("se_pool[P=" + std::to_string(x.pixels()) + ",C=" + std::to_string(C) + "]");
-    pool_partial_kernel<T><<<dim3(chunks, x.n), threads, (size_t)P * C * sizeof(float), cx.st>>>(x.p, HW, C, partial, chunks);
+    cx.begin("se_pool[P=" + std::to_string(x.pixels()) + ",C=" + std::to_string(Cp) + "]");
+    pool_partial_kernel<T><<<dim3(chunks, x.n), threads, (size_t)P * Cp * sizeof(float), cx.st>>>(x.p, HW, Cp, partial, chunks);
     cx.end();
     cx.begin("se_fc");
-    se_fc_kernel<<<x.n, 256, (size_t)(C + Cr) * sizeof(float), cx.st>>>(partial, chunks, HW, C, Cr, w1.d, b1.d, w2.d, b2.d, mode, gate);
+    se_fc_kernel<<<x.n, 256, (size_t)(C + Cr + Cp) * sizeof(float), cx.st>>>(partial, chunks, HW, C, Cr, w1.d, b1.d, w2.d, b2.d, mode, gate,
+                                                                         pre ? pre->d : nullptr, Cp);
     cx.end();
     cx.pool->free(partial);
     return gate;

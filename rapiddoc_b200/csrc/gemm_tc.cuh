@@ -147,6 +147,9 @@ struct Args {
   __half* out; int ldc; int c_off;
   int act;
   float* pmax; int* pidx; float* psum;  // EPI_CTC partials [M, tiles_n * kEpiSubs]
+  // fused RepLKFPN input stage (db_fpn.py:342-363,394-399): out = acc * colscale[image][col] + nearest_up2(up_res)
+  const float* colscale; int rows_per_img;   // per-(image, column) SE factor 1+gate, rows_per_img = H*W of this level
+  const __half* up_res; int up_H, up_W;      // coarser level [n, up_H/2, up_W/2, N] added at (y/2, x/2)
   // EPI_HEAD (fused DBHead tail): rows are pixels of an [n, hH, hW] map, N = 4*24 ConvT outputs; the
   // epilogue applies ReLU, the final ConvT(24->1, 2x2 s2), sigmoid and the DB threshold.
   int hH, hW;
@@ -406,6 +409,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (row_ok) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = apply_act<ACT>(v[j]);
+            if (g.colscale != nullptr) {
+              const int img = (int)(row / g.rows_per_img);
+              const float* sp = g.colscale + (long long)img * g.N + n0 + c0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (full || n0 + c0 + j < g.N) v[j] *= __ldg(sp + j);
+              if (g.up_res != nullptr) {
+                const int rem = (int)(row - (long long)img * g.rows_per_img);
+                const int y = rem / g.up_W, x = rem - y * g.up_W;
+                const __half* up = g.up_res + (((long long)img * (g.up_H >> 1) + (y >> 1)) * (g.up_W >> 1) + (x >> 1)) * g.N + n0 + c0;
+                if (full) {
+                  float a[8], b2[8];
+                  Vec8<__half>::load(up, a);
+                  Vec8<__half>::load(up + 8, b2);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) { v[j] += a[j]; v[8 + j] += b2[j]; }
+                } else {
+                  for (int j = 0; j < 16; ++j) if (n0 + c0 + j < g.N) v[j] += __half2float(up[j]);
+                }
+              }
+            }
             if (g.res != nullptr) {
               const __half* rp = g.res + row * g.ldr + n0 + c0;
               if (full) {
@@ -430,16 +453,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         } else {
-          // fused greedy-decode partials: running (max, argmax, sum exp(x - max)) over this row
+          // fused greedy-decode partials: (max, argmax, sum exp(x - max)) of this 16-column chunk computed with
+          // independent operations (tree max, 16 parallel exps), then ONE merge into the running row state —
+          // a per-element online update would serialise 16 dependent exp/compare steps per chunk
+          float m16 = -INFINITY; int i16 = 0x7fffffff;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            int c = n0 + c0 + j;
-            if (c < g.N) {
-              float x = v[j];
-              if (x > cmax) { csum = csum * __expf(cmax - x) + 1.f; cmax = x; cidx = c; }
-              else csum += __expf(x - cmax);
-            }
+            if (n0 + c0 + j >= g.N) v[j] = -INFINITY;
+            if (v[j] > m16) { m16 = v[j]; i16 = n0 + c0 + j; }      // ascending j: ties keep the lowest index
           }
+          float s16 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) s16 += __expf(v[j] - m16);   // exp(-inf) = 0 for masked columns
+          if (m16 > cmax) { csum = csum * __expf(cmax - m16) + s16; cmax = m16; cidx = i16; }
+          else csum += s16 * __expf(m16 - cmax);
         }
       }
       if (EPI == EPI_CTC && row_ok) {

@@ -226,7 +226,7 @@ class TextRecOutput:
 class B200TextRecognizer:
     """Mirror of rapidocr TextRecognizer + RapidOcrModel.text_recognizer_call (rapid_ocr.py:404-472)."""
 
-    def __init__(self, engine: RecEngine, characters=None, rec_batch_num=64, rec_image_shape=(3, 48, 320)):
+    def __init__(self, engine: RecEngine, characters=None, rec_batch_num=6, rec_image_shape=(3, 48, 320)):
         self.engine = engine
         self.character = characters if characters is not None else W.load_characters()
         self.rec_batch_num = rec_batch_num
@@ -294,7 +294,10 @@ class B200OcrModel:
             mean=tuple(cfg.get("Det.mean", DET_MEAN)), std=tuple(cfg.get("Det.std", DET_STD)), thresh=cfg.get("Det.thresh", 0.3),
             box_thresh=cfg.get("Det.box_thresh", det_db_box_thresh), unclip_ratio=cfg.get("Det.unclip_ratio", det_db_unclip_ratio),
             use_dilation=cfg.get("Det.use_dilation", use_dilation))
-        self.text_recognizer = B200TextRecognizer(rec, rec_batch_num=cfg.get("Rec.rec_batch_num", 64))
+        # rapidocr's default rec_batch_num is 6; the padded width of a batch is set by its widest crop, so the batch
+        # size is part of the numerical contract (results can differ between groupings, in the reference too).
+        # Raise "Rec.rec_batch_num" in ocr_config for throughput, exactly as with RapidOcrModel.
+        self.text_recognizer = B200TextRecognizer(rec, rec_batch_num=cfg.get("Rec.rec_batch_num", 6))
         self.rec_batch_num = self.text_recognizer.rec_batch_num
         self._merge, self._update = _reference_line_utils()
 
