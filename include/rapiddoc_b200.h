@@ -65,6 +65,18 @@ int rdb_det_infer_u8(rdb_det_t* h, const uint8_t* pages, int n, int hgt, int wid
                      const float stdv[3], float thresh, int use_dilation, float* prob, uint8_t* bitmap,
                      void* stream);
 
+/* rdb_det_infer_u8 with DetPreProcess' resize on the GPU too: pages [n,src_h,src_w,3] are resized (cv2 INTER_LINEAR,
+ * bit-exact) to hgt x wid (multiples of 32, chosen by the caller with DetPreProcess' limit_side_len rule), then as above. */
+int rdb_det_infer_u8_resize(rdb_det_t* h, const uint8_t* pages, int n, int src_h, int src_w, int hgt, int wid,
+                            const float mean[3], const float stdv[3], float thresh, int use_dilation, float* prob,
+                            uint8_t* bitmap, void* stream);
+
+/* DetPreProcess' cv2.resize(img, (dw, dh)) (INTER_LINEAR, uint8 HWC), bit-exact with OpenCV's fixed-point path
+ * (rapidocr ch_ppocr_det/utils.py DetPreProcess as pinned by rapid_doc/model/ocr/ocr_patch.py:33-40).
+ * src [n,sh,sw,3] -> dst [n,dh,dw,3]; host or device pointers. */
+int rdb_resize_linear_u8(int device, const uint8_t* src, int n, int sh, int sw, uint8_t* dst, int dh, int dw,
+                         void* stream);
+
 /* DBPostProcess binarise (+ optional cv2.dilate 2x2) on an existing prob map [n,h,w]:
  * rapid_doc/model/ocr/ocr_patch.py:228-235. */
 int rdb_db_bitmap(int device, const float* prob, int n, int hgt, int wid, float thresh, int use_dilation,

@@ -174,12 +174,31 @@ int rdb_det_infer_u8(rdb_det_t* h, const uint8_t* pages, int n, int hgt, int wid
   });
 }
 
+int rdb_det_infer_u8_resize(rdb_det_t* h, const uint8_t* pages, int n, int src_h, int src_w, int hgt, int wid, const float mean[3],
+                            const float stdv[3], float thresh, int use_dilation, float* prob, uint8_t* bitmap, void* stream) {
+  return guarded([&] {
+    RDB_CHECK(h && pages && mean && stdv && (prob || bitmap) && src_h > 0 && src_w > 0, "null argument");
+    rdb::DetInput in;
+    in.u8 = pages; in.src_h = src_h; in.src_w = src_w;
+    for (int i = 0; i < 3; ++i) { in.mean[i] = mean[i]; in.stdv[i] = stdv[i]; }
+    h->e->infer(in, n, hgt, wid, thresh, use_dilation != 0, prob, bitmap, (cudaStream_t)stream);
+  });
+}
+
 int rdb_db_bitmap(int device, const float* prob, int n, int hgt, int wid, float thresh, int use_dilation, uint8_t* bitmap,
                   void* stream) {
   return guarded([&] {
     RDB_CHECK(prob && bitmap && n > 0, "null argument");
     require_device(device);
     rdb::db_bitmap(device, prob, n, hgt, wid, thresh, use_dilation != 0, bitmap, (cudaStream_t)stream);
+  });
+}
+
+int rdb_resize_linear_u8(int device, const uint8_t* src, int n, int sh, int sw, uint8_t* dst, int dh, int dw, void* stream) {
+  return guarded([&] {
+    RDB_CHECK(src && dst, "null argument");
+    require_device(device);
+    rdb::resize_linear_u8(device, src, n, sh, sw, dst, dh, dw, (cudaStream_t)stream);
   });
 }
 

@@ -49,6 +49,8 @@ void DetEngine::ensure_streams() {
   }
 }
 
+static void linear_coeffs(int dsize, int ssize, bool vertical, std::vector<int>& idx, std::vector<short>& ab);
+
 template <typename T>
 void DetEngine::forward_chunk(Ctx& cx, const DetInput& in, int n, int H, int W, float thresh, bool dilate, float* prob,
                               uint8_t* bitmap) {
@@ -201,7 +203,9 @@ void DetEngine::infer(const DetInput& in_host_or_dev, int n, int H, int W, float
   cx.num_sms = num_sms_;
   const void* src = in_host_or_dev.f32 ? (const void*)in_host_or_dev.f32 : (const void*)in_host_or_dev.u8;
   const size_t in_elem = in_host_or_dev.f32 ? sizeof(float) : 1;
-  const size_t page_in = (size_t)3 * H * W * in_elem;
+  const bool do_resize = in_host_or_dev.u8 != nullptr && in_host_or_dev.src_h > 0 && (in_host_or_dev.src_h != H || in_host_or_dev.src_w != W);
+  const int SH = do_resize ? in_host_or_dev.src_h : H, SW = do_resize ? in_host_or_dev.src_w : W;
+  const size_t page_in = (size_t)3 * SH * SW * in_elem;
   const size_t page_px = (size_t)H * W;
   const bool in_dev = is_device_ptr(src);
   const bool prob_dev = prob ? is_device_ptr(prob) : true;
@@ -223,8 +227,24 @@ void DetEngine::infer(const DetInput& in_host_or_dev, int n, int H, int W, float
   void* d_in[2] = {nullptr, nullptr};
   float* d_prob[2] = {nullptr, nullptr};
   uint8_t* d_bm[2] = {nullptr, nullptr};
+  // GPU resize (DetPreProcess): coefficient tables once per call
+  int *d_xi = nullptr, *d_yi = nullptr; short *d_xa = nullptr, *d_ya = nullptr;
+  uint8_t* d_rs[2] = {nullptr, nullptr};
+  if (do_resize) {
+    std::vector<int> xi, yi; std::vector<short> xa, ya;
+    linear_coeffs(W, SW, false, xi, xa);
+    linear_coeffs(H, SH, true, yi, ya);
+    d_xi = pools_[0].alloc_t<int>(W); d_yi = pools_[0].alloc_t<int>(H);
+    d_xa = pools_[0].alloc_t<short>(2 * (size_t)W); d_ya = pools_[0].alloc_t<short>(2 * (size_t)H);
+    RDB_CUDA(cudaMemcpyAsync(d_xi, xi.data(), (size_t)W * 4, cudaMemcpyHostToDevice, st));
+    RDB_CUDA(cudaMemcpyAsync(d_yi, yi.data(), (size_t)H * 4, cudaMemcpyHostToDevice, st));
+    RDB_CUDA(cudaMemcpyAsync(d_xa, xa.data(), (size_t)W * 4, cudaMemcpyHostToDevice, st));
+    RDB_CUDA(cudaMemcpyAsync(d_ya, ya.data(), (size_t)H * 4, cudaMemcpyHostToDevice, st));
+    RDB_CUDA(cudaStreamSynchronize(st));   // the host vectors go out of scope
+  }
   RDB_CUDA(cudaEventRecord(ev_fork_, st));
   for (int l = 0; l < lanes; ++l) {
+    if (do_resize) d_rs[l] = pools_[l].alloc_t<uint8_t>((size_t)chunk * H * W * 3);
     cxs[l] = cx;
     cxs[l].st = lane_[l];
     cxs[l].pool = &pools_[l];
@@ -250,6 +270,13 @@ void DetEngine::infer(const DetInput& in_host_or_dev, int n, int H, int W, float
       dsrc = d_in[l];
     }
     if (any_host && it >= lanes) RDB_CUDA(cudaStreamWaitEvent(ls, ev_out_[l], 0));     // lane's previous D2H done
+    if (do_resize) {
+      cxs[l].begin("resize_linear_u8");
+      resize_linear_u8_kernel<<<cdiv((long long)m * H * W, 256), 256, 0, ls>>>(static_cast<const uint8_t*>(dsrc), m, SH, SW, d_rs[l], H, W, d_xi, d_xa,
+                                                                              d_yi, d_ya);
+      cxs[l].end();
+      dsrc = d_rs[l];
+    }
     if (in.f32) in.f32 = static_cast<const float*>(dsrc); else in.u8 = static_cast<const uint8_t*>(dsrc);
     float* p_out = (prob_dev && prob) ? prob + (size_t)i0 * page_px : d_prob[l];
     uint8_t* b_out = bitmap ? (bm_dev ? bitmap + (size_t)i0 * page_px : d_bm[l]) : nullptr;
@@ -277,9 +304,57 @@ void DetEngine::infer(const DetInput& in_host_or_dev, int n, int H, int W, float
     if (d_in[l]) pools_[l].free(d_in[l]);
     if (d_prob[l]) pools_[l].free(d_prob[l]);
     if (d_bm[l]) pools_[l].free(d_bm[l]);
+    if (d_rs[l]) pools_[l].free(d_rs[l]);
   }
+  if (do_resize) { pools_[0].free(d_xi); pools_[0].free(d_yi); pools_[0].free(d_xa); pools_[0].free(d_ya); }
   if (Profiler::global().on) { RDB_CUDA(cudaDeviceSynchronize()); Profiler::global().resolve(); }
   last_launches_ = launches;
+}
+
+// OpenCV resize() coefficient tables for INTER_LINEAR / 8U (float32 maths as in cv::resize -> saturate_cast<short>)
+// Horizontal taps are clamped with the weight moved onto the edge pixel; vertical taps keep their weights and clamp
+// only the row index (cv::resize builds yofs/beta without the edge adjustment and clips rows in the row loop).
+static void linear_coeffs(int dsize, int ssize, bool vertical, std::vector<int>& idx, std::vector<short>& ab) {
+  idx.resize(dsize); ab.resize(2 * (size_t)dsize);
+  const double inv = (double)dsize / ssize, scale = 1.0 / inv;
+  for (int d = 0; d < dsize; ++d) {
+    float fx = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)floorf(fx);
+    fx -= (float)s;
+    if (!vertical) {
+      if (s < 0) { fx = 0.f; s = 0; }
+      if (s >= ssize - 1) { fx = 0.f; s = ssize - 1; }
+    }
+    idx[d] = s;
+    ab[2 * d] = (short)lrintf((1.f - fx) * 2048.f);
+    ab[2 * d + 1] = (short)lrintf(fx * 2048.f);
+  }
+}
+
+void resize_linear_u8(int device, const uint8_t* src, int n, int sh, int sw, uint8_t* dst, int dh, int dw, cudaStream_t st) {
+  RDB_CUDA(cudaSetDevice(device));
+  RDB_CHECK(n > 0 && sh > 0 && sw > 0 && dh > 0 && dw > 0, "resize: bad shape");
+  std::vector<int> xi, yi; std::vector<short> xa, ya;
+  linear_coeffs(dw, sw, false, xi, xa);
+  linear_coeffs(dh, sh, true, yi, ya);
+  const size_t in_b = (size_t)n * sh * sw * 3, out_b = (size_t)n * dh * dw * 3;
+  const bool s_dev = is_device_ptr(src), d_dev = is_device_ptr(dst);
+  uint8_t* ds = const_cast<uint8_t*>(src); uint8_t* dd = dst;
+  int *dxi, *dyi; short *dxa, *dya;
+  RDB_CUDA(cudaMalloc(&dxi, dw * 4)); RDB_CUDA(cudaMalloc(&dyi, dh * 4)); RDB_CUDA(cudaMalloc(&dxa, dw * 4)); RDB_CUDA(cudaMalloc(&dya, dh * 4));
+  RDB_CUDA(cudaMemcpyAsync(dxi, xi.data(), dw * 4, cudaMemcpyHostToDevice, st));
+  RDB_CUDA(cudaMemcpyAsync(dyi, yi.data(), dh * 4, cudaMemcpyHostToDevice, st));
+  RDB_CUDA(cudaMemcpyAsync(dxa, xa.data(), dw * 4, cudaMemcpyHostToDevice, st));
+  RDB_CUDA(cudaMemcpyAsync(dya, ya.data(), dh * 4, cudaMemcpyHostToDevice, st));
+  if (!s_dev) { RDB_CUDA(cudaMalloc(&ds, in_b)); RDB_CUDA(cudaMemcpyAsync(ds, src, in_b, cudaMemcpyHostToDevice, st)); }
+  if (!d_dev) RDB_CUDA(cudaMalloc(&dd, out_b));
+  resize_linear_u8_kernel<<<cdiv((long long)n * dh * dw, 256), 256, 0, st>>>(ds, n, sh, sw, dd, dh, dw, dxi, dxa, dyi, dya);
+  RDB_LAUNCH_CHECK();
+  if (!d_dev) RDB_CUDA(cudaMemcpyAsync(dst, dd, out_b, cudaMemcpyDeviceToHost, st));
+  RDB_CUDA(cudaStreamSynchronize(st));   // the coefficient tables are freed below
+  cudaFree(dxi); cudaFree(dyi); cudaFree(dxa); cudaFree(dya);
+  if (!s_dev) cudaFree(ds);
+  if (!d_dev) cudaFree(dd);
 }
 
 void db_bitmap(int device, const float* prob, int n, int H, int W, float thresh, bool dilate, uint8_t* bitmap, cudaStream_t st) {

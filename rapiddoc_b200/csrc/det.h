@@ -9,6 +9,7 @@ struct DetInput {
   const float* f32 = nullptr;    // [n,3,H,W] fp32 NCHW (InferSession seam)
   const uint8_t* u8 = nullptr;   // [n,H,W,3] uint8 BGR (facade seam)
   float mean[3] = {0, 0, 0}, stdv[3] = {1, 1, 1};
+  int src_h = 0, src_w = 0;      // u8 only: pages are [n,src_h,src_w,3] and are resized on the GPU (cv2 INTER_LINEAR, bit-exact) to H x W
 };
 
 class DetEngine {
@@ -35,6 +36,9 @@ class DetEngine {
   int num_sms_ = 148;
   long long chunk_pixels_ = 8ll * 1024 * 1024;  // pages per internal chunk = chunk_pixels / (H*W)
 };
+
+// cv2.resize(INTER_LINEAR) on uint8 HWC images [n,sh,sw,3] -> [n,dh,dw,3], bit-exact (host or device pointers)
+void resize_linear_u8(int device, const uint8_t* src, int n, int sh, int sw, uint8_t* dst, int dh, int dw, cudaStream_t st);
 
 void db_bitmap(int device, const float* prob, int n, int H, int W, float thresh, bool dilate, uint8_t* bitmap, cudaStream_t st);
 

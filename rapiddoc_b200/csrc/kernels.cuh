@@ -543,6 +543,32 @@ __global__ void __launch_bounds__(128) head_tail_kernel(const T* __restrict__ in
   }
 }
 
+// cv2.resize(INTER_LINEAR) for uint8 HWC, bit-exact with OpenCV's generic fixed-point path (DetPreProcess resize,
+// SURVEY App. B): 11-bit coefficients (xa/ya, built on the host in float32 exactly as OpenCV does), horizontal pass in
+// int, vertical pass  ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2 >> 2.  One thread per output pixel (3 channels).
+static __global__ void resize_linear_u8_kernel(const uint8_t* __restrict__ src, int N, int SH, int SW, uint8_t* __restrict__ dst, int DH,
+                                               int DW, const int* __restrict__ xi, const short* __restrict__ xa,
+                                               const int* __restrict__ yi, const short* __restrict__ ya) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)N * DH * DW;
+  if (idx >= total) return;
+  int x = idx % DW; int y = (idx / DW) % DH; int n = idx / ((long long)DW * DH);
+  const int x0 = xi[x], x1 = min(x0 + 1, SW - 1);
+  const int ys = yi[y];
+  const int y0 = min(max(ys, 0), SH - 1), y1 = min(max(ys + 1, 0), SH - 1);
+  const int a0 = xa[2 * x], a1 = xa[2 * x + 1], b0 = ya[2 * y], b1 = ya[2 * y + 1];
+  const uint8_t* r0 = src + ((long long)n * SH + y0) * SW * 3;
+  const uint8_t* r1 = src + ((long long)n * SH + y1) * SW * 3;
+  uint8_t* o = dst + idx * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int S0 = r0[x0 * 3 + c] * a0 + r0[x1 * 3 + c] * a1;
+    const int S1 = r1[x0 * 3 + c] * a0 + r1[x1 * 3 + c] * a1;
+    int v = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+    o[c] = (uint8_t)min(max(v, 0), 255);
+  }
+}
+
 // prob -> seg byte (used when the prob map came from elsewhere, e.g. the DB C-ABI entry)
 static __global__ void threshold_kernel(const float* __restrict__ prob, float thresh, uint8_t* __restrict__ seg, long long total) {
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;

@@ -69,10 +69,14 @@ class DetEngine:
         return prob
 
     def infer_u8(self, pages, thresh=0.3, use_dilation=True, prob=None, bitmap=None, want_prob=True, want_bitmap=True,
-                 mean=DET_MEAN, std=DET_STD, stream=None):
-        """pages [n,h,w,3] uint8 BGR (numpy / device tensor) -> (prob [n,h,w] f32, bitmap [n,h,w] u8)."""
+                 mean=DET_MEAN, std=DET_STD, stream=None, resize_to=None):
+        """pages [n,h,w,3] uint8 BGR (numpy / device tensor) -> (prob [n,h,w] f32, bitmap [n,h,w] u8).
+        resize_to=(rh, rw): DetPreProcess' cv2.resize runs on the GPU first (bit-exact); outputs are [n,rh,rw]."""
         n, h, w, c = pages.shape
         assert c == 3
+        src_h, src_w = h, w
+        if resize_to is not None:
+            h, w = int(resize_to[0]), int(resize_to[1])
         is_np = isinstance(pages, np.ndarray)
         if is_np:
             pages = np.ascontiguousarray(pages, dtype=np.uint8)
@@ -90,8 +94,12 @@ class DetEngine:
                 bitmap = torch.empty((n, h, w), dtype=torch.uint8, device=pages.device)
         m = (C.c_float * 3)(*mean)
         s = (C.c_float * 3)(*std)
-        _lib.check(self._lib.rdb_det_infer_u8(self._h, _lib.ptr(pages), n, h, w, m, s, float(thresh), int(bool(use_dilation)),
-                                              _lib.ptr(prob), _lib.ptr(bitmap), _stream_ptr(stream)))
+        if resize_to is not None and (src_h, src_w) != (h, w):
+            _lib.check(self._lib.rdb_det_infer_u8_resize(self._h, _lib.ptr(pages), n, src_h, src_w, h, w, m, s, float(thresh),
+                                                         int(bool(use_dilation)), _lib.ptr(prob), _lib.ptr(bitmap), _stream_ptr(stream)))
+        else:
+            _lib.check(self._lib.rdb_det_infer_u8(self._h, _lib.ptr(pages), n, h, w, m, s, float(thresh), int(bool(use_dilation)),
+                                                  _lib.ptr(prob), _lib.ptr(bitmap), _stream_ptr(stream)))
         return prob, bitmap
 
 

@@ -177,10 +177,8 @@ class B200TextDetector:
         self.limit_side_len, self.limit_type, self.mean, self.std = limit_side_len, limit_type, mean, std
         self.postprocess_op = DBPostProcess(thresh, box_thresh, max_candidates, unclip_ratio, use_dilation)
 
-    def resize(self, img):
-        """DetPreProcess geometry: limit side, round to /32, cv2.resize INTER_LINEAR.
-        The normalisation itself is fused into the first GPU kernel."""
-        h, w = img.shape[:2]
+    def target_size(self, h, w):
+        """DetPreProcess geometry: limit side, round to /32.  Returns (rh, rw) or None."""
         if self.limit_type == "max":
             ratio = float(self.limit_side_len) / max(h, w) if max(h, w) > self.limit_side_len else 1.0
         else:
@@ -189,19 +187,28 @@ class B200TextDetector:
         rh, rw = int(round(rh / 32) * 32), int(round(rw / 32) * 32)
         if rh <= 0 or rw <= 0:
             return None
-        if (rh, rw) == (h, w):
-            return np.ascontiguousarray(img)
-        return cv2.resize(img, (rw, rh))
+        return rh, rw
+
+    def resize(self, img):
+        """Host version of the resize (cv2), kept for callers that want the preprocessed uint8 page."""
+        t = self.target_size(*img.shape[:2])
+        if t is None:
+            return None
+        return np.ascontiguousarray(img) if t == img.shape[:2] else cv2.resize(img, (t[1], t[0]))
 
     def detect_batch(self, imgs):
         """Same-size images -> [(boxes, scores)] (rapid_ocr.py:500-540; the reference requires the
-        bucket to be same-size too)."""
-        resized = [self.resize(im) for im in imgs]
-        if any(r is None for r in resized):
+        bucket to be same-size too).  Pages are uploaded as they are (uint8); the cv2.resize of
+        DetPreProcess, its normalisation, the network and binarise+dilate all run on the GPU."""
+        h, w = imgs[0].shape[:2]
+        assert all(im.shape[:2] == (h, w) for im in imgs), "det batch must be same-size (as in the reference)"
+        t = self.target_size(h, w)
+        if t is None:
             return [(None, []) for _ in imgs]
-        pages = np.stack(resized)
+        pages = np.stack([np.ascontiguousarray(im) for im in imgs])
         po = self.postprocess_op
-        prob, bitmap = self.engine.infer_u8(pages, thresh=po.thresh, use_dilation=po.use_dilation, mean=self.mean, std=self.std)
+        prob, bitmap = self.engine.infer_u8(pages, thresh=po.thresh, use_dilation=po.use_dilation, mean=self.mean, std=self.std,
+                                            resize_to=t)
         out = []
         for i, im in enumerate(imgs):
             boxes, scores = po(prob[i], bitmap[i], im.shape[:2])
