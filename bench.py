@@ -370,7 +370,10 @@ def main():
             pass
         hbm = peaks.get("hbm_gbs", 6650.0)
         n_chunk = max(1, min(B, (args.chunk_pixels or 8 * 1024 * 1024) // (H * Wd))) if wl_key == "det" else min(B, 256)
-        name, (kms, kn) = max(prof.items(), key=lambda kv: kv[1][0])
+        # dominant kernel = largest share of device time among kernels that move a modelled number of bytes
+        # (latency-bound helpers such as the SE FC stack have no byte model; they stay visible in top5)
+        modelled = {k: v for k, v in prof.items() if algorithmic_bytes(k, esz, wl, n_chunk)}
+        name, (kms, kn) = max((modelled or prof).items(), key=lambda kv: kv[1][0])
         ab = algorithmic_bytes(name, esz, wl, n_chunk)
         avg_s = kms / kn / 1e3
         ach = (ab / avg_s / 1e9) if ab else None

@@ -29,28 +29,10 @@ struct Error : std::runtime_error {
 
 #define RDB_LAUNCH_CHECK() RDB_CUDA(cudaGetLastError())
 
-enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SILU = 3, ACT_SIGMOID = 4, ACT_GELU_FAST = 5 };
-
-// erf-GELU with erf from Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the fp16 storage
-// rounding of the mode that uses it): ~16 instructions instead of ~40 for erff — the tcgen05 GEMM
-// epilogue is instruction-issue bound on this activation.
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(t, p, 1.421413741f);
-  p = fmaf(t, p, -0.284496736f);
-  p = fmaf(t, p, 0.254829592f);
-  p *= t;
-  const float e = __expf(-z * z);
-  const float erf_abs = fmaf(-p, e, 1.0f);
-  const float erf_v = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_v);
-}
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SILU = 3, ACT_SIGMOID = 4 };
 
 template <int ACT>
 __device__ __forceinline__ float apply_act(float x) {
-  if (ACT == ACT_GELU_FAST) return gelu_fast(x);
   if (ACT == ACT_RELU) return fmaxf(x, 0.f);
   if (ACT == ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));  // exact erf GELU
   if (ACT == ACT_SILU) return x / (1.f + __expf(-x));

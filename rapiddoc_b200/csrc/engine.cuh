@@ -393,7 +393,7 @@ struct Ops {
     pool_partial_kernel<T><<<dim3(chunks, x.n), threads, (size_t)P * Cp * sizeof(float), cx.st>>>(x.p, HW, Cp, partial, chunks);
     cx.end();
     cx.begin("se_fc");
-    se_fc_kernel<<<x.n, 256, (size_t)(C + Cr + Cp) * sizeof(float), cx.st>>>(partial, chunks, HW, C, Cr, w1.d, b1.d, w2.d, b2.d, mode, gate,
+    se_fc_kernel<<<x.n, 1024, (size_t)(C + Cr + Cp) * sizeof(float), cx.st>>>(partial, chunks, HW, C, Cr, w1.d, b1.d, w2.d, b2.d, mode, gate,
                                                                          pre ? pre->d : nullptr, Cp);
     cx.end();
     cx.pool->free(partial);

@@ -360,10 +360,18 @@ __global__ void __launch_bounds__(256) pool_partial_kernel(const T* __restrict__
 // mode 0: gate = hardsigmoid(z) = clip(z/6+.5,0,1);  mode 1: gate = 1 + clip(.2z+.5,0,1)
 // w0 != null: the pooled tensor is the INPUT of a bias-free 1x1 conv w0 [C][C0] and the SE acts on its output;
 // mean(conv(x)) = w0 * mean(x) (linearity), so the conv output never has to be pooled (RepLKFPN insert_conv).
-static __global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ partial, int chunks, int HW, int C, int Cr,
-                                                         const float* __restrict__ w1, const float* __restrict__ b1,
-                                                         const float* __restrict__ w2, const float* __restrict__ b2, int mode,
-                                                         float* __restrict__ gate, const float* __restrict__ w0, int C0) {
+// Latency-bound by construction (a few hundred MACs): 32 warps, every dot product / partial sum is one warp with
+// the loads of all lanes in flight at once and a fixed-order shuffle tree (deterministic).
+__device__ __forceinline__ float warp_sum(float t) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffff, t, o);
+  return t;
+}
+
+static __global__ void __launch_bounds__(1024) se_fc_kernel(const float* __restrict__ partial, int chunks, int HW, int C, int Cr,
+                                                          const float* __restrict__ w1, const float* __restrict__ b1,
+                                                          const float* __restrict__ w2, const float* __restrict__ b2, int mode,
+                                                          float* __restrict__ gate, const float* __restrict__ w0, int C0) {
   extern __shared__ float sm[];  // mean[C] + hid[Cr] + mean0[C0]
   float* mean = sm;
   float* hid = sm + C;
@@ -372,44 +380,39 @@ static __global__ void __launch_bounds__(256) se_fc_kernel(const float* __restri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int Cp = (w0 != nullptr) ? C0 : C;         // channels of the pooled tensor
   float* pooled = (w0 != nullptr) ? mean0 : mean;
-  // fixed-order (deterministic) sum of the per-chunk partials, 4 independent chains per thread
-  for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
-    const float* pp = partial + (long long)n * chunks * Cp + c;
-    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-    int k = 0;
-    for (; k + 3 < chunks; k += 4) {
-      t0 += pp[(long long)k * Cp]; t1 += pp[(long long)(k + 1) * Cp]; t2 += pp[(long long)(k + 2) * Cp]; t3 += pp[(long long)(k + 3) * Cp];
-    }
-    for (; k < chunks; ++k) t0 += pp[(long long)k * Cp];
-    pooled[c] = ((t0 + t1) + (t2 + t3)) / (float)HW;
+  // per-chunk partials [chunks <= 32][Cp] -> mean: lane = chunk, warp strides the channels
+  for (int c = warp; c < Cp; c += nwarps) {
+    float t = (lane < chunks) ? partial[((long long)n * chunks + lane) * Cp + c] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) pooled[c] = t / (float)HW;
   }
   __syncthreads();
   if (w0 != nullptr) {
     for (int r = warp; r < C; r += nwarps) {
       float t = 0.f;
-      for (int c = lane; c < C0; c += 32) t = fmaf(w0[r * C0 + c], mean0[c], t);
-#pragma unroll
-      for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffff, t, o);
+      for (int c = lane; c < C0; c += 32) t = fmaf(__ldg(w0 + r * C0 + c), mean0[c], t);
+      t = warp_sum(t);
       if (lane == 0) mean[r] = t;
     }
     __syncthreads();
   }
-  // hidden = relu(W1 mean + b1): one warp per output, lanes stride the C inputs
-  for (int r = warp; r < Cr; r += nwarps) {
+  for (int r = warp; r < Cr; r += nwarps) {       // hidden = relu(W1 mean + b1)
     float t = 0.f;
-    for (int c = lane; c < C; c += 32) t = fmaf(w1[r * C + c], mean[c], t);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffff, t, o);
+    for (int c = lane; c < C; c += 32) t = fmaf(__ldg(w1 + r * C + c), mean[c], t);
+    t = warp_sum(t);
     if (lane == 0) hid[r] = fmaxf(t + b1[r], 0.f);
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float t = b2[c];
-    for (int r = 0; r < Cr; ++r) t = fmaf(w2[c * Cr + r], hid[r], t);
-    float gt;
-    if (mode == 0) gt = fminf(fmaxf(t / 6.f + 0.5f, 0.f), 1.f);
-    else gt = 1.f + fminf(fmaxf(0.2f * t + 0.5f, 0.f), 1.f);
-    gate[(long long)n * C + c] = gt;
+  for (int c = warp; c < C; c += nwarps) {        // gate = f(W2 hidden + b2)
+    float t = 0.f;
+    for (int r = lane; r < Cr; r += 32) t = fmaf(__ldg(w2 + c * Cr + r), hid[r], t);
+    t = warp_sum(t) + b2[c];
+    if (lane == 0) {
+      float gt;
+      if (mode == 0) gt = fminf(fmaxf(t / 6.f + 0.5f, 0.f), 1.f);
+      else gt = 1.f + fminf(fmaxf(0.2f * t + 0.5f, 0.f), 1.f);
+      gate[(long long)n * C + c] = gt;
+    }
   }
 }
 

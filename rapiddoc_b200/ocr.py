@@ -230,6 +230,72 @@ class TextRecOutput:
         self.imgs, self.txts, self.scores, self.word_results, self.elapse = imgs, txts, scores, word_results, elapse
 
 
+class WordInfo:
+    """Same fields as rapidocr.ch_ppocr_rec.typings.WordInfo (consumed by CalRecBoxes.cal_ocr_word_box,
+    rapid_doc/model/ocr/ocr_patch.py:261-330)."""
+
+    def __init__(self, words=None, word_cols=None, word_types=None, line_txt_len=0.0, confs=None):
+        self.words = words or []
+        self.word_cols = word_cols or []
+        self.word_types = word_types or []
+        self.line_txt_len = line_txt_len
+        self.confs = confs or []
+
+
+def _has_chinese_char(text):
+    return any("\u4e00" <= ch <= "\u9fff" for ch in text)
+
+
+def _word_types():
+    try:
+        from rapidocr.ch_ppocr_rec.typings import WordType
+        return WordType.CN, WordType.EN_NUM
+    except Exception:
+        return "cn", "en&num"
+
+
+def get_word_info(text, selection):
+    """CTCLabelDecode.get_word_info as patched by rapid_doc/model/ocr/ocr_patch.py:333-389: group the decoded
+    characters into words (CN vs EN/number runs, spaces kept as their own word) with their CTC columns."""
+    CN, EN_NUM = _word_types()
+    word_list, word_col_list, state_list = [], [], []
+    word_content, word_col_content = [], []
+    valid_col = np.where(selection)[0]
+    if len(valid_col) <= 0:
+        return WordInfo()
+    col_width = np.zeros(valid_col.shape)
+    col_width[1:] = valid_col[1:] - valid_col[:-1]
+    col_width[0] = min(3 if _has_chinese_char(text[0]) else 2, int(valid_col[0]))
+    state = None
+
+    def flush():
+        nonlocal word_content, word_col_content
+        if word_content:
+            word_list.append(word_content)
+            word_col_list.append(word_col_content)
+            state_list.append(state)
+            word_content, word_col_content = [], []
+
+    for c_i, char in enumerate(text):
+        if char.isspace():
+            flush()
+            word_list.append([char])
+            word_col_list.append([int(valid_col[c_i])])
+            state_list.append(EN_NUM)
+            state = None
+            continue
+        c_state = CN if _has_chinese_char(char) else EN_NUM
+        if state is None:
+            state = c_state
+        if state != c_state or col_width[c_i] > 5:
+            flush()
+            state = c_state
+        word_content.append(char)
+        word_col_content.append(int(valid_col[c_i]))
+    flush()
+    return WordInfo(words=word_list, word_cols=word_col_list, word_types=state_list)
+
+
 class B200TextRecognizer:
     """Mirror of rapidocr TextRecognizer + RapidOcrModel.text_recognizer_call (rapid_ocr.py:404-472)."""
 
@@ -261,24 +327,34 @@ class B200TextRecognizer:
         ratios = [im.shape[1] / float(im.shape[0]) for im in img_list]
         order = np.argsort(np.array(ratios))
         res = [("", 0.0)] * n
+        words = [None] * n
         _, ih, iw = self.rec_image_shape
         for b0 in range(0, n, self.rec_batch_num):
             idx = order[b0: b0 + self.rec_batch_num]
             mx = max([iw / ih] + [ratios[i] for i in idx])
             buf, vw = self._pack([img_list[i] for i in idx], mx)
             out = self.engine.infer_u8(buf, vw)
+            T = out["ids"].shape[1]
             for j, i in enumerate(idx):
                 ln = int(out["text_len"][j])
                 ids = out["text_ids"][j][:ln]
                 text = "".join(self.character[k] for k in ids)
                 # CTCLabelDecode: float64 mean of the kept float32 max-probs, rounded to 5 decimals
-                sel = np.ones(out["ids"].shape[1], bool)
+                sel = np.ones(T, bool)
                 sel[1:] = out["ids"][j][1:] != out["ids"][j][:-1]
                 sel &= out["ids"][j] != 0
                 conf = np.array(out["probs"][j][sel]).tolist() or [0]
                 res[i] = (text, float(np.mean(conf).round(5)))
+                if return_word_box:
+                    # rapidocr CTCLabelDecode(return_word_box=True): word grouping + the CTC length scaled to the
+                    # crop's share of the padded batch width (wh_ratio / max_wh_ratio)
+                    wi = get_word_info(text, sel) if text else WordInfo()
+                    wi.line_txt_len = T * ratios[i] / mx
+                    wi.confs = conf
+                    words[i] = wi
         txts, scores = (list(zip(*res)) if res else ((), ()))
-        return TextRecOutput(img_list, tuple(txts), tuple(scores), None, time.perf_counter() - t0)
+        return TextRecOutput(img_list, tuple(txts), tuple(scores), tuple(words) if return_word_box else None,
+                             time.perf_counter() - t0)
 
 
 # ----------------------------------------------------------------------------- the model class
@@ -370,7 +446,38 @@ class B200OcrModel:
             return [[np.asarray(b).tolist() for b in boxes]]
         crops = img if isinstance(img, list) else [img]
         r = self.text_recognizer(crops, return_word_box=return_word_box)
+        if return_word_box and ori_img is not None and dt_boxes:
+            return [list(zip(r.txts, r.scores, self.calc_word_boxes(crops, dt_boxes, r, ori_img.shape[0], ori_img.shape[1])))]
         return [list(zip(r.txts, r.scores))]
+
+    def calc_word_boxes(self, crops, dt_boxes, rec_result, raw_h, raw_w):
+        """rapid_ocr.py:301-329: per-word boxes through rapidocr's CalRecBoxes (as patched by ocr_patch.py:261-330).
+        CalRecBoxes is rapidocr code that RapidDoc ships with; it is used as-is when importable."""
+        try:
+            from rapidocr.cal_rec_boxes import CalRecBoxes
+        except Exception as exc:  # pragma: no cover
+            raise NotImplementedError("return_word_box needs rapidocr's CalRecBoxes (installed with RapidDoc)") from exc
+        try:
+            from rapid_doc.model.ocr.ocr_patch import patch_word_box
+            patch_word_box()
+        except Exception:
+            pass
+        boxes = [np.array(b, dtype=np.float32) for b in dt_boxes]
+        out = CalRecBoxes()(crops, boxes, rec_result, False)
+        words = []
+        for line in out.word_results:
+            item = []
+            for txt, score, bbox in line:
+                if bbox is None:
+                    continue
+                pts = np.array([bbox]).astype(np.float64)
+                pts = np.where(pts < 0, 0, pts)
+                pts[..., 0] = np.minimum(pts[..., 0], raw_w)
+                pts[..., 1] = np.minimum(pts[..., 1], raw_h)
+                item.append((txt, score, pts.astype(np.int32).tolist()[0]))
+            if item:
+                words.append(tuple(item))
+        return tuple(words)
 
     def text_recognizer_call(self, args, tqdm_enable=False, tqdm_desc="OCR-rec Predict"):
         imgs = [args.img] if isinstance(args.img, np.ndarray) else args.img

@@ -46,3 +46,18 @@ def test_rotate_crop_shapes():
     tall = np.float32([[10, 10], [30, 10], [30, 150], [10, 150]])
     c = O.get_rotate_crop_image(img, tall)
     assert c.shape[1] > c.shape[0]          # rotated by 90 degrees (h/w >= 2)
+
+
+def test_get_word_info_grouping():
+    """ocr_patch.py:333-389 semantics: CN/EN runs, spaces are their own word, gaps > 5 columns split a word."""
+    sel = np.zeros(40, bool)
+    sel[[2, 4, 6, 9, 15, 17, 19]] = True
+    wi = O.get_word_info("ab c邹12", sel)
+    assert wi.words == [["a", "b"], [" "], ["c"], ["邹"], ["1", "2"]]
+    assert wi.word_cols == [[2, 4], [6], [9], [15], [17, 19]]
+    assert len(wi.word_types) == 5 and wi.word_types[3] != wi.word_types[0]
+    sel = np.zeros(30, bool)
+    sel[[1, 2, 12, 13]] = True                      # 10-column gap inside an EN run -> two words
+    wi = O.get_word_info("abcd", sel)
+    assert wi.words == [["a", "b"], ["c", "d"]]
+    assert O.get_word_info("", np.zeros(5, bool)).words == []

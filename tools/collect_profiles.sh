@@ -1,0 +1,18 @@
+#!/bin/bash
+# copy the judged artefacts of the last gpurun calls from gpurun_out/ (scratch) into profiles/ (tracked)
+set -e
+cd "$(dirname "$0")/.."
+R=${1:-r01}
+mkdir -p profiles
+for f in bench_det_fp16 bench_rec_fp16 bench_det_fp32 bench_ref prof_det_fp16 prof_rec_fp16; do
+  [ -s gpurun_out/$f.json ] && cp gpurun_out/$f.json profiles/${R}_$f.json
+done
+for f in launches_det launches_rec; do
+  [ -s gpurun_out/$f.csv ] && grep -v "^==" gpurun_out/$f.csv > profiles/${R}_ncu_$f.csv
+done
+reps=""
+for f in ncu_dw7 ncu_headconv ncu_gemm_k48 ncu_rec_gemm; do
+  [ -s gpurun_out/$f.ncu-rep ] && reps="$reps gpurun_out/$f.ncu-rep"
+done
+[ -n "$reps" ] && python tools/summarize_ncu.py profiles/${R}_ncu_summary $reps > /dev/null
+ls -la profiles
