@@ -59,16 +59,20 @@ void DetEngine::forward_chunk(Ctx& cx, const DetInput& in, int n, int H, int W, 
   const Weights& w = *weights_;
   const int H1 = H / 2, W1 = W / 2;
   // ---- stem1
-  Act e1 = O::make(cx, n, H1, W1, 24);
+  bool wide = false;   // fp16/tcgen05 path: conv inputs carry one (2x2) or two (3x3) zero pad pixels per row (wide-row TMA)
+  if constexpr (std::is_same<T, __half>::value) wide = cx.use_tc && !env_is("RDB_CONV", "simt") && !env_is("RDB_TC_WIDE", "0");
+  const int e1_wp = wide ? W1 + 1 : W1;
+  Act e1 = O::make(cx, n, H1, e1_wp, 24);
+  e1.w = W1; e1.wp = wide ? e1_wp : 0;
   {
-    long long total = e1.pixels();
+    long long total = (long long)n * H1 * e1_wp;
     cx.begin("stem1");
     if (in.f32 != nullptr) {
       InF32NCHW src{in.f32, H, W};
-      stem1_kernel<T, InF32NCHW, 24><<<cdiv(total, 128), 128, 0, cx.st>>>(src, n, w.get("stem1.w").d, w.get("stem1.b").d, e1.p, H1, W1);
+      stem1_kernel<T, InF32NCHW, 24><<<cdiv(total, 128), 128, 0, cx.st>>>(src, n, w.get("stem1.w").d, w.get("stem1.b").d, e1.p, H1, W1, e1_wp);
     } else {
       InU8HWC src{in.u8, H, W, 0, {in.mean[0], in.mean[1], in.mean[2]}, {in.stdv[0], in.stdv[1], in.stdv[2]}, nullptr};
-      stem1_kernel<T, InU8HWC, 24><<<cdiv(total, 128), 128, 0, cx.st>>>(src, n, w.get("stem1.w").d, w.get("stem1.b").d, e1.p, H1, W1);
+      stem1_kernel<T, InU8HWC, 24><<<cdiv(total, 128), 128, 0, cx.st>>>(src, n, w.get("stem1.w").d, w.get("stem1.b").d, e1.p, H1, W1, e1_wp);
     }
     cx.end();
   }
@@ -137,21 +141,31 @@ void DetEngine::forward_chunk(Ctx& cx, const DetInput& in, int n, int H, int W, 
     ns.f[i] = pq[i].p;
     ns.gate[i] = gates[i];
   }
-  Act neck = O::make(cx, n, pq[0].h, pq[0].w, 96);
+  const int neck_wp = wide ? pq[0].w + 2 : pq[0].w;
+  Act neck = O::make(cx, n, pq[0].h, neck_wp, 96);
+  neck.w = pq[0].w; neck.wp = wide ? neck_wp : 0;
   {
     long long total = neck.pixels() * 12;
     cx.begin("neck_concat");
-    neck_concat_kernel<T><<<cdiv(total, kThreads), kThreads, 0, cx.st>>>(ns, n, neck.h, neck.w, neck.p);
+    neck_concat_kernel<T><<<cdiv(total, kThreads), kThreads, 0, cx.st>>>(ns, n, neck.h, neck.w, neck.p, neck_wp, wide ? 1 : 0);
     cx.end();
+    if (wide) {
+      const long long rows = (long long)n * neck.h;
+      zero_cols_kernel<T><<<cdiv(rows * 12, kThreads), kThreads, 0, cx.st>>>(neck.p, rows, neck_wp, 96, 0, 1);
+      zero_cols_kernel<T><<<cdiv(rows * 12, kThreads), kThreads, 0, cx.st>>>(neck.p, rows, neck_wp, 96, neck_wp - 1, 1);
+      RDB_LAUNCH_CHECK();
+      cx.launches += 2;
+    }
   }
   for (int i = 0; i < 4; ++i) { O::release(cx, pq[i]); cx.pool->free(gates[i]); }
   // ---- DBHead
+  RDB_CHECK(!wide || cx.use_tc, "wide rows need the tcgen05 conv");
   Act hd = O::make(cx, n, neck.h, neck.w, 24);
   bool head_tc = false;
   if constexpr (std::is_same<T, __half>::value) {
     if (cx.use_tc && !env_is("RDB_CONV", "simt")) {
       launch_conv_tc(cx, "head_conv3x3", neck.p, n, neck.h, neck.w, 96, w.get("head.down.w").h, 24, w.get("head.down.b").d, ACT_RELU, 3, 3, 1, 1,
-                     1, 1, hd.p, hd.h, hd.w, 24, 0);
+                     1, 1, hd.p, hd.h, hd.w, 24, 0, wide ? neck_wp : 0, 0);
       head_tc = true;
     }
   }

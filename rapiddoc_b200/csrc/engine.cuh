@@ -251,14 +251,21 @@ inline void launch_gemm_tc(Ctx& cx, const __half* A, int lda, long long M, int K
 
 // tcgen05 implicit-GEMM convolution (dense KHxKW conv, NHWC fp16): the stem 2x2 / 3x3-s2 convs and the
 // DBHead 3x3 conv (rec_lcnetv4.py:152-154, det_db_head.py:104-109) on the tensor cores.
+// in_wp > 0: the input rows are padded to in_wp pixels with zero pad pixels in memory and the conv runs in wide-row patch
+// mode (the KW horizontal taps are one K range).  out_wp > 0: the output is written with that row pitch.
 inline void launch_conv_tc(Ctx& cx, const char* name, const __half* in, int n, int H, int W, int C, const __half* Wh, int N, const float* bias,
-                           int act, int KH, int KW, int sh, int sw, int pt, int pl, __half* out, int OH, int OW, int ldc, int c_off) {
-  tc::Plan p = tc::make_conv_plan(n, H, W, C, N, KH, KW, sh, sw, pt, pl, OH, OW, cx.num_sms);
+                           int act, int KH, int KW, int sh, int sw, int pt, int pl, __half* out, int OH, int OW, int ldc, int c_off,
+                           int in_wp = 0, int out_wp = 0) {
+  const bool wide = in_wp > 0 && sh == 1 && sw == 1;
+  tc::Plan p = wide ? tc::make_conv_plan_wide(n, H, W, C, N, KH, KW, pt, OH, OW, cx.num_sms)
+                    : tc::make_conv_plan(n, H, W, C, N, KH, KW, sh, sw, pt, pl, OH, OW, cx.num_sms);
   tc::Args& a = p.a;
-  a.bias = bias; a.res = nullptr; a.ldr = 0; a.out = out; a.ldc = ldc; a.c_off = c_off; a.act = act;
-  CUtensorMap mA = tc::make_map_nhwc(in, n, H, W, C, a.AW, a.patch ? a.TH + a.KH - 1 : a.TH, a.TW, sh, sw);
+  RDB_CHECK(!wide || (a.patch && a.resident), "conv_tc: wide-row mode needs the weights resident");
+  a.bias = bias; a.res = nullptr; a.ldr = 0; a.out = out; a.ldc = ldc; a.c_off = c_off; a.act = act; a.out_wp = out_wp;
+  CUtensorMap mA = wide ? tc::make_map_wide(in, n, H, W, in_wp, C, KW, a.AW, a.TH + a.KH - 1)
+                        : tc::make_map_nhwc(in, n, H, in_wp > 0 ? in_wp : W, C, a.AW, a.patch ? a.TH + a.KH - 1 : a.TH, a.TW, sh, sw);
   CUtensorMap mB = tc::make_map(Wh, N, KH * KW * C, KH * KW * C, a.AW, a.BN);
-  cx.begin(std::string(name) + (a.patch ? "_tcp[P=" : "_tc[P=") + std::to_string((long long)n * OH * OW) + ",C=" + std::to_string(C) + ",N=" + std::to_string(N) + "]");
+  cx.begin(std::string(name) + (wide ? "_tcw[P=" : (a.patch ? "_tcp[P=" : "_tc[P=")) + std::to_string((long long)n * OH * OW) + ",C=" + std::to_string(C) + ",N=" + std::to_string(N) + "]");
   launch_tc_store(p, mA, mB, act, cx.st);
   cx.end();
 }
@@ -304,6 +311,8 @@ struct Ops {
   // NHWC activation handle
   struct Act {
     T* p = nullptr; int n = 0, h = 0, w = 0, c = 0;
+    int wp = 0;   // row pitch in pixels when the rows carry zero pad pixels (wide-row conv inputs); 0 = w
+    int pitch() const { return wp ? wp : w; }
     long long pixels() const { return (long long)n * h * w; }
     long long numel() const { return pixels() * c; }
   };
@@ -354,15 +363,25 @@ struct Ops {
     }
     if constexpr (std::is_same<T, __half>::value && KH == 3 && KW == 3 && ACT == ACT_NONE && !ADD_IN) {
       if (sh == 1 && sw == 1 && in.c % 16 == 0 && !env_is("RDB_DW", "simple")) {
-        const bool g4 = (in.c % 32 == 0), tall = in.h >= 8;
-        const int G = g4 ? 4 : 2, TH = tall ? 8 : 4, TW = 32;
+        // tile shape: the recogniser's maps are 12 / 6 / 3 rows x 80 columns -> tiles that cover the height exactly and
+        // 16-column tiles (80 = 5 x 16); page-sized maps use 8 x 32
+        const bool g4 = (in.c % 32 == 0);
+        const int G = g4 ? 4 : 2;
+        int TH = in.h >= 8 ? 8 : 4, TW = 32;
+        if (in.h == 12 || in.h == 6 || in.h == 3) { TH = in.h; TW = 16; }
         const size_t sm = (size_t)(TH + 2) * (TW + 2) * (16 * G + 16) + 9 * 8 * G * sizeof(float);
         dim3 grid(cdiv(in.w, TW), cdiv(in.h, TH), in.n * (in.c / (8 * G)));
+        const int threads = G * (TW / 4) * TH;
         cx.begin("dwconv3x3_tiled[P=" + std::to_string(out.pixels()) + ",C=" + std::to_string(in.c) + ",s=1]");
-        if (g4 && tall) dwconv_tiled_kernel<T, 3, 4, 8, 32><<<grid, 4 * 8 * 8, sm, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.d, b.d, out.p);
-        else if (g4) dwconv_tiled_kernel<T, 3, 4, 4, 32><<<grid, 4 * 8 * 4, sm, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.d, b.d, out.p);
-        else if (tall) dwconv_tiled_kernel<T, 3, 2, 8, 32><<<grid, 2 * 8 * 8, sm, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.d, b.d, out.p);
-        else dwconv_tiled_kernel<T, 3, 2, 4, 32><<<grid, 2 * 8 * 4, sm, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.d, b.d, out.p);
+#define RDB_DW3(GG, TTH, TTW) dwconv_tiled_kernel<T, 3, GG, TTH, TTW><<<grid, threads, sm, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.d, b.d, out.p)
+        if (g4) {
+          if (TH == 8) RDB_DW3(4, 8, 32); else if (TH == 4) RDB_DW3(4, 4, 32); else if (TH == 12) RDB_DW3(4, 12, 16);
+          else if (TH == 6) RDB_DW3(4, 6, 16); else RDB_DW3(4, 3, 16);
+        } else {
+          if (TH == 8) RDB_DW3(2, 8, 32); else if (TH == 4) RDB_DW3(2, 4, 32); else if (TH == 12) RDB_DW3(2, 12, 16);
+          else if (TH == 6) RDB_DW3(2, 6, 16); else RDB_DW3(2, 3, 16);
+        }
+#undef RDB_DW3
         cx.end();
         return;
       }
@@ -426,16 +445,26 @@ struct Backbone {
     const int H2 = (H1 - 1) / 2 + 1, W2 = (W1 - 1) / 2 + 1;
     bool tc_path = false;
     if constexpr (std::is_same<T, __half>::value) tc_path = cx.use_tc && !env_is("RDB_CONV", "simt");
+    RDB_CHECK(tc_path || e1.wp == 0, "stem: row-padded input needs the tcgen05 conv path");
     Act cat = O::make(cx, n, H1, W1, C2);
     Act s3 = O::make(cx, n, H2, W2, C1);
     if (tc_path) {
       if constexpr (std::is_same<T, __half>::value) {
-        Act a = O::make(cx, n, H1, W1, CHP);
-        // F.pad(0,1,0,1) + conv2x2 == conv with pt=pl=0 and zero fill past the bottom/right edge
+        // F.pad(0,1,0,1) + conv2x2 == conv with pt=pl=0 and zero fill past the bottom/right edge.  With row-padded
+        // buffers (e1.wp = W1+1) the right pad pixel is real memory and both kx taps are ONE wide TMA row.
+        const int a_wp = e1.wp ? W1 + 1 : 0;
+        Act a = O::make(cx, n, H1, a_wp ? a_wp : W1, CHP);
+        a.w = W1; a.wp = a_wp;
         launch_conv_tc(cx, "stem2a", e1.p, n, H1, W1, C1, w.get("stem2a.wp").h, CHP, w.get("stem2a.bp").d, ACT_RELU, 2, 2, 1, 1, 0, 0,
-                       a.p, H1, W1, CHP, 0);
+                       a.p, H1, W1, CHP, 0, e1.wp, a_wp);
+        if (a_wp) {
+          const long long rows = (long long)n * H1;
+          zero_cols_kernel<T><<<cdiv(rows * (CHP / 8), kThreads), kThreads, 0, cx.st>>>(a.p, rows, a_wp, CHP, W1, 1);
+          RDB_LAUNCH_CHECK();
+          cx.launches++;
+        }
         launch_conv_tc(cx, "stem2b", a.p, n, H1, W1, CHP, w.get("stem2b.wp").h, C1, w.get("stem2b.b").d, ACT_RELU, 2, 2, 1, 1, 0, 0,
-                       cat.p, H1, W1, C2, C1);
+                       cat.p, H1, W1, C2, C1, a_wp, 0);
         O::release(cx, a);
       }
     } else {
@@ -463,7 +492,7 @@ struct Backbone {
     {
       long long total = e1.pixels() * (C1 / 8);
       cx.begin("stem_pool");
-      pool2x2_concat_kernel<T><<<cdiv(total, kThreads), kThreads, 0, cx.st>>>(e1.p, n, H1, W1, C1, cat.p, C2);
+      pool2x2_concat_kernel<T><<<cdiv(total, kThreads), kThreads, 0, cx.st>>>(e1.p, n, H1, W1, C1, cat.p, C2, e1.pitch());
       cx.end();
     }
     O::release(cx, e1);

@@ -164,7 +164,8 @@ struct Args {
   int KW, sh, sw, pt, pl, cchunks, C, tw_shift;
   // patch mode (stride-1 convs, B resident): one TMA box per (kx, channel chunk) holds TH+KH-1 input rows x 8 columns; the
   // KH vertical taps are the SAME smem box read at +8-row (= one swizzle atom) descriptor offsets -> KH x fewer loads/bytes
-  int patch, KH, b_blocks;   // b_blocks: resident B k-blocks (= KH*KW*cchunks in conv modes, k_blocks otherwise)
+  int patch, KH, b_blocks;
+  int out_wp;                // conv epilogue: output row pitch in pixels (>= OW; 0 = OW)   // b_blocks: resident B k-blocks (= KH*KW*cchunks in conv modes, k_blocks otherwise)
 };
 
 constexpr int kEpiSubs = 4;                        // epilogue warps per TMEM lane quarter
@@ -336,7 +337,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int r = q * 32 + lane;
         const int oy = wk.ty * g.TH + (r >> g.tw_shift), ox = wk.tx * g.TW + (r & (g.TW - 1));
         row_ok = (oy < g.OH) && (ox < g.OW);
-        row = ((long long)wk.n * g.OH + oy) * g.OW + ox;
+        row = ((long long)wk.n * g.OH + oy) * (g.out_wp ? g.out_wp : g.OW) + ox;
       }
       const int n0 = tn * g.BN;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * g.BN);
@@ -449,7 +450,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               Vec8<__half>::store(op, a);
               Vec8<__half>::store(op + 8, b2);
             } else {
-              for (int j = 0; j < 16; ++j) if (n0 + c0 + j < g.N) op[j] = __float2half_rn(v[j]);
+              // ragged last chunk (N = 24 -> 8 valid columns): still one 16-byte store for the first 8
+              const int valid = g.N - (n0 + c0);
+              int j0 = 0;
+              if (valid >= 8) {
+                float a[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] = v[j];
+                Vec8<__half>::store(op, a);
+                j0 = 8;
+              }
+              for (int j = j0; j < 16; ++j) if (j < valid) op[j] = __float2half_rn(v[j]);
             }
           }
         } else {
@@ -535,6 +546,23 @@ inline CUtensorMap make_map_nhwc(const void* base, int n, int H, int W, int C, i
   return m;
 }
 
+// "Wide-row" view of an NHWC tensor whose rows are padded to WP pixels: row (x, y, n) = KW adjacent pixels = KW*C contiguous
+// channels starting at padded pixel x (dim-1 stride = ONE pixel, i.e. rows overlap — accepted and delivered by TMA, see
+// tools/tma_overlap.cu).  The KW horizontal taps of a conv become one K range; zero pad pixels in memory replace x-OOB fill.
+inline CUtensorMap make_map_wide(const void* base, int n, int H, int W, int WP, int C, int KW, int aw, int box_rows_y) {
+  CUtensorMap m;
+  cuuint64_t dims[4] = {(cuuint64_t)KW * C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)WP * C * 2, (cuuint64_t)H * WP * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)aw, 8, (cuuint32_t)box_rows_y, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUtensorMapSwizzle swz = aw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (aw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  RDB_CHECK(((uintptr_t)base & 15) == 0 && (C * 2) % 16 == 0, "tma: wide-row base/pixel pitch must be 16-byte aligned");
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error("cuda: cuTensorMapEncodeTiled(wide rows) failed, code " + std::to_string((int)r));
+  return m;
+}
+
 struct Plan {
   Args a;
   size_t smem;
@@ -544,8 +572,16 @@ struct Plan {
 // k-block width (one swizzle span): prefer few wide TMA boxes; a ragged last block is zero-filled by
 // TMA (no HBM traffic for the out-of-bounds part), e.g. K=48 -> one 64-wide block with 16 zero columns.
 inline int pick_aw(int K) {
-  if (K % 64 == 0) return 64;
-  if (K % 32 == 0) return 32;
+  // TMA cost is per box row ("segment"), not per byte (profiles/r01_tma_microbench.txt): use the widest span (64 halves =
+  // 128 B) as soon as K > 32 even when the last block is only partly valid (K = 48, 96, 120, 240 ...)
+  const char* e = std::getenv("RDB_TC_AW");
+  if (e != nullptr && e[0] == 'n') {            // RDB_TC_AW=narrow: previous rule (largest span dividing K), for A/B runs
+    if (K % 64 == 0) return 64;
+    if (K % 32 == 0) return 32;
+    if (K <= 16) return 16;
+    if (K <= 32) return 32;
+    return 64;
+  }
   if (K <= 16) return 16;
   if (K <= 32) return 32;
   return 64;
@@ -660,6 +696,13 @@ inline Plan make_conv_plan_mode(int n, int H, int W, int C, int N, int KH, int K
   a.tmem_cols = cols;
   a.idesc = (1u << 4) | ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   finish_plan(p, num_sms);
+  return p;
+}
+
+// wide-row patch plan (stride-1 conv on a row-padded input): K of one vertical tap = KW*C contiguous channels
+inline Plan make_conv_plan_wide(int n, int H, int W, int C, int N, int KH, int KW, int pt, int OH, int OW, int num_sms) {
+  // identical to a patch-mode conv with KW_eff = 1 and C_eff = KW*C read through make_map_wide (pl is provided by the pad pixels)
+  Plan p = make_conv_plan_mode(n, H, W, KW * C, N, KH, 1, 1, 1, pt, 0, OH, OW, num_sms, true);
   return p;
 }
 

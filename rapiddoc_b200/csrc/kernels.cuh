@@ -39,7 +39,7 @@ struct InU8HWC {
 
 template <typename T, typename IN, int C1>
 __global__ void __launch_bounds__(128) stem1_kernel(IN in, int N, const float* __restrict__ w /*[C1][3][3][3]*/,
-                                                    const float* __restrict__ b, T* __restrict__ out, int OH, int OW) {
+                                                    const float* __restrict__ b, T* __restrict__ out, int OH, int OW, int out_wp) {
   __shared__ float sw[27 * C1];
   __shared__ float sb[C1];
   __shared__ float lut[IN::kU8 ? 768 : 1];
@@ -51,11 +51,20 @@ __global__ void __launch_bounds__(128) stem1_kernel(IN in, int N, const float* _
   if (IN::kU8)
     for (int i = threadIdx.x; i < 768; i += blockDim.x) lut[i] = in.norm(i >> 8, i & 255);
   __syncthreads();
+  // out_wp >= OW: output rows are padded to out_wp pixels (pad pixels are written as zeros: they are the F.pad column
+  // the wide-row stem2a conv reads)
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)N * OH * OW;
+  long long total = (long long)N * OH * out_wp;
   if (idx >= total) return;
-  int ox = idx % OW; int oy = (idx / OW) % OH; int n = idx / ((long long)OW * OH);
+  int ox = idx % out_wp; int oy = (idx / out_wp) % OH; int n = idx / ((long long)out_wp * OH);
   float acc[C1];
+  if (ox >= OW) {
+    T* zp = out + idx * C1;
+    float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < C1; c += 8) Vec8<T>::store(zp + c, z);
+    return;
+  }
 #pragma unroll
   for (int c = 0; c < C1; ++c) acc[c] = sb[c];
 #pragma unroll
@@ -166,7 +175,7 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const T* __restrict__ 
 // first C channels of the concat buffer.  rec_lcnetv4.py:156,165-166
 // =====================================================================================
 template <typename T>
-__global__ void pool2x2_concat_kernel(const T* __restrict__ in, int N, int H, int W, int C, T* __restrict__ out, int ld_out) {
+__global__ void pool2x2_concat_kernel(const T* __restrict__ in, int N, int H, int W, int C, T* __restrict__ out, int ld_out, int in_wp) {
   int G = C / 8;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)N * H * W * G;
@@ -174,13 +183,13 @@ __global__ void pool2x2_concat_kernel(const T* __restrict__ in, int N, int H, in
   int g = idx % G; long long p = idx / G;
   int x = p % W; int y = (p / W) % H; int n = p / ((long long)W * H);
   float m[8];
-  Vec8<T>::load(in + (((long long)n * H + y) * W + x) * C + g * 8, m);
+  Vec8<T>::load(in + (((long long)n * H + y) * in_wp + x) * C + g * 8, m);
 #pragma unroll
   for (int d = 1; d < 4; ++d) {
     int yy = y + (d >> 1), xx = x + (d & 1);
     float v[8];
     if (yy < H && xx < W) {
-      Vec8<T>::load(in + (((long long)n * H + yy) * W + xx) * C + g * 8, v);
+      Vec8<T>::load(in + (((long long)n * H + yy) * in_wp + xx) * C + g * 8, v);
     } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = 0.f;  // F.pad zeros take part in the max
@@ -456,7 +465,7 @@ template <typename T>
 struct NeckSrc { const T* f[4]; const float* gate[4]; };
 
 template <typename T>
-__global__ void neck_concat_kernel(NeckSrc<T> s, int N, int H, int W, T* __restrict__ out) {
+__global__ void neck_concat_kernel(NeckSrc<T> s, int N, int H, int W, T* __restrict__ out, int out_wp, int x_off) {
   // out [N,H,W,96]; channel group j (24 ch) comes from level 3-j (level L has size H>>L)
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)N * H * W * 12;
@@ -471,7 +480,20 @@ __global__ void neck_concat_kernel(NeckSrc<T> s, int N, int H, int W, T* __restr
   const float* gp = s.gate[L] + n * 24 + c8;
 #pragma unroll
   for (int k = 0; k < 8; ++k) v[k] *= gp[k];
-  Vec8<T>::store(out + p * 96 + g * 8, v);
+  Vec8<T>::store(out + (((long long)n * H + y) * out_wp + x + x_off) * 96 + g * 8, v);
+}
+
+// zero the pad pixel columns [c0, c0+nc) of a row-padded NHWC buffer ([rows = n*H][wp][C])
+template <typename T>
+__global__ void zero_cols_kernel(T* __restrict__ buf, long long rows, int wp, int C, int c0, int nc) {
+  int G = C / 8;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = rows * nc * G;
+  if (idx >= total) return;
+  int g = idx % G; long long q = idx / G;
+  int k = q % nc; long long r = q / nc;
+  float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  Vec8<T>::store(buf + (r * wp + c0 + k) * C + g * 8, z);
 }
 
 // =====================================================================================

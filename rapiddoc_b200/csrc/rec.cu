@@ -40,16 +40,20 @@ void RecEngine::forward_chunk(Ctx& cx, const RecInput& in, int n, int W, int32_t
   using Act = typename O::Act;
   const Weights& w = *weights_;
   const int H = 48, H1 = 24, W1 = (W - 1) / 2 + 1;
-  Act e1 = O::make(cx, n, H1, W1, 48);
+  bool wide = false;
+  if constexpr (std::is_same<T, __half>::value) wide = cx.use_tc && !env_is("RDB_CONV", "simt") && !env_is("RDB_TC_WIDE", "0");
+  const int e1_wp = wide ? W1 + 1 : W1;
+  Act e1 = O::make(cx, n, H1, e1_wp, 48);
+  e1.w = W1; e1.wp = wide ? e1_wp : 0;
   {
-    long long total = e1.pixels();
+    long long total = (long long)n * H1 * e1_wp;
     cx.begin("stem1");
     if (in.f32 != nullptr) {
       InF32NCHW src{in.f32, H, W};
-      stem1_kernel<T, InF32NCHW, 48><<<cdiv(total, 128), 128, 0, cx.st>>>(src, n, w.get("stem1.w").d, w.get("stem1.b").d, e1.p, H1, W1);
+      stem1_kernel<T, InF32NCHW, 48><<<cdiv(total, 128), 128, 0, cx.st>>>(src, n, w.get("stem1.w").d, w.get("stem1.b").d, e1.p, H1, W1, e1_wp);
     } else {
       InU8HWC src{in.u8, H, W, 1, {0, 0, 0}, {1, 1, 1}, in.valid_w};
-      stem1_kernel<T, InU8HWC, 48><<<cdiv(total, 128), 128, 0, cx.st>>>(src, n, w.get("stem1.w").d, w.get("stem1.b").d, e1.p, H1, W1);
+      stem1_kernel<T, InU8HWC, 48><<<cdiv(total, 128), 128, 0, cx.st>>>(src, n, w.get("stem1.w").d, w.get("stem1.b").d, e1.p, H1, W1, e1_wp);
     }
     cx.end();
   }
