@@ -28,10 +28,8 @@ DetEngine::~DetEngine() {
   if (copy_in_) {
     cudaStreamDestroy(copy_in_); cudaStreamDestroy(copy_out_);
     cudaEventDestroy(ev_fork_);
-    for (int s = 0; s < 2; ++s) {
-      cudaStreamDestroy(lane_[s]);
-      cudaEventDestroy(ev_in_[s]); cudaEventDestroy(ev_out_[s]); cudaEventDestroy(ev_compute_[s]); cudaEventDestroy(ev_join_[s]);
-    }
+    for (int s = 0; s < 2; ++s) { cudaStreamDestroy(lane_[s]); cudaEventDestroy(ev_join_[s]); }
+    for (int s = 0; s < kSlots; ++s) { cudaEventDestroy(ev_in_[s]); cudaEventDestroy(ev_out_[s]); cudaEventDestroy(ev_compute_[s]); }
   }
 }
 
@@ -42,10 +40,12 @@ void DetEngine::ensure_streams() {
   RDB_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
   for (int s = 0; s < 2; ++s) {
     RDB_CUDA(cudaStreamCreateWithFlags(&lane_[s], cudaStreamNonBlocking));
+    RDB_CUDA(cudaEventCreateWithFlags(&ev_join_[s], cudaEventDisableTiming));
+  }
+  for (int s = 0; s < kSlots; ++s) {
     RDB_CUDA(cudaEventCreateWithFlags(&ev_in_[s], cudaEventDisableTiming));
     RDB_CUDA(cudaEventCreateWithFlags(&ev_out_[s], cudaEventDisableTiming));
     RDB_CUDA(cudaEventCreateWithFlags(&ev_compute_[s], cudaEventDisableTiming));
-    RDB_CUDA(cudaEventCreateWithFlags(&ev_join_[s], cudaEventDisableTiming));
   }
 }
 
@@ -238,9 +238,11 @@ void DetEngine::infer(const DetInput& in_host_or_dev, int n, int H, int W, float
   const int lanes = (n_chunks >= 2 && !env_is("RDB_LANES", "1")) ? 2 : 1;
   ensure_streams();
   Ctx cxs[2];
-  void* d_in[2] = {nullptr, nullptr};
-  float* d_prob[2] = {nullptr, nullptr};
-  uint8_t* d_bm[2] = {nullptr, nullptr};
+  // host staging: kSlots buffers (two per lane), so a chunk's H2D / D2H never stalls the lane that owns the slot
+  const int slots = lanes * 2 <= n_chunks ? lanes * 2 : lanes;
+  void* d_in[kSlots] = {};
+  float* d_prob[kSlots] = {};
+  uint8_t* d_bm[kSlots] = {};
   // GPU resize (DetPreProcess): coefficient tables once per call
   int *d_xi = nullptr, *d_yi = nullptr; short *d_xa = nullptr, *d_ya = nullptr;
   uint8_t* d_rs[2] = {nullptr, nullptr};
@@ -264,26 +266,39 @@ void DetEngine::infer(const DetInput& in_host_or_dev, int n, int H, int W, float
     cxs[l].pool = &pools_[l];
     cxs[l].launches = 0;
     RDB_CUDA(cudaStreamWaitEvent(lane_[l], ev_fork_, 0));
-    if (!in_dev) d_in[l] = pools_[l].alloc(page_in * chunk);
-    if (!(prob_dev && prob)) d_prob[l] = pools_[l].alloc_t<float>(page_px * chunk);
-    if (bitmap && !bm_dev) d_bm[l] = pools_[l].alloc_t<uint8_t>(page_px * chunk);
   }
-  int it = 0;
-  for (int i0 = 0; i0 < n; i0 += chunk, ++it) {
-    const int l = it % lanes;
+  for (int s = 0; s < slots; ++s) {
+    Pool& pl = pools_[s % lanes];
+    if (!in_dev) d_in[s] = pl.alloc(page_in * chunk);
+    if (!(prob_dev && prob)) d_prob[s] = pl.alloc_t<float>(page_px * chunk);
+    if (bitmap && !bm_dev) d_bm[s] = pl.alloc_t<uint8_t>(page_px * chunk);
+  }
+  // chunk schedule: uniform, except that with host buffers the first and last chunks are ramped (c/4, c/2, c ... c/2, c/4)
+  // so the un-overlappable first H2D and last D2H are short
+  std::vector<int> sched;
+  {
+    int head[2] = {chunk / 4, chunk / 2}, rest = n;
+    const bool ramp = any_host && chunk >= 4 && n >= 3 * chunk && !env_is("RDB_RAMP", "0");
+    if (ramp) { sched.push_back(head[0]); sched.push_back(head[1]); rest -= 2 * (head[0] + head[1]); }
+    while (rest > 0) { const int m = rest < chunk ? rest : chunk; sched.push_back(m); rest -= m; }
+    if (ramp) { sched.push_back(head[1]); sched.push_back(head[0]); }
+  }
+  int i0 = 0;
+  for (int it = 0; it < (int)sched.size(); i0 += sched[it], ++it) {
+    const int l = it % lanes, sl = it % slots;
     cudaStream_t ls = lane_[l];
-    int m = (n - i0 < chunk) ? (n - i0) : chunk;
+    const int m = sched[it];
     const uint8_t* src_i = static_cast<const uint8_t*>(src) + (size_t)i0 * page_in;
     DetInput in = in_host_or_dev;
     const void* dsrc = src_i;
     if (!in_dev) {
-      if (it >= lanes) RDB_CUDA(cudaStreamWaitEvent(copy_in_, ev_compute_[l], 0));   // lane's previous reader done
-      RDB_CUDA(cudaMemcpyAsync(d_in[l], src_i, page_in * m, cudaMemcpyHostToDevice, copy_in_));
-      RDB_CUDA(cudaEventRecord(ev_in_[l], copy_in_));
-      RDB_CUDA(cudaStreamWaitEvent(ls, ev_in_[l], 0));
-      dsrc = d_in[l];
+      if (it >= slots) RDB_CUDA(cudaStreamWaitEvent(copy_in_, ev_compute_[sl], 0));   // slot's previous reader done
+      RDB_CUDA(cudaMemcpyAsync(d_in[sl], src_i, page_in * m, cudaMemcpyHostToDevice, copy_in_));
+      RDB_CUDA(cudaEventRecord(ev_in_[sl], copy_in_));
+      RDB_CUDA(cudaStreamWaitEvent(ls, ev_in_[sl], 0));
+      dsrc = d_in[sl];
     }
-    if (any_host && it >= lanes) RDB_CUDA(cudaStreamWaitEvent(ls, ev_out_[l], 0));     // lane's previous D2H done
+    if (any_host && it >= slots) RDB_CUDA(cudaStreamWaitEvent(ls, ev_out_[sl], 0));     // slot's previous D2H done
     if (do_resize) {
       cxs[l].begin("resize_linear_u8");
       resize_linear_u8_kernel<<<cdiv((long long)m * H * W, 256), 256, 0, ls>>>(static_cast<const uint8_t*>(dsrc), m, SH, SW, d_rs[l], H, W, d_xi, d_xa,
@@ -292,16 +307,16 @@ void DetEngine::infer(const DetInput& in_host_or_dev, int n, int H, int W, float
       dsrc = d_rs[l];
     }
     if (in.f32) in.f32 = static_cast<const float*>(dsrc); else in.u8 = static_cast<const uint8_t*>(dsrc);
-    float* p_out = (prob_dev && prob) ? prob + (size_t)i0 * page_px : d_prob[l];
-    uint8_t* b_out = bitmap ? (bm_dev ? bitmap + (size_t)i0 * page_px : d_bm[l]) : nullptr;
+    float* p_out = (prob_dev && prob) ? prob + (size_t)i0 * page_px : d_prob[sl];
+    uint8_t* b_out = bitmap ? (bm_dev ? bitmap + (size_t)i0 * page_px : d_bm[sl]) : nullptr;
     if (precision_ == 0) forward_chunk<float>(cxs[l], in, m, H, W, thresh, dilate, p_out, b_out);
     else forward_chunk<__half>(cxs[l], in, m, H, W, thresh, dilate, p_out, b_out);
     if (any_host) {
-      RDB_CUDA(cudaEventRecord(ev_compute_[l], ls));
-      RDB_CUDA(cudaStreamWaitEvent(copy_out_, ev_compute_[l], 0));
-      if (prob && !prob_dev) RDB_CUDA(cudaMemcpyAsync(prob + (size_t)i0 * page_px, d_prob[l], page_px * m * sizeof(float), cudaMemcpyDeviceToHost, copy_out_));
-      if (bitmap && !bm_dev) RDB_CUDA(cudaMemcpyAsync(bitmap + (size_t)i0 * page_px, d_bm[l], page_px * m, cudaMemcpyDeviceToHost, copy_out_));
-      RDB_CUDA(cudaEventRecord(ev_out_[l], copy_out_));
+      RDB_CUDA(cudaEventRecord(ev_compute_[sl], ls));
+      RDB_CUDA(cudaStreamWaitEvent(copy_out_, ev_compute_[sl], 0));
+      if (prob && !prob_dev) RDB_CUDA(cudaMemcpyAsync(prob + (size_t)i0 * page_px, d_prob[sl], page_px * m * sizeof(float), cudaMemcpyDeviceToHost, copy_out_));
+      if (bitmap && !bm_dev) RDB_CUDA(cudaMemcpyAsync(bitmap + (size_t)i0 * page_px, d_bm[sl], page_px * m, cudaMemcpyDeviceToHost, copy_out_));
+      RDB_CUDA(cudaEventRecord(ev_out_[sl], copy_out_));
     }
   }
   long long launches = 0;
@@ -314,12 +329,13 @@ void DetEngine::infer(const DetInput& in_host_or_dev, int n, int H, int W, float
     RDB_CUDA(cudaStreamSynchronize(copy_out_));
     RDB_CUDA(cudaStreamSynchronize(st));
   }
-  for (int l = 0; l < lanes; ++l) {
-    if (d_in[l]) pools_[l].free(d_in[l]);
-    if (d_prob[l]) pools_[l].free(d_prob[l]);
-    if (d_bm[l]) pools_[l].free(d_bm[l]);
-    if (d_rs[l]) pools_[l].free(d_rs[l]);
+  for (int s = 0; s < slots; ++s) {
+    Pool& pl = pools_[s % lanes];
+    if (d_in[s]) pl.free(d_in[s]);
+    if (d_prob[s]) pl.free(d_prob[s]);
+    if (d_bm[s]) pl.free(d_bm[s]);
   }
+  for (int l = 0; l < lanes; ++l) if (d_rs[l]) pools_[l].free(d_rs[l]);
   if (do_resize) { pools_[0].free(d_xi); pools_[0].free(d_yi); pools_[0].free(d_xa); pools_[0].free(d_ya); }
   if (Profiler::global().on) { RDB_CUDA(cudaDeviceSynchronize()); Profiler::global().resolve(); }
   last_launches_ = launches;

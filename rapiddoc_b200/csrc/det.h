@@ -28,13 +28,14 @@ class DetEngine {
   void ensure_streams();
   int device_, precision_;
   cudaStream_t copy_in_ = nullptr, copy_out_ = nullptr, lane_[2] = {nullptr, nullptr};
-  cudaEvent_t ev_in_[2] = {nullptr, nullptr}, ev_out_[2] = {nullptr, nullptr}, ev_compute_[2] = {nullptr, nullptr};
+  static constexpr int kSlots = 4;   // host-staging buffers: two per lane, so a lane never waits on its own copies
+  cudaEvent_t ev_in_[kSlots] = {}, ev_out_[kSlots] = {}, ev_compute_[kSlots] = {};
   cudaEvent_t ev_join_[2] = {nullptr, nullptr}, ev_fork_ = nullptr;
   std::unique_ptr<Weights> weights_;
   Pool pools_[2];   // one per compute lane
   long long last_launches_ = 0;
   int num_sms_ = 148;
-  long long chunk_pixels_ = 8ll * 1024 * 1024;  // pages per internal chunk = chunk_pixels / (H*W)
+  long long chunk_pixels_ = 16ll * 1024 * 1024;  // pages per internal chunk = chunk_pixels / (H*W)
 };
 
 // cv2.resize(INTER_LINEAR) on uint8 HWC images [n,sh,sw,3] -> [n,dh,dw,3], bit-exact (host or device pointers)
