@@ -291,7 +291,9 @@ int rdb_debug_gemm(int device, int use_tc, int mode, const float* A, const float
       __half* dO = pool.alloc_t<__half>((size_t)M * N);
       float* dOf = pool.alloc_t<float>((size_t)M * N);
       if (use_tc) {
-        rdb::launch_gemm_tc(cx, dAh, K, M, K, dWh, N, dB, act, dRh, N, dO, N, 0);
+        const char* reps_env = getenv("RDB_DEBUG_GEMM_REPS");   // timing aid: repeat the launch (see rdb_profile_*)
+        const int reps = reps_env ? atoi(reps_env) : 1;
+        for (int r = 0; r < (reps > 1 ? reps : 1); ++r) rdb::launch_gemm_tc(cx, dAh, K, M, K, dWh, N, dB, act, dRh, N, dO, N, 0);
       } else {
         rdb::GemmArgs g{};
         g.A = dAh; g.lda = K; g.W = dWf; g.bias = dB; g.res = dRh; g.ldr = N; g.out = dO; g.ldc = N; g.M = M; g.N = N; g.K = K; g.act = act;
@@ -322,6 +324,7 @@ int rdb_debug_gemm(int device, int use_tc, int mode, const float* A, const float
       for (int i = 0; i < M; ++i) { out[2 * i] = (float)hi[i]; out[2 * i + 1] = hp[i]; }
     }
     RDB_CUDA(cudaDeviceSynchronize());
+    if (rdb::Profiler::global().on) rdb::Profiler::global().resolve();
   });
 }
 

@@ -426,6 +426,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                   for (int j = 0; j < 8; ++j) { v[j] += a[j]; v[8 + j] += b2[j]; }
                 } else {
+#pragma unroll
                   for (int j = 0; j < 16; ++j) if (n0 + c0 + j < g.N) v[j] += __half2float(up[j]);
                 }
               }
@@ -439,6 +440,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { v[j] += a[j]; v[8 + j] += b2[j]; }
               } else {
+#pragma unroll
                 for (int j = 0; j < 16; ++j) if (n0 + c0 + j < g.N) v[j] += __half2float(rp[j]);
               }
             }
@@ -451,16 +453,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               Vec8<__half>::store(op + 8, b2);
             } else {
               // ragged last chunk (N = 24 -> 8 valid columns): still one 16-byte store for the first 8
+              // (every loop over v[] is fully unrolled with compile-time indices: one dynamic index would move the
+              // whole accumulator row to local memory)
               const int valid = g.N - (n0 + c0);
-              int j0 = 0;
               if (valid >= 8) {
                 float a[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) a[j] = v[j];
                 Vec8<__half>::store(op, a);
-                j0 = 8;
+#pragma unroll
+                for (int j = 8; j < 16; ++j) if (j < valid) op[j] = __float2half_rn(v[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (j < valid) op[j] = __float2half_rn(v[j]);
               }
-              for (int j = j0; j < 16; ++j) if (j < valid) op[j] = __float2half_rn(v[j]);
             }
           }
         } else {
