@@ -23,12 +23,11 @@ DetEngine::DetEngine(const void* blob, size_t nbytes, int device, int precision)
 DetEngine::~DetEngine() {
   cudaSetDevice(device_);
   cudaDeviceSynchronize();
-  pools_[0].release_all();
-  pools_[1].release_all();
+  for (int s = 0; s < kMaxLanes; ++s) pools_[s].release_all();
   if (copy_in_) {
     cudaStreamDestroy(copy_in_); cudaStreamDestroy(copy_out_);
     cudaEventDestroy(ev_fork_);
-    for (int s = 0; s < 2; ++s) { cudaStreamDestroy(lane_[s]); cudaEventDestroy(ev_join_[s]); }
+    for (int s = 0; s < kMaxLanes; ++s) { cudaStreamDestroy(lane_[s]); cudaEventDestroy(ev_join_[s]); }
     for (int s = 0; s < kSlots; ++s) { cudaEventDestroy(ev_in_[s]); cudaEventDestroy(ev_out_[s]); cudaEventDestroy(ev_compute_[s]); }
   }
 }
@@ -38,7 +37,7 @@ void DetEngine::ensure_streams() {
   RDB_CUDA(cudaStreamCreateWithFlags(&copy_in_, cudaStreamNonBlocking));
   RDB_CUDA(cudaStreamCreateWithFlags(&copy_out_, cudaStreamNonBlocking));
   RDB_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
-  for (int s = 0; s < 2; ++s) {
+  for (int s = 0; s < kMaxLanes; ++s) {
     RDB_CUDA(cudaStreamCreateWithFlags(&lane_[s], cudaStreamNonBlocking));
     RDB_CUDA(cudaEventCreateWithFlags(&ev_join_[s], cudaEventDisableTiming));
   }
@@ -235,9 +234,13 @@ void DetEngine::infer(const DetInput& in_host_or_dev, int n, int H, int W, float
   // With device buffers the call stays asynchronous: lanes fork from `st` and join back into it by events.
   const bool any_host = !in_dev || (prob && !prob_dev) || (bitmap && !bm_dev);
   const int n_chunks = (n + chunk - 1) / chunk;
-  const int lanes = (n_chunks >= 2 && !env_is("RDB_LANES", "1")) ? 2 : 1;
+  int lanes = 2;
+  if (const char* e = std::getenv("RDB_LANES")) lanes = std::atoi(e);
+  if (lanes > kMaxLanes) lanes = kMaxLanes;
+  if (lanes > n_chunks) lanes = n_chunks;
+  if (lanes < 1) lanes = 1;
   ensure_streams();
-  Ctx cxs[2];
+  Ctx cxs[kMaxLanes];
   // host staging: kSlots buffers (two per lane), so a chunk's H2D / D2H never stalls the lane that owns the slot
   const int slots = lanes * 2 <= n_chunks ? lanes * 2 : lanes;
   void* d_in[kSlots] = {};
@@ -245,7 +248,7 @@ void DetEngine::infer(const DetInput& in_host_or_dev, int n, int H, int W, float
   uint8_t* d_bm[kSlots] = {};
   // GPU resize (DetPreProcess): coefficient tables once per call
   int *d_xi = nullptr, *d_yi = nullptr; short *d_xa = nullptr, *d_ya = nullptr;
-  uint8_t* d_rs[2] = {nullptr, nullptr};
+  uint8_t* d_rs[kMaxLanes] = {};
   if (do_resize) {
     std::vector<int> xi, yi; std::vector<short> xa, ya;
     linear_coeffs(W, SW, false, xi, xa);

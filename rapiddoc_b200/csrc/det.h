@@ -27,12 +27,13 @@ class DetEngine {
   void forward_chunk(Ctx& cx, const DetInput& in, int n, int H, int W, float thresh, bool dilate, float* prob, uint8_t* bitmap);
   void ensure_streams();
   int device_, precision_;
-  cudaStream_t copy_in_ = nullptr, copy_out_ = nullptr, lane_[2] = {nullptr, nullptr};
-  static constexpr int kSlots = 4;   // host-staging buffers: two per lane, so a lane never waits on its own copies
+  static constexpr int kMaxLanes = 4;
+  cudaStream_t copy_in_ = nullptr, copy_out_ = nullptr, lane_[kMaxLanes] = {};
+  static constexpr int kSlots = 2 * kMaxLanes;   // host-staging buffers: two per lane, so a lane never waits on its own copies
   cudaEvent_t ev_in_[kSlots] = {}, ev_out_[kSlots] = {}, ev_compute_[kSlots] = {};
-  cudaEvent_t ev_join_[2] = {nullptr, nullptr}, ev_fork_ = nullptr;
+  cudaEvent_t ev_join_[kMaxLanes] = {}, ev_fork_ = nullptr;
   std::unique_ptr<Weights> weights_;
-  Pool pools_[2];   // one per compute lane
+  Pool pools_[kMaxLanes];   // one per compute lane
   long long last_launches_ = 0;
   int num_sms_ = 148;
   long long chunk_pixels_ = 16ll * 1024 * 1024;  // pages per internal chunk = chunk_pixels / (H*W)

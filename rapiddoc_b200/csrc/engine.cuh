@@ -225,6 +225,7 @@ inline void launch_tc_store(const tc::Plan& p, const CUtensorMap& mA, const CUte
     case ACT_NONE: launch_tc_store_act<ACT_NONE>(p, mA, mB, st); break;
     case ACT_RELU: launch_tc_store_act<ACT_RELU>(p, mA, mB, st); break;
     case ACT_GELU: launch_tc_store_act<ACT_GELU>(p, mA, mB, st); break;
+    case ACT_GELUF: launch_tc_store_act<ACT_GELUF>(p, mA, mB, st); break;
     case ACT_SILU: launch_tc_store_act<ACT_SILU>(p, mA, mB, st); break;
     default: throw Error("gemm_tc: bad act");
   }
@@ -351,6 +352,16 @@ struct Ops {
     if constexpr (std::is_same<T, __half>::value && KH == 7 && KW == 7 && ACT == ACT_NONE && !ADD_IN) {
       if (sh == 1 && sw == 1 && in.c % 32 == 0 && !env_is("RDB_DW", "simple")) {
         constexpr int TH = 8, TW = 32, G = 4;
+        if (cx.use_tc && !env_is("RDB_DW7", "f32")) {   // fp16/tcgen05 mode: packed-half row taps, fp32 accumulation across rows
+          auto k = dwconv_tiled_h2_kernel<7, G, TH, TW>;
+          const size_t sm = (size_t)(TH + 6) * (TW + 6) * (16 * G + 16) + 49 * G * 16;
+          set_smem(k, sm);
+          dim3 grid(cdiv(in.w, TW), cdiv(in.h, TH), in.n * (in.c / (8 * G)));
+          cx.begin("dwconv7x7_h2[P=" + std::to_string(out.pixels()) + ",C=" + std::to_string(in.c) + ",s=1]");
+          k<<<grid, G * (TW / 4) * TH, sm, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.h, b.d, out.p);
+          cx.end();
+          return;
+        }
         auto k = dwconv_tiled_kernel<T, 7, G, TH, TW>;
         const size_t sm = (size_t)(TH + 6) * (TW + 6) * (16 * G + 16) + 49 * 8 * G * sizeof(float);
         set_smem(k, sm);
@@ -531,7 +542,10 @@ struct Backbone {
       cx.pool->free(gate);
     }
     Act u = O::make(cx, x.n, OH, OW, 2 * c.cin);
-    O::pw(cx, t, w.get(name + "pw1.w"), &w.get(name + "pw1.b"), ACT_GELU, nullptr, u);
+    // fp16/tcgen05 mode: erf-GELU through the 11-instruction sigmoid form (common.cuh gelu_fast, |err| <= 3.4e-6)
+    int gelu = ACT_GELU;
+    if constexpr (std::is_same<T, __half>::value) { if (cx.use_tc && !env_is("RDB_GELU", "exact")) gelu = ACT_GELUF; }
+    O::pw(cx, t, w.get(name + "pw1.w"), &w.get(name + "pw1.b"), gelu, nullptr, u);
     Act y = O::make(cx, x.n, OH, OW, c.cout);
     const bool rep = (c.sh == 1 && c.sw == 1 && c.cin == c.cout);
     O::pw(cx, u, w.get(name + "pw2.w"), &w.get(name + "pw2.b"), ACT_NONE, rep ? t.p : nullptr, y);

@@ -331,6 +331,81 @@ dwconv_tiled_kernel(const T* __restrict__ in, int N, int H, int W, int C, const 
   }
 }
 
+// Packed-half variant of the tiled depthwise conv for the 7x7 RepLK kernels (fp16 storage mode only).  The fp32 kernel
+// above is instruction-issue bound (49 FFMA + ~18 half->float converts per output element, ncu: 61% issue slots, 9% DRAM);
+// here the K horizontal taps of one kernel row run as HFMA2 on channel PAIRS (inputs already sit in smem as half2, weights
+// staged as half2) and every row's K-term partial sum is flushed into the fp32 accumulators, so the fp16 accumulation depth
+// is K = 7, never K*K: per 4x8 output strip and row 112 HFMA2 + 64 convert/add instead of 224 FFMA + 80 converts.
+template <int K, int G, int TH, int TW>
+__global__ void __launch_bounds__(G * (TW / 4) * TH)
+dwconv_tiled_h2_kernel(const __half* __restrict__ in, int N, int H, int W, int C, const __half* __restrict__ w /*[K][K][C]*/,
+                       const float* __restrict__ b, __half* __restrict__ out) {
+  constexpr int HH = TH + K - 1, HW = TW + K - 1;
+  constexpr int PITCH = 16 * G + 16;                 // bytes per staged pixel
+  constexpr int XS = TW / 4;
+  extern __shared__ __align__(16) uint8_t dsm[];
+  uint8_t* tile = dsm;                                // [HH][HW][PITCH]
+  uint4* sw = reinterpret_cast<uint4*>(dsm + HH * HW * PITCH);  // [K*K][G] x 8 halves
+  const int cblocks = C / (8 * G);
+  const int cb = blockIdx.z % cblocks, n = blockIdx.z / cblocks;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  const int c0 = cb * 8 * G;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < K * K * G; i += blockDim.x) sw[i] = *reinterpret_cast<const uint4*>(w + (i / G) * C + c0 + (i % G) * 8);
+  for (int i = tid; i < HH * HW * G; i += blockDim.x) {
+    const int g = i % G, p = i / G;
+    const int hx = p % HW, hy = p / HW;
+    const int iy = y0 + hy - K / 2, ix = x0 + hx - K / 2;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = *reinterpret_cast<const uint4*>(in + (((long long)n * H + iy) * W + ix) * C + c0 + g * 8);
+    *reinterpret_cast<uint4*>(tile + (hy * HW + hx) * PITCH + g * 16) = v;
+  }
+  __syncthreads();
+  const int g = tid % G, xs = (tid / G) % XS, ty = tid / (G * XS);
+  float acc[4][8];
+  {
+    float4 b0 = __ldg(reinterpret_cast<const float4*>(b + c0 + g * 8));
+    float4 b1 = __ldg(reinterpret_cast<const float4*>(b + c0 + g * 8 + 4));
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      acc[o][0] = b0.x; acc[o][1] = b0.y; acc[o][2] = b0.z; acc[o][3] = b0.w;
+      acc[o][4] = b1.x; acc[o][5] = b1.y; acc[o][6] = b1.z; acc[o][7] = b1.w;
+    }
+  }
+#pragma unroll 1
+  for (int ky = 0; ky < K; ++ky) {
+    uint4 iv[K + 3];
+#pragma unroll
+    for (int i = 0; i < K + 3; ++i) iv[i] = *reinterpret_cast<const uint4*>(tile + ((ty + ky) * HW + xs * 4 + i) * PITCH + g * 16);
+    __half2 r[4][4];
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) {
+      const uint4 wv = sw[(ky * K + kx) * G + g];
+      const __half2* wp = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const __half2* hp = reinterpret_cast<const __half2*>(&iv[o + kx]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) r[o][q] = kx == 0 ? __hmul2(hp[q], wp[q]) : __hfma2(hp[q], wp[q], r[o][q]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __half22float2(r[o][q]);
+        acc[o][2 * q] += f.x; acc[o][2 * q + 1] += f.y;
+      }
+  }
+  const int oy = y0 + ty;
+  if (oy >= H) return;
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    const int ox = x0 + xs * 4 + o;
+    if (ox < W) Vec8<__half>::store(out + (((long long)n * H + oy) * W + ox) * C + c0 + g * 8, acc[o]);
+  }
+}
+
 // =====================================================================================
 // Squeeze-excitation: deterministic two-stage global average pool, the two tiny FCs and
 // the gate.  rec_lcnetv4.py:120-142 (gate = clip(x/6+.5,0,1)), db_fpn.py:288-308
