@@ -63,7 +63,20 @@ void DetEngine::forward_chunk(Ctx& cx, const DetInput& in, int n, int H, int W, 
   const int e1_wp = wide ? W1 + 1 : W1;
   Act e1 = O::make(cx, n, H1, e1_wp, 24);
   e1.w = W1; e1.wp = wide ? e1_wp : 0;
-  {
+  bool stem1_tc = false;
+  if constexpr (std::is_same<T, __half>::value) {
+    if (cx.use_tc && !env_is("RDB_STEM1", "simt")) {
+      stem1_tc = true;
+      if (in.f32 != nullptr) {
+        InF32NCHW src{in.f32, H, W};
+        launch_stem1_tc<InF32NCHW, 24>(cx, src, n, w.get("stem1.w"), w.get("stem1.b"), e1.p, H1, W1, e1_wp);
+      } else {
+        InU8HWC src{in.u8, H, W, 0, {in.mean[0], in.mean[1], in.mean[2]}, {in.stdv[0], in.stdv[1], in.stdv[2]}, nullptr};
+        launch_stem1_tc<InU8HWC, 24>(cx, src, n, w.get("stem1.w"), w.get("stem1.b"), e1.p, H1, W1, e1_wp);
+      }
+    }
+  }
+  if (!stem1_tc) {
     long long total = (long long)n * H1 * e1_wp;
     cx.begin("stem1");
     if (in.f32 != nullptr) {

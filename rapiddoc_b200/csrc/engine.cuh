@@ -556,3 +556,5 @@ struct Backbone {
 };
 
 }  // namespace rdb
+
+#include "stem_tc.cuh"

@@ -19,6 +19,14 @@ struct InF32NCHW {
   }
   __device__ __forceinline__ float norm(int, int) const { return 0.f; }
   __device__ __forceinline__ float look(const float*, int n, int y, int xx, int c) const { return get(n, y, xx, c); }
+  // the 3 pixels x 3 channels [ix0, ix0+3) of row iy as the 9 consecutive K entries (kx*3+ci) of one conv row; 0 outside
+  __device__ __forceinline__ void row9(const float*, int n, int iy, int ix0, float (&v)[9]) const {
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const int ix = ix0 + j / 3;
+      v[j] = (ix >= 0 && ix < W) ? get(n, iy, ix, j % 3) : 0.f;
+    }
+  }
 };
 // norm_mode 0: (v*(1/255) - mean)/std   (DetPreProcess)
 // norm_mode 1: (v/255 - 0.5)/0.5        (resize_norm_img); pixels with xx >= valid_w[n] are 0 (right pad)
@@ -34,6 +42,15 @@ struct InU8HWC {
   __device__ __forceinline__ float look(const float* lut, int n, int y, int xx, int c) const {
     if (norm_mode != 0 && valid_w != nullptr && xx >= valid_w[n]) return 0.f;
     return lut[c * 256 + x[(((long long)n * H + y) * W + xx) * 3 + c]];
+  }
+  __device__ __forceinline__ void row9(const float* lut, int n, int iy, int ix0, float (&v)[9]) const {
+    const uint8_t* p = x + (((long long)n * H + iy) * W + ix0) * 3;    // 9 consecutive bytes (ix0 may be -1: guarded below)
+    const int wlim = (norm_mode != 0 && valid_w != nullptr) ? min(W, valid_w[n]) : W;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const int ix = ix0 + j / 3;
+      v[j] = (ix >= 0 && ix < wlim) ? lut[(j % 3) * 256 + __ldg(p + j)] : 0.f;
+    }
   }
 };
 
