@@ -130,6 +130,9 @@ def algorithmic_bytes(name, esz, wl, n_chunk):
         return a["P"] * a["C"] * esz * (1 + a.get("s", 1))       # stride-s input is s x the output
     if base in ("stem2a", "stem2b", "head_conv3x3") and "P" in a:
         return a["P"] * (a["C"] + a["N"]) * esz                    # stride-1 dense convs: in + out once
+    if base in ("stem_fused", "stem_planar"):
+        c1 = 24 if wl["h"] > 48 else 48
+        return a["P"] * (4 * c1 + 2 * c1) * esz                    # e1 read once (4 px per output px), stem4 output written once
     if base == "stem3" and "P" in a:
         return (4 * a["P"] * a["C"] + a["P"] * a["N"]) * esz       # 3x3 stride 2
     if base == "head_tail" and "P" in a:

@@ -438,6 +438,11 @@ struct Ops {
 };
 
 
+}  // namespace rdb
+#include "stem_fused.cuh"
+#include "stem_planar.cuh"
+namespace rdb {
+
 // PPLCNetV4 block table (cin, cout, stride_h, stride_w, se) — rec_lcnetv4.py:7-43
 struct BlockCfg { int cin, cout, sh, sw, se; };
 
@@ -457,6 +462,15 @@ struct Backbone {
     bool tc_path = false;
     if constexpr (std::is_same<T, __half>::value) tc_path = cx.use_tc && !env_is("RDB_CONV", "simt");
     RDB_CHECK(tc_path || e1.wp == 0, "stem: row-padded input needs the tcgen05 conv path");
+    if constexpr (std::is_same<T, __half>::value && C1 == 24) {
+      if (tc_path && !env_is("RDB_STEM", "unfused")) {   // stem2a .. stem4 in one kernel, intermediates in shared memory
+        Act x = O::make(cx, n, H2, W2, C2);
+        if (env_is("RDB_STEM", "copy")) launch_stem_fused<C1>(cx, w, e1.p, n, H1, W1, e1.pitch(), x.p, H2, W2);   // im2col-copy variant
+        else launch_stem_planar<C1>(cx, w, e1.p, n, H1, W1, e1.pitch(), x.p, H2, W2);
+        O::release(cx, e1);
+        return x;
+      }
+    }
     Act cat = O::make(cx, n, H1, W1, C2);
     Act s3 = O::make(cx, n, H2, W2, C1);
     if (tc_path) {
