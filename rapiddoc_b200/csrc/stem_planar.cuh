@@ -85,6 +85,19 @@ __device__ __forceinline__ uint64_t planar_desc(uint32_t saddr, uint32_t lbo, ui
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
 }
 
+// tcgen05.mma with the two smem descriptors passed as 32-bit halves: the issuing thread only ever adds a constant to the
+// low word (start address in 16-byte units; LBO sits above it) — the single-thread issue rate is what bounds this kernel
+__device__ __forceinline__ void umma_f16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 template <int C1>
 __global__ void __launch_bounds__(kStemThreads + 32, 1) stem_planar_kernel(const StemArgs g) {
   using S = PlanarCfg<C1>;
@@ -129,79 +142,116 @@ __global__ void __launch_bounds__(kStemThreads + 32, 1) stem_planar_kernel(const
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   auto idesc = [](int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); };
+  int n_mark = 0;
+  const int who = tid == 0 ? 0 : (tid == kStemThreads ? 1 : (tid == kStemThreads - 1 ? 2 : -1));
+  auto mark = [&](int t) {
+    if (g.dbg != nullptr && who >= 0 && blockIdx.x == 0 && t == (int)gridDim.x && n_mark < 128) g.dbg[who * 128 + n_mark++] = clock64();
+  };
 
   if (warp == kStemThreads / 32) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      const uint32_t aE1 = tc::smem_u32(sE1), aAT = tc::smem_u32(sAT), aCAT = tc::smem_u32(sCAT), aA2 = tc::smem_u32(sA2);
-      const uint32_t aW2A = tc::smem_u32(sm + S::oW2A), aW2B = tc::smem_u32(sm + S::oW2B), aW3 = tc::smem_u32(sm + S::oW3), aW4 = tc::smem_u32(sm + S::oW4);
-      // B operand K step ks of a 128B-swizzled weight tile with n_pad rows per k-block
-      auto bdesc = [](uint32_t base, int n_pad, int ks) { return tc::make_smem_desc(base + (uint32_t)((ks >> 2) * n_pad * 128), 128) + (uint64_t)(2 * (ks & 3)); };
+      // descriptor words: lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version(1)<<14 | layout<<29
+      const uint32_t loE1 = (tc::smem_u32(sE1) >> 4) | ((uint32_t)(S::EPLANE >> 4) << 16);
+      const uint32_t loAT = (tc::smem_u32(sAT) >> 4) | ((uint32_t)(S::APLANE >> 4) << 16);
+      const uint32_t loCAT = (tc::smem_u32(sCAT) >> 4) | ((uint32_t)(S::CPLANE >> 4) << 16);
+      const uint32_t loA2 = (tc::smem_u32(sA2) >> 4) | ((uint32_t)(S::A2PLANE >> 4) << 16);
+      constexpr uint32_t hiRow = (128u >> 4) | (1u << 14);                       // planar operand, 8-row groups contiguous
+      constexpr uint32_t hiCat = ((uint32_t)(2 * S::CROW) >> 4) | (1u << 14);   // stem3: an 8-row group = one output row = two concat rows apart
+      constexpr uint32_t hiW = (1024u >> 4) | (1u << 14) | (2u << 29);           // weights: 128-byte swizzle k-blocks
+      const uint32_t loW2A = (tc::smem_u32(sm + S::oW2A) >> 4) | (1u << 16), loW2B = (tc::smem_u32(sm + S::oW2B) >> 4) | (1u << 16);
+      const uint32_t loW3 = (tc::smem_u32(sm + S::oW3) >> 4) | (1u << 16), loW4 = (tc::smem_u32(sm + S::oW4) >> 4) | (1u << 16);
+      // K step ks of a weight tile with n_pad rows per 64-wide k-block, in 16-byte units
+      auto wofs = [](int n_pad, int ks) { return (uint32_t)((ks >> 2) * n_pad * 8 + 2 * (ks & 3)); };
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < g.tiles; t += gridDim.x, ph ^= 1u) {
+        mark(t);
         tc::mbar_wait(e1_ready, ph);
         tc::tc_fence_after();
+        mark(t);
         for (int j = 0; j < S::MT2; ++j) {                               // stem2a: 4 taps x ECHP/2 K steps per M-tile
+          const uint32_t aj = loE1 + (uint32_t)(j * 128), dj = tmem_base + (uint32_t)(S::T2 + j * S::N2A);
 #pragma unroll
           for (int tap = 0; tap < 4; ++tap)
 #pragma unroll
-            for (int h = 0; h < S::ECHP / 2; ++h) {
-              const uint32_t a = aE1 + (uint32_t)(2 * h * S::EPLANE + (j * 128 + (tap >> 1) * P + (tap & 1)) * 16);
-              tc::umma_f16(tmem_base + (uint32_t)(S::T2 + j * S::N2A), planar_desc(a, S::EPLANE, 128), bdesc(aW2A, S::N2A, tap * (S::ECHP / 2) + h),
-                           idesc(S::N2A), (tap | h) != 0 ? 1u : 0u);
-            }
+            for (int h = 0; h < S::ECHP / 2; ++h)
+              umma_f16_lh(dj, aj + (uint32_t)(2 * h * (S::EPLANE >> 4) + (tap >> 1) * P + (tap & 1)), hiRow, loW2A + wofs(S::N2A, tap * (S::ECHP / 2) + h), hiW,
+                          idesc(S::N2A), (tap | h) != 0 ? 1u : 0u);
           tc::umma_commit(&done2[j]);
         }
+        mark(t);
         tc::mbar_wait(a_ready, ph);
         tc::tc_fence_after();
+        mark(t);
         for (int j = 0; j < S::MT3; ++j) {                               // stem2b
+          const uint32_t aj = loAT + (uint32_t)(j * 128), dj = tmem_base + (uint32_t)(S::T3 + j * S::N2B);
 #pragma unroll
           for (int tap = 0; tap < 4; ++tap)
 #pragma unroll
-            for (int h = 0; h < S::ACHP / 2; ++h) {
-              const uint32_t a = aAT + (uint32_t)(2 * h * S::APLANE + (j * 128 + (tap >> 1) * P + (tap & 1)) * 16);
-              tc::umma_f16(tmem_base + (uint32_t)(S::T3 + j * S::N2B), planar_desc(a, S::APLANE, 128), bdesc(aW2B, S::N2B, tap * (S::ACHP / 2) + h),
-                           idesc(S::N2B), (tap | h) != 0 ? 1u : 0u);
-            }
+            for (int h = 0; h < S::ACHP / 2; ++h)
+              umma_f16_lh(dj, aj + (uint32_t)(2 * h * (S::APLANE >> 4) + (tap >> 1) * P + (tap & 1)), hiRow, loW2B + wofs(S::N2B, tap * (S::ACHP / 2) + h), hiW,
+                          idesc(S::N2B), (tap | h) != 0 ? 1u : 0u);
           tc::umma_commit(&done3[j]);
         }
+        mark(t);
         tc::mbar_wait(cat_ready, ph);
         tc::tc_fence_after();
+        mark(t);
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {                              // stem3: 3x3 stride 2 on the parity-split concat planes
           const int ky = tap / 3, kx = tap % 3;
 #pragma unroll
-          for (int h = 0; h < S::CCHP / 2; ++h) {
-            const uint32_t a = aCAT + (uint32_t)(2 * h * S::CPLANE + ky * S::CROW + (kx & 1) * S::CPAR + (kx >> 1) * 16);
-            tc::umma_f16(tmem_base + (uint32_t)S::T4, planar_desc(a, S::CPLANE, 2 * S::CROW), bdesc(aW3, S::N3, tap * (S::CCHP / 2) + h), idesc(S::N3),
-                         (tap | h) != 0 ? 1u : 0u);
-          }
+          for (int h = 0; h < S::CCHP / 2; ++h)
+            umma_f16_lh(tmem_base + (uint32_t)S::T4, loCAT + (uint32_t)((2 * h * S::CPLANE + ky * S::CROW + (kx & 1) * S::CPAR + (kx >> 1) * 16) >> 4), hiCat,
+                        loW3 + wofs(S::N3, tap * (S::CCHP / 2) + h), hiW, idesc(S::N3), (tap | h) != 0 ? 1u : 0u);
         }
         tc::umma_commit(done4);
+        mark(t);
         tc::mbar_wait(a2_ready, ph);
         tc::tc_fence_after();
+        mark(t);
 #pragma unroll
         for (int h = 0; h < S::ECHP / 2; ++h)                            // stem4: 1x1
-          tc::umma_f16(tmem_base + (uint32_t)S::T5, planar_desc(aA2 + (uint32_t)(2 * h * S::A2PLANE), S::A2PLANE, 128), bdesc(aW4, S::N4, h), idesc(S::N4),
-                       h != 0 ? 1u : 0u);
+          umma_f16_lh(tmem_base + (uint32_t)S::T5, loA2 + (uint32_t)(2 * h * (S::A2PLANE >> 4)), hiRow, loW4 + wofs(S::N4, h), hiW, idesc(S::N4), h != 0 ? 1u : 0u);
         tc::umma_commit(done5);
+        mark(t);
       }
     }
   } else {
     // ================= workers: halo load, pool, epilogues =================
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
     auto wait_done = [&](uint64_t* b, uint32_t ph) { tc::mbar_wait(b, ph); __syncwarp(); tc::tc_fence_after(); };
+    // tile-invariant gather tables (registers): which halo pixels / pool outputs this thread owns
+    constexpr int NPE = S::ER_H * S::ER_W, NPC = S::CR_H * S::CR_W;
+    constexpr int LDI = (NPE * S::ECH + kStemThreads - 1) / kStemThreads, PLI = (NPC * S::ECH + kStemThreads - 1) / kStemThreads;
+    int ld_yx[LDI], pl_yx[PLI];
+    uint32_t ld_dst[LDI], pl_src[PLI], pl_dst[PLI];
+#pragma unroll
+    for (int k = 0; k < LDI; ++k) {
+      const int i = tid + k * kStemThreads;
+      const int p = i % NPE, c = i / NPE, py = p / S::ER_W, px = p % S::ER_W;   // consecutive threads -> consecutive pixels of one plane
+      ld_yx[k] = i < NPE * S::ECH ? (py | (px << 8) | (c << 16)) : -1;
+      ld_dst[k] = (uint32_t)(c * S::EPLANE + p * 16);
+    }
+#pragma unroll
+    for (int k = 0; k < PLI; ++k) {
+      const int i = tid + k * kStemThreads;
+      const int p = i % NPC, c = i / NPC, py = p / S::CR_W, px = p % S::CR_W;
+      pl_yx[k] = i < NPC * S::ECH ? (py | (px << 8)) : -1;
+      pl_src[k] = (uint32_t)(c * S::EPLANE + (py * P + px) * 16);
+      pl_dst[k] = (uint32_t)(c * S::CPLANE + py * S::CROW + (px & 1) * S::CPAR + (px >> 1) * 16);
+    }
     auto load_e1 = [&](int t) {
       const int tx = t % g.tiles_x, ty = (t / g.tiles_x) % g.tiles_y, n = t / (g.tiles_x * g.tiles_y);
       const int gy0 = 2 * ty * TY - 1, gx0 = 2 * tx * TX - 1;
       const __half* img = g.e1 + (long long)n * g.H1 * g.e1_pitch * C1;
-      for (int i = tid; i < S::ER_H * S::ER_W * S::ECH; i += kStemThreads) {
-        const int p = i % (S::ER_H * S::ER_W), c = i / (S::ER_H * S::ER_W);     // consecutive threads -> consecutive pixels of one plane
-        const int py = p / S::ER_W, px = p % S::ER_W;
-        const int gy = gy0 + py, gx = gx0 + px;
-        const bool ok = gy >= 0 && gy < g.H1 && gx >= 0 && gx < g.W1;
+#pragma unroll
+      for (int k = 0; k < LDI; ++k) {
+        if (ld_yx[k] < 0) continue;
+        const int gy = gy0 + (ld_yx[k] & 255), gx = gx0 + ((ld_yx[k] >> 8) & 255), c = ld_yx[k] >> 16;
+        const bool ok = (unsigned)gy < (unsigned)g.H1 && (unsigned)gx < (unsigned)g.W1;
         const __half* src = ok ? img + ((gy * g.e1_pitch + gx) * C1 + c * 8) : g.e1;
-        cp_async16(sE1 + c * S::EPLANE + p * 16, src, ok);
+        cp_async16(sE1 + ld_dst[k], src, ok);
       }
     };
     uint32_t ph = 0;
@@ -209,29 +259,33 @@ __global__ void __launch_bounds__(kStemThreads + 32, 1) stem_planar_kernel(const
     for (int t = blockIdx.x; t < g.tiles; t += gridDim.x, ph ^= 1u) {
       const int tx = t % g.tiles_x, ty = (t / g.tiles_x) % g.tiles_y, n = t / (g.tiles_x * g.tiles_y);
       const int gy0 = 2 * ty * TY - 1, gx0 = 2 * tx * TX - 1;   // image coords (stem1 resolution) of region pixel (0,0)
+      mark(t);
       cp_async_wait_all();
       tc::fence_proxy_async();
       tc::tc_fence_before();
       tc::mbar_arrive(e1_ready);
+      mark(t);
       stem_worker_sync();       // the pool below reads halo pixels loaded by other threads
+      mark(t);
       // ---- max-pool 2x2 s1 (ceil_mode, on the zero-padded e1) -> concat planes [0, ECH), overlapping the stem2a MMAs
-      for (int i = tid; i < S::CR_H * S::CR_W * S::ECH; i += kStemThreads) {
-        const int p = i % (S::CR_H * S::CR_W), c = i / (S::CR_H * S::CR_W);
-        const int py = p / S::CR_W, px = p % S::CR_W;
-        const bool inimg = (gy0 + py) >= 0 && (gy0 + py) < g.H1 && (gx0 + px) >= 0 && (gx0 + px) < g.W1;
+#pragma unroll
+      for (int k = 0; k < PLI; ++k) {
+        if (pl_yx[k] < 0) continue;
+        const int gy = gy0 + (pl_yx[k] & 255), gx = gx0 + (pl_yx[k] >> 8);
         uint4 o = make_uint4(0, 0, 0, 0);
-        if (inimg) {
-          const uint8_t* e = sE1 + c * S::EPLANE + (py * P + px) * 16;
+        if ((unsigned)gy < (unsigned)g.H1 && (unsigned)gx < (unsigned)g.W1) {
+          const uint8_t* e = sE1 + pl_src[k];
           const uint4 a0 = *reinterpret_cast<const uint4*>(e), a1 = *reinterpret_cast<const uint4*>(e + 16);
           const uint4 a2 = *reinterpret_cast<const uint4*>(e + P * 16), a3 = *reinterpret_cast<const uint4*>(e + P * 16 + 16);
           const __half2* h0 = reinterpret_cast<const __half2*>(&a0); const __half2* h1 = reinterpret_cast<const __half2*>(&a1);
           const __half2* h2 = reinterpret_cast<const __half2*>(&a2); const __half2* h3 = reinterpret_cast<const __half2*>(&a3);
           __half2* ho = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) ho[k] = __hmax2(__hmax2(h0[k], h1[k]), __hmax2(h2[k], h3[k]));
+          for (int kk = 0; kk < 4; ++kk) ho[kk] = __hmax2(__hmax2(h0[kk], h1[kk]), __hmax2(h2[kk], h3[kk]));
         }
-        *reinterpret_cast<uint4*>(sCAT + c * S::CPLANE + py * S::CROW + (px & 1) * S::CPAR + (px >> 1) * 16) = o;
+        *reinterpret_cast<uint4*>(sCAT + pl_dst[k]) = o;
       }
+      mark(t);
       // ---- stem2a epilogue: accumulators -> stem2a planes (pixel index m, pitch P)
       for (int i = sub; i < S::MT2 * S::ACH; i += SUBS) {
         const int j = i / S::ACH, c = i % S::ACH;
@@ -247,12 +301,16 @@ __global__ void __launch_bounds__(kStemThreads + 32, 1) stem_planar_kernel(const
         for (int k = 0; k < 8; ++k) v[k] = inimg ? fmaxf(__uint_as_float(r[k]) + sb2a[c * 8 + k], 0.f) : 0.f;
         Vec8<__half>::store(reinterpret_cast<__half*>(sAT + c * S::APLANE + m * 16), v);
       }
+      mark(t);
       wait_done(&done2[S::MT2 - 1], ph);   // every stem2a MMA has retired: the e1 planes are dead after the pool
       tc::fence_proxy_async();
       tc::tc_fence_before();
       tc::mbar_arrive(a_ready);
-      stem_worker_sync();
+      mark(t);
+      stem_worker_sync();       // pool + stem2a of this tile are done: the halo buffer is free
+      mark(t);
       if (t + (int)gridDim.x < g.tiles) load_e1(t + gridDim.x);
+      mark(t);
       // ---- stem2b epilogue -> concat planes [ECH, 2*ECH)
       for (int i = sub; i < S::MT3 * S::ECH; i += SUBS) {
         const int j = i / S::ECH, c = i % S::ECH;
@@ -271,9 +329,11 @@ __global__ void __launch_bounds__(kStemThreads + 32, 1) stem_planar_kernel(const
       }
       tc::fence_proxy_async();
       tc::tc_fence_before();
+      mark(t);
       tc::mbar_arrive(cat_ready);
       // ---- stem3 epilogue -> A planes of stem4
       wait_done(done4, ph);
+      mark(t);
       for (int c = sub; c < S::ECH; c += SUBS) {
         uint32_t r[8];
         tc::tmem_ld8(tq + (uint32_t)(S::T4 + c * 8), r);
@@ -286,8 +346,10 @@ __global__ void __launch_bounds__(kStemThreads + 32, 1) stem_planar_kernel(const
       tc::fence_proxy_async();
       tc::tc_fence_before();
       tc::mbar_arrive(a2_ready);
+      mark(t);
       // ---- stem4 epilogue -> global
       wait_done(done5, ph);
+      mark(t);
       {
         const int r0 = q * 32 + lane;
         const int oy = ty * TY + r0 / TX, ox = tx * TX + r0 % TX;
@@ -304,6 +366,7 @@ __global__ void __launch_bounds__(kStemThreads + 32, 1) stem_planar_kernel(const
         }
       }
       tc::tc_fence_before();
+      mark(t);
     }
     cp_async_wait_all();
   }
@@ -325,9 +388,23 @@ inline void launch_stem_planar(Ctx& cx, const Weights& w, const __half* e1, int 
   static bool attr_done = false;
   if (!attr_done) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmem)); attr_done = true; }
   const int grid = a.tiles < cx.num_sms ? a.tiles : cx.num_sms;
+  static const bool dbg = std::getenv("RDB_STEM_DBG") != nullptr;
+  if (dbg) { RDB_CUDA(cudaMalloc(&a.dbg, 3 * 128 * sizeof(long long))); RDB_CUDA(cudaMemset(a.dbg, 0, 3 * 128 * sizeof(long long))); }
   cx.begin("stem_planar[P=" + std::to_string((long long)n * H2 * W2) + "]");
   k<<<grid, kStemThreads + 32, S::kSmem, cx.st>>>(a);
   cx.end();
+  if (dbg) {
+    long long h[3 * 128];
+    RDB_CUDA(cudaDeviceSynchronize());
+    RDB_CUDA(cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(a.dbg);
+    const long long t0 = h[0];
+    for (int wv = 0; wv < 3; ++wv) {
+      fprintf(stderr, "stem_dbg who=%d:", wv);
+      for (int i = 0; i < 128 && h[wv * 128 + i] != 0; ++i) fprintf(stderr, " %lld", h[wv * 128 + i] - t0);
+      fprintf(stderr, "\n");
+    }
+  }
 }
 
 }  // namespace rdb
