@@ -153,6 +153,20 @@ void DetEngine::forward_chunk(Ctx& cx, const DetInput& in, int n, int H, int W, 
     ns.f[i] = pq[i].p;
     ns.gate[i] = gates[i];
   }
+  uint8_t* seg = nullptr;
+  if (bitmap != nullptr) seg = dilate ? cx.pool->alloc_t<uint8_t>((size_t)n * H * W) : bitmap;
+  bool head_fused = false;
+  if constexpr (std::is_same<T, __half>::value) {
+    if (cx.use_tc && !env_is("RDB_HEAD", "unfused") && !env_is("RDB_HEAD", "simt") && !env_is("RDB_CONV", "simt")) {
+      // concat + conv3x3 + both transposed convs + sigmoid + threshold in one kernel (head_planar.cuh)
+      const __half* fp[4]; const float* gp[4];
+      for (int i = 0; i < 4; ++i) { fp[i] = pq[i].p; gp[i] = gates[i]; }
+      launch_head_planar(cx, w, fp, gp, n, pq[0].h, pq[0].w, thresh, prob, seg);
+      for (int i = 0; i < 4; ++i) { O::release(cx, pq[i]); cx.pool->free(gates[i]); }
+      head_fused = true;
+    }
+  }
+  if (!head_fused) {
   const int neck_wp = wide ? pq[0].w + 2 : pq[0].w;
   Act neck = O::make(cx, n, pq[0].h, neck_wp, 96);
   neck.w = pq[0].w; neck.wp = wide ? neck_wp : 0;
@@ -191,8 +205,6 @@ void DetEngine::forward_chunk(Ctx& cx, const DetInput& in, int n, int H, int W, 
     cx.end();
   }
   O::release(cx, neck);
-  uint8_t* seg = nullptr;
-  if (bitmap != nullptr) seg = dilate ? cx.pool->alloc_t<uint8_t>((size_t)n * H * W) : bitmap;
   bool tail_tc = false;
   if constexpr (std::is_same<T, __half>::value) {
     if (cx.use_tc && !env_is("RDB_HEAD", "simt")) {
@@ -209,6 +221,7 @@ void DetEngine::forward_chunk(Ctx& cx, const DetInput& in, int n, int H, int W, 
     cx.end();
   }
   O::release(cx, hd);
+  }   // !head_fused
   if (bitmap != nullptr && dilate) {
     long long total = (long long)n * H * (W / 4);
     cx.begin("db_dilate");

@@ -441,6 +441,7 @@ struct Ops {
 }  // namespace rdb
 #include "stem_fused.cuh"
 #include "stem_planar.cuh"
+#include "head_planar.cuh"
 namespace rdb {
 
 // PPLCNetV4 block table (cin, cout, stride_h, stride_w, se) — rec_lcnetv4.py:7-43
