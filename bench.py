@@ -133,6 +133,8 @@ def algorithmic_bytes(name, esz, wl, n_chunk):
     if base in ("stem_fused", "stem_planar"):
         c1 = 24 if wl["h"] > 48 else 48
         return a["P"] * (4 * c1 + 2 * c1) * esz                    # e1 read once (4 px per output px), stem4 output written once
+    if base == "mlp":
+        return a["M"] * (a["C"] + a["N"] + (a["N"] if a.get("res") else 0)) * esz    # block input (+ residual re-read) and output, once each
     if base == "head_planar":
         return int(a["P"] * (24 * esz * (1 + 1 / 4 + 1 / 16 + 1 / 64) + 16 * 5))   # the four 24-ch pyramid maps read once, 4x4 prob f32 + seg u8 written per pixel
     if base == "stem3" and "P" in a:

@@ -442,6 +442,7 @@ struct Ops {
 #include "stem_fused.cuh"
 #include "stem_planar.cuh"
 #include "head_planar.cuh"
+#include "mlp_tc.cuh"
 namespace rdb {
 
 // PPLCNetV4 block table (cin, cout, stride_h, stride_w, se) — rec_lcnetv4.py:7-43
@@ -556,13 +557,27 @@ struct Backbone {
       O::scale(cx, t, gate);
       cx.pool->free(gate);
     }
+    const bool rep = (c.sh == 1 && c.sw == 1 && c.cin == c.cout);
+    if constexpr (std::is_same<T, __half>::value) {
+      // channel mixer (pw1 -> GELU -> pw2 + residual) as one kernel, the 2C-wide intermediate stays in shared memory
+      if (cx.use_tc && !env_is("RDB_MLP", "unfused") && ((c.cin == 48 && (c.cout == 48 || c.cout == 96)) || (c.cin == 96 && c.cout == 96))) {
+        Act y = O::make(cx, x.n, OH, OW, c.cout);
+        const int act = env_is("RDB_GELU", "exact") ? ACT_GELU : ACT_GELUF;
+        const long long M = t.pixels();
+        const Tensor &w1 = w.get(name + "pw1.w"), &b1 = w.get(name + "pw1.b"), &w2 = w.get(name + "pw2.w"), &b2 = w.get(name + "pw2.b");
+        if (c.cin == 48 && c.cout == 48) launch_mlp_tc<48, 48>(cx, t.p, M, w1, b1, w2, b2, rep ? t.p : nullptr, y.p, act);
+        else if (c.cin == 48) launch_mlp_tc<48, 96>(cx, t.p, M, w1, b1, w2, b2, nullptr, y.p, act);
+        else launch_mlp_tc<96, 96>(cx, t.p, M, w1, b1, w2, b2, rep ? t.p : nullptr, y.p, act);
+        O::release(cx, t);
+        return y;
+      }
+    }
     Act u = O::make(cx, x.n, OH, OW, 2 * c.cin);
     // fp16/tcgen05 mode: erf-GELU through the 11-instruction sigmoid form (common.cuh gelu_fast, |err| <= 3.4e-6)
     int gelu = ACT_GELU;
     if constexpr (std::is_same<T, __half>::value) { if (cx.use_tc && !env_is("RDB_GELU", "exact")) gelu = ACT_GELUF; }
     O::pw(cx, t, w.get(name + "pw1.w"), &w.get(name + "pw1.b"), gelu, nullptr, u);
     Act y = O::make(cx, x.n, OH, OW, c.cout);
-    const bool rep = (c.sh == 1 && c.sw == 1 && c.cin == c.cout);
     O::pw(cx, u, w.get(name + "pw2.w"), &w.get(name + "pw2.b"), ACT_NONE, rep ? t.p : nullptr, y);
     O::release(cx, u);
     O::release(cx, t);
