@@ -133,6 +133,8 @@ def algorithmic_bytes(name, esz, wl, n_chunk):
     if base in ("stem_fused", "stem_planar"):
         c1 = 24 if wl["h"] > 48 else 48
         return a["P"] * (4 * c1 + 2 * c1) * esz                    # e1 read once (4 px per output px), stem4 output written once
+    if base == "stem1" and "P" in a:
+        return a["P"] * (4 * 3 + a["N"] * esz)                     # uint8 page (4 input px per output px) in, C1-channel map out
     if base == "mlp":
         return a["M"] * (a["C"] + a["N"] + (a["N"] if a.get("res") else 0)) * esz    # block input (+ residual re-read) and output, once each
     if base == "head_planar":

@@ -250,7 +250,10 @@ void DetEngine::infer(const DetInput& in_host_or_dev, int n, int H, int W, float
   const bool prob_dev = prob ? is_device_ptr(prob) : true;
   const bool bm_dev = bitmap ? is_device_ptr(bitmap) : true;
   // chunk so that one chunk's activations stay a bounded working set
-  long long px_budget = chunk_pixels_;
+  // device-resident buffers: no copies to overlap, so larger chunks (fewer launches, longer persistent kernels) win;
+  // host buffers keep the smaller chunk so H2D / D2H of neighbouring chunks hide behind compute
+  const bool all_dev = is_device_ptr(src) && (prob == nullptr || is_device_ptr(prob)) && (bitmap == nullptr || is_device_ptr(bitmap));
+  long long px_budget = (all_dev && !chunk_pixels_set_) ? 2 * chunk_pixels_ : chunk_pixels_;
   int chunk = (int)(px_budget / (long long)(H * (long long)W));
   if (chunk < 1) chunk = 1;
   if (chunk > n) chunk = n;

@@ -20,7 +20,7 @@ class DetEngine {
   void infer(const DetInput& in, int n, int H, int W, float thresh, bool dilate, float* prob, uint8_t* bitmap, cudaStream_t st);
   long long last_launches() const { return last_launches_; }
   int device() const { return device_; }
-  void set_chunk_pixels(long long px) { chunk_pixels_ = px; }
+  void set_chunk_pixels(long long px) { chunk_pixels_ = px; chunk_pixels_set_ = true; }
 
  private:
   template <typename T>
@@ -36,6 +36,7 @@ class DetEngine {
   Pool pools_[kMaxLanes];   // one per compute lane
   long long last_launches_ = 0;
   int num_sms_ = 148;
+  bool chunk_pixels_set_ = false;
   long long chunk_pixels_ = 16ll * 1024 * 1024;  // pages per internal chunk = chunk_pixels / (H*W)
 };
 

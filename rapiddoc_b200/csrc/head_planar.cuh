@@ -24,6 +24,7 @@ struct HeadArgs {
   const float* w_fin; const float* b_fin;       // [4][24], [1]
   float thresh; float* prob; uint8_t* seg;      // [N, 4H, 4W]
   int tiles_x, tiles_y, tiles;
+  int dbg;                                      // RDB_HEAD_DBG bit mask (timing experiments only): 1 skip the halo build, 2 skip the tail math, 4 skip the conv MMAs
 };
 
 struct HeadCfg {
@@ -40,8 +41,8 @@ struct HeadCfg {
   static constexpr int oZERO = oA2 + 2 * MT * MCH * A2PLANE;
   static constexpr int oW1 = (oZERO + A2PLANE + 1023) / 1024 * 1024;
   static constexpr int oW2 = oW1 + KB1 * N1 * 128;
-  static constexpr int oF = oW2 + N2 * 128;                      // floats: b_down[24] b_up[24] w_fin[96] b_fin[1]
-  static constexpr int oBAR = (oF + (24 + 24 + 96 + 1) * 4 + 15) / 16 * 16;
+  static constexpr int oF = oW2 + N2 * 128;                      // floats: b_down[24] b_up[24] w_fin[24][4] b_fin[4] gates[2][96]
+  static constexpr int oBAR = (oF + (24 + 24 + 96 + 4 + 192) * 4 + 15) / 16 * 16;
   static constexpr int kBars = 2 + 2 + 2 * MT + 2;
   static constexpr int kSmem = oBAR + kBars * 8 + 16 + 1024;
   static constexpr int T1 = 0, T2 = 2 * MT * N1;                 // TMEM: conv acc [2][MT] x 32, tail acc [2][MT] x 96
@@ -54,7 +55,7 @@ static __global__ void __launch_bounds__(kStemThreads + 32, 1) head_planar_kerne
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* sF = reinterpret_cast<float*>(sm + S::oF);
-  float* sbd = sF; float* sbu = sF + 24; float* swf = sF + 48; float* sbf = sF + 144;
+  float* sbd = sF; float* sbu = sF + 24; float* swf = sF + 48; float* sbf = sF + 144; float* sgate = sF + 148;   // swf: [c][4 final taps]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::oBAR);
   uint64_t* planes_ready = bars;            // [2], one arrival per worker
   uint64_t* a2_ready = bars + 2;            // [2]
@@ -75,7 +76,7 @@ static __global__ void __launch_bounds__(kStemThreads + 32, 1) head_planar_kerne
     planar_fill_w(sm + S::oW1, g.w_down, S::CMID, S::N1, 9, S::CIN, S::CIN);
     planar_fill_w(sm + S::oW2, g.w_up, S::N2, S::N2, 1, S::CMID, 32);
     for (int i = tid; i < 24; i += kStemThreads) { sbd[i] = g.b_down[i]; sbu[i] = g.b_up[i]; }
-    for (int i = tid; i < 96; i += kStemThreads) swf[i] = g.w_fin[i];
+    for (int i = tid; i < 96; i += kStemThreads) swf[(i % 24) * 4 + i / 24] = g.w_fin[i];
     if (tid == 0) sbf[0] = g.b_fin[0];
   }
   tc::fence_proxy_async();
@@ -103,7 +104,7 @@ static __global__ void __launch_bounds__(kStemThreads + 32, 1) head_planar_kerne
         for (int j = 0; j < S::MT; ++j) {
           const uint32_t aj = loPL + (uint32_t)(b * S::CCH * (S::PLANE >> 4) + j * 128), dj = tmem_base + (uint32_t)(S::T1 + (b * S::MT + j) * S::N1);
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap)
+          for (int tap = 0; tap < ((g.dbg & 4) ? 1 : 9); ++tap)
 #pragma unroll
             for (int h = 0; h < S::CCH / 2; ++h)
               umma_f16_lh(dj, aj + (uint32_t)(2 * h * (S::PLANE >> 4) + (tap / 3) * S::PITCH + (tap % 3)), hiRow, loW1 + wofs(S::N1, tap * (S::CCH / 2) + h), hiW, idesc1,
@@ -143,26 +144,36 @@ static __global__ void __launch_bounds__(kStemThreads + 32, 1) head_planar_kerne
       int n, y0, x0;
       tile_xy(it, n, y0, x0);
       uint8_t* pl = sm + S::oPL + (it & 1) * S::CCH * S::PLANE;
-      constexpr int NPX = S::RH * S::PITCH;
-#pragma unroll 2
-      for (int i = tid; i < NPX * S::CCH; i += kStemThreads) {
+      float* gt = sgate + (it & 1) * 96;            // (1 + gate) of this tile's image, concat channel order
+      if (tid < 96 && !(g.dbg & 1)) gt[tid] = __ldg(g.gate[3 - tid / 24] + n * 24 + tid % 24);
+      stem_worker_sync();
+      constexpr int NPX = S::RH * S::PITCH, ITEMS = (NPX * S::CCH + kStemThreads - 1) / kStemThreads;
+      uint4 v[ITEMS];
+#pragma unroll
+      for (int k = 0; k < ITEMS; ++k) {             // all global loads of this thread in flight before the first use
+        const int i = tid + k * kStemThreads;
         const int c = i / NPX, p = i % NPX;
         const int gy = y0 - 1 + (p >> 5), gx = x0 - 1 + (p & 31);
-        uint4 o = make_uint4(0, 0, 0, 0);
-        if ((unsigned)gy < (unsigned)g.H && (unsigned)gx < (unsigned)g.W) {
-          const int L = 3 - c / 3, c8 = (c % 3) * 8;
-          const int h = g.H >> L, w = g.W >> L;
-          const uint4 v = __ldg(reinterpret_cast<const uint4*>(g.f[L] + (((long long)n * h + (gy >> L)) * w + (gx >> L)) * 24 + c8));
-          const float4 g0 = __ldg(reinterpret_cast<const float4*>(g.gate[L] + n * 24 + c8));
-          const float4 g1 = __ldg(reinterpret_cast<const float4*>(g.gate[L] + n * 24 + c8 + 4));
-          const __half2* hv = reinterpret_cast<const __half2*>(&v);
-          __half2* ho = reinterpret_cast<__half2*>(&o);
-          float2 f;
-          f = __half22float2(hv[0]); ho[0] = __floats2half2_rn(f.x * g0.x, f.y * g0.y);
-          f = __half22float2(hv[1]); ho[1] = __floats2half2_rn(f.x * g0.z, f.y * g0.w);
-          f = __half22float2(hv[2]); ho[2] = __floats2half2_rn(f.x * g1.x, f.y * g1.y);
-          f = __half22float2(hv[3]); ho[3] = __floats2half2_rn(f.x * g1.z, f.y * g1.w);
+        v[k] = make_uint4(0, 0, 0, 0);
+        if (i < NPX * S::CCH && !(g.dbg & 1) && (unsigned)gy < (unsigned)g.H && (unsigned)gx < (unsigned)g.W) {
+          const int L = 3 - c / 3;
+          v[k] = __ldg(reinterpret_cast<const uint4*>(g.f[L] + (((long long)n * (g.H >> L) + (gy >> L)) * (g.W >> L) + (gx >> L)) * 24 + (c % 3) * 8));
         }
+      }
+#pragma unroll
+      for (int k = 0; k < ITEMS; ++k) {
+        const int i = tid + k * kStemThreads;
+        if (i >= NPX * S::CCH) break;
+        const int c = i / NPX, p = i % NPX;
+        const float4 g0 = *reinterpret_cast<const float4*>(gt + c * 8), g1 = *reinterpret_cast<const float4*>(gt + c * 8 + 4);
+        const __half2* hv = reinterpret_cast<const __half2*>(&v[k]);
+        uint4 o;
+        __half2* ho = reinterpret_cast<__half2*>(&o);
+        float2 f;
+        f = __half22float2(hv[0]); ho[0] = __floats2half2_rn(f.x * g0.x, f.y * g0.y);
+        f = __half22float2(hv[1]); ho[1] = __floats2half2_rn(f.x * g0.z, f.y * g0.w);
+        f = __half22float2(hv[2]); ho[2] = __floats2half2_rn(f.x * g1.x, f.y * g1.y);
+        f = __half22float2(hv[3]); ho[3] = __floats2half2_rn(f.x * g1.z, f.y * g1.w);
         *reinterpret_cast<uint4*>(pl + c * S::PLANE + p * 16) = o;
       }
       tc::fence_proxy_async();
@@ -195,7 +206,7 @@ static __global__ void __launch_bounds__(kStemThreads + 32, 1) head_planar_kerne
       tile_xy(it, n, y0, x0);
       wait_done(&tail_done[b], (uint32_t)(it >> 1) & 1u);
       const int W4 = 4 * g.W;
-      for (int j = 0; j < S::MT; ++j) {
+      for (int j = 0; j < ((g.dbg & 2) ? 0 : S::MT); ++j) {
         uint32_t r16[16], r8[8];
         const uint32_t ta = tq + (uint32_t)(S::T2 + (b * S::MT + j) * S::N2 + 24 * sub);
         tc::tmem_ld16(ta, r16);
@@ -207,8 +218,8 @@ static __global__ void __launch_bounds__(kStemThreads + 32, 1) head_planar_kerne
         for (int c = 0; c < 24; ++c) {
           const float acc = __uint_as_float(c < 16 ? r16[c < 16 ? c : 0] : r8[c >= 16 ? c - 16 : 0]);
           const float hv = fmaxf(acc + sbu[c], 0.f);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) o[k] = fmaf(hv, swf[k * 24 + c], o[k]);
+          const float4 wf = *reinterpret_cast<const float4*>(swf + c * 4);
+          o[0] = fmaf(hv, wf.x, o[0]); o[1] = fmaf(hv, wf.y, o[1]); o[2] = fmaf(hv, wf.z, o[2]); o[3] = fmaf(hv, wf.w, o[3]);
         }
         const int m = j * 128 + q * 32 + lane;
         const int y = y0 + (m >> 5), x = x0 + (m & 31);
@@ -253,6 +264,7 @@ inline void launch_head_planar(Ctx& cx, const Weights& w, const __half* const* f
   a.w_up = w.get("head.up.w").h; a.b_up = w.get("head.up.b").d;
   a.w_fin = w.get("head.final.w").d; a.b_fin = w.get("head.final.b").d;
   a.thresh = thresh; a.prob = prob; a.seg = seg;
+  if (const char* e = std::getenv("RDB_HEAD_DBG")) a.dbg = std::atoi(e);
   a.tiles_x = (W + S::TW - 1) / S::TW; a.tiles_y = (H + S::TH - 1) / S::TH; a.tiles = n * a.tiles_x * a.tiles_y;
   auto k = head_planar_kernel;
   static bool attr_done = false;

@@ -139,7 +139,7 @@ inline void launch_stem1_tc(Ctx& cx, const IN& src, int n, const Tensor& w, cons
   const int tiles = cdiv(total, 128);
   int grid = cx.num_sms * 8;
   if (grid > tiles) grid = tiles;
-  cx.begin("stem1_tc");
+  cx.begin("stem1_tc[P=" + std::to_string((long long)n * OH * OW) + ",N=" + std::to_string(C1) + "]");
   stem1_tc_kernel<IN, C1><<<grid, 128, 0, cx.st>>>(src, n, w.h, b.d, out, OH, OW, out_wp, tiles);
   cx.end();
 }
