@@ -19,6 +19,11 @@ struct InF32NCHW {
   }
   __device__ __forceinline__ float norm(int, int) const { return 0.f; }
   __device__ __forceinline__ float look(const float*, int n, int y, int xx, int c) const { return get(n, y, xx, c); }
+  __device__ __forceinline__ bool row_inside(int, int ix0) const { return ix0 >= 0 && ix0 + 2 < W; }
+  __device__ __forceinline__ void row9_fast(const float*, int n, int iy, int ix0, float (&v)[9]) const {
+#pragma unroll
+    for (int j = 0; j < 9; ++j) v[j] = get(n, iy, ix0 + j / 3, j % 3);
+  }
   // the 3 pixels x 3 channels [ix0, ix0+3) of row iy as the 9 consecutive K entries (kx*3+ci) of one conv row; 0 outside
   __device__ __forceinline__ void row9(const float*, int n, int iy, int ix0, float (&v)[9]) const {
 #pragma unroll
@@ -42,6 +47,16 @@ struct InU8HWC {
   __device__ __forceinline__ float look(const float* lut, int n, int y, int xx, int c) const {
     if (norm_mode != 0 && valid_w != nullptr && xx >= valid_w[n]) return 0.f;
     return lut[c * 256 + x[(((long long)n * H + y) * W + xx) * 3 + c]];
+  }
+  // interior pixels: all three taps of the row are inside the (valid part of the) image -> 9 unpredicated byte loads
+  __device__ __forceinline__ bool row_inside(int n, int ix0) const {
+    const int wlim = (norm_mode != 0 && valid_w != nullptr) ? min(W, valid_w[n]) : W;
+    return ix0 >= 0 && ix0 + 2 < wlim;
+  }
+  __device__ __forceinline__ void row9_fast(const float* lut, int n, int iy, int ix0, float (&v)[9]) const {
+    const uint8_t* p = x + (((long long)n * H + iy) * W + ix0) * 3;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) v[j] = lut[(j % 3) * 256 + __ldg(p + j)];
   }
   __device__ __forceinline__ void row9(const float* lut, int n, int iy, int ix0, float (&v)[9]) const {
     const uint8_t* p = x + (((long long)n * H + iy) * W + ix0) * 3;    // 9 consecutive bytes (ix0 may be -1: guarded below)

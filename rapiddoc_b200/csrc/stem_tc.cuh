@@ -62,12 +62,14 @@ stem1_tc_kernel(IN in, int N, const __half* __restrict__ wh /*[C1][27] = [co][ky
     {
       __half2* hp = reinterpret_cast<__half2*>(row);
       float v[28];
+      const bool xin = real && in.row_inside(n, ox * 2 - 1);
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int iy = oy * 2 - 1 + ky;
         if (real && iy >= 0 && iy < in.H) {
           float r9[9];
-          in.row9(lut, n, iy, ox * 2 - 1, r9);
+          if (xin) in.row9_fast(lut, n, iy, ox * 2 - 1, r9);
+          else in.row9(lut, n, iy, ox * 2 - 1, r9);
 #pragma unroll
           for (int j = 0; j < 9; ++j) v[ky * 9 + j] = r9[j];
         } else {
