@@ -1,5 +1,5 @@
 #!/bin/bash
-# copy the judged artefacts of the last gpurun calls from gpurun_out/ (scratch) into profiles/ (tracked)
+# copy the judged artefacts of the last tools/collect_gpu.sh run from gpurun_out/ (scratch) into profiles/ (tracked)
 set -e
 cd "$(dirname "$0")/.."
 R=${1:-r01}
@@ -10,9 +10,11 @@ done
 for f in launches_det launches_rec; do
   [ -s gpurun_out/$f.csv ] && grep -v "^==" gpurun_out/$f.csv > profiles/${R}_ncu_$f.csv
 done
+[ -s gpurun_out/pytest_gpu.log ] && cp gpurun_out/pytest_gpu.log profiles/${R}_pytest_gpu.log
 reps=""
-for f in ncu_dw7 ncu_headconv ncu_gemm_k48 ncu_rec_gemm; do
+for f in ncu_det_top ncu_rec_top; do
   [ -s gpurun_out/$f.ncu-rep ] && reps="$reps gpurun_out/$f.ncu-rep"
 done
 [ -n "$reps" ] && python tools/summarize_ncu.py profiles/${R}_ncu_summary $reps > /dev/null
+python tools/ncu_traffic.py profiles/${R}_ncu_summary.json > profiles/ncu_traffic.json
 ls -la profiles
