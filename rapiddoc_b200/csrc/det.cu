@@ -309,11 +309,15 @@ void DetEngine::infer(const DetInput& in_host_or_dev, int n, int H, int W, float
   // so the un-overlappable first H2D and last D2H are short
   std::vector<int> sched;
   {
-    int head[2] = {chunk / 4, chunk / 2}, rest = n;
-    const bool ramp = any_host && chunk >= 4 && n >= 3 * chunk && !env_is("RDB_RAMP", "0");
-    if (ramp) { sched.push_back(head[0]); sched.push_back(head[1]); rest -= 2 * (head[0] + head[1]); }
+    int rest = n;
+    int ramp = (any_host && chunk >= 4 && n >= 2 * chunk) ? 1 : 0;    // 1: one half-size chunk at each end; 2: quarter + half
+    if (const char* e = std::getenv("RDB_RAMP")) ramp = (any_host && chunk >= 4 && n >= 2 * chunk) ? std::atoi(e) : 0;
+    std::vector<int> head;
+    if (ramp >= 2) head.push_back(chunk / 4);
+    if (ramp >= 1) head.push_back(chunk / 2);
+    for (int h : head) { sched.push_back(h); rest -= 2 * h; }
     while (rest > 0) { const int m = rest < chunk ? rest : chunk; sched.push_back(m); rest -= m; }
-    if (ramp) { sched.push_back(head[1]); sched.push_back(head[0]); }
+    for (int i = (int)head.size() - 1; i >= 0; --i) sched.push_back(head[i]);
   }
   int i0 = 0;
   for (int it = 0; it < (int)sched.size(); i0 += sched[it], ++it) {

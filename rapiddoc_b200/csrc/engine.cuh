@@ -353,12 +353,18 @@ struct Ops {
       if (sh == 1 && sw == 1 && in.c % 32 == 0 && !env_is("RDB_DW", "simple")) {
         constexpr int TH = 8, TW = 32, G = 4;
         if (cx.use_tc && !env_is("RDB_DW7", "f32")) {   // fp16/tcgen05 mode: packed-half row taps, fp32 accumulation across rows
-          auto k = dwconv_tiled_h2_kernel<7, G, TH, TW>;
           const size_t sm = (size_t)(TH + 6) * (TW + 6) * (16 * G + 16) + 49 * G * 16;
-          set_smem(k, sm);
           dim3 grid(cdiv(in.w, TW), cdiv(in.h, TH), in.n * (in.c / (8 * G)));
           cx.begin("dwconv7x7_h2[P=" + std::to_string(out.pixels()) + ",C=" + std::to_string(in.c) + ",s=1]");
-          k<<<grid, G * (TW / 4) * TH, sm, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.h, b.d, out.p);
+          if (env_is("RDB_DW7_ROWS", "2")) {   // experiment: two kernel rows (14 taps) per fp16 partial sum
+            auto k = dwconv_tiled_h2_kernel<7, G, TH, TW, 2>;
+            set_smem(k, sm);
+            k<<<grid, G * (TW / 4) * TH, sm, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.h, b.d, out.p);
+          } else {
+            auto k = dwconv_tiled_h2_kernel<7, G, TH, TW, 1>;
+            set_smem(k, sm);
+            k<<<grid, G * (TW / 4) * TH, sm, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.h, b.d, out.p);
+          }
           cx.end();
           return;
         }
@@ -383,6 +389,14 @@ struct Ops {
         const size_t sm = (size_t)(TH + 2) * (TW + 2) * (16 * G + 16) + 9 * 8 * G * sizeof(float);
         dim3 grid(cdiv(in.w, TW), cdiv(in.h, TH), in.n * (in.c / (8 * G)));
         const int threads = G * (TW / 4) * TH;
+        if (cx.use_tc && env_is("RDB_DW3", "h2") && g4 && TH == 8) {   // experiment: packed-half 3x3, all 9 taps in one fp16 partial sum
+          auto k = dwconv_tiled_h2_kernel<3, 4, 8, 32, 3>;
+          const size_t smh = (size_t)(8 + 2) * (32 + 2) * (16 * 4 + 16) + 9 * 4 * 16;
+          cx.begin("dwconv3x3_h2[P=" + std::to_string(out.pixels()) + ",C=" + std::to_string(in.c) + ",s=1]");
+          k<<<grid, threads, smh, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.h, b.d, out.p);
+          cx.end();
+          return;
+        }
         cx.begin("dwconv3x3_tiled[P=" + std::to_string(out.pixels()) + ",C=" + std::to_string(in.c) + ",s=1]");
 #define RDB_DW3(GG, TTH, TTW) dwconv_tiled_kernel<T, 3, GG, TTH, TTW><<<grid, threads, sm, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.d, b.d, out.p)
         if (g4) {

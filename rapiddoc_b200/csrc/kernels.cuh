@@ -368,7 +368,7 @@ dwconv_tiled_kernel(const T* __restrict__ in, int N, int H, int W, int C, const 
 // here the K horizontal taps of one kernel row run as HFMA2 on channel PAIRS (inputs already sit in smem as half2, weights
 // staged as half2) and every row's K-term partial sum is flushed into the fp32 accumulators, so the fp16 accumulation depth
 // is K = 7, never K*K: per 4x8 output strip and row 112 HFMA2 + 64 convert/add instead of 224 FFMA + 80 converts.
-template <int K, int G, int TH, int TW>
+template <int K, int G, int TH, int TW, int ROWS>
 __global__ void __launch_bounds__(G * (TW / 4) * TH)
 dwconv_tiled_h2_kernel(const __half* __restrict__ in, int N, int H, int W, int C, const __half* __restrict__ w /*[K][K][C]*/,
                        const float* __restrict__ b, __half* __restrict__ out) {
@@ -404,21 +404,29 @@ dwconv_tiled_h2_kernel(const __half* __restrict__ in, int N, int H, int W, int C
       acc[o][4] = b1.x; acc[o][5] = b1.y; acc[o][6] = b1.z; acc[o][7] = b1.w;
     }
   }
+  // ROWS kernel rows share one packed-half partial sum before it is flushed into the fp32 accumulators
+  // (fp16 accumulation depth = ROWS*K taps)
 #pragma unroll 1
-  for (int ky = 0; ky < K; ++ky) {
-    uint4 iv[K + 3];
-#pragma unroll
-    for (int i = 0; i < K + 3; ++i) iv[i] = *reinterpret_cast<const uint4*>(tile + ((ty + ky) * HW + xs * 4 + i) * PITCH + g * 16);
+  for (int ky0 = 0; ky0 < K; ky0 += ROWS) {
     __half2 r[4][4];
 #pragma unroll
-    for (int kx = 0; kx < K; ++kx) {
-      const uint4 wv = sw[(ky * K + kx) * G + g];
-      const __half2* wp = reinterpret_cast<const __half2*>(&wv);
+    for (int kr = 0; kr < ROWS; ++kr) {
+      const int ky = ky0 + kr;
+      if (ky < K) {
+        uint4 iv[K + 3];
 #pragma unroll
-      for (int o = 0; o < 4; ++o) {
-        const __half2* hp = reinterpret_cast<const __half2*>(&iv[o + kx]);
+        for (int i = 0; i < K + 3; ++i) iv[i] = *reinterpret_cast<const uint4*>(tile + ((ty + ky) * HW + xs * 4 + i) * PITCH + g * 16);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) r[o][q] = kx == 0 ? __hmul2(hp[q], wp[q]) : __hfma2(hp[q], wp[q], r[o][q]);
+        for (int kx = 0; kx < K; ++kx) {
+          const uint4 wv = sw[(ky * K + kx) * G + g];
+          const __half2* wp = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            const __half2* hp = reinterpret_cast<const __half2*>(&iv[o + kx]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) r[o][q] = (kr == 0 && kx == 0) ? __hmul2(hp[q], wp[q]) : __hfma2(hp[q], wp[q], r[o][q]);
+          }
+        }
       }
     }
 #pragma unroll

@@ -45,7 +45,10 @@ struct PlanarCfg {
   static_assert(TEND <= 512, "stem_planar: TMEM accumulators exceed 512 columns");
   // smem
   static constexpr int oE1 = 0;
-  static constexpr int oAT = oE1 + ECHP * EPLANE;
+#ifndef RDB_STEM_PAD
+#define RDB_STEM_PAD 0
+#endif
+  static constexpr int oAT = oE1 + ECHP * EPLANE + RDB_STEM_PAD;
   static constexpr int oCAT = oAT + ACHP * APLANE;
   static constexpr int oA2 = oCAT + CCHP * CPLANE;
   static constexpr int oTILES_END = oA2 + ECHP * A2PLANE;
