@@ -356,15 +356,9 @@ struct Ops {
           const size_t sm = (size_t)(TH + 6) * (TW + 6) * (16 * G + 16) + 49 * G * 16;
           dim3 grid(cdiv(in.w, TW), cdiv(in.h, TH), in.n * (in.c / (8 * G)));
           cx.begin("dwconv7x7_h2[P=" + std::to_string(out.pixels()) + ",C=" + std::to_string(in.c) + ",s=1]");
-          if (env_is("RDB_DW7_ROWS", "2")) {   // experiment: two kernel rows (14 taps) per fp16 partial sum
-            auto k = dwconv_tiled_h2_kernel<7, G, TH, TW, 2>;
-            set_smem(k, sm);
-            k<<<grid, G * (TW / 4) * TH, sm, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.h, b.d, out.p);
-          } else {
-            auto k = dwconv_tiled_h2_kernel<7, G, TH, TW, 1>;
-            set_smem(k, sm);
-            k<<<grid, G * (TW / 4) * TH, sm, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.h, b.d, out.p);
-          }
+          auto k = dwconv_tiled_h2_kernel<7, G, TH, TW, 1>;
+          set_smem(k, sm);
+          k<<<grid, G * (TW / 4) * TH, sm, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.h, b.d, out.p);
           cx.end();
           return;
         }
@@ -389,11 +383,21 @@ struct Ops {
         const size_t sm = (size_t)(TH + 2) * (TW + 2) * (16 * G + 16) + 9 * 8 * G * sizeof(float);
         dim3 grid(cdiv(in.w, TW), cdiv(in.h, TH), in.n * (in.c / (8 * G)));
         const int threads = G * (TW / 4) * TH;
-        if (cx.use_tc && env_is("RDB_DW3", "h2") && g4 && TH == 8) {   // experiment: packed-half 3x3, all 9 taps in one fp16 partial sum
-          auto k = dwconv_tiled_h2_kernel<3, 4, 8, 32, 3>;
-          const size_t smh = (size_t)(8 + 2) * (32 + 2) * (16 * 4 + 16) + 9 * 4 * 16;
+        if (cx.use_tc && env_is("RDB_DW3", "h2")) {
+          // EXPERIMENT, off by default: packed-half 3x3 taps with fp16-rounded weights.  +2.8 % det / +4.9 % rec, but the 14
+          // backbone blocks compound the extra rounding: max |prob - oracle| reaches 4.3e-2 on a noise page (> the 3e-2 this
+          // mode promises, tools/err_stats.py), so the fp32-FMA kernel below stays the product path
+          const size_t smh = (size_t)(TH + 2) * (TW + 2) * (16 * G + 16) + 9 * G * 16;
           cx.begin("dwconv3x3_h2[P=" + std::to_string(out.pixels()) + ",C=" + std::to_string(in.c) + ",s=1]");
-          k<<<grid, threads, smh, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.h, b.d, out.p);
+#define RDB_DW3H(GG, TTH, TTW) dwconv_tiled_h2_kernel<3, GG, TTH, TTW, 1><<<grid, threads, smh, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.h, b.d, out.p)
+          if (g4) {
+            if (TH == 8) RDB_DW3H(4, 8, 32); else if (TH == 4) RDB_DW3H(4, 4, 32); else if (TH == 12) RDB_DW3H(4, 12, 16);
+            else if (TH == 6) RDB_DW3H(4, 6, 16); else RDB_DW3H(4, 3, 16);
+          } else {
+            if (TH == 8) RDB_DW3H(2, 8, 32); else if (TH == 4) RDB_DW3H(2, 4, 32); else if (TH == 12) RDB_DW3H(2, 12, 16);
+            else if (TH == 6) RDB_DW3H(2, 6, 16); else RDB_DW3H(2, 3, 16);
+          }
+#undef RDB_DW3H
           cx.end();
           return;
         }
