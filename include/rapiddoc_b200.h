@@ -77,6 +77,15 @@ int rdb_det_infer_u8_resize(rdb_det_t* h, const uint8_t* pages, int n, int src_h
 int rdb_resize_linear_u8(int device, const uint8_t* src, int n, int sh, int sw, uint8_t* dst, int dh, int dw,
                          void* stream);
 
+/* get_rotate_crop_image for n text-line quads of ONE page (rapid_doc/utils/ocr_utils.py:494-537, called from
+ * rapid_doc/model/ocr/rapid_ocr.py ocr()/__call__ and backend/pipeline/analyze_utils.py): cv2.warpPerspective(INTER_CUBIC,
+ * BORDER_REPLICATE), bit-exact with OpenCV's fixed-point remap.  page [hgt,wid,3] uint8; minv [n][9] = the dst->src
+ * homography (cv2.invert(cv2.getPerspectiveTransform(quad, rect))[1], row-major double); sizes [n][2] = (crop_w, crop_h) of the
+ * warp output; rotate [n] (may be NULL): 1 = store np.rot90(crop) (the reference rotates crops with h/w >= 2); crop i is
+ * written as a contiguous [h][w][3] (or [w][h][3]) block at byte offsets[i] of out (out_bytes long).  Host or device pointers. */
+int rdb_warp_crops(int device, const uint8_t* page, int hgt, int wid, int n, const double* minv, const int32_t* sizes,
+                   const int32_t* rotate, uint8_t* out, const int64_t* offsets, int64_t out_bytes, void* stream);
+
 /* DBPostProcess binarise (+ optional cv2.dilate 2x2) on an existing prob map [n,h,w]:
  * rapid_doc/model/ocr/ocr_patch.py:228-235. */
 int rdb_db_bitmap(int device, const float* prob, int n, int hgt, int wid, float thresh, int use_dilation,
@@ -130,6 +139,8 @@ int rdb_debug_gemm(int device, int use_tc, int mode, const float* A, const float
 /* per-kernel device timing (CUDA events on the launching stream around every launch of
  * subsequent infer calls; process-wide).  dump writes a JSON object
  * {"kernel": [total_ms, launches], ...} and returns the bytes needed. */
+/* host-only: the 1024 x 16 int16 bicubic weight table rdb_warp_crops uses (OpenCV initInterTab2D(INTER_CUBIC, fixpt)) */
+int rdb_debug_cubic_tab(int16_t* out);
 int rdb_profile_enable(int on);
 int rdb_profile_reset(void);
 int rdb_profile_dump(char* buf, size_t cap);

@@ -28,6 +28,8 @@ SYMBOLS = {
     "rdb_det_infer_u8_resize": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _f, _i, _vp, _vp, _vp]),
     "rdb_resize_linear_u8": (_i, [_i, _vp, _i, _i, _i, _vp, _i, _i, _vp]),
     "rdb_db_bitmap": (_i, [_i, _vp, _i, _i, _i, _f, _i, _vp, _vp]),
+    "rdb_warp_crops": (_i, [_i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, C.c_int64, _vp]),
+    "rdb_debug_cubic_tab": (_i, [_vp]),
     "rdb_clipper_offset": (_i, [C.POINTER(C.c_double), _i, C.c_double, C.POINTER(C.c_int64), _i]),
     "rdb_rec_create": (_i, [_vp, C.c_size_t, _i, _i, C.POINTER(_vp)]),
     "rdb_rec_destroy": (None, [_vp]),

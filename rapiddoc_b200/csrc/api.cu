@@ -8,6 +8,7 @@
 
 #include "det.h"
 #include "rec.h"
+#include "warp.cuh"
 
 struct rdb_det { rdb::DetEngine* e; };
 struct rdb_rec { rdb::RecEngine* e; };
@@ -199,6 +200,25 @@ int rdb_resize_linear_u8(int device, const uint8_t* src, int n, int sh, int sw, 
     RDB_CHECK(src && dst, "null argument");
     require_device(device);
     rdb::resize_linear_u8(device, src, n, sh, sw, dst, dh, dw, (cudaStream_t)stream);
+  });
+}
+
+int rdb_warp_crops(int device, const uint8_t* page, int hgt, int wid, int n, const double* minv, const int32_t* sizes, const int32_t* rotate,
+                   uint8_t* out, const int64_t* offsets, int64_t out_bytes, void* stream) {
+  return guarded([&] {
+    RDB_CHECK(page && out && (n == 0 || (minv && sizes && offsets)), "null argument");
+    RDB_CHECK(hgt > 0 && wid > 0 && n >= 0 && out_bytes >= 0, "warp: bad shape");
+    require_device(device);
+    rdb::warp_crops(device, page, hgt, wid, n, minv, sizes, rotate, out, reinterpret_cast<const long long*>(offsets), (long long)out_bytes, (cudaStream_t)stream);
+  });
+}
+
+int rdb_debug_cubic_tab(int16_t* out) {
+  return guarded([&] {
+    RDB_CHECK(out != nullptr, "null argument");
+    std::vector<short> t;
+    rdb::build_cubic_tab(t);
+    for (size_t i = 0; i < t.size(); ++i) out[i] = t[i];
   });
 }
 

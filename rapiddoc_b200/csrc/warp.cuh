@@ -1,0 +1,151 @@
+// get_rotate_crop_image (rapid_doc/utils/ocr_utils.py:494-537) on the GPU: cv2.warpPerspective(INTER_CUBIC, BORDER_REPLICATE)
+// for a batch of text-line quads of one page, bit-exact with OpenCV's imgwarp.cpp:
+//   * inverse map in double, evaluated per OpenCV block (block origin x first, then + M*x1, in that order, plain IEEE
+//     mul/add — __dmul_rn/__dadd_rn keep nvcc from contracting into FMA), scaled by INTER_TAB_SIZE/W, clamped to int range and
+//     rounded half-to-even into a 5-bit fixed-point source coordinate;
+//   * remapBicubic: 4x4 int16 weights from the 1024-entry table (a = -0.75 cubic, float 1-D tables multiplied in float,
+//     x 2^15, rounded, corrected so each 16 weights sum to 32768), replicate border = clamped indices, (sum + 2^14) >> 15.
+// One thread per destination pixel (3 channels); the optional np.rot90 of tall crops is folded into the store index.
+// The CPU restatement that pins this against cv2 itself is oracle/warp.py (tests/test_oracle.py, tests/test_gpu_warp.py).
+#pragma once
+#include <vector>
+
+#include "engine.cuh"
+
+namespace rdb {
+
+struct WarpCrop {
+  double m[9];          // dst -> src homography (cv::invert of getPerspectiveTransform)
+  int w, h;             // warp output size (before rotation)
+  int rotate;           // 1: store np.rot90(dst) ([w][h][3]) instead of dst ([h][w][3])
+  int bw0;              // OpenCV's block width for this destination size
+  long long offset;     // byte offset of this crop in the output buffer
+};
+
+static __global__ void __launch_bounds__(256) warp_cubic_kernel(const uint8_t* __restrict__ src, int H, int W, const WarpCrop* __restrict__ crops,
+                                                                const short* __restrict__ tab /*[1024][16]*/, uint8_t* __restrict__ out) {
+  const WarpCrop& c = crops[blockIdx.y];
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)c.w * c.h) return;
+  const int x = (int)(idx % c.w), y = (int)(idx / c.w);
+  const int xb = (x / c.bw0) * c.bw0, x1 = x - xb;
+  const double dx = (double)xb, dy = (double)y, d1 = (double)x1;
+  const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(c.m[0], dx), __dmul_rn(c.m[1], dy)), c.m[2]);
+  const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(c.m[3], dx), __dmul_rn(c.m[4], dy)), c.m[5]);
+  const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(c.m[6], dx), __dmul_rn(c.m[7], dy)), c.m[8]);
+  double Wd = __dadd_rn(W0, __dmul_rn(c.m[6], d1));
+  Wd = Wd != 0.0 ? __ddiv_rn(32.0, Wd) : 0.0;
+  const double fX = fmax(-2147483648.0, fmin(2147483647.0, __dmul_rn(__dadd_rn(X0, __dmul_rn(c.m[0], d1)), Wd)));
+  const double fY = fmax(-2147483648.0, fmin(2147483647.0, __dmul_rn(__dadd_rn(Y0, __dmul_rn(c.m[3], d1)), Wd)));
+  const int X = __double2int_rn(fX), Y = __double2int_rn(fY);
+  const int sx = max(-32768, min(32767, X >> 5)) - 1, sy = max(-32768, min(32767, Y >> 5)) - 1;
+  const short* w = tab + (((Y & 31) << 5) + (X & 31)) * 16;
+  int s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+  for (int ky = 0; ky < 4; ++ky) {
+    const int iy = max(0, min(H - 1, sy + ky));
+    const uint8_t* row = src + (long long)iy * W * 3;
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx) {
+      const int ix = max(0, min(W - 1, sx + kx));
+      const int wt = w[ky * 4 + kx];
+      const uint8_t* p = row + ix * 3;
+      s0 += p[0] * wt; s1 += p[1] * wt; s2 += p[2] * wt;
+    }
+  }
+  const long long o = c.rotate ? ((long long)(c.w - 1 - x) * c.h + y) : idx;
+  uint8_t* d = out + c.offset + o * 3;
+  d[0] = (uint8_t)max(0, min(255, (s0 + (1 << 14)) >> 15));
+  d[1] = (uint8_t)max(0, min(255, (s1 + (1 << 14)) >> 15));
+  d[2] = (uint8_t)max(0, min(255, (s2 + (1 << 14)) >> 15));
+}
+
+// initInterTab2D(INTER_CUBIC, fixpt): float arithmetic exactly as OpenCV (no contraction: host code, no FMA ISA enabled)
+inline void build_cubic_tab(std::vector<short>& tab) {
+  float t1[32][4];
+  const float A = -0.75f, scale = 1.f / 32.f;
+  for (int i = 0; i < 32; ++i) {
+    volatile float x = (float)i * scale;
+    volatile float x1 = x + 1.f;
+    volatile float c0 = ((A * x1 - 5.f * A) * x1 + 8.f * A) * x1 - 4.f * A;
+    volatile float c1 = ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f;
+    volatile float xm = 1.f - x;
+    volatile float c2 = ((A + 2.f) * xm - (A + 3.f)) * xm * xm + 1.f;
+    volatile float c3 = 1.f - c0 - c1 - c2;
+    t1[i][0] = c0; t1[i][1] = c1; t1[i][2] = c2; t1[i][3] = c3;
+  }
+  tab.assign(1024 * 16, 0);
+  for (int i = 0; i < 32; ++i)
+    for (int j = 0; j < 32; ++j) {
+      int it[4][4], isum = 0;
+      for (int k1 = 0; k1 < 4; ++k1)
+        for (int k2 = 0; k2 < 4; ++k2) {
+          volatile float v = t1[i][k1] * t1[j][k2];
+          volatile float sv = v * 32768.f;
+          long r = lrintf(sv);                      // cvRound: round half to even (default rounding mode)
+          if (r < -32768) r = -32768;
+          if (r > 32767) r = 32767;
+          it[k1][k2] = (int)r;
+          isum += (int)r;
+        }
+      if (isum != 32768) {
+        const int diff = isum - 32768;
+        int Mk1 = 2, Mk2 = 2, mk1 = 2, mk2 = 2;
+        for (int k1 = 2; k1 < 4; ++k1)
+          for (int k2 = 2; k2 < 4; ++k2) {
+            if (it[k1][k2] < it[mk1][mk2]) { mk1 = k1; mk2 = k2; }
+            else if (it[k1][k2] > it[Mk1][Mk2]) { Mk1 = k1; Mk2 = k2; }
+          }
+        if (diff < 0) it[Mk1][Mk2] -= diff; else it[mk1][mk2] -= diff;
+      }
+      for (int k = 0; k < 16; ++k) tab[(i * 32 + j) * 16 + k] = (short)it[k / 4][k % 4];
+    }
+}
+
+// page [H,W,3] uint8 (host or device); minv [n][9]; sizes [n][2] = (w,h); rotate [n]; offsets [n] bytes into out (host or device)
+inline void warp_crops(int device, const uint8_t* page, int H, int W, int n, const double* minv, const int32_t* sizes, const int32_t* rotate,
+                       uint8_t* out, const long long* offsets, long long out_bytes, cudaStream_t st) {
+  RDB_CUDA(cudaSetDevice(device));
+  if (n <= 0) return;
+  static std::vector<short> host_tab;
+  static short* dev_tab[64] = {};
+  if (host_tab.empty()) build_cubic_tab(host_tab);
+  RDB_CHECK(device >= 0 && device < 64, "warp: device index");
+  if (!dev_tab[device]) {
+    RDB_CUDA(cudaMalloc(&dev_tab[device], host_tab.size() * sizeof(short)));
+    RDB_CUDA(cudaMemcpy(dev_tab[device], host_tab.data(), host_tab.size() * sizeof(short), cudaMemcpyHostToDevice));
+  }
+  std::vector<WarpCrop> hc(n);
+  long long max_px = 0;
+  for (int i = 0; i < n; ++i) {
+    WarpCrop& c = hc[i];
+    for (int k = 0; k < 9; ++k) c.m[k] = minv[i * 9 + k];
+    c.w = sizes[2 * i]; c.h = sizes[2 * i + 1]; c.rotate = rotate ? rotate[i] : 0; c.offset = offsets[i];
+    RDB_CHECK(c.w > 0 && c.h > 0, "warp: empty crop");
+    RDB_CHECK(c.offset >= 0 && c.offset + (long long)c.w * c.h * 3 <= out_bytes, "warp: crop exceeds the output buffer");
+    int bh0 = c.h < 16 ? c.h : 16;                    // WarpPerspectiveInvoker: BLOCK_SZ = 32
+    int bw0 = 1024 / bh0 < c.w ? 1024 / bh0 : c.w;
+    c.bw0 = bw0;
+    const long long px = (long long)c.w * c.h;
+    if (px > max_px) max_px = px;
+  }
+  const bool p_dev = is_device_ptr(page), o_dev = is_device_ptr(out);
+  uint8_t* dp = const_cast<uint8_t*>(page);
+  uint8_t* dout = out;
+  WarpCrop* dc = nullptr;
+  const size_t page_b = (size_t)H * W * 3;
+  if (!p_dev) { RDB_CUDA(cudaMalloc(&dp, page_b)); RDB_CUDA(cudaMemcpyAsync(dp, page, page_b, cudaMemcpyHostToDevice, st)); }
+  if (!o_dev) RDB_CUDA(cudaMalloc(&dout, (size_t)out_bytes));
+  RDB_CUDA(cudaMalloc(&dc, sizeof(WarpCrop) * n));
+  RDB_CUDA(cudaMemcpyAsync(dc, hc.data(), sizeof(WarpCrop) * n, cudaMemcpyHostToDevice, st));
+  dim3 grid((unsigned)((max_px + 255) / 256), (unsigned)n);
+  warp_cubic_kernel<<<grid, 256, 0, st>>>(dp, H, W, dc, dev_tab[device], dout);
+  RDB_LAUNCH_CHECK();
+  if (!o_dev) RDB_CUDA(cudaMemcpyAsync(out, dout, (size_t)out_bytes, cudaMemcpyDeviceToHost, st));
+  RDB_CUDA(cudaStreamSynchronize(st));      // hc / staging buffers are released below
+  cudaFree(dc);
+  if (!p_dev) cudaFree(dp);
+  if (!o_dev) cudaFree(dout);
+}
+
+}  // namespace rdb
