@@ -86,6 +86,14 @@ int rdb_resize_linear_u8(int device, const uint8_t* src, int n, int sh, int sw, 
 int rdb_warp_crops(int device, const uint8_t* page, int hgt, int wid, int n, const double* minv, const int32_t* sizes,
                    const int32_t* rotate, uint8_t* out, const int64_t* offsets, int64_t out_bytes, void* stream);
 
+/* resize_norm_img geometry for one recognition batch (rapidocr TextRecognizer.resize_norm_img as driven by
+ * rapid_doc/model/ocr/rapid_ocr.py:423-440): crop i ([sizes[i][1]][sizes[i][0]][3] uint8 at byte src_offsets[i] of the packed
+ * buffer src, e.g. the output of rdb_warp_crops) is cv2.resize'd (INTER_LINEAR, bit-exact) to hgt x dst_w[i] and written
+ * left-aligned into dst [n][hgt][wid_max][3]; columns >= dst_w[i] are zero.  The (x/255-0.5)/0.5 normalisation and the zero pad
+ * after it are applied by rdb_rec_infer_u8 (valid_w = dst_w).  Host or device pointers. */
+int rdb_resize_pack_u8(int device, const uint8_t* src, int64_t src_bytes, int n, const int64_t* src_offsets, const int32_t* sizes,
+                       const int32_t* dst_w, uint8_t* dst, int hgt, int wid_max, void* stream);
+
 /* DBPostProcess binarise (+ optional cv2.dilate 2x2) on an existing prob map [n,h,w]:
  * rapid_doc/model/ocr/ocr_patch.py:228-235. */
 int rdb_db_bitmap(int device, const float* prob, int n, int hgt, int wid, float thresh, int use_dilation,

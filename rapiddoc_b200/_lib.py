@@ -29,6 +29,7 @@ SYMBOLS = {
     "rdb_resize_linear_u8": (_i, [_i, _vp, _i, _i, _i, _vp, _i, _i, _vp]),
     "rdb_db_bitmap": (_i, [_i, _vp, _i, _i, _i, _f, _i, _vp, _vp]),
     "rdb_warp_crops": (_i, [_i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, C.c_int64, _vp]),
+    "rdb_resize_pack_u8": (_i, [_i, _vp, C.c_int64, _i, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "rdb_debug_cubic_tab": (_i, [_vp]),
     "rdb_clipper_offset": (_i, [C.POINTER(C.c_double), _i, C.c_double, C.POINTER(C.c_int64), _i]),
     "rdb_rec_create": (_i, [_vp, C.c_size_t, _i, _i, C.POINTER(_vp)]),

@@ -213,6 +213,16 @@ int rdb_warp_crops(int device, const uint8_t* page, int hgt, int wid, int n, con
   });
 }
 
+int rdb_resize_pack_u8(int device, const uint8_t* src, int64_t src_bytes, int n, const int64_t* src_offsets, const int32_t* sizes, const int32_t* dst_w,
+                       uint8_t* dst, int hgt, int wid_max, void* stream) {
+  return guarded([&] {
+    RDB_CHECK(src && dst && (n == 0 || (src_offsets && sizes && dst_w)), "null argument");
+    RDB_CHECK(n >= 0 && hgt > 0 && wid_max > 0 && src_bytes >= 0, "resize_pack: bad shape");
+    require_device(device);
+    rdb::resize_pack_u8(device, src, (long long)src_bytes, n, reinterpret_cast<const long long*>(src_offsets), sizes, dst_w, dst, hgt, wid_max, (cudaStream_t)stream);
+  });
+}
+
 int rdb_debug_cubic_tab(int16_t* out) {
   return guarded([&] {
     RDB_CHECK(out != nullptr, "null argument");

@@ -397,6 +397,8 @@ static void linear_coeffs(int dsize, int ssize, bool vertical, std::vector<int>&
   }
 }
 
+void linear_coeffs_cv(int dsize, int ssize, bool vertical, std::vector<int>& idx, std::vector<short>& ab) { linear_coeffs(dsize, ssize, vertical, idx, ab); }
+
 void resize_linear_u8(int device, const uint8_t* src, int n, int sh, int sw, uint8_t* dst, int dh, int dw, cudaStream_t st) {
   RDB_CUDA(cudaSetDevice(device));
   RDB_CHECK(n > 0 && sh > 0 && sw > 0 && dh > 0 && dw > 0, "resize: bad shape");

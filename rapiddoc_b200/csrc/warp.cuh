@@ -148,4 +148,87 @@ inline void warp_crops(int device, const uint8_t* page, int H, int W, int n, con
   if (!o_dev) cudaFree(dout);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// resize_norm_img geometry on the GPU (rapidocr TextRecognizer.resize_norm_img as called from
+// rapid_doc/model/ocr/rapid_ocr.py:423-440): every crop of a recognition batch is cv2.resize'd (INTER_LINEAR, uint8, bit-exact
+// 11-bit fixed-point path, same arithmetic as resize_linear_u8_kernel) to height dh and its own width dst_w[i], written
+// left-aligned into a [n][dh][dw_max][3] batch; the columns right of dst_w[i] are zero (the rec stem applies the zero pad after
+// normalisation).  Crops are ragged: per-crop coefficient tables are built on the host with OpenCV's float32 rule.
+struct ResizeCrop {
+  long long src_off;    // byte offset of the crop in the packed source buffer
+  int sw, sh, dw;       // source size, destination width
+  int tab_off;          // offset (in ints) of this crop's tables: xi[dw] yi[dh] then shorts xa[2*dw] ya[2*dh] at tab_off_s
+  int tab_off_s;
+};
+
+static __global__ void __launch_bounds__(256) resize_pack_kernel(const uint8_t* __restrict__ src, const ResizeCrop* __restrict__ crops, const int* __restrict__ itab,
+                                                                 const short* __restrict__ stab, uint8_t* __restrict__ dst, int dh, int dw_max) {
+  const ResizeCrop& c = crops[blockIdx.y];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= dh * dw_max) return;
+  const int x = idx % dw_max, y = idx / dw_max;
+  uint8_t* o = dst + ((long long)blockIdx.y * dh * dw_max + idx) * 3;
+  if (x >= c.dw) { o[0] = 0; o[1] = 0; o[2] = 0; return; }
+  const int* xi = itab + c.tab_off; const int* yi = xi + c.dw;
+  const short* xa = stab + c.tab_off_s; const short* ya = xa + 2 * c.dw;
+  const int x0 = xi[x], x1 = min(x0 + 1, c.sw - 1);
+  const int ys = yi[y];
+  const int y0 = min(max(ys, 0), c.sh - 1), y1 = min(max(ys + 1, 0), c.sh - 1);
+  const int a0 = xa[2 * x], a1 = xa[2 * x + 1], b0 = ya[2 * y], b1 = ya[2 * y + 1];
+  const uint8_t* r0 = src + c.src_off + (long long)y0 * c.sw * 3;
+  const uint8_t* r1 = src + c.src_off + (long long)y1 * c.sw * 3;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const int S0 = r0[x0 * 3 + ch] * a0 + r0[x1 * 3 + ch] * a1;
+    const int S1 = r1[x0 * 3 + ch] * a0 + r1[x1 * 3 + ch] * a1;
+    const int v = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+    o[ch] = (uint8_t)min(max(v, 0), 255);
+  }
+}
+
+void linear_coeffs_cv(int dsize, int ssize, bool vertical, std::vector<int>& idx, std::vector<short>& ab);   // det.cu
+
+// src: packed crops (host or device), crop i = [sizes[i][1]][sizes[i][0]][3] at src_offsets[i]; dst [n][dh][dw_max][3] (host or device)
+inline void resize_pack_u8(int device, const uint8_t* src, long long src_bytes, int n, const long long* src_offsets, const int32_t* sizes, const int32_t* dst_w,
+                           uint8_t* dst, int dh, int dw_max, cudaStream_t st) {
+  RDB_CUDA(cudaSetDevice(device));
+  if (n <= 0) return;
+  std::vector<ResizeCrop> hc(n);
+  std::vector<int> itab;
+  std::vector<short> stab;
+  std::vector<int> xi, yi;
+  std::vector<short> xa, ya;
+  for (int i = 0; i < n; ++i) {
+    ResizeCrop& c = hc[i];
+    c.src_off = src_offsets[i]; c.sw = sizes[2 * i]; c.sh = sizes[2 * i + 1]; c.dw = dst_w[i];
+    RDB_CHECK(c.sw > 0 && c.sh > 0 && c.dw > 0 && c.dw <= dw_max, "resize_pack: bad crop geometry");
+    RDB_CHECK(c.src_off >= 0 && c.src_off + (long long)c.sw * c.sh * 3 <= src_bytes, "resize_pack: crop exceeds the source buffer");
+    linear_coeffs_cv(c.dw, c.sw, false, xi, xa);
+    linear_coeffs_cv(dh, c.sh, true, yi, ya);
+    c.tab_off = (int)itab.size(); c.tab_off_s = (int)stab.size();
+    itab.insert(itab.end(), xi.begin(), xi.end()); itab.insert(itab.end(), yi.begin(), yi.end());
+    stab.insert(stab.end(), xa.begin(), xa.end()); stab.insert(stab.end(), ya.begin(), ya.end());
+  }
+  const bool s_dev = is_device_ptr(src), d_dev = is_device_ptr(dst);
+  const size_t dst_b = (size_t)n * dh * dw_max * 3;
+  uint8_t* ds = const_cast<uint8_t*>(src); uint8_t* dd = dst;
+  ResizeCrop* dc; int* dit; short* dst_tab;
+  if (!s_dev) { RDB_CUDA(cudaMalloc(&ds, (size_t)src_bytes)); RDB_CUDA(cudaMemcpyAsync(ds, src, (size_t)src_bytes, cudaMemcpyHostToDevice, st)); }
+  if (!d_dev) RDB_CUDA(cudaMalloc(&dd, dst_b));
+  RDB_CUDA(cudaMalloc(&dc, sizeof(ResizeCrop) * n));
+  RDB_CUDA(cudaMalloc(&dit, sizeof(int) * itab.size()));
+  RDB_CUDA(cudaMalloc(&dst_tab, sizeof(short) * stab.size()));
+  RDB_CUDA(cudaMemcpyAsync(dc, hc.data(), sizeof(ResizeCrop) * n, cudaMemcpyHostToDevice, st));
+  RDB_CUDA(cudaMemcpyAsync(dit, itab.data(), sizeof(int) * itab.size(), cudaMemcpyHostToDevice, st));
+  RDB_CUDA(cudaMemcpyAsync(dst_tab, stab.data(), sizeof(short) * stab.size(), cudaMemcpyHostToDevice, st));
+  dim3 grid((unsigned)((dh * dw_max + 255) / 256), (unsigned)n);
+  resize_pack_kernel<<<grid, 256, 0, st>>>(ds, dc, dit, dst_tab, dd, dh, dw_max);
+  RDB_LAUNCH_CHECK();
+  if (!d_dev) RDB_CUDA(cudaMemcpyAsync(dst, dd, dst_b, cudaMemcpyDeviceToHost, st));
+  RDB_CUDA(cudaStreamSynchronize(st));
+  cudaFree(dc); cudaFree(dit); cudaFree(dst_tab);
+  if (!s_dev) cudaFree(ds);
+  if (!d_dev) cudaFree(dd);
+}
+
 }  // namespace rdb

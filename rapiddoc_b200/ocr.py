@@ -72,13 +72,50 @@ def crop_geometry(points):
     return cw, ch, np.ascontiguousarray(minv, np.float64), int(ch * 1.0 / cw >= 2)
 
 
-def get_rotate_crop_images_gpu(img, boxes, device=0):
+class DeviceCrops:
+    """The crops of one page kept in GPU memory: a packed uint8 buffer (torch tensor) + per-crop stored (h, w) and byte offsets.
+    The recogniser resizes / packs them on the device (rdb_resize_pack_u8); `numpy(i)` fetches one crop for host-side users."""
+
+    def __init__(self, buf, offsets, shapes, device):
+        self.buf, self.offsets, self.shapes, self.device = buf, np.asarray(offsets, np.int64), list(shapes), int(device)
+
+    def __len__(self):
+        return len(self.shapes)
+
+    def numpy(self, i):
+        h, w = self.shapes[i]
+        o = int(self.offsets[i])
+        return self.buf[o: o + h * w * 3].cpu().numpy().reshape(h, w, 3)
+
+    def to_list(self):
+        host = self.buf.cpu().numpy()
+        return [host[int(o): int(o) + h * w * 3].reshape(h, w, 3) for o, (h, w) in zip(self.offsets, self.shapes)]
+
+
+def get_rotate_crop_images_gpu(img, boxes, device=0, keep_on_device=False):
     """All crops of one page in ONE GPU call (rdb_warp_crops), bit-identical to get_rotate_crop_image per box.
-    img [H,W,3] uint8 numpy (or a device tensor); returns a list of numpy crops (None where the quad is degenerate)."""
+    img [H,W,3] uint8 numpy (or a device tensor); returns a list of numpy crops (None where the quad is degenerate), or — with
+    keep_on_device and no degenerate quad — a DeviceCrops whose pixels never visit the host."""
     geo = [crop_geometry(b) for b in boxes]
     live = [g for g in geo if g is not None]
     if not live:
         return [None] * len(geo)
+    if keep_on_device and len(live) == len(geo):
+        import torch
+        lib = _lib.load()
+        minv = np.stack([g[2].reshape(9) for g in live])
+        sizes = np.array([[g[0], g[1]] for g in live], np.int32)
+        rot = np.array([g[3] for g in live], np.int32)
+        nbytes = sizes[:, 0].astype(np.int64) * sizes[:, 1] * 3
+        offs = np.concatenate([[0], np.cumsum(nbytes)[:-1]]).astype(np.int64)
+        dev = torch.device("cuda", int(device))
+        out = torch.empty(int(nbytes.sum()), dtype=torch.uint8, device=dev)
+        if isinstance(img, np.ndarray):
+            img = torch.from_numpy(np.ascontiguousarray(img, dtype=np.uint8)).to(dev)
+        _lib.check(lib.rdb_warp_crops(int(device), _lib.ptr(img), int(img.shape[0]), int(img.shape[1]), len(live), _lib.ptr(minv), _lib.ptr(sizes),
+                                      _lib.ptr(rot), _lib.ptr(out), _lib.ptr(offs), int(out.numel()), None))
+        shapes = [((g[0], g[1]) if g[3] else (g[1], g[0])) for g in live]      # stored (h, w): rot90 swaps them
+        return DeviceCrops(out, offs, shapes, device)
     lib = _lib.load()
     minv = np.stack([g[2].reshape(9) for g in live])
     sizes = np.array([[g[0], g[1]] for g in live], np.int32)
@@ -364,12 +401,26 @@ class B200TextRecognizer:
             vw[i] = rw
         return buf, vw
 
+    def _pack_device(self, dc, idx, max_wh_ratio):
+        """_pack for crops that live on the GPU: the same geometry on the host, the cv2.resize arithmetic in rdb_resize_pack_u8."""
+        import torch
+        _, ih, _ = self.rec_image_shape
+        iw = int(ih * max_wh_ratio)
+        sizes = np.array([[dc.shapes[i][1], dc.shapes[i][0]] for i in idx], np.int32)
+        vw = np.array([iw if math.ceil(ih * (w / float(h))) > iw else int(math.ceil(ih * (w / float(h)))) for w, h in sizes], np.int32)
+        offs = np.ascontiguousarray(dc.offsets[list(idx)], np.int64)
+        buf = torch.empty((len(idx), ih, iw, 3), dtype=torch.uint8, device=dc.buf.device)
+        _lib.check(_lib.load().rdb_resize_pack_u8(dc.device, _lib.ptr(dc.buf), int(dc.buf.numel()), len(idx), _lib.ptr(offs), _lib.ptr(sizes),
+                                                  _lib.ptr(vw), _lib.ptr(buf), ih, iw, None))
+        return buf, vw
+
     def __call__(self, img_list, return_word_box=False):
         if isinstance(img_list, np.ndarray):
             img_list = [img_list]
         t0 = time.perf_counter()
         n = len(img_list)
-        ratios = [im.shape[1] / float(im.shape[0]) for im in img_list]
+        on_dev = isinstance(img_list, DeviceCrops)
+        ratios = [w / float(h) for h, w in img_list.shapes] if on_dev else [im.shape[1] / float(im.shape[0]) for im in img_list]
         order = np.argsort(np.array(ratios))
         res = [("", 0.0)] * n
         words = [None] * n
@@ -377,8 +428,12 @@ class B200TextRecognizer:
         for b0 in range(0, n, self.rec_batch_num):
             idx = order[b0: b0 + self.rec_batch_num]
             mx = max([iw / ih] + [ratios[i] for i in idx])
-            buf, vw = self._pack([img_list[i] for i in idx], mx)
-            out = self.engine.infer_u8(buf, vw)
+            if on_dev:
+                buf, vw = self._pack_device(img_list, idx, mx)
+                out = self.engine.infer_u8(buf, vw, outs=self.engine._outs(len(idx), self.engine.tokens(buf.shape[2]), vw, False))
+            else:
+                buf, vw = self._pack([img_list[i] for i in idx], mx)
+                out = self.engine.infer_u8(buf, vw)
             T = out["ids"].shape[1]
             for j, i in enumerate(idx):
                 ln = int(out["text_len"][j])
@@ -465,8 +520,10 @@ class B200OcrModel:
         dt_boxes = self._post_boxes(det.boxes, mfd_res)
         if getattr(self, "gpu_crop", True) and len(dt_boxes):
             # all quads of the page in one rdb_warp_crops call (bit-identical to cv2.warpPerspective per box)
-            crops = get_rotate_crop_images_gpu(ori, dt_boxes, self.text_detector.engine.device)
-            crops = [c if c is not None else get_rotate_crop_image(ori, copy.deepcopy(b)) for c, b in zip(crops, dt_boxes)]
+            # ... and the crops stay on the device: resize + batch packing happen there too (rdb_resize_pack_u8)
+            crops = get_rotate_crop_images_gpu(ori, dt_boxes, self.text_detector.engine.device, keep_on_device=True)
+            if not isinstance(crops, DeviceCrops):
+                crops = [c if c is not None else get_rotate_crop_image(ori, copy.deepcopy(b)) for c, b in zip(crops, dt_boxes)]
         else:
             crops = [get_rotate_crop_image(ori, copy.deepcopy(b)) for b in dt_boxes]
         rec = self.text_recognizer(crops)

@@ -86,3 +86,45 @@ def test_gpu_warp_device_page_and_large_crop():
     got = get_rotate_crop_images_gpu(torch.from_numpy(img).cuda(), quads)
     for g, p in zip(got, quads):
         assert np.array_equal(g, _cv2_crop(img, p))
+
+
+@pytest.mark.gpu
+def test_gpu_resize_pack_bit_exact_vs_cv2():
+    """resize_norm_img geometry: ragged crops -> [n,48,iw,3], each cv2.resize'd to its own width, zero to the right."""
+    import math
+    rng = np.random.default_rng(9)
+    shapes = [(31, 200), (96, 412), (48, 320), (24, 77), (60, 15), (144, 300), (17, 640), (5, 9)]   # incl. exact 2x / 3x / identity height
+    crops = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in shapes]
+    ih = 48
+    mx = max([320 / 48] + [w / float(h) for h, w in shapes])
+    iw = int(ih * mx)
+    vw = np.array([iw if math.ceil(ih * (w / float(h))) > iw else int(math.ceil(ih * (w / float(h)))) for h, w in shapes], np.int32)
+    src = np.concatenate([c.reshape(-1) for c in crops])
+    nb = np.array([c.size for c in crops], np.int64)
+    offs = np.concatenate([[0], np.cumsum(nb)[:-1]]).astype(np.int64)
+    sizes = np.array([[w, h] for h, w in shapes], np.int32)
+    out = np.full((len(crops), ih, iw, 3), 7, np.uint8)
+    _lib.check(_lib.load().rdb_resize_pack_u8(0, src.ctypes.data, int(src.size), len(crops), offs.ctypes.data, sizes.ctypes.data, vw.ctypes.data,
+                                              out.ctypes.data, ih, iw, None))
+    for i, c in enumerate(crops):
+        assert np.array_equal(out[i, :, :vw[i]], cv2.resize(c, (int(vw[i]), ih))), shapes[i]
+        assert not out[i, :, vw[i]:].any()
+
+
+@pytest.mark.gpu
+def test_facade_device_crops_equal_host_crops(golden_dir):
+    """B200OcrModel with the crops kept on the GPU (warp + resize + pack on the device) returns exactly the boxes, texts and
+    scores of the host cv2 path: both stages are bit-exact, so the recogniser sees identical bytes."""
+    import os
+    from rapiddoc_b200 import PREC_FP16
+    from rapiddoc_b200.ocr import B200OcrModel
+    g = np.load(os.path.join(golden_dir, "page_img5_e2e.npz"))
+    img = cv2.imdecode(g["png"], cv2.IMREAD_COLOR)
+    model = B200OcrModel(det_db_box_thresh=0.3, det_db_unclip_ratio=1.8, enable_merge_det_boxes=False, precision=PREC_FP16)
+    model.gpu_crop = True
+    a = model.ocr(img, det=True, rec=True)[0]
+    model.gpu_crop = False
+    b = model.ocr(img, det=True, rec=True)[0]
+    assert len(a) == len(b) and len(a) > 5
+    for x, y in zip(a, b):
+        assert x[0] == y[0] and x[1][0] == y[1][0] and x[1][1] == y[1][1]
