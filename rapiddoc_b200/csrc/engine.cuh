@@ -67,18 +67,29 @@ class Weights {
     RDB_CUDA(cudaDeviceSynchronize());
     for (auto& kv : map_) kv.second.h = half_ + (kv.second.d - reinterpret_cast<const float*>(dev_));
   }
-  ~Weights() { if (dev_) cudaFree(dev_); if (half_) cudaFree(half_); }
+  ~Weights() { if (dev_) cudaFree(dev_); if (half_) cudaFree(half_); for (auto& kv : derived_) cudaFree(kv.second); }
   const Tensor& get(const std::string& name) const {
     auto it = map_.find(name);
     if (it == map_.end()) throw Error("weight tensor missing: " + name);
     return it->second;
   }
   bool has(const std::string& name) const { return map_.count(name) != 0; }
+  // derived device buffers (e.g. weight slices pre-arranged as shared-memory images), built once on first use and owned here
+  __half* derived(const std::string& key, size_t halves, bool* fresh) const {
+    auto it = derived_.find(key);
+    *fresh = it == derived_.end();
+    if (!*fresh) return it->second;
+    __half* p = nullptr;
+    RDB_CUDA(cudaMalloc(&p, halves * sizeof(__half)));
+    derived_[key] = p;
+    return p;
+  }
 
  private:
   void* dev_ = nullptr;
   __half* half_ = nullptr;
   std::unordered_map<std::string, Tensor> map_;
+  mutable std::unordered_map<std::string, __half*> derived_;
 };
 
 // ---------------------------------------------------------------- device buffer pool
@@ -578,14 +589,16 @@ struct Backbone {
     const bool rep = (c.sh == 1 && c.sw == 1 && c.cin == c.cout);
     if constexpr (std::is_same<T, __half>::value) {
       // channel mixer (pw1 -> GELU -> pw2 + residual) as one kernel, the 2C-wide intermediate stays in shared memory
-      if (cx.use_tc && !env_is("RDB_MLP", "unfused") && ((c.cin == 48 && (c.cout == 48 || c.cout == 96)) || (c.cin == 96 && c.cout == 96))) {
+      const bool big = c.cin == 192 && c.cout == 192 && !env_is("RDB_MLP", "small");   // weights streamed in three 128-column slices
+      if (cx.use_tc && !env_is("RDB_MLP", "unfused") && ((c.cin == 48 && (c.cout == 48 || c.cout == 96)) || (c.cin == 96 && c.cout == 96) || big)) {
         Act y = O::make(cx, x.n, OH, OW, c.cout);
         const int act = env_is("RDB_GELU", "exact") ? ACT_GELU : ACT_GELUF;
         const long long M = t.pixels();
         const Tensor &w1 = w.get(name + "pw1.w"), &b1 = w.get(name + "pw1.b"), &w2 = w.get(name + "pw2.w"), &b2 = w.get(name + "pw2.b");
         if (c.cin == 48 && c.cout == 48) launch_mlp_tc<48, 48>(cx, t.p, M, w1, b1, w2, b2, rep ? t.p : nullptr, y.p, act);
         else if (c.cin == 48) launch_mlp_tc<48, 96>(cx, t.p, M, w1, b1, w2, b2, nullptr, y.p, act);
-        else launch_mlp_tc<96, 96>(cx, t.p, M, w1, b1, w2, b2, rep ? t.p : nullptr, y.p, act);
+        else if (c.cin == 96) launch_mlp_tc<96, 96>(cx, t.p, M, w1, b1, w2, b2, rep ? t.p : nullptr, y.p, act);
+        else launch_mlp_big<192, 192, 3, 1>(cx, w, name, t.p, M, w1, b1, w2, b2, rep ? t.p : nullptr, y.p, act);
         O::release(cx, t);
         return y;
       }
