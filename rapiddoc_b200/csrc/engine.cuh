@@ -358,8 +358,19 @@ struct Ops {
     gemm(cx, in.p, in.c, in.pixels(), in.c, W, bias, act, res, out.c, out.p, out.c, 0);
   }
 
+  // tile shape of the smem-tiled 3x3 depthwise kernel for a map of h x w
+  static void dw3_tile(int h, int& TH, int& TW) {
+    TH = h >= 8 ? 8 : 4; TW = 32;
+    if (h == 12 || h == 6 || h == 3) { TH = h; TW = 16; }
+  }
+  static int dw3_tiles(int h, int w) { int TH, TW; dw3_tile(h, TH, TW); return cdiv(w, TW) * cdiv(h, TH); }
+
+  // pool_partial != null (3x3 stride-1 only): the kernel also writes per-tile channel sums [n][tiles][C] for the SE pool
+  // and *pooled is set when it did
   template <int KH, int KW, int ACT, bool ADD_IN>
-  static void dwconv(Ctx& cx, const Act& in, int sh, int sw, const Tensor& w, const Tensor& b, Act& out) {
+  static void dwconv(Ctx& cx, const Act& in, int sh, int sw, const Tensor& w, const Tensor& b, Act& out, float* pool_partial = nullptr,
+                     bool* pooled = nullptr) {
+    if (pooled) *pooled = false;
     if constexpr (std::is_same<T, __half>::value && KH == 7 && KW == 7 && ACT == ACT_NONE && !ADD_IN) {
       if (sh == 1 && sw == 1 && in.c % 32 == 0 && !env_is("RDB_DW", "simple")) {
         constexpr int TH = 8, TW = 32, G = 4;
@@ -378,7 +389,7 @@ struct Ops {
         set_smem(k, sm);
         dim3 grid(cdiv(in.w, TW), cdiv(in.h, TH), in.n * (in.c / (8 * G)));
         cx.begin("dwconv7x7_tiled[P=" + std::to_string(out.pixels()) + ",C=" + std::to_string(in.c) + ",s=1]");
-        k<<<grid, G * (TW / 4) * TH, sm, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.d, b.d, out.p);
+        k<<<grid, G * (TW / 4) * TH, sm, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.d, b.d, out.p, nullptr);
         cx.end();
         return;
       }
@@ -389,8 +400,8 @@ struct Ops {
         // 16-column tiles (80 = 5 x 16); page-sized maps use 8 x 32
         const bool g4 = (in.c % 32 == 0);
         const int G = g4 ? 4 : 2;
-        int TH = in.h >= 8 ? 8 : 4, TW = 32;
-        if (in.h == 12 || in.h == 6 || in.h == 3) { TH = in.h; TW = 16; }
+        int TH, TW;
+        dw3_tile(in.h, TH, TW);
         const size_t sm = (size_t)(TH + 2) * (TW + 2) * (16 * G + 16) + 9 * 8 * G * sizeof(float);
         dim3 grid(cdiv(in.w, TW), cdiv(in.h, TH), in.n * (in.c / (8 * G)));
         const int threads = G * (TW / 4) * TH;
@@ -413,7 +424,8 @@ struct Ops {
           return;
         }
         cx.begin("dwconv3x3_tiled[P=" + std::to_string(out.pixels()) + ",C=" + std::to_string(in.c) + ",s=1]");
-#define RDB_DW3(GG, TTH, TTW) dwconv_tiled_kernel<T, 3, GG, TTH, TTW><<<grid, threads, sm, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.d, b.d, out.p)
+        if (pooled) *pooled = pool_partial != nullptr;
+#define RDB_DW3(GG, TTH, TTW) dwconv_tiled_kernel<T, 3, GG, TTH, TTW><<<grid, threads, sm, cx.st>>>(in.p, in.n, in.h, in.w, in.c, w.d, b.d, out.p, pool_partial)
         if (g4) {
           if (TH == 8) RDB_DW3(4, 8, 32); else if (TH == 4) RDB_DW3(4, 4, 32); else if (TH == 12) RDB_DW3(4, 12, 16);
           else if (TH == 6) RDB_DW3(4, 6, 16); else RDB_DW3(4, 3, 16);
@@ -435,10 +447,20 @@ struct Ops {
 
   // SE gate (mode 0: hardsigmoid; mode 1: 1+clip(.2z+.5)) -> float gate[n][C] from pool.
   // pre != null: x is the input of the bias-free 1x1 conv `pre` [C][x.c] and the SE acts on the conv OUTPUT (C channels).
+  // partial != null: per-tile channel sums [n][chunks_in][x.c] already written by the producer of x (fused pool)
   static float* se_gate(Ctx& cx, const Act& x, const Tensor& w1, const Tensor& b1, const Tensor& w2, const Tensor& b2, int mode,
-                        const Tensor* pre = nullptr) {
+                        const Tensor* pre = nullptr, float* partial_in = nullptr, int chunks_in = 0) {
     int HW = x.h * x.w, Cp = x.c, Cr = w1.shape[0];
     const int C = pre ? pre->shape[0] : Cp;
+    RDB_CHECK(Cp <= 512, "se: more than 512 pooled channels");
+    if (partial_in != nullptr && !env_is("RDB_SE_SKIP", "1")) {
+      float* gate = cx.pool->alloc_t<float>((size_t)x.n * C);
+      cx.begin("se_fc");
+      se_fc_kernel<<<x.n, 512, (size_t)(2 * C + Cr + Cp + 512) * sizeof(float), cx.st>>>(partial_in, chunks_in, HW, C, Cr, w1.d, b1.d, w2.d, b2.d, mode, gate,
+                                                                          pre ? pre->d : nullptr, Cp);
+      cx.end();
+      return gate;
+    }
     int G = Cp / 8;
     int threads = 256;
     int P = threads / G;
@@ -446,19 +468,25 @@ struct Ops {
     int chunks = HW / (P * 16);
     if (chunks < 1) chunks = 1;
     if (chunks > 32) chunks = 32;
+    if (env_is("RDB_SE_SKIP", "1")) {   // timing experiment only (wrong results): what do all SE pool/FC launches cost?
+      float* g0 = cx.pool->alloc_t<float>((size_t)x.n * C);
+      RDB_CUDA(cudaMemsetAsync(g0, 0x3f, (size_t)x.n * C * sizeof(float), cx.st));
+      return g0;
+    }
     float* partial = cx.pool->alloc_t<float>((size_t)x.n * chunks * Cp);
     float* gate = cx.pool->alloc_t<float>((size_t)x.n * C);
     cx.begin("se_pool[P=" + std::to_string(x.pixels()) + ",C=" + std::to_string(Cp) + "]");
     pool_partial_kernel<T><<<dim3(chunks, x.n), threads, (size_t)P * Cp * sizeof(float), cx.st>>>(x.p, HW, Cp, partial, chunks);
     cx.end();
     cx.begin("se_fc");
-    se_fc_kernel<<<x.n, 1024, (size_t)(C + Cr + Cp) * sizeof(float), cx.st>>>(partial, chunks, HW, C, Cr, w1.d, b1.d, w2.d, b2.d, mode, gate,
+    se_fc_kernel<<<x.n, 512, (size_t)(2 * C + Cr + Cp + 512) * sizeof(float), cx.st>>>(partial, chunks, HW, C, Cr, w1.d, b1.d, w2.d, b2.d, mode, gate,
                                                                          pre ? pre->d : nullptr, Cp);
     cx.end();
     cx.pool->free(partial);
     return gate;
   }
   static void scale(Ctx& cx, Act& x, const float* gate) {
+    if (env_is("RDB_SE_SKIP", "1")) return;
     long long total8 = x.numel() / 8;
     cx.begin("se_scale[P=" + std::to_string(x.pixels()) + ",C=" + std::to_string(x.c) + "]");
     scale_channels_kernel<T><<<cdiv(total8, kThreads), kThreads, 0, cx.st>>>(x.p, (long long)x.h * x.w, x.c, gate, total8);
@@ -579,13 +607,19 @@ struct Backbone {
   static Act block(Ctx& cx, const Weights& w, const std::string& name, const BlockCfg& c, Act& x, bool keep_in) {
     const int OH = (x.h + 2 - 3) / c.sh + 1, OW = (x.w + 2 - 3) / c.sw + 1;
     Act t = O::make(cx, x.n, OH, OW, c.cin);
-    O::template dwconv<3, 3, ACT_NONE, false>(cx, x, c.sh, c.sw, w.get(name + "dw.w"), w.get(name + "dw.b"), t);
+    float* pool_partial = nullptr;
+    bool pooled = false;
+    const int tiles = O::dw3_tiles(x.h, x.w);
+    if (c.se && c.sh == 1 && c.sw == 1 && !env_is("RDB_SE_POOL", "separate")) pool_partial = cx.pool->template alloc_t<float>((size_t)x.n * tiles * c.cin);
+    O::template dwconv<3, 3, ACT_NONE, false>(cx, x, c.sh, c.sw, w.get(name + "dw.w"), w.get(name + "dw.b"), t, pool_partial, &pooled);
     if (!keep_in) O::release(cx, x);
     if (c.se) {
-      float* gate = O::se_gate(cx, t, w.get(name + "se.w1"), w.get(name + "se.b1"), w.get(name + "se.w2"), w.get(name + "se.b2"), 0);
+      float* gate = O::se_gate(cx, t, w.get(name + "se.w1"), w.get(name + "se.b1"), w.get(name + "se.w2"), w.get(name + "se.b2"), 0, nullptr,
+                               pooled ? pool_partial : nullptr, tiles);
       O::scale(cx, t, gate);
       cx.pool->free(gate);
     }
+    if (pool_partial) cx.pool->free(pool_partial);
     const bool rep = (c.sh == 1 && c.sw == 1 && c.cin == c.cout);
     if constexpr (std::is_same<T, __half>::value) {
       // channel mixer (pw1 -> GELU -> pw2 + residual) as one kernel, the 2C-wide intermediate stays in shared memory

@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ in, i
 template <typename T, int K, int G, int TH, int TW>
 __global__ void __launch_bounds__(G * (TW / 4) * TH)
 dwconv_tiled_kernel(const T* __restrict__ in, int N, int H, int W, int C, const float* __restrict__ w /*[K][K][C]*/,
-                    const float* __restrict__ b, T* __restrict__ out) {
+                    const float* __restrict__ b, T* __restrict__ out, float* __restrict__ pool = nullptr) {
   constexpr int HH = TH + K - 1, HW = TW + K - 1;
   constexpr int PITCH = 16 * G + 16;                 // bytes per staged pixel
   constexpr int XS = TW / 4;
@@ -355,11 +355,38 @@ dwconv_tiled_kernel(const T* __restrict__ in, int N, int H, int W, int C, const 
     }
   }
   const int oy = y0 + ty;
-  if (oy >= H) return;
+  if (oy < H) {
 #pragma unroll
-  for (int o = 0; o < 4; ++o) {
-    const int ox = x0 + xs * 4 + o;
-    if (ox < W) Vec8<T>::store(out + (((long long)n * H + oy) * W + ox) * C + c0 + g * 8, acc[o]);
+    for (int o = 0; o < 4; ++o) {
+      const int ox = x0 + xs * 4 + o;
+      if (ox < W) Vec8<T>::store(out + (((long long)n * H + oy) * W + ox) * C + c0 + g * 8, acc[o]);
+    }
+  }
+  if (pool != nullptr) {
+    // squeeze-excitation pool fused into the producer: this block's channel sums (valid pixels only, fp32, fixed order) go to
+    // pool[n][tile][C]; se_fc_kernel adds the tiles up — the separate pooling pass over the whole tensor disappears
+    __syncthreads();                                   // every thread is done reading the staged tile: reuse it
+    float* red = reinterpret_cast<float*>(dsm);        // [XS*TH][8*G]
+    float sacc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sacc[j] = 0.f;
+    if (oy < H) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+        if (x0 + xs * 4 + o < W) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sacc[j] += acc[o][j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[(xs + XS * ty) * 8 * G + g * 8 + j] = sacc[j];
+    __syncthreads();
+    if (tid < 8 * G) {
+      float t = 0.f;
+      for (int k = 0; k < XS * TH; ++k) t += red[k * 8 * G + tid];
+      const int tiles = gridDim.x * gridDim.y, tile_id = blockIdx.y * gridDim.x + blockIdx.x;
+      pool[((long long)n * tiles + tile_id) * C + c0 + tid] = t;
+    }
   }
 }
 
@@ -492,51 +519,78 @@ __device__ __forceinline__ float warp_sum(float t) {
   return t;
 }
 
-static __global__ void __launch_bounds__(1024) se_fc_kernel(const float* __restrict__ partial, int chunks, int HW, int C, int Cr,
-                                                          const float* __restrict__ w1, const float* __restrict__ b1,
-                                                          const float* __restrict__ w2, const float* __restrict__ b2, int mode,
-                                                          float* __restrict__ gate, const float* __restrict__ w0, int C0) {
-  extern __shared__ float sm[];  // mean[C] + hid[Cr] + mean0[C0]
+// 512 threads; every stage spreads its loads over the whole block so that a stage costs about one memory latency:
+//   pool   : thread (channel c, part j) adds the chunks j, j+P, ... ; the P parts are then added in a fixed order
+//   matvec : 16 threads per output row, each with K/64 independent float4 loads, xor-shuffle tree inside the 16-lane group
+// (the first version used one warp per row and C/32 dependent rounds: 14.5 us per launch, 3 % of a det step over 26 launches).
+// All sums run in a fixed order: deterministic.
+__device__ __forceinline__ void se_matvec16(const float* __restrict__ Wm, const float* vec, int rows, int K, float* out_sm) {
+  // out_sm[r] = dot(Wm[r][0..K), vec), K % 4 == 0 handled by float4, any K by the scalar tail
+  const int t16 = threadIdx.x & 15, grp = threadIdx.x >> 4, ngrp = blockDim.x >> 4;
+  for (int r0 = 0; r0 < rows; r0 += ngrp) {
+    const int r = r0 + grp;
+    float t = 0.f;
+    if (r < rows) {
+      const float* wr = Wm + (long long)r * K;
+      if ((K & 3) == 0) {
+        const float4* w4 = reinterpret_cast<const float4*>(wr);
+        for (int c = t16; c < K / 4; c += 16) { const float4 w = __ldg(w4 + c); t = fmaf(w.x, vec[4 * c], fmaf(w.y, vec[4 * c + 1], fmaf(w.z, vec[4 * c + 2], fmaf(w.w, vec[4 * c + 3], t)))); }
+      } else {
+        for (int c = t16; c < K; c += 16) t = fmaf(__ldg(wr + c), vec[c], t);
+      }
+    }
+#pragma unroll
+    for (int o = 8; o; o >>= 1) t += __shfl_xor_sync(0xffffffff, t, o);
+    if (r < rows && t16 == 0) out_sm[r] = t;
+  }
+}
+
+static __global__ void __launch_bounds__(512) se_fc_kernel(const float* __restrict__ partial, int chunks, int HW, int C, int Cr,
+                                                         const float* __restrict__ w1, const float* __restrict__ b1,
+                                                         const float* __restrict__ w2, const float* __restrict__ b2, int mode,
+                                                         float* __restrict__ gate, const float* __restrict__ w0, int C0) {
+  extern __shared__ float sm[];  // mean[C] + hid[Cr] + mean0[C0] + red[512] + tmp[C]
   float* mean = sm;
   float* hid = sm + C;
   float* mean0 = hid + Cr;
   const int n = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int Cp = (w0 != nullptr) ? C0 : C;         // channels of the pooled tensor
   float* pooled = (w0 != nullptr) ? mean0 : mean;
-  // per-chunk partials [chunks <= 32][Cp] -> mean: lane = chunk, warp strides the channels
-  for (int c = warp; c < Cp; c += nwarps) {
-    float t = (lane < chunks) ? partial[((long long)n * chunks + lane) * Cp + c] : 0.f;
-    t = warp_sum(t);
-    if (lane == 0) pooled[c] = t / (float)HW;
-  }
-  __syncthreads();
-  if (w0 != nullptr) {
-    for (int r = warp; r < C; r += nwarps) {
+  float* red = mean0 + ((w0 != nullptr) ? C0 : 0);
+  float* tmp = red + 512;
+  {
+    const int P = blockDim.x / Cp > 0 ? blockDim.x / Cp : 1;   // parts per channel
+    const int c = threadIdx.x % Cp, j = threadIdx.x / Cp;
+    if (j < P) {
+      const float* p = partial + (long long)n * chunks * Cp + c;
       float t = 0.f;
-      for (int c = lane; c < C0; c += 32) t = fmaf(__ldg(w0 + r * C0 + c), mean0[c], t);
-      t = warp_sum(t);
-      if (lane == 0) mean[r] = t;
+      for (int k = j; k < chunks; k += P) t += p[(long long)k * Cp];
+      red[j * Cp + c] = t;
+    }
+    __syncthreads();
+    for (int cc = threadIdx.x; cc < Cp; cc += blockDim.x) {
+      float t = 0.f;
+      for (int jj = 0; jj < P; ++jj) t += red[jj * Cp + cc];
+      pooled[cc] = t / (float)HW;
     }
     __syncthreads();
   }
-  for (int r = warp; r < Cr; r += nwarps) {       // hidden = relu(W1 mean + b1)
-    float t = 0.f;
-    for (int c = lane; c < C; c += 32) t = fmaf(__ldg(w1 + r * C + c), mean[c], t);
-    t = warp_sum(t);
-    if (lane == 0) hid[r] = fmaxf(t + b1[r], 0.f);
+  if (w0 != nullptr) {                                           // mean of the 1x1 conv output = W0 * mean of its input
+    se_matvec16(w0, mean0, C, C0, mean);
+    __syncthreads();
   }
+  se_matvec16(w1, mean, Cr, C, tmp);                             // hidden = relu(W1 mean + b1)
   __syncthreads();
-  for (int c = warp; c < C; c += nwarps) {        // gate = f(W2 hidden + b2)
-    float t = 0.f;
-    for (int r = lane; r < Cr; r += 32) t = fmaf(__ldg(w2 + c * Cr + r), hid[r], t);
-    t = warp_sum(t) + b2[c];
-    if (lane == 0) {
-      float gt;
-      if (mode == 0) gt = fminf(fmaxf(t / 6.f + 0.5f, 0.f), 1.f);
-      else gt = 1.f + fminf(fmaxf(0.2f * t + 0.5f, 0.f), 1.f);
-      gate[(long long)n * C + c] = gt;
-    }
+  for (int r = threadIdx.x; r < Cr; r += blockDim.x) hid[r] = fmaxf(tmp[r] + b1[r], 0.f);
+  __syncthreads();
+  se_matvec16(w2, hid, C, Cr, tmp);                              // gate = f(W2 hidden + b2)
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float t = tmp[c] + b2[c];
+    float gt;
+    if (mode == 0) gt = fminf(fmaxf(t / 6.f + 0.5f, 0.f), 1.f);
+    else gt = 1.f + fminf(fmaxf(0.2f * t + 0.5f, 0.f), 1.f);
+    gate[(long long)n * C + c] = gt;
   }
 }
 
