@@ -255,6 +255,8 @@ def main():
     import torch.distributed as dist
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"        # NCCL's version banner goes to stdout: keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from rapiddoc_b200 import _lib, PREC_FP16, PREC_FP32, synth, weights as W

@@ -25,6 +25,11 @@ for r in rows:
         c, n = int(m.group(1)), int(m.group(2))
         M = PX // 16 if (c, n) == (48, 48) else PX // 64
         name = f"mlp_tc[M={M},C={c},N={n},res={1 if c == n else 0}]"
+    elif "mlp_big_kernel" in sig:
+        m = re.search(r"mlp_big_kernel<(\d+), (\d+)", sig)
+        c, n = int(m.group(1)), int(m.group(2))
+        M = 122880 if "ncu_rec_top" in r["report"] else PX // 256
+        name = f"mlp_tc[M={M},C={c},N={n},res=1]"
     if name and name not in [o["kernel"] for o in out]:
         out.append({"kernel": name, "dram_bytes": r["dram_bytes"], "source": f"profiles/r01_ncu_summary.txt ({r['report']}: {sig.split('(')[0]}, dram__bytes_read.sum + dram__bytes_write.sum, one launch)"})
 # carried over from the first capture of this round (kernel's data movement unchanged since: same tiles, same operands)
