@@ -61,3 +61,19 @@ def test_get_word_info_grouping():
     wi = O.get_word_info("abcd", sel)
     assert wi.words == [["a", "b"], ["c", "d"]]
     assert O.get_word_info("", np.zeros(5, bool)).words == []
+
+
+def test_bench_roofline_model_knows_every_fused_kernel():
+    """bench.py's algorithmic-bytes model (roofline.achieved) must cover the launch names the engines emit."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    wl = bench.WORKLOADS["det"]
+    P = 32 * 1024 * 1024 // 16
+    assert bench.algorithmic_bytes(f"stem_planar[P={P}]", 2, wl, 32) == P * (4 * 24 + 48) * 2
+    assert bench.algorithmic_bytes(f"head_planar[P={P}]", 2, wl, 32) > P * 16 * 5
+    assert bench.algorithmic_bytes(f"mlp_tc[M={P},C=48,N=48,res=1]", 2, wl, 32) == P * (48 + 48 + 48) * 2
+    assert bench.algorithmic_bytes(f"stem1_tc[P={4 * P},N=24]", 2, wl, 32) == 4 * P * (12 + 48)
+    assert bench.algorithmic_bytes(f"dwconv7x7_h2[P={P},C=96,s=1]", 2, wl, 32) == P * 96 * 2 * 2
+    assert bench.algorithmic_bytes("se_fc", 2, wl, 32) is None       # latency-bound helper: no byte model, never the roofline kernel
