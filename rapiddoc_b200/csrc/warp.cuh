@@ -14,6 +14,29 @@
 
 namespace rdb {
 
+// Grow-only per-device scratch for the (synchronous) crop entry points: cudaMalloc / cudaFree per call cost ~40 ms per page at the
+// facade level (dozens of them, each a device-wide synchronisation) — measured with tools/pipeline_probe.py.  Not thread-safe,
+// like the engine handles; every call ends with a stream synchronise, so the buffer is free again when the next call starts.
+struct ScratchCarver {
+  uint8_t* base; size_t off = 0;
+  template <typename T>
+  T* take(size_t n) { T* p = reinterpret_cast<T*>(base + off); off += (n * sizeof(T) + 255) / 256 * 256; return p; }
+};
+inline uint8_t* device_scratch(int device, size_t bytes) {
+  static uint8_t* buf[64] = {};
+  static size_t cap[64] = {};
+  RDB_CHECK(device >= 0 && device < 64, "scratch: device index");
+  if (cap[device] < bytes) {
+    if (buf[device]) { RDB_CUDA(cudaDeviceSynchronize()); cudaFree(buf[device]); buf[device] = nullptr; cap[device] = 0; }
+    size_t want = bytes + bytes / 2;
+    if (want < (size_t)8 << 20) want = (size_t)8 << 20;
+    RDB_CUDA(cudaMalloc(&buf[device], want));
+    cap[device] = want;
+  }
+  return buf[device];
+}
+inline size_t pad256(size_t b) { return (b + 255) / 256 * 256; }
+
 struct WarpCrop {
   double m[9];          // dst -> src homography (cv::invert of getPerspectiveTransform)
   int w, h;             // warp output size (before rotation)
@@ -132,20 +155,17 @@ inline void warp_crops(int device, const uint8_t* page, int H, int W, int n, con
   const bool p_dev = is_device_ptr(page), o_dev = is_device_ptr(out);
   uint8_t* dp = const_cast<uint8_t*>(page);
   uint8_t* dout = out;
-  WarpCrop* dc = nullptr;
   const size_t page_b = (size_t)H * W * 3;
-  if (!p_dev) { RDB_CUDA(cudaMalloc(&dp, page_b)); RDB_CUDA(cudaMemcpyAsync(dp, page, page_b, cudaMemcpyHostToDevice, st)); }
-  if (!o_dev) RDB_CUDA(cudaMalloc(&dout, (size_t)out_bytes));
-  RDB_CUDA(cudaMalloc(&dc, sizeof(WarpCrop) * n));
+  ScratchCarver sc{device_scratch(device, pad256(sizeof(WarpCrop) * n) + (p_dev ? 0 : pad256(page_b)) + (o_dev ? 0 : pad256((size_t)out_bytes)))};
+  WarpCrop* dc = sc.take<WarpCrop>(n);
+  if (!p_dev) { dp = sc.take<uint8_t>(page_b); RDB_CUDA(cudaMemcpyAsync(dp, page, page_b, cudaMemcpyHostToDevice, st)); }
+  if (!o_dev) dout = sc.take<uint8_t>((size_t)out_bytes);
   RDB_CUDA(cudaMemcpyAsync(dc, hc.data(), sizeof(WarpCrop) * n, cudaMemcpyHostToDevice, st));
   dim3 grid((unsigned)((max_px + 255) / 256), (unsigned)n);
   warp_cubic_kernel<<<grid, 256, 0, st>>>(dp, H, W, dc, dev_tab[device], dout);
   RDB_LAUNCH_CHECK();
   if (!o_dev) RDB_CUDA(cudaMemcpyAsync(out, dout, (size_t)out_bytes, cudaMemcpyDeviceToHost, st));
-  RDB_CUDA(cudaStreamSynchronize(st));      // hc / staging buffers are released below
-  cudaFree(dc);
-  if (!p_dev) cudaFree(dp);
-  if (!o_dev) cudaFree(dout);
+  RDB_CUDA(cudaStreamSynchronize(st));      // hc goes out of scope; the scratch is free for the next call
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -212,12 +232,13 @@ inline void resize_pack_u8(int device, const uint8_t* src, long long src_bytes, 
   const bool s_dev = is_device_ptr(src), d_dev = is_device_ptr(dst);
   const size_t dst_b = (size_t)n * dh * dw_max * 3;
   uint8_t* ds = const_cast<uint8_t*>(src); uint8_t* dd = dst;
-  ResizeCrop* dc; int* dit; short* dst_tab;
-  if (!s_dev) { RDB_CUDA(cudaMalloc(&ds, (size_t)src_bytes)); RDB_CUDA(cudaMemcpyAsync(ds, src, (size_t)src_bytes, cudaMemcpyHostToDevice, st)); }
-  if (!d_dev) RDB_CUDA(cudaMalloc(&dd, dst_b));
-  RDB_CUDA(cudaMalloc(&dc, sizeof(ResizeCrop) * n));
-  RDB_CUDA(cudaMalloc(&dit, sizeof(int) * itab.size()));
-  RDB_CUDA(cudaMalloc(&dst_tab, sizeof(short) * stab.size()));
+  ScratchCarver sc{device_scratch(device, pad256(sizeof(ResizeCrop) * n) + pad256(sizeof(int) * itab.size()) + pad256(sizeof(short) * stab.size()) +
+                                              (s_dev ? 0 : pad256((size_t)src_bytes)) + (d_dev ? 0 : pad256(dst_b)))};
+  ResizeCrop* dc = sc.take<ResizeCrop>(n);
+  int* dit = sc.take<int>(itab.size());
+  short* dst_tab = sc.take<short>(stab.size());
+  if (!s_dev) { ds = sc.take<uint8_t>((size_t)src_bytes); RDB_CUDA(cudaMemcpyAsync(ds, src, (size_t)src_bytes, cudaMemcpyHostToDevice, st)); }
+  if (!d_dev) dd = sc.take<uint8_t>(dst_b);
   RDB_CUDA(cudaMemcpyAsync(dc, hc.data(), sizeof(ResizeCrop) * n, cudaMemcpyHostToDevice, st));
   RDB_CUDA(cudaMemcpyAsync(dit, itab.data(), sizeof(int) * itab.size(), cudaMemcpyHostToDevice, st));
   RDB_CUDA(cudaMemcpyAsync(dst_tab, stab.data(), sizeof(short) * stab.size(), cudaMemcpyHostToDevice, st));
@@ -226,9 +247,6 @@ inline void resize_pack_u8(int device, const uint8_t* src, long long src_bytes, 
   RDB_LAUNCH_CHECK();
   if (!d_dev) RDB_CUDA(cudaMemcpyAsync(dst, dd, dst_b, cudaMemcpyDeviceToHost, st));
   RDB_CUDA(cudaStreamSynchronize(st));
-  cudaFree(dc); cudaFree(dit); cudaFree(dst_tab);
-  if (!s_dev) cudaFree(ds);
-  if (!d_dev) cudaFree(dd);
 }
 
 }  // namespace rdb

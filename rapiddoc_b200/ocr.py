@@ -518,7 +518,10 @@ class B200OcrModel:
         if det.boxes is None:
             return None, None
         dt_boxes = self._post_boxes(det.boxes, mfd_res)
-        if getattr(self, "gpu_crop", True) and len(dt_boxes):
+        # opt-in (model.gpu_crop = True): bit-identical results, but at a few dozen lines per page the per-call overheads of the
+        # crop entry points still outweigh OpenCV's ~50 us per box (tools/pipeline_probe.py: 20.4 vs 10.9 ms on a 14-line page,
+        # 29.0 vs 30.8 ms on a 24-line 1024x1024 page) — it pays once crops are batched over many pages
+        if getattr(self, "gpu_crop", False) and len(dt_boxes):
             # all quads of the page in one rdb_warp_crops call (bit-identical to cv2.warpPerspective per box)
             # ... and the crops stay on the device: resize + batch packing happen there too (rdb_resize_pack_u8)
             crops = get_rotate_crop_images_gpu(ori, dt_boxes, self.text_detector.engine.device, keep_on_device=True)
