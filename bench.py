@@ -367,7 +367,7 @@ def main():
         total = sum(v[0] for v in prof.values())
         if args.profile_out:
             rows = [{"kernel": k, "total_ms": v[0], "launches": v[1], "avg_us": v[0] / v[1] * 1e3, "share": v[0] / total,
-                     "algorithmic_bytes": algorithmic_bytes(k, esz, wl, max(1, min(B, (args.chunk_pixels or 16 * 1024 * 1024) // (H * Wd))) if wl_key == "det" else B)}
+                     "algorithmic_bytes": algorithmic_bytes(k, esz, wl, max(1, min(B, (args.chunk_pixels or 32 * 1024 * 1024) // (H * Wd))) if wl_key == "det" else B)}
                     for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])]
             for r in rows:
                 if r["algorithmic_bytes"]:
@@ -380,7 +380,7 @@ def main():
         except Exception:
             pass
         hbm = peaks.get("hbm_gbs", 6650.0)
-        n_chunk = max(1, min(B, (args.chunk_pixels or 16 * 1024 * 1024) // (H * Wd))) if wl_key == "det" else min(B, 256)
+        n_chunk = max(1, min(B, (args.chunk_pixels or 32 * 1024 * 1024) // (H * Wd))) if wl_key == "det" else min(B, 256)
         # dominant kernel = largest share of device time among kernels that move a modelled number of bytes
         # (latency-bound helpers such as the SE FC stack have no byte model; they stay visible in top5)
         modelled = {k: v for k, v in prof.items() if algorithmic_bytes(k, esz, wl, n_chunk)}
