@@ -10,6 +10,8 @@ SOURCES = ["api.cu", "det.cu", "rec.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--use_fast_math" if os.environ.get("RDB_FAST_MATH") else "-DRDB_NO_FAST_MATH", "-cudart", "static"]
+if os.environ.get("RDB_SMEM_BASE") == "shared":      # build-time experiment, see gemm_tc.cuh RDB_ALIGNED_SMEM
+    FLAGS.append("-DRDB_SMEM_SHARED_BASE")
 
 
 def _stale(obj, deps):

@@ -127,6 +127,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t span
   return d;
 }
 
+// 1024-byte aligned base of the dynamic shared memory.  The default re-derives the pointer through an integer cast, which makes
+// nvcc treat everything behind it as GENERIC memory (LD.E/ST.E instead of LDS/STS — see DESIGN.md section 6).  Building with
+// RDB_SMEM_BASE=shared (rapiddoc_b200/build.py -> -DRDB_SMEM_SHARED_BASE) keeps the address space; it has not run on a GPU yet,
+// so it is a build-time experiment, not the default.
+#ifdef RDB_SMEM_SHARED_BASE
+#define RDB_ALIGNED_SMEM(raw) ((raw) + ((1024u - (::rdb::tc::smem_u32(raw) & 1023u)) & 1023u))
+#else
+#define RDB_ALIGNED_SMEM(raw) reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023)
+#endif
+
 // ------------------------------------------------------------------------ kernel
 struct Args {
   int M, N, K;

@@ -53,7 +53,7 @@ struct HeadCfg {
 static __global__ void __launch_bounds__(kStemThreads + 32, 1) head_planar_kernel(const HeadArgs g) {
   using S = HeadCfg;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sm = RDB_ALIGNED_SMEM(smem_raw);
   float* sF = reinterpret_cast<float*>(sm + S::oF);
   float* sbd = sF; float* sbu = sF + 24; float* swf = sF + 48; float* sbf = sF + 144; float* sgate = sF + 148;   // swf: [c][4 final taps]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::oBAR);

@@ -54,7 +54,7 @@ template <int C, int COUT, int ACT>
 __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const MlpArgs g) {
   using S = MlpCfg<C, COUT>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sm = RDB_ALIGNED_SMEM(smem_raw);
   float* sb1 = reinterpret_cast<float*>(sm + S::oB);
   float* sb2 = sb1 + S::N1;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::oBAR);
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
 mlp_big_kernel(const __grid_constant__ CUtensorMap tmA, const MlpArgs g) {
   using S = MlpBigCfg<C, COUT, NCH, WS>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sm = RDB_ALIGNED_SMEM(smem_raw);
   float* sb1 = reinterpret_cast<float*>(sm + S::oB);
   float* sb2 = sb1 + 2 * C;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::oBAR);

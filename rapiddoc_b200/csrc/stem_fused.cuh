@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kStemThreads + 32, 1) stem_fused_kernel(const 
   constexpr int ECH = C1 / 8, ACH = CA / 8, CCH = C2 / 8;    // 16-byte chunks per pixel
   constexpr int SUBS = kStemThreads / 128;                   // epilogue warps per TMEM lane quarter
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sm = RDB_ALIGNED_SMEM(smem_raw);
   uint8_t* sA = sm + S::oA;
   uint8_t* sE1 = sm + S::oE1;
   uint8_t* sAT = sm + S::oAT;

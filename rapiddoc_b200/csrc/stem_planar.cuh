@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kStemThreads + 32, 1) stem_planar_kernel(const
   constexpr int TY = S::TY, TX = S::TX, CA = S::CA, C2 = S::C2, P = S::ER_W;
   constexpr int SUBS = kStemThreads / 128;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sm = RDB_ALIGNED_SMEM(smem_raw);
   uint8_t* sE1 = sm + S::oE1;
   uint8_t* sAT = sm + S::oAT;
   uint8_t* sCAT = sm + S::oCAT;
