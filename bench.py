@@ -4,11 +4,15 @@
   python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
   python bench.py --impl reference ...                     (reference CPU arm, rank 0 only)
 
-Workload (config.workload): `det_dbnet_b64_1024` = BASELINE.json configs[1], "RapidOCR DBNet
-text-detection, batch=64 1024x1024 synthetic pages": one STEP = one pass of the hot path
-(fused normalise -> PP-OCRv6-small DBNet forward -> DB binarise + 2x2 dilate) over one batch
-of 64 synthetic uint8 BGR pages per GPU.  `--workload rec` runs configs[2] (512 48x320 crops,
-forward + fused CTC greedy decode) with the same contract.
+Default workload (config.workload) `ocr_pipeline_b64_1024x1024` = BASELINE.json's metric, "pages/sec (full det+rec
+pipeline)", on configs[1]'s input (batch = 64 synthetic 1024x1024 pages per GPU): one STEP = one pass of the whole OCR
+hot path over the batch — DBNet detection, DB post-process (boxes), text-line crops, LightSVTR recognition, CTC decode,
+texts — through `B200OcrModel.ocr_pages` (the fused form of the reference's `_run_ocr_det_batch` +
+`_run_ocr_rec_postprocess` window flow).  The line also carries `secondary` (the det-only and rec-only kernel-level
+numbers of configs[1] / configs[2]), `parity` (decision flips against the CPU oracle on pages / crops of the timed
+batch) and `fp32_exact` (the same pipeline at the reference's precision).
+`--workload det` / `--workload rec` run configs[1] / configs[2] alone: det = fused normalise -> DBNet forward -> DB
+binarise + 2x2 dilate over 64 pages; rec = 512 48x320 crops, forward + fused CTC greedy decode.
 
 value = whole-job pages/s (crops/s) with the batch resident in HBM, timed with CUDA events
         on the stream the kernels are launched on, barrier + synchronize on both sides,
@@ -39,6 +43,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
+    "pipeline": dict(name="ocr_pipeline_b64_1024x1024", batch=64, h=1024, w=1024, unit="pages/s", metric="pages/sec (full det+rec pipeline)"),
     "det": dict(name="det_dbnet_b64_1024x1024", batch=64, h=1024, w=1024, unit="pages/s", metric="pages/sec (DBNet text-detection hot path)"),
     "rec": dict(name="rec_svtr_ctc_b512_48x320", batch=512, h=48, w=320, unit="crops/s", metric="SVTR text-line crops/sec"),
 }
@@ -50,10 +55,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("RDB_BENCH_WORKLOAD", "det"), choices=list(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("RDB_BENCH_WORKLOAD", "pipeline"), choices=list(WORKLOADS))
     ap.add_argument("--precision", default=os.environ.get("RDB_BENCH_PRECISION", "fp16"), choices=["fp16", "fp32"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rec-batch", type=int, default=int(os.environ.get("RDB_BENCH_REC_BATCH", "64")), help="Rec.rec_batch_num of the pipeline workload (both arms)")
+    ap.add_argument("--no-secondary", action="store_true", help="pipeline workload: skip the det-only / rec-only / fp32 legs")
     ap.add_argument("--chunk-pixels", type=int, default=0)
     ap.add_argument("--profile-out", default="", help="write the full per-kernel table of the profiled pass to this JSON file")
     return ap.parse_args()
@@ -212,6 +219,270 @@ def time_cpu(wl_key, data, sample, reps=1):
     return sample / dt, dt
 
 
+# ------------------------------------------------------------------------------- pipeline workload
+PIPE = dict(limit_side_len=1024, box_thresh=0.3, unclip_ratio=1.8, merge=True)   # page OCR settings of model_init.py:106-111
+
+
+def cpu_step_pipeline(pages, rec_batch, detail=False):
+    from oracle import pipeline as OP
+    return OP.ocr_pages(list(pages), limit_side_len=PIPE["limit_side_len"], box_thresh=PIPE["box_thresh"], unclip_ratio=PIPE["unclip_ratio"],
+                        merge=PIPE["merge"], rec_batch_num=rec_batch, return_detail=detail)
+
+
+def make_pipeline_model(device, prec, rec_batch, blobs=None):
+    from rapiddoc_b200.ocr import B200OcrModel
+    return B200OcrModel(det_db_box_thresh=PIPE["box_thresh"], det_db_unclip_ratio=PIPE["unclip_ratio"], enable_merge_det_boxes=PIPE["merge"],
+                        ocr_config={"Det.limit_side_len": PIPE["limit_side_len"], "Rec.rec_batch_num": rec_batch}, device=device,
+                        precision=prec, blobs=blobs)
+
+
+def parity_report(model, pages, want, detail):
+    """Decision-level differences between the B200 pipeline and the CPU oracle on the same pages (flips are
+    counted and reported, not hidden in a tolerance)."""
+    n = len(pages)
+    rep = {"pages_checked": n}
+    # detection maps
+    prob, bitmap = model.text_detector.engine.infer_u8(np.stack(pages), thresh=0.3, use_dilation=True)
+    oprob = np.stack([m[0] for m in detail["maps"]])
+    obm = np.stack([m[1] for m in detail["maps"]])
+    rep["max_abs_dprob"] = float(np.abs(prob - oprob).max())
+    rep["bitmap_flips"] = int((bitmap != obm).sum())
+    rep["bitmap_pixels"] = int(obm.size)
+    # boxes (after sort / merge), end-to-end texts
+    got = model.ocr_pages(list(pages))
+    box_mismatch, box_count_diff, box_max_px, text_mismatch, lines = 0, 0, 0.0, 0, 0
+    for g, w in zip(got, want):
+        g, w = g or [], w or []
+        box_count_diff += abs(len(g) - len(w))
+        for (gb, (gt, _)), (wb, (wt, _)) in zip(g, w):
+            d = float(np.abs(np.asarray(gb, np.float64) - np.asarray(wb, np.float64)).max())
+            box_mismatch += d > 0
+            box_max_px = max(box_max_px, d)
+            text_mismatch += gt != wt
+            lines += 1
+    rep.update(lines_checked=lines, box_count_diff=box_count_diff, box_mismatch=int(box_mismatch), box_max_px=box_max_px,
+               text_mismatch=int(text_mismatch))
+    # recognition on the ORACLE's crops (identical inputs for both sides): per-step argmax flips, decoded text, confidence
+    crops = detail["crops"]
+    if crops:
+        model.text_recognizer.keep_ids = True
+        r = model.text_recognizer(crops)
+        model.text_recognizer.keep_ids = False
+        flips = sum(int((np.asarray(a) != np.asarray(b)).sum()) for a, b in zip(model.text_recognizer.last_ids, detail["ids"]))
+        steps = sum(len(b) for b in detail["ids"])
+        rep.update(crops_checked=len(crops), ctc_steps_checked=int(steps), argmax_flips=int(flips),
+                   crop_text_mismatch=int(sum(a != b[0] for a, b in zip(r.txts, detail["rec"]))),
+                   max_abs_dconf=float(max(abs(a - b[1]) for a, b in zip(r.scores, detail["rec"]))))
+    return rep
+
+
+def aggregate_roofline(prof, esz, wl_det, wl_rec, hbm, peak_src):
+    """The pipeline step launches each kernel at many shapes (every recognition batch has its own width): kernels are grouped
+    by family, achieved = sum(algorithmic bytes) / sum(device time) over all launches of the dominant family."""
+    fam = {}
+    total = sum(v[0] for v in prof.values()) or 1.0
+    for name, (ms, cnt) in prof.items():
+        kind, a = _kv(name)
+        wl = wl_det if (a.get("P", 0) >= 1 << 18 or kind.startswith(("head_planar", "stem_planar", "db_", "dwconv7", "se_", "neck"))) else wl_rec
+        ab = algorithmic_bytes(name, esz, wl, 16)
+        f = fam.setdefault(kind, {"ms": 0.0, "launches": 0, "bytes": 0.0, "modelled_ms": 0.0})
+        f["ms"] += ms
+        f["launches"] += cnt
+        if ab:
+            f["bytes"] += float(ab) * cnt
+            f["modelled_ms"] += ms
+    modelled = {k: v for k, v in fam.items() if v["bytes"] > 0}
+    kind, f = max((modelled or fam).items(), key=lambda kv: kv[1]["ms"])
+    ach = f["bytes"] / (f["modelled_ms"] / 1e3) / 1e9 if f["modelled_ms"] else None
+    return {"kernel": kind, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": (ach / hbm) if ach else None, "traffic": None,
+            "peak_source": peak_src, "launches_profiled": f["launches"], "avg_launch_us": f["ms"] / f["launches"] * 1e3,
+            "algorithmic_bytes_per_launch": f["bytes"] / f["launches"], "share_of_step": f["ms"] / total,
+            "top5": [{"kernel": k, "share": v["ms"] / total, "launches": v["launches"], "avg_us": v["ms"] / v["launches"] * 1e3,
+                      "gbps": (v["bytes"] / (v["modelled_ms"] / 1e3) / 1e9) if v["modelled_ms"] else None}
+                     for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])[:5]]}
+
+
+def run_pipeline(args, wl):
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from rapiddoc_b200 import _lib, PREC_FP16, PREC_FP32, synth, weights as W
+    from rapiddoc_b200.parallel import broadcast_blob
+    prec = PREC_FP16 if args.precision == "fp16" else PREC_FP32
+    esz = 2 if prec == PREC_FP16 else 4
+    blobs = (broadcast_blob(W.det_blob() if rank == 0 else None, local), broadcast_blob(W.rec_blob() if rank == 0 else None, local))
+    B, H, Wd = wl["batch"], wl["h"], wl["w"]
+    uniq = min(B, 8)
+    base = synth.det_pages(uniq, H, Wd, seed=1 + rank)
+    host = torch.empty((B, H, Wd, 3), dtype=torch.uint8).pin_memory()
+    for i in range(B):   # distinct pages: the unique ones rolled by a per-page offset (text lines move, content stays text)
+        host[i] = torch.from_numpy(np.roll(base[i % uniq], shift=(7 * (i // uniq), 13 * (i // uniq)), axis=(0, 1)))
+    host_np = host.numpy()
+    pages = [host_np[i] for i in range(B)]
+    dev_pages = host.cuda()
+    model = make_pipeline_model(local, prec, args.rec_batch, blobs)
+    det_t, rec_t = model.text_detector, model.text_recognizer
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reset_stats():
+        for t in (det_t, rec_t):
+            for k in t.stats:
+                t.stats[k] = 0
+
+    # ---- value: pages resident in HBM, CUDA events on the launching (torch current) stream
+    for _ in range(max(args.warmup, 3)):
+        res = model.ocr_pages(dev_pages)
+    lines_per_step = sum(len(r or []) for r in res)
+    sampler = ClockSampler(local)
+    sampler.start()
+    sampler.wait_first()
+    barrier()
+    reset_stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        model.ocr_pages(dev_pages)
+    e1.record()
+    barrier()
+    clocks = sampler.stop(t_begin, time.time())
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = det_t.stats["launches"] + rec_t.stats["launches"]
+    crops_per_step = rec_t.stats["crops"] / args.steps
+    value = world * B * args.steps / (ms / 1e3)
+    # ---- e2e: host (pinned) pages in, python results out; every copy inside the timed region
+    for _ in range(2):
+        model.ocr_pages(pages)
+    barrier()
+    reset_stats()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        model.ocr_pages(pages)
+    torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e = world * B * args.steps / dt
+    h2d = (det_t.stats["h2d_bytes"] + rec_t.stats["h2d_bytes"]) / args.steps
+    d2h = (det_t.stats["d2h_bytes"] + rec_t.stats["d2h_bytes"]) / args.steps
+    line = None
+    if rank == 0:
+        # ---- roofline: per-kernel device time of one profiled step (events around every launch), grouped by kernel family
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        os.environ["RDB_LANES"] = "1"
+        _lib.profile(True)
+        _lib.profile_reset()
+        model.ocr_pages(dev_pages)
+        torch.cuda.synchronize()
+        prof = _lib.profile_dump()
+        _lib.profile(False)
+        os.environ.pop("RDB_LANES", None)
+        roofline = aggregate_roofline(prof, esz, WORKLOADS["det"], WORKLOADS["rec"], hbm,
+                                      "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)")
+        if args.profile_out:
+            tot = sum(v[0] for v in prof.values())
+            json.dump({"workload": wl["name"], "precision": args.precision, "total_ms": tot,
+                       "kernels": [{"kernel": k, "total_ms": v[0], "launches": v[1], "share": v[0] / tot} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])]},
+                      open(args.profile_out, "w"), indent=1)
+        cpu = parity = secondary = fp32 = None
+        if world == 1 and not args.no_cpu_baseline:
+            # ---- CPU baseline + parity: the oracle port of the same window flow on a bounded sample of this step's pages
+            sample = 4
+            threads = pick_cpu_threads("det", host_np[:1])
+            t0 = time.perf_counter()
+            want, detail = cpu_step_pipeline(pages[:sample], args.rec_batch, detail=True)
+            dt_cpu = time.perf_counter() - t0
+            cpu = {"value": sample / dt_cpu, "unit": wl["unit"], "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
+                   "sample": f"{sample} pages of this step's batch through the CPU oracle port of the whole flow (torch CPU fp32 nets + OpenCV + "
+                             f"CTC decode, rec_batch_num {args.rec_batch}), {dt_cpu:.1f}s"}
+            parity = parity_report(model, pages[:sample], want, detail)
+            if not args.no_secondary and prec == PREC_FP16:
+                m32 = make_pipeline_model(local, PREC_FP32, args.rec_batch, blobs)
+                m32.ocr_pages(dev_pages[:16])
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                m32.ocr_pages(dev_pages)
+                torch.cuda.synchronize()
+                fp32 = {"value": B / (time.perf_counter() - t0), "unit": wl["unit"], "note": "same step in RDB_PREC_FP32 (fp32 storage + fp32 SIMT math, the reference's precision), 1 step",
+                        "parity": parity_report(m32, pages[:sample], want, detail)}
+                del m32
+        if not args.no_secondary:
+            secondary = secondary_numbers(model, dev_pages, B, H, Wd)
+        line = {"metric": wl["metric"], "value": value, "unit": wl["unit"], "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f16" if prec == PREC_FP16 else "f32", "data": "synthetic",
+                "config": {"workload": wl["name"], "batch_per_gpu": B, "h": H, "w": Wd, "precision": args.precision, "input": "uint8 BGR HWC pages",
+                           "flow": "det (limit_side_len 1024, thresh .3, box_thresh .3, unclip 1.8) -> sorted/merged boxes -> get_rotate_crop_image -> rec",
+                           "rec_batch_num": args.rec_batch, "text_lines_per_step": int(lines_per_step), "crops_per_step": crops_per_step,
+                           "l2": f"inputs {host.numel() / 1e6:.0f} MB + activations per step exceed the 126 MB L2 (no explicit flush)",
+                           "parallelism": f"page-parallel replicas x{world}, NCCL weight broadcast at init only"},
+                "clocks": clocks, "e2e": {"value": e2e, "unit": wl["unit"], "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "fp32_exact": fp32, "secondary": secondary,
+                "skipped": SKIPPED_CONFIGS}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        barrier()
+        dist.destroy_process_group()
+
+
+SKIPPED_CONFIGS = {
+    "configs[0] single 960x960 page PP-DocLayout-S via onnxruntime CPU": "skipped: weights unavailable (PP-DocLayout-S is downloaded at first run; not on disk) and onnxruntime is not installed",
+    "configs[3] SLANet_plus + UNET table structure, batch=32 488x488": "skipped: weights unavailable (SLANet_plus / UNET model files are downloaded at first run; not on disk)",
+    "configs[4] full PP-DocLayoutV3 + OCRv5 det/rec + FormulaNet_plus-M, 1200 A4 pages": "skipped: weights unavailable for layout / formula / table (only the OCR det+rec part runs: this line)",
+}
+
+
+def secondary_numbers(model, dev_pages, B, H, Wd, steps=5):
+    """det-only (configs[1]) and rec-only (configs[2]) device-resident numbers of the same engines, a few steps each."""
+    import torch
+    from rapiddoc_b200 import synth
+    det, rec = model.text_detector.engine, model.text_recognizer.engine
+    d_prob = torch.empty((B, H, Wd), dtype=torch.float32, device="cuda")
+    d_bm = torch.empty((B, H, Wd), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream()
+
+    def timed(fn, units):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return units * steps / (e0.elapsed_time(e1) / 1e3)
+    out = {"det_pages_per_s": timed(lambda: det.infer_u8(dev_pages, prob=d_prob, bitmap=d_bm, stream=st), B), "det_config": f"{B} pages {H}x{Wd}, forward + DB bitmap, device-resident"}
+    del d_prob, d_bm
+    n = 512
+    crops = torch.from_numpy(synth.rec_crops(n, 48, 320, seed=2)).cuda()
+    vw = torch.full((n,), 320, dtype=torch.int32, device="cuda")
+    outs = rec._outs(n, rec.tokens(320), crops, False)
+    out["rec_crops_per_s"] = timed(lambda: rec.infer_u8(crops, vw, stream=st, outs=outs), n)
+    out["rec_config"] = f"{n} crops 48x320, forward + fused CTC decode, device-resident"
+    return out
+
+
 # ------------------------------------------------------------------------------- main arms
 def run_reference(args, wl_key, wl):
     """Reference arm: the reference's own CPU implementation of the path.  RapidDoc is pure
@@ -222,10 +493,10 @@ def run_reference(args, wl_key, wl):
     if rank != 0:
         return
     from rapiddoc_b200 import synth
-    sample = 4 if wl_key == "det" else 64
-    data = synth.det_pages(sample, wl["h"], wl["w"], seed=1) if wl_key == "det" else synth.rec_crops(sample, wl["h"], wl["w"], seed=2)
-    fn = cpu_step_det if wl_key == "det" else cpu_step_rec
-    threads = pick_cpu_threads(wl_key, data)
+    sample = {"det": 4, "rec": 64, "pipeline": 2}[wl_key]
+    data = synth.rec_crops(sample, wl["h"], wl["w"], seed=2) if wl_key == "rec" else synth.det_pages(sample, wl["h"], wl["w"], seed=1)
+    fn = {"det": cpu_step_det, "rec": cpu_step_rec, "pipeline": lambda d: cpu_step_pipeline(d, args.rec_batch)}[wl_key]
+    threads = pick_cpu_threads("rec" if wl_key == "rec" else "det", data)
     for _ in range(args.warmup):
         fn(data)
     t0 = time.perf_counter()
@@ -236,7 +507,8 @@ def run_reference(args, wl_key, wl):
     line = {"impl": "reference", "metric": wl["metric"], "value": v, "unit": wl["unit"], "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"], "sample": f"{sample} of the {wl['batch']} per step", "engine": "torch CPU fp32 (oracle port of the reference nets)"},
+            "config": {"workload": wl["name"], "sample": f"{sample} of the {wl['batch']} per step", "engine": "torch CPU fp32 (oracle port of the reference nets)",
+                       **({"rec_batch_num": args.rec_batch} if wl_key == "pipeline" else {})},
             "cpu_baseline": {"value": v, "unit": wl["unit"], "cores": threads, "host_cores": os.cpu_count(), "kind": "port", "sample": f"{sample} {wl['unit'].split('/')[0]} per step x {args.steps} steps"},
             "e2e": {"value": v, "unit": wl["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -250,6 +522,8 @@ def main():
         wl["batch"] = args.batch
     if args.impl == "reference":
         return run_reference(args, wl_key, wl)
+    if wl_key == "pipeline":
+        return run_pipeline(args, wl)
 
     import torch
     import torch.distributed as dist

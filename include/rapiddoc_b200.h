@@ -94,6 +94,42 @@ int rdb_warp_crops(int device, const uint8_t* page, int hgt, int wid, int n, con
 int rdb_resize_pack_u8(int device, const uint8_t* src, int64_t src_bytes, int n, const int64_t* src_offsets, const int32_t* sizes,
                        const int32_t* dst_w, uint8_t* dst, int hgt, int wid_max, void* stream);
 
+/* get_rotate_crop_image for the quads of a whole WINDOW of same-size pages in one launch (cross-page batching of
+ * rapid_doc/backend/pipeline/analyze_utils.py:193-212 -> utils/ocr_utils.py:494-537): as rdb_warp_crops, with
+ * pages [n_pages,hgt,wid,3] and page_idx [n] selecting each quad's page. */
+int rdb_warp_crops_batch(int device, const uint8_t* pages, int n_pages, int hgt, int wid, int n, const int32_t* page_idx,
+                         const double* minv, const int32_t* sizes, const int32_t* rotate, uint8_t* out, const int64_t* offsets,
+                         int64_t out_bytes, void* stream);
+
+/* resize_norm_img geometry for EVERY recognition batch of a window in one launch (the batches of
+ * rapid_doc/model/ocr/rapid_ocr.py:423-440 keep their own padded width): crop i is cv2.resize'd (INTER_LINEAR, bit-exact) to
+ * hgt x dst_w[i] into its slot [hgt][dst_pitch[i]][3] at byte dst_offsets[i] of dst; slot columns >= dst_w[i] are zero.
+ * src / dst are DEVICE buffers, the per-crop arrays host arrays. */
+int rdb_resize_pack_slots(int device, const uint8_t* src, int64_t src_bytes, int n, const int64_t* src_offsets, const int32_t* sizes,
+                          const int32_t* dst_w, const int64_t* dst_offsets, const int32_t* dst_pitch, uint8_t* dst, int64_t dst_bytes,
+                          int hgt, void* stream);
+
+/* DBPostProcess.box_score_fast for m mini-box quads over n same-size prob maps (rapidocr DBPostProcess as patched by
+ * rapid_doc/model/ocr/ocr_patch.py:223-241; upstream boxes_from_bitmap -> box_score_fast): scores[i] = cv2.mean of
+ * prob[page_idx[i]] over cv2.fillPoly's raster of the bbox-shifted, int32-truncated quad (same pixels as OpenCV; the
+ * float64 sum differs from cv2.mean only in summation order, <= 1e-12).  prob [n,hgt,wid] f32 host or DEVICE (the point:
+ * the map stays on the GPU); quads [m,4,2] f32, page_idx [m] (NULL = page 0), scores [m] f64, flags [m] i32 are host arrays.
+ * flags[i] = 1: a vertex of quad i lies outside its clipped bounding box (mini box sticking out of the page) — not scored
+ * here; the caller scores those from an ROI with cv2 so that every score follows OpenCV's raster rule. */
+int rdb_db_box_scores(int device, const float* prob, int n, int hgt, int wid, int m, const float* quads, const int32_t* page_idx,
+                      double* scores, int32_t* flags, void* stream);
+
+/* host-only diagnostic: the cv2.fillPoly(mask, [quad], 1) raster rdb_db_box_scores uses, for a quad whose vertices lie
+ * inside the mw x mh mask; pts_xy [4][2] int32, mask [mh][mw] uint8 (zero-initialised by the caller). */
+int rdb_debug_fill_quad(const int32_t* pts_xy, int mw, int mh, uint8_t* mask);
+
+/* device-memory hygiene: each engine caches its call-scoped buffers per compute lane (best-fit reuse); idle cached bytes
+ * beyond the cap go back to the driver at the end of a call (default 12 GiB per lane). */
+int rdb_det_set_pool_cap_bytes(rdb_det_t* h, size_t bytes);
+int rdb_rec_set_pool_cap_bytes(rdb_rec_t* h, size_t bytes);
+long long rdb_det_pool_bytes(rdb_det_t* h);
+long long rdb_rec_pool_bytes(rdb_rec_t* h);
+
 /* DBPostProcess binarise (+ optional cv2.dilate 2x2) on an existing prob map [n,h,w]:
  * rapid_doc/model/ocr/ocr_patch.py:228-235. */
 int rdb_db_bitmap(int device, const float* prob, int n, int hgt, int wid, float thresh, int use_dilation,

@@ -108,17 +108,16 @@ def clipper_offset_round(path, delta, arc_tolerance=0.25):
     for j in range(n):
         nk, nj = normals[k], normals[j]
         sin_a = nk[0] * nj[1] - nj[0] * nk[1]
-        done = False
         if abs(sin_a * delta) < 1.0:
             cos_a = nk[0] * nj[0] + nj[1] * nk[1]
-            if cos_a > 0:
+            if cos_a > 0:     # OffsetPoint returns here, before its trailing `k = j`
                 out.append((_cround(src[j][0] + nk[0] * delta), _cround(src[j][1] + nk[1] * delta)))
-                done = True
+                continue
         elif sin_a > 1.0:
             sin_a = 1.0
         elif sin_a < -1.0:
             sin_a = -1.0
-        if not done:
+        if True:
             if sin_a * delta < 0:
                 out.append((_cround(src[j][0] + nk[0] * delta), _cround(src[j][1] + nk[1] * delta)))
                 out.append(src[j])

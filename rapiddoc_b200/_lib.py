@@ -30,6 +30,14 @@ SYMBOLS = {
     "rdb_db_bitmap": (_i, [_i, _vp, _i, _i, _i, _f, _i, _vp, _vp]),
     "rdb_warp_crops": (_i, [_i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, C.c_int64, _vp]),
     "rdb_resize_pack_u8": (_i, [_i, _vp, C.c_int64, _i, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "rdb_warp_crops_batch": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, _vp]),
+    "rdb_resize_pack_slots": (_i, [_i, _vp, C.c_int64, _i, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, _i, _vp]),
+    "rdb_db_box_scores": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "rdb_debug_fill_quad": (_i, [_vp, _i, _i, _vp]),
+    "rdb_det_set_pool_cap_bytes": (_i, [_vp, C.c_size_t]),
+    "rdb_rec_set_pool_cap_bytes": (_i, [_vp, C.c_size_t]),
+    "rdb_det_pool_bytes": (C.c_longlong, [_vp]),
+    "rdb_rec_pool_bytes": (C.c_longlong, [_vp]),
     "rdb_debug_cubic_tab": (_i, [_vp]),
     "rdb_clipper_offset": (_i, [C.POINTER(C.c_double), _i, C.c_double, C.POINTER(C.c_int64), _i]),
     "rdb_rec_create": (_i, [_vp, C.c_size_t, _i, _i, C.POINTER(_vp)]),

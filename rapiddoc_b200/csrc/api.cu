@@ -9,6 +9,7 @@
 #include "det.h"
 #include "rec.h"
 #include "warp.cuh"
+#include "dbpost.cuh"
 
 struct rdb_det { rdb::DetEngine* e; };
 struct rdb_rec { rdb::RecEngine* e; };
@@ -76,16 +77,15 @@ int clipper_offset(const double* xy, int n_in, double delta, int64_t* out, int m
     int k = n - 1;
     for (int j = 0; j < n; ++j) {
       double sin_a = nx[k] * ny[j] - nx[j] * ny[k];
-      bool done = false;
       if (std::fabs(sin_a * delta) < 1.0) {
         double cos_a = nx[k] * nx[j] + ny[j] * ny[k];
-        if (cos_a > 0) {
+        if (cos_a > 0) {   // angle ~ 0: OffsetPoint returns here, BEFORE its trailing `k = j` (Clipper 6.4.2 clipper.cpp)
           dst.push_back({cround(src[j].x + nx[k] * delta), cround(src[j].y + ny[k] * delta)});
-          done = true;
+          continue;
         }
       } else if (sin_a > 1.0) sin_a = 1.0;
       else if (sin_a < -1.0) sin_a = -1.0;
-      if (!done) {
+      {
         if (sin_a * delta < 0) {
           dst.push_back({cround(src[j].x + nx[k] * delta), cround(src[j].y + ny[k] * delta)});
           dst.push_back(src[j]);
@@ -146,18 +146,20 @@ int rdb_det_create(const void* weights, size_t nbytes, int device, int precision
     RDB_CHECK(weights && out, "null argument");
     RDB_CHECK(precision == RDB_PREC_FP32 || precision == RDB_PREC_FP16, "bad precision");
     require_device(device);
+    rdb::DeviceGuard g(device);
     *out = new rdb_det{new rdb::DetEngine(weights, nbytes, device, precision)};
   });
   if (rc == RDB_ERR_CUDA && g_err.find("no CUDA device") != std::string::npos) rc = RDB_ERR_NO_DEVICE;
   return rc;
 }
 void rdb_det_destroy(rdb_det_t* h) {
-  if (h) { delete h->e; delete h; }
+  if (h) { rdb::DeviceGuard g(h->e->device()); delete h->e; delete h; }
 }
 
 int rdb_det_infer_f32(rdb_det_t* h, const float* x, int n, int hgt, int wid, float* prob, void* stream) {
   return guarded([&] {
     RDB_CHECK(h && x && prob, "null argument");
+    rdb::DeviceGuard g(h->e->device());
     rdb::DetInput in;
     in.f32 = x;
     h->e->infer(in, n, hgt, wid, 0.3f, false, prob, nullptr, (cudaStream_t)stream);
@@ -168,6 +170,7 @@ int rdb_det_infer_u8(rdb_det_t* h, const uint8_t* pages, int n, int hgt, int wid
                      float thresh, int use_dilation, float* prob, uint8_t* bitmap, void* stream) {
   return guarded([&] {
     RDB_CHECK(h && pages && mean && stdv && (prob || bitmap), "null argument");
+    rdb::DeviceGuard g(h->e->device());
     rdb::DetInput in;
     in.u8 = pages;
     for (int i = 0; i < 3; ++i) { in.mean[i] = mean[i]; in.stdv[i] = stdv[i]; }
@@ -179,6 +182,7 @@ int rdb_det_infer_u8_resize(rdb_det_t* h, const uint8_t* pages, int n, int src_h
                             const float stdv[3], float thresh, int use_dilation, float* prob, uint8_t* bitmap, void* stream) {
   return guarded([&] {
     RDB_CHECK(h && pages && mean && stdv && (prob || bitmap) && src_h > 0 && src_w > 0, "null argument");
+    rdb::DeviceGuard g(h->e->device());
     rdb::DetInput in;
     in.u8 = pages; in.src_h = src_h; in.src_w = src_w;
     for (int i = 0; i < 3; ++i) { in.mean[i] = mean[i]; in.stdv[i] = stdv[i]; }
@@ -191,6 +195,7 @@ int rdb_db_bitmap(int device, const float* prob, int n, int hgt, int wid, float 
   return guarded([&] {
     RDB_CHECK(prob && bitmap && n > 0, "null argument");
     require_device(device);
+    rdb::DeviceGuard g(device);
     rdb::db_bitmap(device, prob, n, hgt, wid, thresh, use_dilation != 0, bitmap, (cudaStream_t)stream);
   });
 }
@@ -199,6 +204,7 @@ int rdb_resize_linear_u8(int device, const uint8_t* src, int n, int sh, int sw, 
   return guarded([&] {
     RDB_CHECK(src && dst, "null argument");
     require_device(device);
+    rdb::DeviceGuard g(device);
     rdb::resize_linear_u8(device, src, n, sh, sw, dst, dh, dw, (cudaStream_t)stream);
   });
 }
@@ -209,6 +215,7 @@ int rdb_warp_crops(int device, const uint8_t* page, int hgt, int wid, int n, con
     RDB_CHECK(page && out && (n == 0 || (minv && sizes && offsets)), "null argument");
     RDB_CHECK(hgt > 0 && wid > 0 && n >= 0 && out_bytes >= 0, "warp: bad shape");
     require_device(device);
+    rdb::DeviceGuard g(device);
     rdb::warp_crops(device, page, hgt, wid, n, minv, sizes, rotate, out, reinterpret_cast<const long long*>(offsets), (long long)out_bytes, (cudaStream_t)stream);
   });
 }
@@ -219,9 +226,60 @@ int rdb_resize_pack_u8(int device, const uint8_t* src, int64_t src_bytes, int n,
     RDB_CHECK(src && dst && (n == 0 || (src_offsets && sizes && dst_w)), "null argument");
     RDB_CHECK(n >= 0 && hgt > 0 && wid_max > 0 && src_bytes >= 0, "resize_pack: bad shape");
     require_device(device);
+    rdb::DeviceGuard g(device);
     rdb::resize_pack_u8(device, src, (long long)src_bytes, n, reinterpret_cast<const long long*>(src_offsets), sizes, dst_w, dst, hgt, wid_max, (cudaStream_t)stream);
   });
 }
+
+int rdb_warp_crops_batch(int device, const uint8_t* pages, int n_pages, int hgt, int wid, int n, const int32_t* page_idx, const double* minv,
+                         const int32_t* sizes, const int32_t* rotate, uint8_t* out, const int64_t* offsets, int64_t out_bytes, void* stream) {
+  return guarded([&] {
+    RDB_CHECK(pages && out && (n == 0 || (minv && sizes && offsets)), "null argument");
+    RDB_CHECK(hgt > 0 && wid > 0 && n >= 0 && n_pages > 0 && out_bytes >= 0, "warp: bad shape");
+    require_device(device);
+    rdb::DeviceGuard g(device);
+    rdb::warp_crops(device, pages, hgt, wid, n, minv, sizes, rotate, out, reinterpret_cast<const long long*>(offsets), (long long)out_bytes,
+                    (cudaStream_t)stream, n_pages, page_idx);
+  });
+}
+
+int rdb_resize_pack_slots(int device, const uint8_t* src, int64_t src_bytes, int n, const int64_t* src_offsets, const int32_t* sizes,
+                          const int32_t* dst_w, const int64_t* dst_offsets, const int32_t* dst_pitch, uint8_t* dst, int64_t dst_bytes, int hgt,
+                          void* stream) {
+  return guarded([&] {
+    RDB_CHECK(src && dst && (n == 0 || (src_offsets && sizes && dst_w && dst_offsets && dst_pitch)), "null argument");
+    RDB_CHECK(n >= 0 && hgt > 0 && src_bytes >= 0 && dst_bytes >= 0, "resize_pack_slots: bad shape");
+    require_device(device);
+    rdb::DeviceGuard g(device);
+    rdb::resize_pack_slots(device, src, (long long)src_bytes, n, reinterpret_cast<const long long*>(src_offsets), sizes, dst_w,
+                           reinterpret_cast<const long long*>(dst_offsets), dst_pitch, dst, (long long)dst_bytes, hgt, (cudaStream_t)stream);
+  });
+}
+
+int rdb_db_box_scores(int device, const float* prob, int n, int hgt, int wid, int m, const float* quads, const int32_t* page_idx, double* scores,
+                      int32_t* flags, void* stream) {
+  return guarded([&] {
+    RDB_CHECK(prob && (m == 0 || (quads && scores && flags)), "null argument");
+    RDB_CHECK(n > 0 && hgt > 0 && wid > 0 && m >= 0, "box_scores: bad shape");
+    require_device(device);
+    rdb::DeviceGuard g(device);
+    rdb::db_box_scores(device, prob, n, hgt, wid, m, quads, page_idx, scores, flags, (cudaStream_t)stream);
+  });
+}
+
+int rdb_debug_fill_quad(const int32_t* pts_xy, int mw, int mh, uint8_t* mask) {
+  return guarded([&] {
+    RDB_CHECK(pts_xy && mask && mw > 0 && mh > 0, "null argument");
+    for (int i = 0; i < 4; ++i)
+      RDB_CHECK(pts_xy[2 * i] >= 0 && pts_xy[2 * i] < mw && pts_xy[2 * i + 1] >= 0 && pts_xy[2 * i + 1] < mh, "fill_quad: vertex outside the mask");
+    rdb::debug_fill_quad(pts_xy, mw, mh, mask);
+  });
+}
+
+int rdb_det_set_pool_cap_bytes(rdb_det_t* h, size_t bytes) { if (!h) return RDB_ERR_INVALID; h->e->set_pool_cap(bytes); return RDB_OK; }
+int rdb_rec_set_pool_cap_bytes(rdb_rec_t* h, size_t bytes) { if (!h) return RDB_ERR_INVALID; h->e->set_pool_cap(bytes); return RDB_OK; }
+long long rdb_det_pool_bytes(rdb_det_t* h) { return h ? (long long)h->e->pool_bytes() : -1; }
+long long rdb_rec_pool_bytes(rdb_rec_t* h) { return h ? (long long)h->e->pool_bytes() : -1; }
 
 int rdb_debug_cubic_tab(int16_t* out) {
   return guarded([&] {
@@ -246,13 +304,14 @@ int rdb_rec_create(const void* weights, size_t nbytes, int device, int precision
     RDB_CHECK(weights && out, "null argument");
     RDB_CHECK(precision == RDB_PREC_FP32 || precision == RDB_PREC_FP16, "bad precision");
     require_device(device);
+    rdb::DeviceGuard g(device);
     *out = new rdb_rec{new rdb::RecEngine(weights, nbytes, device, precision)};
   });
   if (rc == RDB_ERR_CUDA && g_err.find("no CUDA device") != std::string::npos) rc = RDB_ERR_NO_DEVICE;
   return rc;
 }
 void rdb_rec_destroy(rdb_rec_t* h) {
-  if (h) { delete h->e; delete h; }
+  if (h) { rdb::DeviceGuard g(h->e->device()); delete h->e; delete h; }
 }
 int rdb_rec_vocab(rdb_rec_t* h) { return h ? h->e->vocab() : RDB_ERR_INVALID; }
 int rdb_rec_tokens(int wid) { return rdb::RecEngine::tokens_for_width(wid); }
@@ -261,6 +320,7 @@ int rdb_rec_infer_f32(rdb_rec_t* h, const float* x, int n, int wid, int32_t* ids
                       int32_t* text_len, float* conf, float* softmax, void* stream) {
   return guarded([&] {
     RDB_CHECK(h && x, "null argument");
+    rdb::DeviceGuard g(h->e->device());
     rdb::RecInput in;
     in.f32 = x;
     rdb::RecOutput o;
@@ -273,6 +333,7 @@ int rdb_rec_infer_u8(rdb_rec_t* h, const uint8_t* crops, const int32_t* valid_w,
                      int32_t* text_ids, int32_t* text_len, float* conf, void* stream) {
   return guarded([&] {
     RDB_CHECK(h && crops, "null argument");
+    rdb::DeviceGuard g(h->e->device());
     rdb::RecInput in;
     in.u8 = crops;
     in.valid_w = valid_w;
@@ -301,6 +362,7 @@ int rdb_debug_gemm(int device, int use_tc, int mode, const float* A, const float
                    int N, int K, int act, float* out) {
   return guarded([&] {
     require_device(device);
+    rdb::DeviceGuard g(device);
     RDB_CUDA(cudaSetDevice(device));
     rdb::Pool pool;
     rdb::Ctx cx;

@@ -29,6 +29,28 @@ struct Error : std::runtime_error {
 
 #define RDB_LAUNCH_CHECK() RDB_CUDA(cudaGetLastError())
 
+// cudaFuncSetAttribute is per DEVICE: one-time flags are kept per device index, so a second engine on another GPU of the
+// same process sets its kernels' dynamic shared memory limit too.
+constexpr int kMaxDevices = 64;
+inline bool first_on_device(bool (&flags)[kMaxDevices]) {
+  int d = 0;
+  cudaGetDevice(&d);
+  if (d < 0 || d >= kMaxDevices) return true;
+  if (flags[d]) return false;
+  flags[d] = true;
+  return true;
+}
+
+// Every C-ABI entry point selects its engine's device; the caller's current device (torch's, for instance) is put back on exit.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+    if (device != prev) cudaSetDevice(device);
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SILU = 3, ACT_SIGMOID = 4, ACT_GELUF = 5 };
 
 // erf-GELU for the fp16 path, 11 issue slots instead of erff's ~24 (the GELU GEMM epilogues are issue-bound):

@@ -231,7 +231,7 @@ void DetEngine::forward_chunk(Ctx& cx, const DetInput& in, int n, int H, int W, 
   }
 }
 
-void DetEngine::infer(const DetInput& in_host_or_dev, int n, int H, int W, float thresh, bool dilate, float* prob, uint8_t* bitmap,
+void DetEngine::infer_impl(const DetInput& in_host_or_dev, int n, int H, int W, float thresh, bool dilate, float* prob, uint8_t* bitmap,
                       cudaStream_t st) {
   RDB_CUDA(cudaSetDevice(device_));
   RDB_CHECK(n > 0 && H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0, "det: h and w must be positive multiples of 32");
@@ -375,6 +375,17 @@ void DetEngine::infer(const DetInput& in_host_or_dev, int n, int H, int W, float
   if (do_resize) { pools_[0].free(d_xi); pools_[0].free(d_yi); pools_[0].free(d_xa); pools_[0].free(d_ya); }
   if (Profiler::global().on) { RDB_CUDA(cudaDeviceSynchronize()); Profiler::global().resolve(); }
   last_launches_ = launches;
+}
+
+void DetEngine::infer(const DetInput& in, int n, int H, int W, float thresh, bool dilate, float* prob, uint8_t* bitmap, cudaStream_t st) {
+  try {
+    infer_impl(in, n, H, W, thresh, dilate, prob, bitmap, st);
+  } catch (...) {   // the call's pool blocks go back to the cache instead of staying "live" for ever
+    cudaDeviceSynchronize();
+    for (auto& p : pools_) p.reclaim();
+    throw;
+  }
+  for (auto& p : pools_) p.enforce_cap();
 }
 
 // OpenCV resize() coefficient tables for INTER_LINEAR / 8U (float32 maths as in cv::resize -> saturate_cast<short>)

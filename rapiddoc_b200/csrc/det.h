@@ -18,11 +18,14 @@ class DetEngine {
   ~DetEngine();
   // prob [n,H,W] f32 / bitmap [n,H,W] u8: host or device pointers, may be null.
   void infer(const DetInput& in, int n, int H, int W, float thresh, bool dilate, float* prob, uint8_t* bitmap, cudaStream_t st);
+  void set_pool_cap(size_t bytes) { for (auto& p : pools_) p.set_cap(bytes); }
+  size_t pool_bytes() const { size_t t = 0; for (auto& p : pools_) t += p.total_bytes(); return t; }
   long long last_launches() const { return last_launches_; }
   int device() const { return device_; }
   void set_chunk_pixels(long long px) { chunk_pixels_ = px; chunk_pixels_set_ = true; }
 
  private:
+  void infer_impl(const DetInput& in, int n, int H, int W, float thresh, bool dilate, float* prob, uint8_t* bitmap, cudaStream_t st);
   template <typename T>
   void forward_chunk(Ctx& cx, const DetInput& in, int n, int H, int W, float thresh, bool dilate, float* prob, uint8_t* bitmap);
   void ensure_streams();

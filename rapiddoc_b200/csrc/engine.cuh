@@ -1,6 +1,7 @@
 // Host-side runtime shared by the det / rec engines: weight blob, device buffer pool,
 // launch helpers.  One engine = one (GPU, model); all work of a call goes to one stream.
 #pragma once
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
@@ -93,24 +94,37 @@ class Weights {
 };
 
 // ---------------------------------------------------------------- device buffer pool
-// Size-keyed caching allocator.  Every alloc/free of one engine call happens in program
-// order on ONE stream, so a block may be handed out again as soon as it is freed.
+// Caching allocator for the call-scoped activation / staging buffers of one compute lane.  Every alloc/free of one engine
+// call happens in program order on ONE stream, so a block may be handed out again as soon as it is freed.
+//  * best-fit reuse: a request takes the smallest cached block of [bytes, 2*bytes] (RapidDoc feeds many page / crop shapes:
+//    det buckets at 64-px granularity, rec widths per batch — exact-size keys would keep one full set per shape);
+//  * the cache is bounded: when the cached (idle) bytes exceed the cap (default 12 GiB per lane, RDB_POOL_CAP_MB or
+//    rdb_set_pool_cap_bytes) the least recently used blocks go back to the driver, so the torch models that share the GPU
+//    keep their memory;
+//  * reclaim(): after an exception unwound an infer call, its live blocks return to the cache instead of leaking.
 class Pool {
  public:
+  Pool() {
+    if (const char* e = std::getenv("RDB_POOL_CAP_MB")) cap_ = (size_t)std::atoll(e) << 20;
+  }
   ~Pool() { release_all(); }
   void* alloc(size_t bytes) {
     bytes = (bytes + 511) / 512 * 512;
     if (bytes == 0) bytes = 512;
-    auto it = free_.find(bytes);
-    if (it != free_.end() && !it->second.empty()) {
-      void* p = it->second.back();
+    auto it = free_.lower_bound(bytes);
+    while (it != free_.end() && it->second.empty()) it = free_.erase(it);
+    if (it != free_.end() && it->first <= 2 * bytes) {
+      Block b = it->second.back();
       it->second.pop_back();
-      live_[p] = bytes;
-      return p;
+      if (it->second.empty()) free_.erase(it);
+      cached_ -= b.bytes;
+      live_[b.p] = b.bytes;
+      return b.p;
     }
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, bytes);
     if (e != cudaSuccess) {
+      cudaGetLastError();
       trim();
       RDB_CUDA(cudaMalloc(&p, bytes));
     }
@@ -124,26 +138,57 @@ class Pool {
     if (!p) return;
     auto it = live_.find(p);
     RDB_CHECK(it != live_.end(), "pool: free of unknown pointer");
-    free_[it->second].push_back(p);
+    free_[it->second].push_back(Block{p, it->second, ++tick_});
+    cached_ += it->second;
     live_.erase(it);
   }
-  void trim() {  // give cached blocks back to the driver
+  // called by the engines at the end of a call: evict least-recently-used cached blocks down to the cap
+  void enforce_cap() {
+    if (cached_ <= cap_) return;
+    std::vector<Block> all;
+    for (auto& kv : free_) for (auto& b : kv.second) all.push_back(b);
+    std::sort(all.begin(), all.end(), [](const Block& a, const Block& b) { return a.tick < b.tick; });
+    std::unordered_map<void*, bool> drop;
+    size_t c = cached_;
+    for (auto& b : all) { if (c <= cap_) break; drop[b.p] = true; c -= b.bytes; }
+    cudaDeviceSynchronize();
+    for (auto it = free_.begin(); it != free_.end();) {
+      auto& v = it->second;
+      for (size_t i = 0; i < v.size();) {
+        if (drop.count(v[i].p)) { cudaFree(v[i].p); total_ -= v[i].bytes; cached_ -= v[i].bytes; v[i] = v.back(); v.pop_back(); }
+        else ++i;
+      }
+      it = v.empty() ? free_.erase(it) : std::next(it);
+    }
+  }
+  void trim() {  // give every cached block back to the driver
     cudaDeviceSynchronize();
     for (auto& kv : free_)
-      for (void* p : kv.second) { cudaFree(p); total_ -= kv.first; }
+      for (auto& b : kv.second) { cudaFree(b.p); total_ -= b.bytes; }
     free_.clear();
+    cached_ = 0;
+  }
+  void reclaim() {  // an exception unwound the call that owned the live blocks
+    std::vector<void*> ps;
+    for (auto& kv : live_) ps.push_back(kv.first);
+    for (void* p : ps) free(p);
   }
   void release_all() {
     trim();
     for (auto& kv : live_) cudaFree(kv.first);
     live_.clear();
   }
+  void set_cap(size_t bytes) { cap_ = bytes; }
   size_t total_bytes() const { return total_; }
+  size_t cached_bytes() const { return cached_; }
+  size_t live_blocks() const { return live_.size(); }
 
  private:
-  std::map<size_t, std::vector<void*>> free_;
+  struct Block { void* p; size_t bytes; unsigned long long tick; };
+  std::map<size_t, std::vector<Block>> free_;
   std::unordered_map<void*, size_t> live_;
-  size_t total_ = 0;
+  size_t total_ = 0, cached_ = 0, cap_ = (size_t)12 << 30;
+  unsigned long long tick_ = 0;
 };
 
 inline bool is_device_ptr(const void* p) {
@@ -227,8 +272,8 @@ inline bool env_gemm_simt() {
 template <int ACT>
 inline void launch_tc_store_act(const tc::Plan& p, const CUtensorMap& mA, const CUtensorMap& mB, cudaStream_t st) {
   auto k = tc::gemm_tc_kernel<tc::EPI_STORE, ACT>;
-  static bool attr_done = false;
-  if (!attr_done) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
+  static bool attr_done[rdb::kMaxDevices] = {};
+  if (rdb::first_on_device(attr_done)) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); }
   k<<<p.grid, tc::kThreadsTc, p.smem, st>>>(mA, mB, p.a);
 }
 inline void launch_tc_store(const tc::Plan& p, const CUtensorMap& mA, const CUtensorMap& mB, int act, cudaStream_t st) {
@@ -294,8 +339,8 @@ inline void launch_head_tail_tc(Ctx& cx, const __half* hd, int n, int H, int W, 
   CUtensorMap mA = tc::make_map(hd, M, 24, 24, a.AW, 128);
   CUtensorMap mB = tc::make_map(w_up_h, 96, 24, 24, a.AW, a.BN);
   auto k = tc::gemm_tc_kernel<tc::EPI_HEAD, ACT_NONE>;
-  static bool attr_done = false;
-  if (!attr_done) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
+  static bool attr_done[rdb::kMaxDevices] = {};
+  if (rdb::first_on_device(attr_done)) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); }
   cx.begin("head_tail_tc[P=" + std::to_string(M) + "]");
   k<<<p.grid, tc::kThreadsTc, p.smem, cx.st>>>(mA, mB, a);
   cx.end();
@@ -310,8 +355,8 @@ inline void launch_gemm_tc_ctc(Ctx& cx, const __half* A, int lda, long long M, i
   CUtensorMap mA = tc::make_map(A, M, K, lda, a.AW, 128);
   CUtensorMap mB = tc::make_map(Wh, N, K, K, a.AW, a.BN);
   auto k = tc::gemm_tc_kernel<tc::EPI_CTC, ACT_NONE>;
-  static bool attr_done = false;
-  if (!attr_done) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
+  static bool attr_done[rdb::kMaxDevices] = {};
+  if (rdb::first_on_device(attr_done)) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); }
   cx.begin("gemm_tc_ctc[M=" + std::to_string(M) + ",K=" + std::to_string(K) + ",N=" + std::to_string(N) + "]");
   k<<<p.grid, tc::kThreadsTc, p.smem, cx.st>>>(mA, mB, a);
   cx.end();

@@ -267,8 +267,8 @@ inline void launch_head_planar(Ctx& cx, const Weights& w, const __half* const* f
   if (const char* e = std::getenv("RDB_HEAD_DBG")) a.dbg = std::atoi(e);
   a.tiles_x = (W + S::TW - 1) / S::TW; a.tiles_y = (H + S::TH - 1) / S::TH; a.tiles = n * a.tiles_x * a.tiles_y;
   auto k = head_planar_kernel;
-  static bool attr_done = false;
-  if (!attr_done) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmem)); attr_done = true; }
+  static bool attr_done[rdb::kMaxDevices] = {};
+  if (rdb::first_on_device(attr_done)) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmem)); }
   const int grid = a.tiles < cx.num_sms ? a.tiles : cx.num_sms;
   cx.begin("head_planar[P=" + std::to_string((long long)n * H * W) + "]");
   k<<<grid, kStemThreads + 32, S::kSmem, cx.st>>>(a);

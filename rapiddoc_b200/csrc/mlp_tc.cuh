@@ -223,13 +223,13 @@ inline void launch_mlp_tc(Ctx& cx, const __half* x, long long M, const Tensor& w
   cx.begin("mlp_tc[M=" + std::to_string(M) + ",C=" + std::to_string(C) + ",N=" + std::to_string(COUT) + ",res=" + (res ? "1" : "0") + "]");
   if (act == ACT_GELU) {
     auto k = mlp_tc_kernel<C, COUT, ACT_GELU>;
-    static bool done = false;
-    if (!done) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmem)); done = true; }
+    static bool done[rdb::kMaxDevices] = {};
+    if (rdb::first_on_device(done)) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmem)); }
     k<<<grid, kMlpThreads, S::kSmem, cx.st>>>(mA, a);
   } else {
     auto k = mlp_tc_kernel<C, COUT, ACT_GELUF>;
-    static bool done = false;
-    if (!done) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmem)); done = true; }
+    static bool done[rdb::kMaxDevices] = {};
+    if (rdb::first_on_device(done)) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmem)); }
     k<<<grid, kMlpThreads, S::kSmem, cx.st>>>(mA, a);
   }
   cx.end();
@@ -535,13 +535,13 @@ inline void launch_mlp_big(Ctx& cx, const Weights& wts, const std::string& name,
   cx.begin("mlp_tc[M=" + std::to_string(M) + ",C=" + std::to_string(C) + ",N=" + std::to_string(COUT) + ",res=" + (res ? "1" : "0") + "]");
   if (act == ACT_GELU) {
     auto k = mlp_big_kernel<C, COUT, NCH, WS, ACT_GELU>;
-    static bool done = false;
-    if (!done) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmem)); done = true; }
+    static bool done[rdb::kMaxDevices] = {};
+    if (rdb::first_on_device(done)) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmem)); }
     k<<<grid, kMlpThreads, S::kSmem, cx.st>>>(mA, a);
   } else {
     auto k = mlp_big_kernel<C, COUT, NCH, WS, ACT_GELUF>;
-    static bool done = false;
-    if (!done) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmem)); done = true; }
+    static bool done[rdb::kMaxDevices] = {};
+    if (rdb::first_on_device(done)) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmem)); }
     k<<<grid, kMlpThreads, S::kSmem, cx.st>>>(mA, a);
   }
   cx.end();

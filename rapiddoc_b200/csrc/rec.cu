@@ -185,7 +185,7 @@ void RecEngine::forward_chunk(Ctx& cx, const RecInput& in, int n, int W, int32_t
   O::release(cx, seq);
 }
 
-void RecEngine::infer(const RecInput& in0, int n, int W, const RecOutput& out, cudaStream_t st) {
+void RecEngine::infer_impl(const RecInput& in0, int n, int W, const RecOutput& out, cudaStream_t st) {
   RDB_CUDA(cudaSetDevice(device_));
   RDB_CHECK(n > 0 && W >= 16, "rec: width must be >= 16");
   RDB_CHECK((in0.f32 != nullptr) != (in0.u8 != nullptr), "rec: exactly one input");
@@ -273,6 +273,17 @@ void RecEngine::infer(const RecInput& in0, int n, int W, const RecOutput& out, c
   if (d_vw && d_vw != in0.valid_w) pools_[0].free(d_vw);
   if (Profiler::global().on) { RDB_CUDA(cudaDeviceSynchronize()); Profiler::global().resolve(); }
   last_launches_ = launches;
+}
+
+void RecEngine::infer(const RecInput& in, int n, int W, const RecOutput& out, cudaStream_t st) {
+  try {
+    infer_impl(in, n, W, out, st);
+  } catch (...) {
+    cudaDeviceSynchronize();
+    for (auto& p : pools_) p.reclaim();
+    throw;
+  }
+  for (auto& p : pools_) p.enforce_cap();
 }
 
 void RecEngine::ensure_streams() {

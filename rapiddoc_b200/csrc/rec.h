@@ -22,6 +22,8 @@ class RecEngine {
   RecEngine(const void* blob, size_t nbytes, int device, int precision);
   ~RecEngine();
   void infer(const RecInput& in, int n, int W, const RecOutput& out, cudaStream_t st);
+  void set_pool_cap(size_t bytes) { for (auto& p : pools_) p.set_cap(bytes); }
+  size_t pool_bytes() const { size_t t = 0; for (auto& p : pools_) t += p.total_bytes(); return t; }
   int vocab() const { return vocab_; }
   // T for an input of width W: stem1 s2, stem3 s2, avg_pool [3,2]  (rec_lcnetv4.py:151,154,311)
   static int tokens_for_width(int W) { int w1 = (W - 1) / 2 + 1; int w2 = (w1 - 1) / 2 + 1; return w2 / 2; }
@@ -30,6 +32,7 @@ class RecEngine {
   void set_chunk_crops(int c) { chunk_crops_ = c; }
 
  private:
+  void infer_impl(const RecInput& in, int n, int W, const RecOutput& out, cudaStream_t st);
   template <typename T>
   void forward_chunk(Ctx& cx, const RecInput& in, int n, int W, int32_t* ids, float* probs, int32_t* text_ids, int32_t* text_len,
                      float* conf, float* softmax);

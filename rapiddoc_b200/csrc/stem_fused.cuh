@@ -430,8 +430,8 @@ inline void launch_stem_fused(Ctx& cx, const Weights& w, const __half* e1, int n
   a.out = out; a.H2 = H2; a.W2 = W2;
   a.tiles_x = (W2 + S::TX - 1) / S::TX; a.tiles_y = (H2 + S::TY - 1) / S::TY; a.tiles = n * a.tiles_x * a.tiles_y;
   auto k = stem_fused_kernel<C1>;
-  static bool attr_done = false;
-  if (!attr_done) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmem)); attr_done = true; }
+  static bool attr_done[rdb::kMaxDevices] = {};
+  if (rdb::first_on_device(attr_done)) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmem)); }
   const int grid = a.tiles < cx.num_sms ? a.tiles : cx.num_sms;
   static const bool dbg = std::getenv("RDB_STEM_DBG") != nullptr;
   if (dbg) { RDB_CUDA(cudaMalloc(&a.dbg, 3 * 128 * sizeof(long long))); RDB_CUDA(cudaMemset(a.dbg, 0, 3 * 128 * sizeof(long long))); }

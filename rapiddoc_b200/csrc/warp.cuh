@@ -43,6 +43,7 @@ struct WarpCrop {
   int rotate;           // 1: store np.rot90(dst) ([w][h][3]) instead of dst ([h][w][3])
   int bw0;              // OpenCV's block width for this destination size
   long long offset;     // byte offset of this crop in the output buffer
+  long long src_off;    // byte offset of this crop's page in the page buffer (pages are same-size [n_pages,H,W,3])
 };
 
 static __global__ void __launch_bounds__(256) warp_cubic_kernel(const uint8_t* __restrict__ src, int H, int W, const WarpCrop* __restrict__ crops,
@@ -67,7 +68,7 @@ static __global__ void __launch_bounds__(256) warp_cubic_kernel(const uint8_t* _
 #pragma unroll
   for (int ky = 0; ky < 4; ++ky) {
     const int iy = max(0, min(H - 1, sy + ky));
-    const uint8_t* row = src + (long long)iy * W * 3;
+    const uint8_t* row = src + c.src_off + (long long)iy * W * 3;
 #pragma unroll
     for (int kx = 0; kx < 4; ++kx) {
       const int ix = max(0, min(W - 1, sx + kx));
@@ -127,12 +128,11 @@ inline void build_cubic_tab(std::vector<short>& tab) {
 
 // page [H,W,3] uint8 (host or device); minv [n][9]; sizes [n][2] = (w,h); rotate [n]; offsets [n] bytes into out (host or device)
 inline void warp_crops(int device, const uint8_t* page, int H, int W, int n, const double* minv, const int32_t* sizes, const int32_t* rotate,
-                       uint8_t* out, const long long* offsets, long long out_bytes, cudaStream_t st) {
+                       uint8_t* out, const long long* offsets, long long out_bytes, cudaStream_t st, int n_pages = 1, const int32_t* page_idx = nullptr) {
   RDB_CUDA(cudaSetDevice(device));
   if (n <= 0) return;
-  static std::vector<short> host_tab;
+  static const std::vector<short> host_tab = [] { std::vector<short> t; build_cubic_tab(t); return t; }();   // thread-safe one-time init
   static short* dev_tab[64] = {};
-  if (host_tab.empty()) build_cubic_tab(host_tab);
   RDB_CHECK(device >= 0 && device < 64, "warp: device index");
   if (!dev_tab[device]) {
     RDB_CUDA(cudaMalloc(&dev_tab[device], host_tab.size() * sizeof(short)));
@@ -144,6 +144,9 @@ inline void warp_crops(int device, const uint8_t* page, int H, int W, int n, con
     WarpCrop& c = hc[i];
     for (int k = 0; k < 9; ++k) c.m[k] = minv[i * 9 + k];
     c.w = sizes[2 * i]; c.h = sizes[2 * i + 1]; c.rotate = rotate ? rotate[i] : 0; c.offset = offsets[i];
+    const int pg = page_idx ? page_idx[i] : 0;
+    RDB_CHECK(pg >= 0 && pg < n_pages, "warp: page index out of range");
+    c.src_off = (long long)pg * H * W * 3;
     RDB_CHECK(c.w > 0 && c.h > 0, "warp: empty crop");
     RDB_CHECK(c.offset >= 0 && c.offset + (long long)c.w * c.h * 3 <= out_bytes, "warp: crop exceeds the output buffer");
     int bh0 = c.h < 16 ? c.h : 16;                    // WarpPerspectiveInvoker: BLOCK_SZ = 32
@@ -155,7 +158,7 @@ inline void warp_crops(int device, const uint8_t* page, int H, int W, int n, con
   const bool p_dev = is_device_ptr(page), o_dev = is_device_ptr(out);
   uint8_t* dp = const_cast<uint8_t*>(page);
   uint8_t* dout = out;
-  const size_t page_b = (size_t)H * W * 3;
+  const size_t page_b = (size_t)n_pages * H * W * 3;
   ScratchCarver sc{device_scratch(device, pad256(sizeof(WarpCrop) * n) + (p_dev ? 0 : pad256(page_b)) + (o_dev ? 0 : pad256((size_t)out_bytes)))};
   WarpCrop* dc = sc.take<WarpCrop>(n);
   if (!p_dev) { dp = sc.take<uint8_t>(page_b); RDB_CUDA(cudaMemcpyAsync(dp, page, page_b, cudaMemcpyHostToDevice, st)); }
@@ -247,6 +250,82 @@ inline void resize_pack_u8(int device, const uint8_t* src, long long src_bytes, 
   RDB_LAUNCH_CHECK();
   if (!d_dev) RDB_CUDA(cudaMemcpyAsync(dst, dd, dst_b, cudaMemcpyDeviceToHost, st));
   RDB_CUDA(cudaStreamSynchronize(st));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// The same resize for EVERY recognition batch of a window in one launch (cross-page batching): crop i goes to its
+// own slot [dh][pitch_i][3] at byte dst_off[i] of one packed buffer (a batch = consecutive slots of equal pitch), columns
+// >= dw_i of the slot are zeroed.  OpenCV's coefficient rule (float32, 11-bit fixed point) is evaluated in the kernel with
+// explicitly rounded IEEE operations, so no per-crop tables travel and the call needs no synchronisation of its own.
+struct ResizeSlot {
+  long long src_off, dst_off;
+  int sw, sh, dw, pitch;
+};
+
+__device__ __forceinline__ void cv_linear_coeff(int d, int dsize, int ssize, bool vertical, int* idx, int* a0, int* a1) {
+  const double inv = __ddiv_rn((double)dsize, (double)ssize), scale = __ddiv_rn(1.0, inv);
+  float fx = __double2float_rn(__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5));
+  int s = (int)floorf(fx);
+  fx = __fsub_rn(fx, (float)s);
+  if (!vertical) {
+    if (s < 0) { fx = 0.f; s = 0; }
+    if (s >= ssize - 1) { fx = 0.f; s = ssize - 1; }
+  }
+  *idx = s;
+  *a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, fx), 2048.f));
+  *a1 = __float2int_rn(__fmul_rn(fx, 2048.f));
+}
+
+static __global__ void __launch_bounds__(256) resize_slots_kernel(const uint8_t* __restrict__ src, const ResizeSlot* __restrict__ slots, uint8_t* __restrict__ dst, int dh) {
+  const ResizeSlot c = slots[blockIdx.y];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= dh * c.pitch) return;
+  const int x = idx % c.pitch, y = idx / c.pitch;
+  uint8_t* o = dst + c.dst_off + (long long)idx * 3;
+  if (x >= c.dw) { o[0] = 0; o[1] = 0; o[2] = 0; return; }
+  int x0, a0, a1, ys, b0, b1;
+  cv_linear_coeff(x, c.dw, c.sw, false, &x0, &a0, &a1);
+  cv_linear_coeff(y, dh, c.sh, true, &ys, &b0, &b1);
+  const int x1 = min(x0 + 1, c.sw - 1);
+  const int y0 = min(max(ys, 0), c.sh - 1), y1 = min(max(ys + 1, 0), c.sh - 1);
+  const uint8_t* r0 = src + c.src_off + (long long)y0 * c.sw * 3;
+  const uint8_t* r1 = src + c.src_off + (long long)y1 * c.sw * 3;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const int S0 = r0[x0 * 3 + ch] * a0 + r0[x1 * 3 + ch] * a1;
+    const int S1 = r1[x0 * 3 + ch] * a0 + r1[x1 * 3 + ch] * a1;
+    const int v = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+    o[ch] = (uint8_t)min(max(v, 0), 255);
+  }
+}
+
+// src / dst: DEVICE buffers; the per-crop arrays are host arrays
+inline void resize_pack_slots(int device, const uint8_t* src, long long src_bytes, int n, const long long* src_offsets, const int32_t* sizes,
+                              const int32_t* dst_w, const long long* dst_offsets, const int32_t* dst_pitch, uint8_t* dst, long long dst_bytes, int dh,
+                              cudaStream_t st) {
+  RDB_CUDA(cudaSetDevice(device));
+  if (n <= 0) return;
+  RDB_CHECK(is_device_ptr(src) && is_device_ptr(dst), "resize_pack_slots: src and dst must be device buffers");
+  std::vector<ResizeSlot> hs(n);
+  int max_pitch = 1;
+  for (int i = 0; i < n; ++i) {
+    ResizeSlot& c = hs[i];
+    c.src_off = src_offsets[i]; c.dst_off = dst_offsets[i]; c.sw = sizes[2 * i]; c.sh = sizes[2 * i + 1]; c.dw = dst_w[i]; c.pitch = dst_pitch[i];
+    RDB_CHECK(c.sw > 0 && c.sh > 0 && c.dw > 0 && c.dw <= c.pitch, "resize_pack_slots: bad crop geometry");
+    RDB_CHECK(c.src_off >= 0 && c.src_off + (long long)c.sw * c.sh * 3 <= src_bytes, "resize_pack_slots: crop exceeds the source buffer");
+    RDB_CHECK(c.dst_off >= 0 && c.dst_off + (long long)dh * c.pitch * 3 <= dst_bytes, "resize_pack_slots: slot exceeds the destination buffer");
+    if (c.pitch > max_pitch) max_pitch = c.pitch;
+  }
+  ScratchCarver sc{device_scratch(device, pad256(sizeof(ResizeSlot) * n))};
+  ResizeSlot* ds = sc.take<ResizeSlot>(n);
+  RDB_CUDA(cudaMemcpyAsync(ds, hs.data(), sizeof(ResizeSlot) * n, cudaMemcpyHostToDevice, st));
+  for (int i0 = 0; i0 < n; i0 += 32768) {     // grid.y limit
+    const int m = n - i0 < 32768 ? n - i0 : 32768;
+    dim3 grid((unsigned)((dh * max_pitch + 255) / 256), (unsigned)m);
+    resize_slots_kernel<<<grid, 256, 0, st>>>(src, ds + i0, dst, dh);
+    RDB_LAUNCH_CHECK();
+  }
+  RDB_CUDA(cudaStreamSynchronize(st));      // the slot table lives in the shared scratch
 }
 
 }  // namespace rdb

@@ -1,0 +1,234 @@
+"""Host half of DBPostProcess for a whole WINDOW of pages (product code; no oracle import).
+
+Reference: rapidocr `DBPostProcess` as patched by rapid_doc/model/ocr/ocr_patch.py:223-241 (`__call__`), :161-172
+(`unclip`), ctor defaults :145-153; upstream `boxes_from_bitmap` / `get_mini_boxes` / `box_score_fast` /
+`filter_det_res` (PaddleOCR db_postprocess.py).  Division of labour on the B200 path:
+
+  GPU    binarise + 2x2 dilate (det engine), box_score_fast over the device-resident prob map (rdb_db_box_scores)
+  host   cv2.findContours / cv2.minAreaRect on the 1-byte bitmap (the same OpenCV calls the reference makes, run for all
+         pages of the window on a thread pool — OpenCV releases the GIL), Clipper offset in C++ (rdb_clipper_offset),
+         and everything that is plain arithmetic on [n,4,2] arrays VECTORISED over all boxes of a page with the
+         reference's operation order and dtypes, so results are identical to the per-box loops.
+
+`score_fn(quads[m,4,2] f32, page_idx[m]) -> scores[m] f64` is injected: the detector passes the GPU scorer, the CPU
+tests pass cv2's.
+"""
+import ctypes as C
+from concurrent.futures import ThreadPoolExecutor
+import os
+
+import cv2
+import numpy as np
+
+from . import _lib
+
+_POOL = None
+
+
+def pool():
+    """Process-wide worker pool for the per-page OpenCV calls."""
+    global _POOL
+    if _POOL is None:
+        _POOL = ThreadPoolExecutor(max_workers=max(2, min(32, (os.cpu_count() or 8))))
+    return _POOL
+
+
+def mini_boxes(rect_pts):
+    """get_mini_boxes' corner ordering for k boxes at once.  rect_pts [k,4,2] f32 = cv2.boxPoints of each min-area rect.
+    Python's sorted(key=x) is stable, so is the argsort here."""
+    if len(rect_pts) == 0:
+        return rect_pts.reshape(0, 4, 2)
+    order = np.argsort(rect_pts[:, :, 0], axis=1, kind="stable")
+    p = np.take_along_axis(rect_pts, order[:, :, None], axis=1)
+    first = p[:, 1, 1] > p[:, 0, 1]
+    i1 = np.where(first, 0, 1)
+    i4 = np.where(first, 1, 0)
+    second = p[:, 3, 1] > p[:, 2, 1]
+    i2 = np.where(second, 2, 3)
+    i3 = np.where(second, 3, 2)
+    idx = np.stack([i1, i2, i3, i4], axis=1)
+    return np.take_along_axis(p, idx[:, :, None], axis=1)
+
+
+def page_candidates(bitmap, max_candidates=1000, min_size=3):
+    """findContours -> minAreaRect -> ordered mini boxes with short side >= min_size.  bitmap [h,w] uint8 {0,1}
+    (cv2.findContours treats any non-zero pixel as foreground, so the reference's `* 255` is not needed).
+    Returns quads [k,4,2] f32 in contour order."""
+    res = cv2.findContours(bitmap, cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
+    contours = res[0] if len(res) == 2 else res[1]
+    contours = contours[:max_candidates]
+    if not contours:
+        return np.zeros((0, 4, 2), np.float32)
+    rects = [cv2.minAreaRect(c) for c in contours]
+    ss = np.array([min(r[1]) for r in rects])
+    keep = np.nonzero(~(ss < min_size))[0]
+    if len(keep) == 0:
+        return np.zeros((0, 4, 2), np.float32)
+    pts = np.stack([cv2.boxPoints(rects[i]) for i in keep])
+    return mini_boxes(pts)
+
+
+def contour_area_f32(boxes):
+    """cv2.contourArea for k float32 quads: double accumulation of (double)prev.x * p.y - (double)prev.y * p.x in vertex order
+    (OpenCV shapedescr.cpp contourArea), |0.5 * a|."""
+    b = boxes.astype(np.float64)
+    prev = np.roll(b, 1, axis=1)
+    t = prev[:, :, 0] * b[:, :, 1] - prev[:, :, 1] * b[:, :, 0]
+    a = t[:, 0].copy()
+    for i in range(1, b.shape[1]):
+        a = a + t[:, i]
+    return np.abs(a * 0.5)
+
+
+def arc_length_f32(boxes):
+    """cv2.arcLength(box, True) for k float32 quads: float32 dx*dx + dy*dy and sqrt per edge, summed into a double in OpenCV's
+    order (the buffer is drained back to front)."""
+    b = boxes.astype(np.float32)
+    prev = np.roll(b, 1, axis=1)
+    dx = b[:, :, 0] - prev[:, :, 0]
+    dy = b[:, :, 1] - prev[:, :, 1]
+    seg = np.sqrt(dx * dx + dy * dy).astype(np.float64)
+    p = np.zeros(len(b), np.float64)
+    for i in range(b.shape[1] - 1, -1, -1):
+        p = p + seg[:, i]
+    return p
+
+
+def clipper_offset(box, distance, cap=512):
+    """DBPostProcess.unclip's pyclipper call (ocr_patch.py:166-171) on the library's native Clipper restatement."""
+    xy = (C.c_double * 8)(*[float(v) for v in np.asarray(box, np.float64).reshape(-1)])
+    out = (C.c_int64 * (2 * cap))()
+    n = _lib.check(_lib.load().rdb_clipper_offset(xy, 4, float(distance), out, cap))
+    return np.frombuffer(out, dtype=np.int64)[: 2 * n].reshape(-1, 1, 2).astype(np.int32)
+
+
+def order_points_clockwise(boxes):
+    """filter_det_res' order_points_clockwise for k boxes [k,4,2] (np.argsort on 4 elements is an insertion sort: stable)."""
+    o = np.argsort(boxes[:, :, 0], axis=1, kind="stable")
+    xs = np.take_along_axis(boxes, o[:, :, None], axis=1)
+    left, right = xs[:, :2], xs[:, 2:]
+    lo = np.argsort(left[:, :, 1], axis=1, kind="stable")
+    left = np.take_along_axis(left, lo[:, :, None], axis=1)
+    ro = np.argsort(right[:, :, 1], axis=1, kind="stable")
+    right = np.take_along_axis(right, ro[:, :, None], axis=1)
+    return np.stack([left[:, 0], right[:, 0], right[:, 1], left[:, 1]], axis=1).astype(np.float32)
+
+
+def finish_page(quads, scores, bitmap_shape, ori_shape, box_thresh, unclip_ratio, min_size=3):
+    """Everything after box_score_fast for one page: threshold, unclip, second mini box, scale to the source page, int32,
+    filter_det_res.  quads [k,4,2] f32 (mini boxes), scores [k] f64.  Returns (boxes [n,4,2] f32, scores list)."""
+    height, width = bitmap_shape
+    src_h, src_w = ori_shape
+    keep = np.nonzero(~(box_thresh > scores))[0]
+    if len(keep) == 0:
+        return np.zeros((0, 4, 2), np.float32), []
+    q = quads[keep]
+    sc = scores[keep]
+    area = contour_area_f32(q)
+    length = arc_length_f32(q)
+    out_pts, out_sc = [], []
+    for i in range(len(q)):
+        if length[i] <= 0:
+            continue
+        exp = clipper_offset(q[i], area[i] * unclip_ratio / length[i])
+        if len(exp) == 0:
+            continue
+        rect = cv2.minAreaRect(exp)
+        if min(rect[1]) < min_size + 2:
+            continue
+        out_pts.append(cv2.boxPoints(rect))
+        out_sc.append(float(sc[i]))
+    if not out_pts:
+        return np.zeros((0, 4, 2), np.float32), []
+    box = mini_boxes(np.stack(out_pts))                      # float32
+    box[:, :, 0] = np.clip(np.round(box[:, :, 0] / width * src_w), 0, src_w)
+    box[:, :, 1] = np.clip(np.round(box[:, :, 1] / height * src_h), 0, src_h)
+    box = box.astype(np.int32)
+    # filter_det_res
+    b = order_points_clockwise(box)
+    b[:, :, 0] = np.clip(b[:, :, 0], 0, src_w - 1).astype(np.int64)
+    b[:, :, 1] = np.clip(b[:, :, 1], 0, src_h - 1).astype(np.int64)
+    d01 = b[:, 0] - b[:, 1]
+    d03 = b[:, 0] - b[:, 3]
+    rw = np.sqrt((d01 * d01).sum(1)).astype(np.int64)        # int(np.linalg.norm(...)) on float32 vectors
+    rh = np.sqrt((d03 * d03).sum(1)).astype(np.int64)
+    ok = ~((rw <= 3) | (rh <= 3))
+    return b[ok], [s for s, k in zip(out_sc, ok) if k]
+
+
+def window_boxes(bitmaps, ori_shapes, score_fn, box_thresh=0.5, unclip_ratio=1.6, max_candidates=1000, min_size=3,
+                 parallel=True):
+    """DBPostProcess for every page of a window.  bitmaps [n,h,w] uint8 (host), ori_shapes n x (src_h, src_w).
+    Returns [(boxes [k,4,2] f32, scores)] per page, identical to running the reference's per-page loop."""
+    n = len(bitmaps)
+    run = pool().map if (parallel and n > 1) else map
+    cands = list(run(lambda bm: page_candidates(bm, max_candidates, min_size), bitmaps))
+    counts = [len(c) for c in cands]
+    total = sum(counts)
+    if total:
+        quads = np.ascontiguousarray(np.concatenate(cands), np.float32)
+        page_idx = np.repeat(np.arange(n, dtype=np.int32), counts)
+        scores = np.asarray(score_fn(quads, page_idx), np.float64)
+    else:
+        scores = np.zeros(0, np.float64)
+    offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    shape = bitmaps[0].shape
+    jobs = [(cands[i], scores[offs[i]:offs[i + 1]], shape, ori_shapes[i]) for i in range(n)]
+    return list(run(lambda j: finish_page(j[0], j[1], j[2], j[3], box_thresh, unclip_ratio, min_size), jobs))
+
+
+def cv2_score_fn(prob):
+    """box_score_fast with cv2 itself over host prob maps [n,h,w] — the scorer of the CPU tests and the fallback for quads the
+    GPU scorer flags (vertex outside its clipped bounding box)."""
+    def score_one(p, box):
+        h, w = p.shape[:2]
+        b = box.copy()
+        xmin = int(np.clip(np.floor(b[:, 0].min()), 0, w - 1)); xmax = int(np.clip(np.ceil(b[:, 0].max()), 0, w - 1))
+        ymin = int(np.clip(np.floor(b[:, 1].min()), 0, h - 1)); ymax = int(np.clip(np.ceil(b[:, 1].max()), 0, h - 1))
+        mask = np.zeros((ymax - ymin + 1, xmax - xmin + 1), dtype=np.uint8)
+        b[:, 0] -= xmin
+        b[:, 1] -= ymin
+        cv2.fillPoly(mask, b.reshape(1, -1, 2).astype(np.int32), 1)
+        return cv2.mean(p[ymin:ymax + 1, xmin:xmax + 1], mask)[0]
+
+    def fn(quads, page_idx):
+        return np.array([score_one(prob[int(pi)], q) for q, pi in zip(quads, page_idx)], np.float64)
+    fn.score_one = score_one
+    return fn
+
+
+def gpu_score_fn(device, prob_dev, n, h, w):
+    """rdb_db_box_scores over the device-resident prob maps (torch tensor or raw device pointer); quads whose vertices leave
+    their clipped bounding box are scored with cv2 on the ROI fetched from the device."""
+    lib = _lib.load()
+
+    def fn(quads, page_idx):
+        m = len(quads)
+        scores = np.zeros(m, np.float64)
+        flags = np.zeros(m, np.int32)
+        _lib.check(lib.rdb_db_box_scores(int(device), _lib.ptr(prob_dev), int(n), int(h), int(w), m, _lib.ptr(quads), _lib.ptr(page_idx),
+                                         _lib.ptr(scores), _lib.ptr(flags), None))
+        bad = np.nonzero(flags)[0]
+        if len(bad):
+            one = cv2_score_fn(None).score_one
+            for i in bad:
+                q = quads[i]
+                x0 = int(np.clip(np.floor(q[:, 0].min()), 0, w - 1)); x1 = int(np.clip(np.ceil(q[:, 0].max()), 0, w - 1))
+                y0 = int(np.clip(np.floor(q[:, 1].min()), 0, h - 1)); y1 = int(np.clip(np.ceil(q[:, 1].max()), 0, h - 1))
+                roi = prob_dev[int(page_idx[i]), y0:y1 + 1, x0:x1 + 1].cpu().numpy()
+                # same arithmetic as box_score_fast on the full map: the ROI is the bounding rectangle it would slice out
+                full = _RoiView(roi, x0, y0, w, h)
+                scores[i] = one(full, q)
+        return scores
+    return fn
+
+
+class _RoiView:
+    """Looks like the [h,w] prob map to box_score_fast but only holds the bounding rectangle that function reads."""
+
+    def __init__(self, roi, x0, y0, w, h):
+        self.roi, self.x0, self.y0, self.shape = roi, x0, y0, (h, w)
+
+    def __getitem__(self, key):
+        ys, xs = key
+        return self.roi[ys.start - self.y0: ys.stop - self.y0, xs.start - self.x0: xs.stop - self.x0]

@@ -17,6 +17,32 @@ DET_MEAN = (0.485, 0.456, 0.406)   # rapid_doc/model/ocr/rapid_ocr.py:61-62
 DET_STD = (0.229, 0.224, 0.225)
 
 
+_NP2NAME = {np.dtype(np.uint8): "uint8", np.dtype(np.float32): "float32", np.dtype(np.int32): "int32"}
+
+
+def _check_buf(name, a, dtype, numel, device):
+    """A caller-supplied buffer goes to the C-ABI as a raw pointer: refuse anything whose dtype, contiguity, size or
+    GPU does not match (a permuted / float page tensor or a tensor on another GPU would otherwise be silent garbage or an
+    illegal address).  numpy arrays are host buffers; torch tensors may be host (pinned) or on the engine's device."""
+    if a is None:
+        return
+    want = _NP2NAME[np.dtype(dtype)]
+    if isinstance(a, np.ndarray):
+        if a.dtype != np.dtype(dtype) or not a.flags.c_contiguous or a.size < numel:
+            raise _lib.B200Error(f"{name}: need a C-contiguous {want} array of >= {numel} elements, got {a.dtype} {a.shape} "
+                                 f"contiguous={a.flags.c_contiguous}")
+        return
+    if hasattr(a, "data_ptr"):
+        got = str(a.dtype).replace("torch.", "")
+        if got != want or not a.is_contiguous() or a.numel() < numel:
+            raise _lib.B200Error(f"{name}: need a contiguous {want} tensor of >= {numel} elements, got {got} {tuple(a.shape)} "
+                                 f"contiguous={a.is_contiguous()}")
+        if a.is_cuda and a.device.index != device:
+            raise _lib.B200Error(f"{name}: tensor lives on cuda:{a.device.index}, the engine on cuda:{device}")
+        return
+    raise _lib.B200Error(f"{name}: unsupported buffer type {type(a)}")
+
+
 def _stream_ptr(stream):
     if stream is None:
         return None
@@ -65,6 +91,8 @@ class DetEngine:
                 prob = torch.empty((n, 1, h, w), dtype=torch.float32, device=x.device)
         if isinstance(x, np.ndarray):
             x = np.ascontiguousarray(x, dtype=np.float32)
+        _check_buf("x", x, np.float32, n * 3 * h * w, self.device)
+        _check_buf("prob", prob, np.float32, n * h * w, self.device)
         _lib.check(self._lib.rdb_det_infer_f32(self._h, _lib.ptr(x), n, h, w, _lib.ptr(prob), _stream_ptr(stream)))
         return prob
 
@@ -92,6 +120,9 @@ class DetEngine:
             else:
                 import torch
                 bitmap = torch.empty((n, h, w), dtype=torch.uint8, device=pages.device)
+        _check_buf("pages", pages, np.uint8, n * src_h * src_w * 3, self.device)
+        _check_buf("prob", prob, np.float32, n * h * w, self.device)
+        _check_buf("bitmap", bitmap, np.uint8, n * h * w, self.device)
         m = (C.c_float * 3)(*mean)
         s = (C.c_float * 3)(*std)
         if resize_to is not None and (src_h, src_w) != (h, w):
@@ -154,6 +185,7 @@ class RecEngine:
         if isinstance(x, np.ndarray):
             x = np.ascontiguousarray(x, dtype=np.float32)
         o = self._outs(n, self.tokens(w), x, want_softmax)
+        _check_buf("x", x, np.float32, n * 3 * 48 * w, self.device)
         _lib.check(self._lib.rdb_rec_infer_f32(self._h, _lib.ptr(x), n, w, _lib.ptr(o["ids"]), _lib.ptr(o["probs"]),
                                                _lib.ptr(o["text_ids"]), _lib.ptr(o["text_len"]), _lib.ptr(o["conf"]),
                                                _lib.ptr(o["softmax"]), _stream_ptr(stream)))
@@ -167,11 +199,23 @@ class RecEngine:
             crops = np.ascontiguousarray(crops, dtype=np.uint8)
             if valid_w is not None:
                 valid_w = np.ascontiguousarray(valid_w, dtype=np.int32)
-        o = outs if outs is not None else self._outs(n, self.tokens(w), crops, False)
+        T = self.tokens(w)
+        o = outs if outs is not None else self._outs(n, T, crops, False)
+        _check_buf("crops", crops, np.uint8, n * 48 * w * 3, self.device)
+        _check_buf("valid_w", valid_w, np.int32, n, self.device)
+        for k, dt, ne in (("ids", np.int32, n * T), ("probs", np.float32, n * T), ("text_ids", np.int32, n * T), ("text_len", np.int32, n),
+                          ("conf", np.float32, n)):
+            _check_buf(k, o.get(k), dt, ne, self.device)
         _lib.check(self._lib.rdb_rec_infer_u8(self._h, _lib.ptr(crops), _lib.ptr(valid_w), n, w, _lib.ptr(o["ids"]),
                                               _lib.ptr(o["probs"]), _lib.ptr(o["text_ids"]), _lib.ptr(o["text_len"]),
                                               _lib.ptr(o["conf"]), _stream_ptr(stream)))
         return o
+
+    def infer_u8_raw(self, crops_ptr, valid_w_ptr, n, w, ids_ptr, probs_ptr, stream=None):
+        """rdb_rec_infer_u8 on raw DEVICE addresses (ints): crops [n,48,w,3] u8, valid_w [n] i32 -> ids / probs [n,T].
+        Asynchronous on `stream`; used by the window-level recogniser, which carves all of these out of a few big buffers."""
+        _lib.check(self._lib.rdb_rec_infer_u8(self._h, int(crops_ptr), int(valid_w_ptr), int(n), int(w), int(ids_ptr), int(probs_ptr),
+                                              None, None, None, _stream_ptr(stream)))
 
 
 # ------------------------------------------------------------------ InferSession protocol

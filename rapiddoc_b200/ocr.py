@@ -25,23 +25,31 @@ import time
 import cv2
 import numpy as np
 
-from . import _lib, weights as W
+from . import _lib, dbpost, weights as W
 from .engine import DET_MEAN, DET_STD, DetEngine, RecEngine
+from .lines import merge_det_boxes, sorted_boxes, update_det_boxes
 
 
 # ----------------------------------------------------------------------------- small utils
-def sorted_boxes(dt_boxes):
-    """rapid_doc/utils/ocr_utils.py:105-127."""
-    n = len(dt_boxes)
-    boxes = sorted(dt_boxes, key=lambda b: (b[0][1], b[0][0]))
-    boxes = list(boxes)
-    for i in range(n - 1):
-        for j in range(i, -1, -1):
-            if abs(boxes[j + 1][0][1] - boxes[j][0][1]) < 10 and boxes[j + 1][0][0] < boxes[j][0][0]:
-                boxes[j], boxes[j + 1] = boxes[j + 1], boxes[j]
-            else:
-                break
-    return boxes
+def check_img(img):
+    """rapid_doc/utils/ocr_utils.py:73-78: bytes are decoded, 2-D grayscale becomes BGR."""
+    if isinstance(img, bytes):
+        img = cv2.imdecode(np.frombuffer(img, dtype=np.uint8), cv2.IMREAD_UNCHANGED)
+    if isinstance(img, np.ndarray) and img.ndim == 2:
+        img = cv2.cvtColor(img, cv2.COLOR_GRAY2BGR)
+    return img
+
+
+def preprocess_image(img):
+    """rapid_doc/utils/ocr_utils.py:81-102 (alpha_to_color on white): BGRA is composited onto a white background."""
+    if img.ndim == 3 and img.shape[2] == 4:
+        B, G, R, A = cv2.split(img)
+        alpha = A / 255
+        R = (255 * (1 - alpha) + R * alpha).astype(np.uint8)
+        G = (255 * (1 - alpha) + G * alpha).astype(np.uint8)
+        B = (255 * (1 - alpha) + B * alpha).astype(np.uint8)
+        img = cv2.merge((B, G, R))
+    return img
 
 
 def get_rotate_crop_image(img, points):
@@ -138,16 +146,6 @@ def get_rotate_crop_images_gpu(img, boxes, device=0, keep_on_device=False):
         crops.append(a.reshape((cw, ch, 3) if r else (ch, cw, 3)))
         k += 1
     return crops
-
-
-def _reference_line_utils():
-    """merge_det_boxes / update_det_boxes are CPU glue of the caller (SURVEY D8, 'negligible');
-    when RapidDoc is importable the reference's own functions are used unchanged."""
-    try:
-        from rapid_doc.utils.ocr_utils import merge_det_boxes, update_det_boxes
-        return merge_det_boxes, update_det_boxes
-    except Exception:
-        return None, None
 
 
 def unclip_quad(box, unclip_ratio):
@@ -257,6 +255,7 @@ class B200TextDetector:
                  box_thresh=0.5, unclip_ratio=1.6, use_dilation=True, max_candidates=1000):
         self.engine = engine
         self.limit_side_len, self.limit_type, self.mean, self.std = limit_side_len, limit_type, mean, std
+        self.stats = {"h2d_bytes": 0, "d2h_bytes": 0, "launches": 0}
         self.postprocess_op = DBPostProcess(thresh, box_thresh, max_candidates, unclip_ratio, use_dilation)
 
     def target_size(self, h, w):
@@ -278,24 +277,83 @@ class B200TextDetector:
             return None
         return np.ascontiguousarray(img) if t == img.shape[:2] else cv2.resize(img, (t[1], t[0]))
 
-    def detect_batch(self, imgs):
-        """Same-size images -> [(boxes, scores)] (rapid_ocr.py:500-540; the reference requires the
-        bucket to be same-size too).  Pages are uploaded as they are (uint8); the cv2.resize of
-        DetPreProcess, its normalisation, the network and binarise+dilate all run on the GPU."""
+    def _stage(self, imgs):
+        """The same-size pages as ONE contiguous host array [n,h,w,3].  A caller that already holds them in one buffer (e.g.
+        views into a pinned window buffer, as a raster producer would fill) pays no copy; otherwise the pages are gathered
+        into a grow-only pinned staging buffer on the worker pool (numpy's copy releases the GIL)."""
+        import torch
+        n = len(imgs)
         h, w = imgs[0].shape[:2]
-        assert all(im.shape[:2] == (h, w) for im in imgs), "det batch must be same-size (as in the reference)"
+        if isinstance(imgs, np.ndarray) and imgs.ndim == 4 and imgs.flags.c_contiguous and imgs.dtype == np.uint8:
+            return imgs
+        step = h * w * 3
+        a0 = imgs[0]
+        if all(isinstance(im, np.ndarray) and im.dtype == np.uint8 and im.flags.c_contiguous and im.shape == a0.shape and
+               im.ctypes.data == a0.ctypes.data + k * step for k, im in enumerate(imgs)):
+            return np.lib.stride_tricks.as_strided(a0, shape=(n, h, w, 3), strides=(step,) + a0.strides)   # keeps a0 alive
+        need = n * step
+        if getattr(self, "_pin", None) is None or self._pin.numel() < need:
+            self._pin = torch.empty(need + need // 4, dtype=torch.uint8).pin_memory()
+        stage = self._pin.numpy()[:need].reshape(n, h, w, 3)
+        list(dbpost.pool().map(lambda k: np.copyto(stage[k], imgs[k]), range(n)))
+        return stage
+
+    def detect_window(self, imgs, keep_pages=False, sub_batch=32):
+        """Same-size pages -> [(boxes [k,4,2] f32, scores)] (rapid_ocr.py:500-540 for a whole window; the reference requires a
+        det batch to be same-size too).  Pages are uploaded as raw uint8 once; DetPreProcess' cv2.resize + normalisation, the
+        network and binarise + dilate run on the GPU; the fp32 prob map STAYS on the GPU, where box_score_fast is evaluated
+        (rdb_db_box_scores); only the 1-byte bitmap comes back for cv2.findContours.  The window is cut into sub-batches
+        so that the host post-processing of one overlaps the GPU work of the next (the GPU call runs on a worker thread;
+        ctypes releases the GIL).  keep_pages: also return the device copy of the pages (for the GPU crop path)."""
+        import torch
+        h, w = int(imgs[0].shape[0]), int(imgs[0].shape[1])
+        assert all(tuple(im.shape[:2]) == (h, w) for im in imgs), "det batch must be same-size (as in the reference)"
+        n = len(imgs)
         t = self.target_size(h, w)
         if t is None:
-            return [(None, []) for _ in imgs]
-        pages = np.stack([np.ascontiguousarray(im) for im in imgs])
+            return [(None, []) for _ in imgs], None
+        rh, rw = t
         po = self.postprocess_op
-        prob, bitmap = self.engine.infer_u8(pages, thresh=po.thresh, use_dilation=po.use_dilation, mean=self.mean, std=self.std,
-                                            resize_to=t)
-        out = []
-        for i, im in enumerate(imgs):
-            boxes, scores = po(prob[i], bitmap[i], im.shape[:2])
-            out.append((boxes, scores))
-        return out
+        dev = torch.device("cuda", self.engine.device)
+        resident = hasattr(imgs, "is_cuda") and imgs.is_cuda           # a [n,h,w,3] uint8 tensor already on this GPU
+        if resident:
+            assert imgs.dtype == torch.uint8 and imgs.is_contiguous() and imgs.device.index == self.engine.device
+            host, pages_dev = None, imgs
+        else:
+            host = self._stage(imgs)
+            pages_dev = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
+            self.stats["h2d_bytes"] += host.size
+        self.stats["d2h_bytes"] += n * rh * rw
+        need = n * rh * rw
+        if getattr(self, "_pin_bm", None) is None or self._pin_bm.numel() < need:
+            self._pin_bm = torch.empty(need + need // 4, dtype=torch.uint8).pin_memory()
+        bitmaps = self._pin_bm.numpy()[:need].reshape(n, rh, rw)
+        probs = torch.empty((n, rh, rw), dtype=torch.float32, device=dev)
+
+        def gpu(lo, hi):
+            with torch.cuda.device(dev):
+                if host is not None:
+                    pages_dev[lo:hi].copy_(torch.from_numpy(host[lo:hi]), non_blocking=True)
+                self.engine.infer_u8(pages_dev[lo:hi], thresh=po.thresh, use_dilation=po.use_dilation, mean=self.mean, std=self.std,
+                                     resize_to=t, prob=probs[lo:hi], bitmap=bitmaps[lo:hi], stream=torch.cuda.current_stream(dev))
+            return lo, hi
+
+        cuts = [(lo, min(n, lo + sub_batch)) for lo in range(0, n, sub_batch)]
+        out = [None] * n
+        fut = dbpost.pool().submit(gpu, *cuts[0])
+        for k, (lo, hi) in enumerate(cuts):
+            fut.result()
+            self.stats["launches"] += self.engine.last_launches + 1          # + the box scorer
+            if k + 1 < len(cuts):
+                fut = dbpost.pool().submit(gpu, *cuts[k + 1])
+            score_fn = dbpost.gpu_score_fn(self.engine.device, probs[lo:hi], hi - lo, rh, rw)
+            res = dbpost.window_boxes(bitmaps[lo:hi], [(h, w)] * (hi - lo), score_fn, po.box_thresh,
+                                      po.unclip_ratio, po.max_candidates, po.min_size)
+            out[lo:hi] = res
+        return out, (pages_dev if keep_pages else None)
+
+    def detect_batch(self, imgs):
+        return self.detect_window(imgs)[0]
 
     def __call__(self, img):
         t0 = time.perf_counter()
@@ -386,6 +444,7 @@ class B200TextRecognizer:
         self.character = characters if characters is not None else W.load_characters()
         self.rec_batch_num = rec_batch_num
         self.rec_image_shape = list(rec_image_shape)
+        self.stats = {"h2d_bytes": 0, "d2h_bytes": 0, "launches": 0, "crops": 0}
 
     def _pack(self, crops, max_wh_ratio):
         """resize_norm_img geometry: height 48, width min(imgW, ceil(48*w/h)); uint8, right part is the
@@ -414,47 +473,151 @@ class B200TextRecognizer:
                                                   _lib.ptr(vw), _lib.ptr(buf), ih, iw, None))
         return buf, vw
 
+    def upload(self, crops):
+        """Host crops (list of [h,w,3] uint8 arrays of any size) -> DeviceCrops: one packed pinned buffer, one H2D copy."""
+        import torch
+        shapes = [(int(c.shape[0]), int(c.shape[1])) for c in crops]
+        nbytes = np.array([h * w * 3 for h, w in shapes], np.int64)
+        offs = np.concatenate([[0], np.cumsum(nbytes)[:-1]]).astype(np.int64)
+        total = int(nbytes.sum())
+        if getattr(self, "_pin", None) is None or self._pin.numel() < total:
+            self._pin = torch.empty(total + total // 4 + 1024, dtype=torch.uint8).pin_memory()
+        stage = self._pin.numpy()
+
+        def put(k):
+            h, w = shapes[k]
+            np.copyto(stage[offs[k]: offs[k] + nbytes[k]].reshape(h, w, 3), crops[k])
+        if len(crops) >= 32:
+            list(dbpost.pool().map(put, range(len(crops))))
+        else:
+            for k in range(len(crops)):
+                put(k)
+        dev = torch.device("cuda", self.engine.device)
+        buf = torch.empty(total, dtype=torch.uint8, device=dev)
+        buf.copy_(self._pin[:total], non_blocking=True)
+        self.stats["h2d_bytes"] += total
+        return DeviceCrops(buf, offs, shapes, self.engine.device)
+
+    def plan(self, shapes):
+        """text_recognizer_call's batching (rapid_ocr.py:411-440): crops sorted by w/h, consecutive batches of rec_batch_num,
+        every batch padded to int(48 * max(320/48, its widest ratio)).  Returns (order, ratios, [(lo, hi, imgW, max_ratio)])."""
+        _, ih, iw = self.rec_image_shape
+        ratios = [w / float(h) for h, w in shapes]
+        order = np.argsort(np.array(ratios))
+        batches = []
+        for b0 in range(0, len(shapes), self.rec_batch_num):
+            idx = order[b0: b0 + self.rec_batch_num]
+            mx = max([iw / ih] + [ratios[i] for i in idx])
+            batches.append((b0, b0 + len(idx), int(ih * mx), mx))
+        return order, ratios, batches
+
     def __call__(self, img_list, return_word_box=False):
+        """All crops of a window in one go (cross-page batching): one upload (unless they already live on the
+        GPU), ONE launch that cv2.resizes every crop into its batch slot, then the recogniser once per reference batch —
+        enqueued back to back on the stream, nothing synchronises until the (id, prob) pairs of the whole window are
+        copied back.  Same batches, same padded widths, same results as the reference's batch loop."""
+        import torch
         if isinstance(img_list, np.ndarray):
             img_list = [img_list]
         t0 = time.perf_counter()
         n = len(img_list)
-        on_dev = isinstance(img_list, DeviceCrops)
-        ratios = [w / float(h) for h, w in img_list.shapes] if on_dev else [im.shape[1] / float(im.shape[0]) for im in img_list]
-        order = np.argsort(np.array(ratios))
-        res = [("", 0.0)] * n
-        words = [None] * n
-        _, ih, iw = self.rec_image_shape
-        for b0 in range(0, n, self.rec_batch_num):
-            idx = order[b0: b0 + self.rec_batch_num]
-            mx = max([iw / ih] + [ratios[i] for i in idx])
-            if on_dev:
-                buf, vw = self._pack_device(img_list, idx, mx)
-                out = self.engine.infer_u8(buf, vw, outs=self.engine._outs(len(idx), self.engine.tokens(buf.shape[2]), vw, False))
-            else:
-                buf, vw = self._pack([img_list[i] for i in idx], mx)
-                out = self.engine.infer_u8(buf, vw)
-            T = out["ids"].shape[1]
-            for j, i in enumerate(idx):
-                ln = int(out["text_len"][j])
-                ids = out["text_ids"][j][:ln]
-                text = "".join(self.character[k] for k in ids)
-                # CTCLabelDecode: float64 mean of the kept float32 max-probs, rounded to 5 decimals
-                sel = np.ones(T, bool)
-                sel[1:] = out["ids"][j][1:] != out["ids"][j][:-1]
-                sel &= out["ids"][j] != 0
-                conf = np.array(out["probs"][j][sel]).tolist() or [0]
-                res[i] = (text, float(np.mean(conf).round(5)))
-                if return_word_box:
-                    # rapidocr CTCLabelDecode(return_word_box=True): word grouping + the CTC length scaled to the
-                    # crop's share of the padded batch width (wh_ratio / max_wh_ratio)
-                    wi = get_word_info(text, sel) if text else WordInfo()
-                    wi.line_txt_len = T * ratios[i] / mx
-                    wi.confs = conf
-                    words[i] = wi
-        txts, scores = (list(zip(*res)) if res else ((), ()))
+        if n == 0:
+            return TextRecOutput(img_list, (), (), () if return_word_box else None, 0.0)
+        dc = img_list if isinstance(img_list, DeviceCrops) else self.upload(img_list)
+        _, ih, _ = self.rec_image_shape
+        order, ratios, batches = self.plan(dc.shapes)
+        dev = dc.buf.device
+        # slot table in batch order
+        sizes = np.array([[dc.shapes[i][1], dc.shapes[i][0]] for i in order], np.int32)            # (w, h)
+        src_offs = np.ascontiguousarray(dc.offsets[order], np.int64)
+        dst_w = np.empty(n, np.int32)
+        pitch = np.empty(n, np.int32)
+        dst_offs = np.empty(n, np.int64)
+        tok_off, base, toks = [], 0, 0
+        cw_all = np.ceil(ih * (sizes[:, 0].astype(np.float64) / sizes[:, 1].astype(np.float64)))    # math.ceil(48 * (w / float(h)))
+        for lo, hi, imgW, _mx in batches:
+            dst_w[lo:hi] = np.minimum(cw_all[lo:hi], imgW).astype(np.int32)
+            pitch[lo:hi] = imgW
+            dst_offs[lo:hi] = base + np.arange(hi - lo, dtype=np.int64) * (ih * imgW * 3)
+            base += (hi - lo) * ih * imgW * 3
+            tok_off.append(toks)
+            toks += (hi - lo) * self.engine.tokens(imgW)
+        with torch.cuda.device(dev):
+            packed = torch.empty(base, dtype=torch.uint8, device=dev)
+            st = torch.cuda.current_stream(dev)
+            _lib.check(_lib.load().rdb_resize_pack_slots(dc.device, _lib.ptr(dc.buf), int(dc.buf.numel()), n, _lib.ptr(src_offs), _lib.ptr(sizes),
+                                                         _lib.ptr(dst_w), _lib.ptr(dst_offs), _lib.ptr(pitch), _lib.ptr(packed), int(base), ih,
+                                                         st.cuda_stream or None))
+            vw_dev = torch.from_numpy(dst_w).to(dev)
+            ids_all = torch.empty(toks, dtype=torch.int32, device=dev)
+            probs_all = torch.empty(toks, dtype=torch.float32, device=dev)
+            for (lo, hi, imgW, _mx), to in zip(batches, tok_off):
+                self.engine.infer_u8_raw(packed.data_ptr() + int(dst_offs[lo]), vw_dev.data_ptr() + 4 * lo, hi - lo, imgW,
+                                         ids_all.data_ptr() + 4 * to, probs_all.data_ptr() + 4 * to, st.cuda_stream or None)
+                self.stats["launches"] += self.engine.last_launches
+            self.stats["launches"] += 1                                           # resize_slots
+            self.stats["h2d_bytes"] += n * (32 + 4)                               # slot table + valid widths
+            self.stats["d2h_bytes"] += toks * 8
+            self.stats["crops"] += n
+            ids_h = ids_all.cpu().numpy()
+            probs_h = probs_all.cpu().numpy()
+        if getattr(self, "keep_ids", False):      # diagnostics (bench parity report): per-crop argmax ids in input order
+            self.last_ids = [None] * n
+            for (lo, hi, imgW, _mx), to in zip(batches, tok_off):
+                T = self.engine.tokens(imgW)
+                for j in range(hi - lo):
+                    self.last_ids[int(order[lo + j])] = ids_h[to + j * T: to + (j + 1) * T].copy()
+        res, words = self.decode_window(ids_h, probs_h, batches, tok_off, order, ratios, return_word_box)
+        txts, scores = list(zip(*res))
         return TextRecOutput(img_list, tuple(txts), tuple(scores), tuple(words) if return_word_box else None,
                              time.perf_counter() - t0)
+
+    def decode_window(self, ids_h, probs_h, batches, tok_off, order, ratios, return_word_box=False):
+        """CTCLabelDecode (rapidocr ch_ppocr_rec/utils.py) for every batch of a window, vectorised per batch: keep t where
+        id != previous id and id != blank; text = chars[ids]; conf = float64 mean of the kept float32 max-probs, rounded to
+        5 decimals.  ids_h / probs_h: flat host arrays, batch k = [b, T_k] at tok_off[k]."""
+        n = len(order)
+        chars = self._chars()
+        res = [("", 0.0)] * n
+        words = [None] * n
+        for (lo, hi, imgW, mx), to in zip(batches, tok_off):
+            b = hi - lo
+            T = self.engine.tokens(imgW)
+            ids = ids_h[to: to + b * T].reshape(b, T)
+            pr = probs_h[to: to + b * T].reshape(b, T)
+            sel = np.ones((b, T), bool)
+            sel[:, 1:] = ids[:, 1:] != ids[:, :-1]
+            sel &= ids != 0
+            cnt = sel.sum(1)
+            flat = pr[sel].astype(np.float64)
+            starts = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+            conf = np.zeros(b, np.float64)
+            nz = cnt > 0
+            if flat.size:
+                # np.add.reduceat sums each [start, next start) run with numpy's pairwise reduction, i.e. exactly what
+                # np.mean does on the run alone; the sentinel keeps the start of an empty trailing run in range, and the
+                # last run is summed on its own so that the sentinel never joins a reduction
+                sums = np.add.reduceat(np.concatenate([flat, [0.0]]), starts)
+                sums[b - 1] = flat[starts[b - 1]:].sum() if cnt[b - 1] else 0.0
+                conf[nz] = sums[nz] / cnt[nz]
+            conf = conf.round(5)
+            kept = ids[sel]
+            for j in range(b):
+                i = int(order[lo + j])
+                seg = kept[starts[j]: starts[j] + cnt[j]]
+                text = "".join(chars[seg])
+                res[i] = (text, float(conf[j]))
+                if return_word_box:
+                    wi = get_word_info(text, sel[j]) if text else WordInfo()
+                    wi.line_txt_len = T * ratios[i] / mx
+                    wi.confs = pr[j][sel[j]].tolist() or [0]
+                    words[i] = wi
+        return res, words
+
+    def _chars(self):
+        if getattr(self, "_char_arr", None) is None:
+            self._char_arr = np.array(self.character, dtype=object)
+        return self._char_arr
 
 
 # ----------------------------------------------------------------------------- the model class
@@ -462,7 +625,8 @@ class B200OcrModel:
     """Drop-in for `RapidOcrModel` (rapid_doc/model/ocr/rapid_ocr.py:43-162) on one B200."""
 
     def __init__(self, det_db_box_thresh=0.5, lang=None, ocr_config=None, use_dilation=True, det_db_unclip_ratio=1.8,
-                 enable_merge_det_boxes=True, is_seal=False, device=0, precision=None):
+                 enable_merge_det_boxes=True, is_seal=False, device=0, precision=None, blobs=None):
+        """blobs=(det_blob, rec_blob): packed weights handed in by the caller (multi-GPU: rank 0 packs, NCCL broadcast)."""
         if is_seal:
             raise NotImplementedError("seal OCR (PP-OCRv4 seal det) is outside the B200 hot path; use RapidOcrModel(is_seal=True)")
         cfg = dict(ocr_config or {})
@@ -470,8 +634,8 @@ class B200OcrModel:
         self.enable_merge_det_boxes = enable_merge_det_boxes
         self.is_seal = False
         prec = _lib.PREC_FP16 if precision is None else precision
-        det = DetEngine(device=device, precision=prec, weights_path=cfg.get("Det.model_path"))
-        rec = RecEngine(device=device, precision=prec, weights_path=cfg.get("Rec.model_path"))
+        det = DetEngine(device=device, precision=prec, weights_path=cfg.get("Det.model_path"), blob=blobs[0] if blobs else None)
+        rec = RecEngine(device=device, precision=prec, weights_path=cfg.get("Rec.model_path"), blob=blobs[1] if blobs else None)
         self.text_detector = B200TextDetector(
             det, limit_side_len=cfg.get("Det.limit_side_len", 960), limit_type=cfg.get("Det.limit_type", "max"),
             mean=tuple(cfg.get("Det.mean", DET_MEAN)), std=tuple(cfg.get("Det.std", DET_STD)), thresh=cfg.get("Det.thresh", 0.3),
@@ -482,79 +646,140 @@ class B200OcrModel:
         # Raise "Rec.rec_batch_num" in ocr_config for throughput, exactly as with RapidOcrModel.
         self.text_recognizer = B200TextRecognizer(rec, rec_batch_num=cfg.get("Rec.rec_batch_num", 6))
         self.rec_batch_num = self.text_recognizer.rec_batch_num
-        self._merge, self._update = _reference_line_utils()
+        self.det_window = int(cfg.get("Det.window", 64))      # pages per GPU pass (memory bound only; results do not depend on it)
 
     # ---- rapid_ocr.py:474-540
     def det_batch_predict(self, img_list, max_batch_size=8):
-        if not img_list:
+        """[(boxes, elapse)] per image.  `max_batch_size` bounds the reference's session batch; results here do not depend
+        on the batch split (the kernels are batch-invariant), so same-size images are processed as one window, cut only
+        for memory (`self.det_window` pages per GPU pass)."""
+        if img_list is None or len(img_list) == 0:
             return []
-        out = []
-        for i in range(0, len(img_list), max_batch_size):
-            batch = img_list[i:i + max_batch_size]
-            t0 = time.time()
-            res = self.text_detector.detect_batch(batch)
-            el = (time.time() - t0) / len(batch)
-            for boxes, _ in res:
-                if boxes is None:
-                    out.append((None, 0))
-                else:
-                    out.append((np.array(sorted_boxes(boxes)) if len(boxes) else boxes, el))
+        groups = {}
+        for i, im in enumerate(img_list):
+            groups.setdefault(tuple(im.shape[:2]), []).append(i)
+        out = [None] * len(img_list)
+        for idxs in groups.values():
+            for c0 in range(0, len(idxs), self.det_window):
+                part = idxs[c0: c0 + self.det_window]
+                t0 = time.time()
+                whole = len(part) == len(img_list)
+                res = self.text_detector.detect_batch(img_list if whole else [img_list[i] for i in part])
+                el = (time.time() - t0) / len(part)
+                for i, (boxes, _) in zip(part, res):
+                    if boxes is None:
+                        out[i] = (None, 0)
+                    else:
+                        out[i] = (np.array(sorted_boxes(boxes)) if len(boxes) else boxes, el)
         return out
 
     def _post_boxes(self, dt_boxes, mfd_res):
+        """sorted_boxes -> merge_det_boxes -> update_det_boxes (rapid_ocr.py:262-269, analyze_utils.py:193-203)."""
         dt_boxes = sorted_boxes(dt_boxes)
-        if self.enable_merge_det_boxes and self._merge is not None:
-            dt_boxes = self._merge(dt_boxes)
-        if mfd_res and self._update is not None:
-            dt_boxes = self._update(dt_boxes, mfd_res)
+        if self.enable_merge_det_boxes:
+            dt_boxes = merge_det_boxes(dt_boxes)
+        if mfd_res:
+            dt_boxes = update_det_boxes(dt_boxes, mfd_res)
         return dt_boxes
 
     # ---- rapid_ocr.py:351-401
     def __call__(self, img, mfd_res=None):
         if img is None:
             return None, None
-        ori = img.copy()
-        det = self.text_detector(img)
-        if det.boxes is None:
+        res = self.ocr_pages([img], mfd_res_list=[mfd_res])[0]
+        if res is None:
             return None, None
-        dt_boxes = self._post_boxes(det.boxes, mfd_res)
-        # opt-in (model.gpu_crop = True): bit-identical results, but at a few dozen lines per page the per-call overheads of the
-        # crop entry points still outweigh OpenCV's ~50 us per box (tools/pipeline_probe.py: 20.4 vs 10.9 ms on a 14-line page,
-        # 29.0 vs 30.8 ms on a 24-line 1024x1024 page) — it pays once crops are batched over many pages
-        if getattr(self, "gpu_crop", False) and len(dt_boxes):
-            # all quads of the page in one rdb_warp_crops call (bit-identical to cv2.warpPerspective per box)
-            # ... and the crops stay on the device: resize + batch packing happen there too (rdb_resize_pack_u8)
-            crops = get_rotate_crop_images_gpu(ori, dt_boxes, self.text_detector.engine.device, keep_on_device=True)
-            if not isinstance(crops, DeviceCrops):
-                crops = [c if c is not None else get_rotate_crop_image(ori, copy.deepcopy(b)) for c, b in zip(crops, dt_boxes)]
-        else:
-            crops = [get_rotate_crop_image(ori, copy.deepcopy(b)) for b in dt_boxes]
-        rec = self.text_recognizer(crops)
-        boxes, res = [], []
-        for box, r in zip(dt_boxes, zip(rec.txts, rec.scores)):
-            if r[1] >= self.drop_score:
-                boxes.append(box)
-                res.append(r)
-        return boxes, res
+        return [np.asarray(b, np.float32) for b, _ in res], [r for _, r in res]
+
+    def ocr_pages(self, pages, mfd_res_list=None, drop_score=None):
+        """det + rec for a WINDOW of pages — the fused equivalent of the reference's window flow
+        (`_run_ocr_det_batch` analyze_utils.py:105-212 then `_run_ocr_rec_postprocess` :216-292, or `__call__`
+        rapid_ocr.py:351-401 per page): det on all pages -> sorted/merged boxes -> every text-line crop of the window
+        warped on the GPU from the resident pages (get_rotate_crop_image, bit-exact) -> one recognition pass over all crops.
+        Returns per page: None (no boxes) or [[box (4x2 list), (text, score)], ...] with score >= drop_score."""
+        import torch
+        drop = self.drop_score if drop_score is None else drop_score
+        n = len(pages)
+        out = [None] * n
+        groups = {}
+        for i, im in enumerate(pages):
+            groups.setdefault((int(im.shape[0]), int(im.shape[1])), []).append(i)
+        dev_index = self.text_detector.engine.device
+        for (h, w), idxs in groups.items():
+            for c0 in range(0, len(idxs), self.det_window):
+                part = idxs[c0: c0 + self.det_window]
+                whole = len(part) == n
+                if whole:
+                    sub = pages
+                elif hasattr(pages, "is_cuda"):
+                    sub = pages[part[0]: part[-1] + 1] if part == list(range(part[0], part[-1] + 1)) else pages[part]
+                else:
+                    sub = [pages[i] for i in part]
+                res, pages_dev = self.text_detector.detect_window(sub, keep_pages=True)
+                boxes_per_page, geo, page_idx = [], [], []
+                for k, (i, (boxes, _)) in enumerate(zip(part, res)):
+                    if boxes is None or len(boxes) == 0:
+                        boxes_per_page.append([])
+                        continue
+                    # the detector sorts its boxes (TextDetector.sorted_boxes), __call__ sorts them again (rapid_ocr.py:372)
+                    bl = self._post_boxes(np.array(sorted_boxes(boxes)), mfd_res_list[i] if mfd_res_list else None)
+                    keep = []
+                    for b in bl:
+                        g = crop_geometry(b)
+                        if g is None:      # degenerate quad: the reference's warp would fail on it too
+                            continue
+                        keep.append(b)
+                        geo.append(g)
+                        page_idx.append(k)
+                    boxes_per_page.append(keep)
+                if not geo:
+                    continue
+                minv = np.stack([g[2].reshape(9) for g in geo])
+                sizes = np.array([[g[0], g[1]] for g in geo], np.int32)
+                rot = np.array([g[3] for g in geo], np.int32)
+                nbytes = sizes[:, 0].astype(np.int64) * sizes[:, 1] * 3
+                offs = np.concatenate([[0], np.cumsum(nbytes)[:-1]]).astype(np.int64)
+                dev = torch.device("cuda", dev_index)
+                with torch.cuda.device(dev):
+                    buf = torch.empty(int(nbytes.sum()), dtype=torch.uint8, device=dev)
+                    _lib.check(_lib.load().rdb_warp_crops_batch(dev_index, _lib.ptr(pages_dev), len(part), h, w, len(geo),
+                                                                _lib.ptr(np.asarray(page_idx, np.int32)), _lib.ptr(minv), _lib.ptr(sizes),
+                                                                _lib.ptr(rot), _lib.ptr(buf), _lib.ptr(offs), int(buf.numel()),
+                                                                torch.cuda.current_stream(dev).cuda_stream or None))
+                self.text_recognizer.stats["launches"] += 1                        # warp_cubic
+                self.text_recognizer.stats["h2d_bytes"] += len(geo) * 104
+                shapes = [((g[0], g[1]) if g[3] else (g[1], g[0])) for g in geo]
+                rec = self.text_recognizer(DeviceCrops(buf, offs, shapes, dev_index))
+                q = 0
+                for k, i in enumerate(part):
+                    page_res = []
+                    for b in boxes_per_page[k]:
+                        t, sc = rec.txts[q], rec.scores[q]
+                        q += 1
+                        if sc >= drop:
+                            page_res.append([np.asarray(b).tolist(), (t, sc)])
+                    out[i] = page_res or None
+        return out
 
     # ---- rapid_ocr.py:225-299
     def ocr(self, img, det=True, rec=True, mfd_res=None, tqdm_enable=False, tqdm_desc="OCR-rec Predict", return_word_box=False,
             ori_img=None, dt_boxes=None):
-        assert isinstance(img, (np.ndarray, list))
+        assert isinstance(img, (np.ndarray, list, bytes))
         if isinstance(img, list) and det:
             raise ValueError("When input a list of images, det must be false")
+        img = check_img(img)
         if det and rec:
-            boxes, res = self.__call__(img, mfd_res=mfd_res)
+            boxes, res = self.__call__(preprocess_image(img), mfd_res=mfd_res)
             if not boxes and not res:
                 return [None]
             return [[[np.asarray(b).tolist(), r] for b, r in zip(boxes, res)]]
         if det and not rec:
-            d = self.text_detector(img)
+            d = self.text_detector(preprocess_image(img))
             if d.boxes is None:
                 return [None]
             boxes = self._post_boxes(np.array(d.boxes), mfd_res)
             return [[np.asarray(b).tolist() for b in boxes]]
-        crops = img if isinstance(img, list) else [img]
+        crops = img if isinstance(img, list) else [preprocess_image(img)]
         r = self.text_recognizer(crops, return_word_box=return_word_box)
         if return_word_box and ori_img is not None and dt_boxes:
             return [list(zip(r.txts, r.scores, self.calc_word_boxes(crops, dt_boxes, r, ori_img.shape[0], ori_img.shape[1])))]

@@ -44,26 +44,30 @@ class B200OcrCustomModel(CustomBaseModel):
         return out
 
 
-def make_ocr_model_init(device=0, precision=None, fallback=None):
-    """Factory with the signature of model_init.ocr_model_init (model_init.py:45-54)."""
+def make_ocr_model_init(device=0, precision=None, fallback=None, devices=None):
+    """Factory with the signature of model_init.ocr_model_init (model_init.py:45-54).  devices=[0, 1, ...]: the model is a
+    `B200OcrPool` that shards pages / text-line batches over those GPUs (rapiddoc_b200/multi.py)."""
     def ocr_model_init(det_db_box_thresh=0.5, lang=None, ocr_config=None, det_db_unclip_ratio=1.8, enable_merge_det_boxes=True,
                        is_seal=False):
         if is_seal:
             if fallback is None:
                 raise NotImplementedError("seal OCR is outside the B200 hot path")
             return fallback(det_db_box_thresh, lang, ocr_config, det_db_unclip_ratio, enable_merge_det_boxes, is_seal)
+        kw = dict(det_db_box_thresh=det_db_box_thresh, lang=lang, ocr_config=ocr_config, use_dilation=True,
+                  det_db_unclip_ratio=det_db_unclip_ratio, enable_merge_det_boxes=enable_merge_det_boxes, precision=precision)
+        if devices is not None and len(devices) > 1:
+            from .multi import B200OcrPool
+            return B200OcrPool(devices, **kw)
         from .ocr import B200OcrModel
-        return B200OcrModel(det_db_box_thresh=det_db_box_thresh, lang=lang, ocr_config=ocr_config, use_dilation=True,
-                            det_db_unclip_ratio=det_db_unclip_ratio, enable_merge_det_boxes=enable_merge_det_boxes, device=device,
-                            precision=precision)
+        return B200OcrModel(device=devices[0] if devices else device, **kw)
     return ocr_model_init
 
 
-def install(device=0, precision=None):
-    """Seam 2: rebind RapidDoc's OCR model factory.  Returns the original factory."""
+def install(device=0, precision=None, devices=None):
+    """Seam 2: rebind RapidDoc's OCR model factory.  Returns the original factory.  devices=[...] shards over several GPUs."""
     from rapid_doc.backend.pipeline import model_init as mi
     orig = mi.ocr_model_init
-    mi.ocr_model_init = make_ocr_model_init(device, precision, fallback=orig)
+    mi.ocr_model_init = make_ocr_model_init(device, precision, fallback=orig, devices=devices)
     mi.AtomModelSingleton._models.clear()
     return orig
 
