@@ -141,6 +141,11 @@ int rdb_db_bitmap(int device, const float* prob, int n, int hgt, int wid, float 
  * max_pts points to out_xy, returns the count (or a negative error). */
 int rdb_clipper_offset(const double* box_xy, int n_pts, double distance, int64_t* out_xy, int max_pts);
 
+/* rdb_clipper_offset for m quads in one call (every box of a window): boxes_xy [m][4][2], distances [m]; the polygons are
+ * written back to back into out_xy (max_pts_total points), counts[i] = points of polygon i; returns the total. */
+int rdb_clipper_offset_batch(const double* boxes_xy, int m, const double* distances, int64_t* out_xy, int max_pts_total,
+                             int32_t* counts);
+
 /* ---- text recognition ----------------------------------------------------------------- */
 int rdb_rec_create(const void* weights, size_t nbytes, int device, int precision, rdb_rec_t** out);
 void rdb_rec_destroy(rdb_rec_t* h);

@@ -40,6 +40,7 @@ SYMBOLS = {
     "rdb_rec_pool_bytes": (C.c_longlong, [_vp]),
     "rdb_debug_cubic_tab": (_i, [_vp]),
     "rdb_clipper_offset": (_i, [C.POINTER(C.c_double), _i, C.c_double, C.POINTER(C.c_int64), _i]),
+    "rdb_clipper_offset_batch": (_i, [_vp, _i, _vp, _vp, _i, _vp]),
     "rdb_rec_create": (_i, [_vp, C.c_size_t, _i, _i, C.POINTER(_vp)]),
     "rdb_rec_destroy": (None, [_vp]),
     "rdb_rec_vocab": (_i, [_vp]),

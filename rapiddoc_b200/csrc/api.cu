@@ -133,12 +133,17 @@ int rdb_pinned_free(void* p) {
 }
 
 static void require_device(int device) {
+  // cudaGetDeviceProperties costs milliseconds per call: the verdict per device index is cached (it cannot change within a process)
+  static int ok[rdb::kMaxDevices] = {};
+  if (device >= 0 && device < rdb::kMaxDevices && ok[device]) return;
   int n = rdb_device_count();
   if (n <= 0) throw rdb::Error("cuda: no CUDA device visible — rapiddoc_b200 has no CPU fallback");
   if (device < 0 || device >= n) throw rdb::Error("invalid device index");
-  cudaDeviceProp p;
-  RDB_CUDA(cudaGetDeviceProperties(&p, device));
-  if (p.major != 10) throw rdb::Error(std::string("cuda: device is sm_") + std::to_string(p.major * 10 + p.minor) + ", this library is built for sm_100a only");
+  int major = 0, minor = 0;
+  RDB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  RDB_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+  if (major != 10) throw rdb::Error(std::string("cuda: device is sm_") + std::to_string(major * 10 + minor) + ", this library is built for sm_100a only");
+  if (device < rdb::kMaxDevices) ok[device] = 1;
 }
 
 int rdb_det_create(const void* weights, size_t nbytes, int device, int precision, rdb_det_t** out) {
@@ -297,6 +302,19 @@ int rdb_clipper_offset(const double* box_xy, int n_pts, double distance, int64_t
     cnt = clipper_offset(box_xy, n_pts, distance, out_xy, max_pts);
   });
   return rc == RDB_OK ? cnt : rc;
+}
+
+int rdb_clipper_offset_batch(const double* boxes_xy, int m, const double* distances, int64_t* out_xy, int max_pts_total, int32_t* counts) {
+  int total = 0;
+  int rc = guarded([&] {
+    RDB_CHECK(m >= 0 && (m == 0 || (boxes_xy && distances && out_xy && counts)), "null argument");
+    for (int i = 0; i < m; ++i) {
+      const int n = clipper_offset(boxes_xy + (size_t)i * 8, 4, distances[i], out_xy + (size_t)total * 2, max_pts_total - total);
+      counts[i] = n;
+      total += n;
+    }
+  });
+  return rc == RDB_OK ? total : rc;
 }
 
 int rdb_rec_create(const void* weights, size_t nbytes, int device, int precision, rdb_rec_t** out) {

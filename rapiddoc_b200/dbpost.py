@@ -23,6 +23,20 @@ import numpy as np
 from . import _lib
 
 _POOL = None
+TIMES = {}          # cumulative wall-clock seconds per host stage (diagnostics: tools/pipeline_profile.py prints them)
+
+
+class timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        import time
+        self.t = time.perf_counter()
+
+    def __exit__(self, *a):
+        import time
+        TIMES[self.name] = TIMES.get(self.name, 0.0) + time.perf_counter() - self.t
 
 
 def pool():
@@ -48,24 +62,6 @@ def mini_boxes(rect_pts):
     i3 = np.where(second, 3, 2)
     idx = np.stack([i1, i2, i3, i4], axis=1)
     return np.take_along_axis(p, idx[:, :, None], axis=1)
-
-
-def page_candidates(bitmap, max_candidates=1000, min_size=3):
-    """findContours -> minAreaRect -> ordered mini boxes with short side >= min_size.  bitmap [h,w] uint8 {0,1}
-    (cv2.findContours treats any non-zero pixel as foreground, so the reference's `* 255` is not needed).
-    Returns quads [k,4,2] f32 in contour order."""
-    res = cv2.findContours(bitmap, cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
-    contours = res[0] if len(res) == 2 else res[1]
-    contours = contours[:max_candidates]
-    if not contours:
-        return np.zeros((0, 4, 2), np.float32)
-    rects = [cv2.minAreaRect(c) for c in contours]
-    ss = np.array([min(r[1]) for r in rects])
-    keep = np.nonzero(~(ss < min_size))[0]
-    if len(keep) == 0:
-        return np.zeros((0, 4, 2), np.float32)
-    pts = np.stack([cv2.boxPoints(rects[i]) for i in keep])
-    return mini_boxes(pts)
 
 
 def contour_area_f32(boxes):
@@ -114,67 +110,107 @@ def order_points_clockwise(boxes):
     return np.stack([left[:, 0], right[:, 0], right[:, 1], left[:, 1]], axis=1).astype(np.float32)
 
 
-def finish_page(quads, scores, bitmap_shape, ori_shape, box_thresh, unclip_ratio, min_size=3):
-    """Everything after box_score_fast for one page: threshold, unclip, second mini box, scale to the source page, int32,
-    filter_det_res.  quads [k,4,2] f32 (mini boxes), scores [k] f64.  Returns (boxes [n,4,2] f32, scores list)."""
-    height, width = bitmap_shape
-    src_h, src_w = ori_shape
-    keep = np.nonzero(~(box_thresh > scores))[0]
-    if len(keep) == 0:
-        return np.zeros((0, 4, 2), np.float32), []
-    q = quads[keep]
-    sc = scores[keep]
-    area = contour_area_f32(q)
-    length = arc_length_f32(q)
-    out_pts, out_sc = [], []
-    for i in range(len(q)):
-        if length[i] <= 0:
-            continue
-        exp = clipper_offset(q[i], area[i] * unclip_ratio / length[i])
-        if len(exp) == 0:
-            continue
-        rect = cv2.minAreaRect(exp)
-        if min(rect[1]) < min_size + 2:
-            continue
-        out_pts.append(cv2.boxPoints(rect))
-        out_sc.append(float(sc[i]))
-    if not out_pts:
-        return np.zeros((0, 4, 2), np.float32), []
-    box = mini_boxes(np.stack(out_pts))                      # float32
-    box[:, :, 0] = np.clip(np.round(box[:, :, 0] / width * src_w), 0, src_w)
-    box[:, :, 1] = np.clip(np.round(box[:, :, 1] / height * src_h), 0, src_h)
-    box = box.astype(np.int32)
-    # filter_det_res
-    b = order_points_clockwise(box)
-    b[:, :, 0] = np.clip(b[:, :, 0], 0, src_w - 1).astype(np.int64)
-    b[:, :, 1] = np.clip(b[:, :, 1], 0, src_h - 1).astype(np.int64)
-    d01 = b[:, 0] - b[:, 1]
-    d03 = b[:, 0] - b[:, 3]
-    rw = np.sqrt((d01 * d01).sum(1)).astype(np.int64)        # int(np.linalg.norm(...)) on float32 vectors
-    rh = np.sqrt((d03 * d03).sum(1)).astype(np.int64)
-    ok = ~((rw <= 3) | (rh <= 3))
-    return b[ok], [s for s, k in zip(out_sc, ok) if k]
+def clipper_offset_batch(boxes, distances):
+    """rdb_clipper_offset for every box of a window in one C call.  Returns (points int32 [total,1,2], starts int64 [m+1])."""
+    m = len(boxes)
+    xy = np.ascontiguousarray(boxes, np.float64).reshape(m, 8)
+    dist = np.ascontiguousarray(distances, np.float64)
+    # JT_ROUND emits ~ pi * sqrt(delta / 0.25) / 2 points per corner; sized generously, regrown on overflow
+    cap = int(m * 64 + 4 * float(np.sum(np.sqrt(np.maximum(dist, 0.0)))) * 4) + 64
+    counts = np.zeros(m, np.int32)
+    lib = _lib.load()
+    while True:
+        out = np.empty((cap, 2), np.int64)
+        rc = lib.rdb_clipper_offset_batch(_lib.ptr(xy), m, _lib.ptr(dist), _lib.ptr(out), cap, _lib.ptr(counts))
+        if rc >= 0:
+            break
+        if cap > (1 << 26):
+            _lib.check(rc)
+        cap *= 4
+    starts = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    return out[:rc].astype(np.int32).reshape(-1, 1, 2), starts
 
 
 def window_boxes(bitmaps, ori_shapes, score_fn, box_thresh=0.5, unclip_ratio=1.6, max_candidates=1000, min_size=3,
                  parallel=True):
     """DBPostProcess for every page of a window.  bitmaps [n,h,w] uint8 (host), ori_shapes n x (src_h, src_w).
-    Returns [(boxes [k,4,2] f32, scores)] per page, identical to running the reference's per-page loop."""
+    Returns [(boxes [k,4,2] f32, scores)] per page, identical to running the reference's per-page loop.
+
+    Only cv2.findContours runs on the worker pool (it releases the GIL and is the one heavy call); the per-contour
+    cv2.minAreaRect / cv2.boxPoints calls stay on the calling thread (microseconds each — threads would only fight over the
+    GIL), and all array arithmetic is done ONCE for the boxes of the whole window."""
     n = len(bitmaps)
+    height, width = bitmaps[0].shape
+    if len(set(tuple(s) for s in ori_shapes)) != 1:      # mixed source sizes: page by page (the reference's own loop)
+        return [window_boxes(bitmaps[i:i + 1], ori_shapes[i:i + 1], _shift_pages(score_fn, i), box_thresh, unclip_ratio, max_candidates,
+                             min_size, False)[0] for i in range(n)]
+    src_h, src_w = ori_shapes[0]
     run = pool().map if (parallel and n > 1) else map
-    cands = list(run(lambda bm: page_candidates(bm, max_candidates, min_size), bitmaps))
-    counts = [len(c) for c in cands]
-    total = sum(counts)
-    if total:
-        quads = np.ascontiguousarray(np.concatenate(cands), np.float32)
-        page_idx = np.repeat(np.arange(n, dtype=np.int32), counts)
+    with timed("det.findContours"):
+        found = list(run(lambda bm: cv2.findContours(bm, cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE), bitmaps))
+    with timed("det.minAreaRect"):
+        pts, ss, page_idx = [], [], []
+        for i, res in enumerate(found):
+            contours = res[0] if len(res) == 2 else res[1]
+            for c in contours[:max_candidates]:
+                r = cv2.minAreaRect(c)
+                ss.append(min(r[1]))
+                pts.append(cv2.boxPoints(r))
+                page_idx.append(i)
+    empty = (np.zeros((0, 4, 2), np.float32), [])
+    if not pts:
+        return [empty for _ in range(n)]
+    ss = np.array(ss)
+    keep = np.nonzero(~(ss < min_size))[0]
+    if len(keep) == 0:
+        return [empty for _ in range(n)]
+    quads = np.ascontiguousarray(mini_boxes(np.stack(pts)[keep]), np.float32)
+    page_idx = np.asarray(page_idx, np.int32)[keep]
+    with timed("det.box_scores(gpu)"):
         scores = np.asarray(score_fn(quads, page_idx), np.float64)
-    else:
-        scores = np.zeros(0, np.float64)
-    offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-    shape = bitmaps[0].shape
-    jobs = [(cands[i], scores[offs[i]:offs[i + 1]], shape, ori_shapes[i]) for i in range(n)]
-    return list(run(lambda j: finish_page(j[0], j[1], j[2], j[3], box_thresh, unclip_ratio, min_size), jobs))
+    with timed("det.unclip+filter"):
+        keep = np.nonzero(~(box_thresh > scores))[0]
+        quads, scores, page_idx = quads[keep], scores[keep], page_idx[keep]
+        area = contour_area_f32(quads)
+        length = arc_length_f32(quads)
+        ok = length > 0
+        quads, scores, page_idx, area, length = quads[ok], scores[ok], page_idx[ok], area[ok], length[ok]
+        if len(quads) == 0:
+            return [empty for _ in range(n)]
+        poly, starts = clipper_offset_batch(quads, area * unclip_ratio / length)
+        out_pts, sel = [], []
+        for i in range(len(quads)):
+            if starts[i + 1] == starts[i]:
+                continue
+            rect = cv2.minAreaRect(poly[starts[i]:starts[i + 1]])
+            if min(rect[1]) < min_size + 2:
+                continue
+            out_pts.append(cv2.boxPoints(rect))
+            sel.append(i)
+        if not out_pts:
+            return [empty for _ in range(n)]
+        sel = np.asarray(sel)
+        scores, page_idx = scores[sel], page_idx[sel]
+        box = mini_boxes(np.stack(out_pts))                      # float32
+        box[:, :, 0] = np.clip(np.round(box[:, :, 0] / width * src_w), 0, src_w)
+        box[:, :, 1] = np.clip(np.round(box[:, :, 1] / height * src_h), 0, src_h)
+        box = box.astype(np.int32)
+        # filter_det_res
+        b = order_points_clockwise(box)
+        b[:, :, 0] = np.clip(b[:, :, 0], 0, src_w - 1).astype(np.int64)
+        b[:, :, 1] = np.clip(b[:, :, 1], 0, src_h - 1).astype(np.int64)
+        d01 = b[:, 0] - b[:, 1]
+        d03 = b[:, 0] - b[:, 3]
+        rw = np.sqrt((d01 * d01).sum(1)).astype(np.int64)        # int(np.linalg.norm(...)) on float32 vectors
+        rh = np.sqrt((d03 * d03).sum(1)).astype(np.int64)
+        ok = ~((rw <= 3) | (rh <= 3))
+        b, scores, page_idx = b[ok], scores[ok], page_idx[ok]
+        cuts = np.searchsorted(page_idx, np.arange(n + 1))           # page_idx is non-decreasing (contours were visited page by page)
+        return [(b[cuts[i]:cuts[i + 1]], [float(v) for v in scores[cuts[i]:cuts[i + 1]]]) for i in range(n)]
+
+
+def _shift_pages(score_fn, page):
+    return lambda quads, page_idx: score_fn(quads, page_idx + page)
 
 
 def cv2_score_fn(prob):
@@ -197,9 +233,10 @@ def cv2_score_fn(prob):
     return fn
 
 
-def gpu_score_fn(device, prob_dev, n, h, w):
+def gpu_score_fn(device, prob_dev, n, h, w, stream=None):
     """rdb_db_box_scores over the device-resident prob maps (torch tensor or raw device pointer); quads whose vertices leave
-    their clipped bounding box are scored with cv2 on the ROI fetched from the device."""
+    their clipped bounding box are scored with cv2 on the ROI fetched from the device.  stream: raw cudaStream_t of a stream
+    that does not wait on the detector's next sub-batch (the legacy default stream would)."""
     lib = _lib.load()
 
     def fn(quads, page_idx):
@@ -207,7 +244,7 @@ def gpu_score_fn(device, prob_dev, n, h, w):
         scores = np.zeros(m, np.float64)
         flags = np.zeros(m, np.int32)
         _lib.check(lib.rdb_db_box_scores(int(device), _lib.ptr(prob_dev), int(n), int(h), int(w), m, _lib.ptr(quads), _lib.ptr(page_idx),
-                                         _lib.ptr(scores), _lib.ptr(flags), None))
+                                         _lib.ptr(scores), _lib.ptr(flags), stream))
         bad = np.nonzero(flags)[0]
         if len(bad):
             one = cv2_score_fn(None).score_one

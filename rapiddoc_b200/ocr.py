@@ -80,6 +80,48 @@ def crop_geometry(points):
     return cw, ch, np.ascontiguousarray(minv, np.float64), int(ch * 1.0 / cw >= 2)
 
 
+def crop_geometry_batch(boxes):
+    """crop_geometry for all quads of a window.  Returns (keep indices, sizes [k,2] (w,h) i32, minv [k,9] f64, rotate [k] i32).
+    Text-line boxes have integer coordinates (DBPostProcess rounds them, merge / update keep integers), for which the four
+    float32 np.linalg.norm calls per box reduce to exact integer arithmetic and are evaluated for the whole window at once.
+    An axis-aligned box whose crop size equals its extent maps onto the crop by a pure integer translation: cv2's
+    getPerspectiveTransform + invert give that matrix up to ~1e-13 noise, which cannot move any 1/32-pixel fixed-point source
+    coordinate of warpPerspective (they are integers plus that noise), so the exact translation is used instead of two LU
+    solves per box.  Every other quad goes through the same cv2 calls as the reference."""
+    m = len(boxes)
+    if m == 0:
+        return np.zeros(0, np.int64), np.zeros((0, 2), np.int32), np.zeros((0, 9), np.float64), np.zeros(0, np.int32)
+    pts = np.asarray(boxes, dtype=np.float32).reshape(m, 4, 2)
+    if not np.array_equal(pts, np.round(pts)) or np.abs(pts).max() >= 4096:
+        geo = [crop_geometry(b) for b in pts]
+        keep = np.array([i for i, g in enumerate(geo) if g is not None], np.int64)
+        live = [geo[i] for i in keep]
+        return (keep, np.array([[g[0], g[1]] for g in live], np.int32).reshape(-1, 2),
+                np.array([g[2].reshape(9) for g in live], np.float64).reshape(-1, 9), np.array([g[3] for g in live], np.int32))
+
+    def norm(a, b):       # float32 sqrt of an exactly representable integer sum of squares == np.linalg.norm(pts[a] - pts[b])
+        d = pts[:, a] - pts[:, b]
+        return np.sqrt((d * d).sum(1))
+    cw = np.maximum(norm(0, 1), norm(2, 3)).astype(np.int64)      # int(max(...)): truncation
+    ch = np.maximum(norm(0, 3), norm(1, 2)).astype(np.int64)
+    keep = np.nonzero((cw >= 1) & (ch >= 1))[0]
+    pts, cw, ch = pts[keep], cw[keep], ch[keep]
+    rot = (ch * 1.0 / cw >= 2).astype(np.int32)
+    x0, y0, x1, y1 = pts[:, 0, 0], pts[:, 0, 1], pts[:, 2, 0], pts[:, 2, 1]
+    aligned = ((pts[:, 1, 1] == y0) & (pts[:, 1, 0] == x1) & (pts[:, 3, 0] == x0) & (pts[:, 3, 1] == y1) &
+               (x1 - x0 == cw) & (y1 - y0 == ch))
+    minv = np.zeros((len(keep), 9), np.float64)
+    minv[:, 0] = 1.0
+    minv[:, 4] = 1.0
+    minv[:, 8] = 1.0
+    minv[:, 2] = x0
+    minv[:, 5] = y0
+    for i in np.nonzero(~aligned)[0]:
+        std = np.float32([[0, 0], [cw[i], 0], [cw[i], ch[i]], [0, ch[i]]])
+        minv[i] = cv2.invert(cv2.getPerspectiveTransform(pts[i], std))[1].reshape(9)
+    return keep, np.stack([cw, ch], 1).astype(np.int32), minv, rot
+
+
 class DeviceCrops:
     """The crops of one page kept in GPU memory: a packed uint8 buffer (torch tensor) + per-crop stored (h, w) and byte offsets.
     The recogniser resizes / packs them on the device (rdb_resize_pack_u8); `numpy(i)` fetches one crop for host-side users."""
@@ -320,7 +362,8 @@ class B200TextDetector:
             assert imgs.dtype == torch.uint8 and imgs.is_contiguous() and imgs.device.index == self.engine.device
             host, pages_dev = None, imgs
         else:
-            host = self._stage(imgs)
+            with dbpost.timed("det.stage"):
+                host = self._stage(imgs)
             pages_dev = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
             self.stats["h2d_bytes"] += host.size
         self.stats["d2h_bytes"] += n * rh * rw
@@ -342,11 +385,14 @@ class B200TextDetector:
         out = [None] * n
         fut = dbpost.pool().submit(gpu, *cuts[0])
         for k, (lo, hi) in enumerate(cuts):
-            fut.result()
+            with dbpost.timed("det.wait_gpu"):
+                fut.result()
             self.stats["launches"] += self.engine.last_launches + 1          # + the box scorer
             if k + 1 < len(cuts):
                 fut = dbpost.pool().submit(gpu, *cuts[k + 1])
-            score_fn = dbpost.gpu_score_fn(self.engine.device, probs[lo:hi], hi - lo, rh, rw)
+            if getattr(self, "_post_stream", None) is None:
+                self._post_stream = torch.cuda.Stream(dev)
+            score_fn = dbpost.gpu_score_fn(self.engine.device, probs[lo:hi], hi - lo, rh, rw, self._post_stream.cuda_stream)
             res = dbpost.window_boxes(bitmaps[lo:hi], [(h, w)] * (hi - lo), score_fn, po.box_thresh,
                                       po.unclip_ratio, po.max_candidates, po.min_size)
             out[lo:hi] = res
@@ -551,23 +597,28 @@ class B200TextRecognizer:
             vw_dev = torch.from_numpy(dst_w).to(dev)
             ids_all = torch.empty(toks, dtype=torch.int32, device=dev)
             probs_all = torch.empty(toks, dtype=torch.float32, device=dev)
+            t_l = dbpost.timed("rec.launch")
+            t_l.__enter__()
             for (lo, hi, imgW, _mx), to in zip(batches, tok_off):
                 self.engine.infer_u8_raw(packed.data_ptr() + int(dst_offs[lo]), vw_dev.data_ptr() + 4 * lo, hi - lo, imgW,
                                          ids_all.data_ptr() + 4 * to, probs_all.data_ptr() + 4 * to, st.cuda_stream or None)
                 self.stats["launches"] += self.engine.last_launches
+            t_l.__exit__()
             self.stats["launches"] += 1                                           # resize_slots
             self.stats["h2d_bytes"] += n * (32 + 4)                               # slot table + valid widths
             self.stats["d2h_bytes"] += toks * 8
             self.stats["crops"] += n
-            ids_h = ids_all.cpu().numpy()
-            probs_h = probs_all.cpu().numpy()
+            with dbpost.timed("rec.sync+d2h"):
+                ids_h = ids_all.cpu().numpy()
+                probs_h = probs_all.cpu().numpy()
         if getattr(self, "keep_ids", False):      # diagnostics (bench parity report): per-crop argmax ids in input order
             self.last_ids = [None] * n
             for (lo, hi, imgW, _mx), to in zip(batches, tok_off):
                 T = self.engine.tokens(imgW)
                 for j in range(hi - lo):
                     self.last_ids[int(order[lo + j])] = ids_h[to + j * T: to + (j + 1) * T].copy()
-        res, words = self.decode_window(ids_h, probs_h, batches, tok_off, order, ratios, return_word_box)
+        with dbpost.timed("rec.decode"):
+            res, words = self.decode_window(ids_h, probs_h, batches, tok_off, order, ratios, return_word_box)
         txts, scores = list(zip(*res))
         return TextRecOutput(img_list, tuple(txts), tuple(scores), tuple(words) if return_word_box else None,
                              time.perf_counter() - t0)
@@ -715,41 +766,49 @@ class B200OcrModel:
                     sub = pages[part[0]: part[-1] + 1] if part == list(range(part[0], part[-1] + 1)) else pages[part]
                 else:
                     sub = [pages[i] for i in part]
-                res, pages_dev = self.text_detector.detect_window(sub, keep_pages=True)
-                boxes_per_page, geo, page_idx = [], [], []
+                with dbpost.timed("pages.det_window"):
+                    res, pages_dev = self.text_detector.detect_window(sub, keep_pages=True)
+                t_geo = dbpost.timed("pages.sort/merge+crop_geometry")
+                t_geo.__enter__()
+                boxes_per_page, flat, page_idx = [], [], []
                 for k, (i, (boxes, _)) in enumerate(zip(part, res)):
                     if boxes is None or len(boxes) == 0:
                         boxes_per_page.append([])
                         continue
                     # the detector sorts its boxes (TextDetector.sorted_boxes), __call__ sorts them again (rapid_ocr.py:372)
                     bl = self._post_boxes(np.array(sorted_boxes(boxes)), mfd_res_list[i] if mfd_res_list else None)
-                    keep = []
-                    for b in bl:
-                        g = crop_geometry(b)
-                        if g is None:      # degenerate quad: the reference's warp would fail on it too
-                            continue
-                        keep.append(b)
-                        geo.append(g)
-                        page_idx.append(k)
-                    boxes_per_page.append(keep)
-                if not geo:
+                    boxes_per_page.append(bl)
+                    flat.extend(bl)
+                    page_idx.extend([k] * len(bl))
+                keep, sizes, minv, rot = crop_geometry_batch(flat)
+                if len(keep) != len(flat):      # degenerate quads (the reference's warp would fail on them too) are dropped
+                    alive = set(int(v) for v in keep)
+                    q, pruned = 0, []
+                    for bl in boxes_per_page:
+                        pruned.append([b for j, b in enumerate(bl) if (q + j) in alive])
+                        q += len(bl)
+                    boxes_per_page = pruned
+                    page_idx = [page_idx[int(v)] for v in keep]
+                t_geo.__exit__()
+                if len(keep) == 0:
                     continue
-                minv = np.stack([g[2].reshape(9) for g in geo])
-                sizes = np.array([[g[0], g[1]] for g in geo], np.int32)
-                rot = np.array([g[3] for g in geo], np.int32)
+                pidx = np.asarray(page_idx, np.int32)          # named: the array must outlive the ctypes call
+                minv = np.ascontiguousarray(minv)
+                sizes = np.ascontiguousarray(sizes)
                 nbytes = sizes[:, 0].astype(np.int64) * sizes[:, 1] * 3
                 offs = np.concatenate([[0], np.cumsum(nbytes)[:-1]]).astype(np.int64)
                 dev = torch.device("cuda", dev_index)
                 with torch.cuda.device(dev):
                     buf = torch.empty(int(nbytes.sum()), dtype=torch.uint8, device=dev)
-                    _lib.check(_lib.load().rdb_warp_crops_batch(dev_index, _lib.ptr(pages_dev), len(part), h, w, len(geo),
-                                                                _lib.ptr(np.asarray(page_idx, np.int32)), _lib.ptr(minv), _lib.ptr(sizes),
+                    _lib.check(_lib.load().rdb_warp_crops_batch(dev_index, _lib.ptr(pages_dev), len(part), h, w, len(keep),
+                                                                _lib.ptr(pidx), _lib.ptr(minv), _lib.ptr(sizes),
                                                                 _lib.ptr(rot), _lib.ptr(buf), _lib.ptr(offs), int(buf.numel()),
                                                                 torch.cuda.current_stream(dev).cuda_stream or None))
                 self.text_recognizer.stats["launches"] += 1                        # warp_cubic
-                self.text_recognizer.stats["h2d_bytes"] += len(geo) * 104
-                shapes = [((g[0], g[1]) if g[3] else (g[1], g[0])) for g in geo]
-                rec = self.text_recognizer(DeviceCrops(buf, offs, shapes, dev_index))
+                self.text_recognizer.stats["h2d_bytes"] += len(keep) * 104
+                shapes = [((int(cw), int(ch)) if r else (int(ch), int(cw))) for (cw, ch), r in zip(sizes, rot)]
+                with dbpost.timed("pages.rec"):
+                    rec = self.text_recognizer(DeviceCrops(buf, offs, shapes, dev_index))
                 q = 0
                 for k, i in enumerate(part):
                     page_res = []

@@ -77,3 +77,42 @@ def test_bench_roofline_model_knows_every_fused_kernel():
     assert bench.algorithmic_bytes(f"stem1_tc[P={4 * P},N=24]", 2, wl, 32) == 4 * P * (12 + 48)
     assert bench.algorithmic_bytes(f"dwconv7x7_h2[P={P},C=96,s=1]", 2, wl, 32) == P * 96 * 2 * 2
     assert bench.algorithmic_bytes("se_fc", 2, wl, 32) is None       # latency-bound helper: no byte model, never the roofline kernel
+
+
+def test_crop_geometry_batch_equals_per_box_and_translation_shortcut_is_exact():
+    """crop_geometry_batch: sizes / rot90 decisions identical to the per-box reference arithmetic; for axis-aligned integer
+    boxes the exact translation it substitutes for cv2's getPerspectiveTransform + invert yields the very same warp
+    (checked through the cv2-pinned CPU restatement of warpPerspective and against cv2 itself)."""
+    import cv2
+    from oracle import warp
+    from rapiddoc_b200.ocr import crop_geometry, crop_geometry_batch
+    rng = np.random.default_rng(3)
+    page = rng.integers(0, 256, (300, 400, 3), dtype=np.uint8)
+    boxes = []
+    for t in range(80):
+        x0, y0 = int(rng.integers(0, 300)), int(rng.integers(0, 250))
+        w, h = int(rng.integers(1, 100)), int(rng.integers(1, 50))
+        if t % 4 == 0:       # rotated / skewed integer quad
+            boxes.append([[x0, y0 + 3], [x0 + w, y0], [x0 + w + 2, y0 + h], [x0 + 1, y0 + h + 4]])
+        elif t % 9 == 0:     # tall box -> rot90
+            boxes.append([[x0, y0], [x0 + 8, y0], [x0 + 8, y0 + 40], [x0, y0 + 40]])
+        else:
+            boxes.append([[x0, y0], [x0 + w, y0], [x0 + w, y0 + h], [x0, y0 + h]])
+    boxes.append([[5, 5], [5, 5], [5, 5], [5, 5]])        # degenerate
+    keep, sizes, minv, rot = crop_geometry_batch(boxes)
+    per = [crop_geometry(b) for b in boxes]
+    assert list(keep) == [i for i, g in enumerate(per) if g is not None]
+    for k, i in enumerate(keep):
+        cw, ch, mi, r = per[i]
+        assert (int(sizes[k][0]), int(sizes[k][1]), int(rot[k])) == (cw, ch, r)
+        assert np.abs(minv[k] - mi.reshape(9)).max() <= 1e-9
+        a = warp.warp_perspective_cubic_replicate(page, minv[k].reshape(3, 3), (cw, ch))
+        pts = np.float32(boxes[i])
+        M = cv2.getPerspectiveTransform(pts, np.float32([[0, 0], [cw, 0], [cw, ch], [0, ch]]))
+        want = cv2.warpPerspective(page, M, (cw, ch), borderMode=cv2.BORDER_REPLICATE, flags=cv2.INTER_CUBIC)
+        assert np.array_equal(a, want)
+    # non-integer coordinates fall back to the per-box cv2 path
+    fb = [[[1.5, 2.25], [60.5, 2.0], [60.0, 20.5], [1.0, 21.0]]]
+    keep, sizes, minv, rot = crop_geometry_batch(fb)
+    g = crop_geometry(fb[0])
+    assert (int(sizes[0][0]), int(sizes[0][1]), int(rot[0])) == (g[0], g[1], g[3]) and np.array_equal(minv[0], g[2].reshape(9))
