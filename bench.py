@@ -59,7 +59,7 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("RDB_BENCH_PRECISION", "fp16"), choices=["fp16", "fp32"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--rec-batch", type=int, default=int(os.environ.get("RDB_BENCH_REC_BATCH", "64")), help="Rec.rec_batch_num of the pipeline workload (both arms)")
+    ap.add_argument("--rec-batch", type=int, default=int(os.environ.get("RDB_BENCH_REC_BATCH", "256")), help="Rec.rec_batch_num of the pipeline workload (both arms)")
     ap.add_argument("--no-secondary", action="store_true", help="pipeline workload: skip the det-only / rec-only / fp32 legs")
     ap.add_argument("--chunk-pixels", type=int, default=0)
     ap.add_argument("--profile-out", default="", help="write the full per-kernel table of the profiled pass to this JSON file")

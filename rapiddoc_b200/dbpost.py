@@ -145,12 +145,14 @@ def window_boxes(bitmaps, ori_shapes, score_fn, box_thresh=0.5, unclip_ratio=1.6
         return [window_boxes(bitmaps[i:i + 1], ori_shapes[i:i + 1], _shift_pages(score_fn, i), box_thresh, unclip_ratio, max_candidates,
                              min_size, False)[0] for i in range(n)]
     src_h, src_w = ori_shapes[0]
-    run = pool().map if (parallel and n > 1) else map
-    with timed("det.findContours"):
-        found = list(run(lambda bm: cv2.findContours(bm, cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE), bitmaps))
-    with timed("det.minAreaRect"):
+    find = lambda bm: cv2.findContours(bm, cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)      # noqa: E731
+    futs = [pool().submit(find, bm) for bm in bitmaps] if (parallel and n > 1) else None
+    with timed("det.findContours+minAreaRect"):
+        # pages are consumed in order while the pool is still tracing the later ones: the per-contour cv2 calls on this thread
+        # (GIL held) overlap cv2.findContours on the workers (GIL released)
         pts, ss, page_idx = [], [], []
-        for i, res in enumerate(found):
+        for i in range(n):
+            res = futs[i].result() if futs else find(bitmaps[i])
             contours = res[0] if len(res) == 2 else res[1]
             for c in contours[:max_candidates]:
                 r = cv2.minAreaRect(c)
