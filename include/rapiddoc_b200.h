@@ -146,6 +146,26 @@ int rdb_clipper_offset(const double* box_xy, int n_pts, double distance, int64_t
 int rdb_clipper_offset_batch(const double* boxes_xy, int m, const double* distances, int64_t* out_xy, int max_pts_total,
                              int32_t* counts);
 
+/* ---- layout / table post-processing -------------------------------------------------------------------
+ * PP-DocLayout class-aware greedy NMS for a window of pages in one launch (one CTA per page): replaces the Python loop
+ * `nms` rapid_doc/model/layout/rapid_layout_self/model_handler/pp_doclayout/post_process.py:948-979 (+ `iou` :925-946, the +1
+ * pixel convention).  boxes [total][stride] f32 rows = [cls, score, x1, y1, x2, y2, ...]; offsets [pages+1] delimit the pages;
+ * order [total] = per page np.argsort(scores)[::-1] (made by the caller, so ties fall as NumPy leaves them); keep [total]
+ * receives per page (at the page's offset) the kept row indices in selection order, keep_n [pages] their number.  All host arrays.
+ * float32 arithmetic with the reference's operation order: keep-sets are bit-identical. */
+int rdb_layout_nms(int device, const float* boxes, int stride, const int32_t* order, const int32_t* offsets, int pages, float iou_same,
+                   float iou_diff, int32_t* keep, int32_t* keep_n, void* stream);
+
+/* `check_containment` post_process.py:996-1022 (+ `is_contained` :981-994) for a window of pages: formula_index /
+ * category_index < 0 = None; mode 0 = None, 1 = "large", 2 = "small".  contains_other / contained_by_other [total] i32. */
+int rdb_layout_containment(int device, const float* boxes, int stride, const int32_t* offsets, int pages, int formula_index,
+                           int category_index, int mode, int32_t* contains_other, int32_t* contained_by_other, void* stream);
+
+/* argmax / max over the last axis of x [rows][V] f32 (first maximum wins, as np.argmax): the reduction TableLabelDecode.decode
+ * starts with, rapid_doc/model/table/rapid_table_self/table_structure/pp_structure/post_process.py:49-50 (structure_probs
+ * [B,T,50] -> idx, prob).  x host or device; idx / val host or device (both on the same side). */
+int rdb_argmax_rows(int device, const float* x, long long rows, int vocab, int32_t* idx, float* val, void* stream);
+
 /* ---- text recognition ----------------------------------------------------------------- */
 int rdb_rec_create(const void* weights, size_t nbytes, int device, int precision, rdb_rec_t** out);
 void rdb_rec_destroy(rdb_rec_t* h);

@@ -38,6 +38,9 @@ SYMBOLS = {
     "rdb_rec_set_pool_cap_bytes": (_i, [_vp, C.c_size_t]),
     "rdb_det_pool_bytes": (C.c_longlong, [_vp]),
     "rdb_rec_pool_bytes": (C.c_longlong, [_vp]),
+    "rdb_layout_nms": (_i, [_i, _vp, _i, _vp, _vp, _i, _f, _f, _vp, _vp, _vp]),
+    "rdb_layout_containment": (_i, [_i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "rdb_argmax_rows": (_i, [_i, _vp, C.c_longlong, _i, _vp, _vp, _vp]),
     "rdb_debug_cubic_tab": (_i, [_vp]),
     "rdb_clipper_offset": (_i, [C.POINTER(C.c_double), _i, C.c_double, C.POINTER(C.c_int64), _i]),
     "rdb_clipper_offset_batch": (_i, [_vp, _i, _vp, _vp, _i, _vp]),

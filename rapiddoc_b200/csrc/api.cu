@@ -10,6 +10,7 @@
 #include "rec.h"
 #include "warp.cuh"
 #include "dbpost.cuh"
+#include "layout.cuh"
 
 struct rdb_det { rdb::DetEngine* e; };
 struct rdb_rec { rdb::RecEngine* e; };
@@ -285,6 +286,36 @@ int rdb_det_set_pool_cap_bytes(rdb_det_t* h, size_t bytes) { if (!h) return RDB_
 int rdb_rec_set_pool_cap_bytes(rdb_rec_t* h, size_t bytes) { if (!h) return RDB_ERR_INVALID; h->e->set_pool_cap(bytes); return RDB_OK; }
 long long rdb_det_pool_bytes(rdb_det_t* h) { return h ? (long long)h->e->pool_bytes() : -1; }
 long long rdb_rec_pool_bytes(rdb_rec_t* h) { return h ? (long long)h->e->pool_bytes() : -1; }
+
+int rdb_layout_nms(int device, const float* boxes, int stride, const int32_t* order, const int32_t* offsets, int pages, float iou_same, float iou_diff,
+                   int32_t* keep, int32_t* keep_n, void* stream) {
+  return guarded([&] {
+    RDB_CHECK(boxes && order && offsets && keep && keep_n && stride >= 6 && pages >= 0, "null argument");
+    require_device(device);
+    rdb::DeviceGuard g(device);
+    rdb::layout_nms(device, boxes, stride, order, offsets, pages, iou_same, iou_diff, keep, keep_n, (cudaStream_t)stream);
+  });
+}
+
+int rdb_layout_containment(int device, const float* boxes, int stride, const int32_t* offsets, int pages, int formula_index, int category_index,
+                           int mode, int32_t* contains_other, int32_t* contained_by_other, void* stream) {
+  return guarded([&] {
+    RDB_CHECK(boxes && offsets && contains_other && contained_by_other && stride >= 6 && pages >= 0, "null argument");
+    require_device(device);
+    rdb::DeviceGuard g(device);
+    rdb::layout_containment(device, boxes, stride, offsets, pages, formula_index, category_index, mode, contains_other, contained_by_other,
+                            (cudaStream_t)stream);
+  });
+}
+
+int rdb_argmax_rows(int device, const float* x, long long rows, int vocab, int32_t* idx, float* val, void* stream) {
+  return guarded([&] {
+    RDB_CHECK(x && idx && val && rows >= 0 && vocab > 0, "null argument");
+    require_device(device);
+    rdb::DeviceGuard g(device);
+    rdb::argmax_rows(device, x, rows, vocab, idx, val, (cudaStream_t)stream);
+  });
+}
 
 int rdb_debug_cubic_tab(int16_t* out) {
   return guarded([&] {
