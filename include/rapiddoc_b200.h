@@ -166,6 +166,46 @@ int rdb_layout_containment(int device, const float* boxes, int stride, const int
  * [B,T,50] -> idx, prob).  x host or device; idx / val host or device (both on the same side). */
 int rdb_argmax_rows(int device, const float* x, long long rows, int vocab, int32_t* idx, float* val, void* stream);
 
+/* ---- formula engine ops ------------------------------------------------------------------------------
+ * PP-FormulaNet_plus = PPHGNetV2-B6 encoder (rapid_doc/model/formula/rapid_formula_self/networks/backbones/rec_pphgnetv2.py:
+ * 858-1207, 1587-1642) + MBart decoder with greedy generation (networks/heads/rec_unimernet_head.py:502-748,931-976 and
+ * networks/heads/rec_ppformulanet_head.py:400-632,1052-1171).  The reference runs it as a torch module behind
+ * `InferSession.__call__` (rapid_formula_self/inference_engine/torch.py:25-131); here the host side
+ * (rapiddoc_b200/formula.py) walks the network and enqueues these ops on DEVICE buffers (NHWC activations = [pixels, C]
+ * matrices with a row pitch).  All pointers are device pointers; nothing synchronises; prec = RDB_PREC_FP32 (fp32 SIMT,
+ * exact-parity mode) or RDB_PREC_FP16 (fp16 storage, tcgen05 GEMMs).  act: 0 none, 1 ReLU, 2 GELU(erf). */
+const char* rdb_ops_last_error(void);
+/* out[M, c_off : c_off+N] (row pitch ldc) = act(A[M,K] (pitch lda) * W[N,K]^T + bias) (+ res [M,N] pitch ldr): every conv1x1 /
+ * nn.Linear, and every dense k x k conv after rdb_op_im2col.  W fp32 (prec 0) or fp16 (prec 1); bias fp32. */
+int rdb_op_gemm(int device, int prec, const void* A, int lda, long long M, int K, const void* W, int N, const float* bias, int act,
+                const void* res, int ldr, void* out, int ldc, int c_off, void* stream);
+/* x [n,h,w,c] (pixel pitch ld) -> out [n*oh*ow, kh*kw*c], K order (ky, kx, c) = the packed conv weight order */
+int rdb_op_im2col(int device, int prec, const void* x, int n, int h, int w, int c, int ld, int kh, int kw, int sh, int sw, int pt, int pl,
+                  int oh, int ow, void* out, void* stream);
+/* depthwise k x k conv + folded BN (+ ReLU): LightConvBNAct.conv2 and the stage downsample (rec_pphgnetv2.py:916-959,1177-1187) */
+int rdb_op_dwconv(int device, int prec, const void* x, int n, int h, int w, int c, int ld_in, int k, int stride, const float* wt,
+                  const float* bias, int relu, void* out, int oh, int ow, int ld_out, int c_off, void* stream);
+/* PaddingSameAsPaddleMaxPool2d(2, stride 1) (rec_pphgnetv2.py:962-976) into a channel slice */
+int rdb_op_maxpool2x2s1(int device, int prec, const void* x, int n, int h, int w, int c, int ld_in, void* out, int ld_out, int c_off,
+                        void* stream);
+/* rows of c (pitch ld_in) -> channel slice of a wider buffer, with dtype change (0 fp32 / 1 fp16) */
+int rdb_op_copy_cols(int device, int src_prec, int dst_prec, const void* x, long long rows, int c, int ld_in, void* out, int ld_out,
+                     int c_off, void* stream);
+int rdb_op_layernorm(int device, const float* x, long long rows, int c, const float* gamma, const float* beta, float eps, float* out,
+                     void* stream);
+/* embed_tokens[id] * scale + embed_positions[pos + 2]  (MBartLearnedPositionalEmbedding, offset 2) */
+int rdb_op_embed(int device, const int64_t* ids, int batch, int dim, const float* tok, float scale, const float* pos_tab, int pos,
+                 float* out, void* stream);
+/* softmax(q k^T) v for ONE new query per row against t cached positions: q [B, heads*head_dim] (already scaled),
+ * k / v caches [B, t_cap, heads*head_dim] (MBartAttention.forward with tgt_len 1) */
+int rdb_op_attn_decode(int device, const float* q, const float* k, const float* v, int batch, int t, int t_cap, int heads, int head_dim,
+                       float* out, void* stream);
+int rdb_op_add(int device, const float* a, const float* b, float* out, long long n, void* stream);
+/* one greedy step of generate_export (rec_ppformulanet_head.py:1118-1160) on the device: next token = argmax (eos when force_eos),
+ * finished rows emit pad, a row finishes on eos; *all_done = every row has produced an eos */
+int rdb_op_greedy_step(int device, const int32_t* argmax, int batch, int force_eos, int eos, int pad, int64_t* next, int32_t* unfinished,
+                       int32_t* has_eos, int32_t* all_done, void* stream);
+
 /* ---- text recognition ----------------------------------------------------------------- */
 int rdb_rec_create(const void* weights, size_t nbytes, int device, int precision, rdb_rec_t** out);
 void rdb_rec_destroy(rdb_rec_t* h);

@@ -64,3 +64,22 @@ def characters():
     chars = ["blank"] + [l.rstrip("\n") for l in open(f"{REF}/rapid_doc/resources/ppocrv6_small_dict.txt", encoding="utf-8")] + [" "]
     assert len(chars) == 18710
     return chars
+
+
+def formula_net(max_new_tokens=16):
+    """The reference's PP-FormulaNet_plus-M torch module (random init; load a state_dict into it), imported by path:
+    rapid_doc/model/formula/rapid_formula_self/networks (arch config pp_formulanet_arch_config.yaml).
+    x [B,1,384,384] f32 -> ids [B,L] int64 (BaseModel.forward -> PPFormulaNet_Head.generate_export in eval mode)."""
+    import os
+    import yaml
+    os.environ["RAPID_FORMULA_DEVICE_MODE"] = "cpu"
+    if "rapid_doc" not in sys.modules:
+        _stub("rapid_doc", f"{REF}/rapid_doc")
+    for sub in ["model", "model.formula", "model.formula.rapid_formula_self", "model.formula.rapid_formula_self.networks"]:
+        if "rapid_doc." + sub not in sys.modules:
+            _stub("rapid_doc." + sub, f"{REF}/rapid_doc/" + sub.replace(".", "/"))
+    from rapid_doc.model.formula.rapid_formula_self.networks.architectures.base_model import BaseModel
+    cfg = yaml.safe_load(open(f"{REF}/rapid_doc/model/formula/rapid_formula_self/networks/pp_formulanet_arch_config.yaml"))["PP-FormulaNet_plus-M"]
+    cfg = copy.deepcopy(cfg)
+    cfg["Head"]["max_new_tokens"] = int(max_new_tokens)
+    return BaseModel(cfg).eval()

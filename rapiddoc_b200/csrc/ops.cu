@@ -1,0 +1,321 @@
+// Tensor ops of the formula path (PP-FormulaNet_plus: PPHGNetV2-B6 encoder + MBart decoder) behind the
+// C-ABI (include/rapiddoc_b200.h, "formula engine ops").  The host side (rapiddoc_b200/formula.py) walks the network and
+// calls these on DEVICE buffers; every op is enqueued on the caller's stream and returns without synchronising.
+//
+// Layout: NHWC activations, a feature map is a [pixels, C] matrix with a row pitch `ld` — so the dense concatenation of an
+// HGV2 block (rec_pphgnetv2.py:1124-1136: input + 6 layer outputs, 672..5632 channels) is never copied: every layer writes
+// its channel slice of the block's wide buffer (ldc / c_off) and the next layer reads its input slice in place (lda).
+//   conv kxk dense   im2col (one pass, K order = ky,kx,c = the packed weight order) + GEMM
+//   conv 1x1 / linear  GEMM straight on the activations
+//   GEMM             prec 0: fp32 SIMT (exact-parity mode)        prec 1: fp16 tcgen05 / TMEM / TMA (gemm_tc.cuh)
+//   depthwise k x k, 2x2/s1 max-pool, LayerNorm, token embedding, single-query attention over a KV cache, row argmax
+#include "../../include/rapiddoc_b200.h"
+
+#include "engine.cuh"
+
+namespace rdb {
+namespace ops {
+
+template <typename T>
+__global__ void im2col_kernel(const T* __restrict__ x, int n, int H, int W, int C, int ld, int KH, int KW, int sh, int sw, int pt, int pl, int OH, int OW,
+                              T* __restrict__ out) {
+  // one thread per (output pixel, tap, 8-channel group) when C % 8 == 0, else per element
+  const long long K = (long long)KH * KW * C;
+  const long long total = (long long)n * OH * OW * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / K;
+    const int k = (int)(i % K);
+    const int c = k % C, tap = k / C, kx = tap % KW, ky = tap / KW;
+    const int ox = (int)(row % OW), oy = (int)((row / OW) % OH), b = (int)(row / ((long long)OW * OH));
+    const int iy = oy * sh - pt + ky, ix = ox * sw - pl + kx;
+    T v = from_f32<T>(0.f);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[((long long)(b * H + iy) * W + ix) * ld + c];
+    out[i] = v;
+  }
+}
+
+// depthwise k x k, pad (k-1)/2, stride s, weights [k][k][C] fp32, bias [C]; in pitch ld_in, out pitch ld_out (+ c_off)
+template <typename T>
+__global__ void dwconv_generic_kernel(const T* __restrict__ x, int n, int H, int W, int C, int ld_in, int K, int s, const float* __restrict__ w,
+                                      const float* __restrict__ bias, int relu, T* __restrict__ out, int OH, int OW, int ld_out, int c_off) {
+  const long long total = (long long)n * OH * OW * C;
+  const int p = (K - 1) / 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long px = i / C;
+    const int ox = (int)(px % OW), oy = (int)((px / OW) % OH), b = (int)(px / ((long long)OW * OH));
+    float acc = 0.f;
+    for (int ky = 0; ky < K; ++ky) {
+      const int iy = oy * s - p + ky;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < K; ++kx) {
+        const int ix = ox * s - p + kx;
+        if (ix < 0 || ix >= W) continue;
+        acc = fmaf(to_f32<T>(x[((long long)(b * H + iy) * W + ix) * ld_in + c]), w[(ky * K + kx) * C + c], acc);
+      }
+    }
+    acc += bias[c];
+    if (relu) acc = fmaxf(acc, 0.f);
+    out[px * ld_out + c_off + c] = from_f32<T>(acc);
+  }
+}
+
+// PaddingSameAsPaddleMaxPool2d(kernel 2, stride 1) (rec_pphgnetv2.py:962-976): zero pad one row / column at the bottom / right
+template <typename T>
+__global__ void maxpool2x2s1_kernel(const T* __restrict__ x, int n, int H, int W, int C, int ld_in, T* __restrict__ out, int ld_out, int c_off) {
+  const long long total = (long long)n * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long px = i / C;
+    const int ox = (int)(px % W), oy = (int)((px / W) % H), b = (int)(px / ((long long)W * H));
+    float m = -INFINITY;
+    for (int dy = 0; dy < 2; ++dy)
+      for (int dx = 0; dx < 2; ++dx) {
+        const int iy = oy + dy, ix = ox + dx;
+        const float v = (iy < H && ix < W) ? to_f32<T>(x[((long long)(b * H + iy) * W + ix) * ld_in + c]) : 0.f;
+        m = fmaxf(m, v);
+      }
+    out[px * ld_out + c_off + c] = from_f32<T>(m);
+  }
+}
+
+// rows of C (pitch ld_in) -> channel slice of a wider buffer, optional dtype change
+template <typename TI, typename TO>
+__global__ void copy_cols_kernel(const TI* __restrict__ x, long long rows, int C, int ld_in, TO* __restrict__ out, int ld_out, int c_off) {
+  const long long total = rows * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C;
+    const int c = (int)(i % C);
+    out[r * ld_out + c_off + c] = from_f32<TO>(to_f32<TI>(x[r * ld_in + c]));
+  }
+}
+
+// MBart decoder input (rec_unimernet_head.py:440-456, rec_ppformulanet_head.py:449-486): embed_tokens[id] * embed_scale +
+// embed_positions[pos + 2]
+__global__ void embed_kernel(const long long* __restrict__ ids, int B, int D, const float* __restrict__ tok, float scale, const float* __restrict__ pos_tab,
+                             int pos, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * D) return;
+  const int b = i / D, d = i % D;
+  out[i] = tok[ids[b] * D + d] * scale + pos_tab[(long long)(pos + 2) * D + d];
+}
+
+// one query per (batch row, head) against T cached keys / values: q [B, H*HD] (already scaled), k / v [B, Tcap, H*HD]
+// softmax(q k^T) v in fp32 (MBartAttention.forward, rec_unimernet_head.py:541-633, tgt_len = 1, no mask needed)
+__global__ void attn_decode_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int T, int Tcap, int H, int HD,
+                                   float* __restrict__ out) {
+  extern __shared__ float sc[];          // scores [T]
+  const int b = blockIdx.x / H, h = blockIdx.x % H, D = H * HD;
+  const float* qp = q + (long long)b * D + h * HD;
+  const float* kp = k + (long long)b * Tcap * D + h * HD;
+  const float* vp = v + (long long)b * Tcap * D + h * HD;
+  float mx = -INFINITY;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    float s = 0.f;
+    for (int d = 0; d < HD; ++d) s = fmaf(qp[d], kp[(long long)t * D + d], s);
+    sc[t] = s;
+    mx = fmaxf(mx, s);
+  }
+  __shared__ float red[32];
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < (blockDim.x + 31) / 32; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) { const float e = expf(sc[t] - mx); sc[t] = e; sum += e; }
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < (blockDim.x + 31) / 32; ++i) sum += red[i];
+  const float inv = 1.f / sum;
+  for (int d = threadIdx.x; d < HD; d += blockDim.x) {
+    float acc = 0.f;
+    for (int t = 0; t < T; ++t) acc = fmaf(sc[t], vp[(long long)t * D + d], acc);
+    out[(long long)b * D + h * HD + d] = acc * inv;
+  }
+}
+
+__global__ void add_kernel(const float* a, const float* b, float* out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+
+// greedy step bookkeeping of PPFormulaNet_Head.generate_export (rec_ppformulanet_head.py:1118-1160): next = argmax (or eos when
+// the forced-EOS length is reached), finished rows emit pad; a row finishes when it emits eos.  all_done: every row has an eos.
+__global__ void greedy_step_kernel(const int* __restrict__ arg, int B, int force_eos, int eos, int pad, long long* __restrict__ next, int* __restrict__ unfinished,
+                                   int* __restrict__ has_eos, int* __restrict__ all_done) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) {
+    long long t = force_eos ? eos : arg[b];
+    t = unfinished[b] ? t : pad;
+    next[b] = t;
+    if (t == eos) { unfinished[b] = 0; has_eos[b] = 1; }
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {   // B <= blockDim.x * gridDim.x with gridDim.x == 1 (checked by the launcher)
+    int d = 1;
+    for (int i = 0; i < B; ++i) d &= has_eos[i];
+    *all_done = d;
+  }
+}
+
+inline int grid_for(long long total) { long long g = (total + 255) / 256; return (int)(g > 148 * 32 ? 148 * 32 : (g < 1 ? 1 : g)); }
+
+}  // namespace ops
+}  // namespace rdb
+
+namespace {
+thread_local std::string g_ops_err;
+template <typename F>
+int op_guard(F&& f) {
+  try { f(); return RDB_OK; }
+  catch (const std::exception& e) { g_ops_err = e.what(); return g_ops_err.find("cuda") != std::string::npos ? RDB_ERR_CUDA : RDB_ERR_INVALID; }
+}
+rdb::Pool& ops_pool(int device) {       // gemm_tc needs no workspace; the pool only satisfies the launch context
+  static rdb::Pool pools[rdb::kMaxDevices];
+  return pools[device];
+}
+int sm_count(int device) {
+  static int n[rdb::kMaxDevices] = {};
+  if (!n[device]) RDB_CUDA(cudaDeviceGetAttribute(&n[device], cudaDevAttrMultiProcessorCount, device));
+  return n[device];
+}
+}  // namespace
+
+extern "C" {
+
+const char* rdb_ops_last_error(void) { return g_ops_err.c_str(); }
+
+int rdb_op_gemm(int device, int prec, const void* A, int lda, long long M, int K, const void* W, int N, const float* bias, int act, const void* res,
+                int ldr, void* out, int ldc, int c_off, void* stream) {
+  return op_guard([&] {
+    RDB_CHECK(A && W && out && M > 0 && K > 0 && N > 0, "gemm: bad argument");
+    rdb::DeviceGuard g(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (prec == RDB_PREC_FP32) {
+      rdb::GemmArgs a{};
+      a.A = A; a.lda = lda; a.W = static_cast<const float*>(W); a.bias = bias; a.res = res; a.ldr = ldr; a.out = out; a.ldc = ldc; a.c_off = c_off;
+      a.M = (int)M; a.N = N; a.K = K; a.act = act;
+      RDB_CHECK(M < (1ll << 31), "gemm: M too large");
+      rdb::launch_gemm_simt<float, float>(a, st);
+    } else {
+      RDB_CHECK(K % 8 == 0 && lda % 8 == 0 && c_off % 8 == 0 && ldc % 8 == 0, "gemm fp16: K, lda, ldc, c_off must be multiples of 8 (16-byte TMA rows)");
+      rdb::Ctx cx;
+      cx.st = st; cx.pool = &ops_pool(device); cx.precision = 1; cx.use_tc = true; cx.num_sms = sm_count(device);
+      rdb::launch_gemm_tc(cx, static_cast<const __half*>(A), lda, M, K, static_cast<const __half*>(W), N, bias, act == rdb::ACT_GELU ? rdb::ACT_GELU : act,
+                          static_cast<const __half*>(res), ldr, static_cast<__half*>(out), ldc, c_off);
+    }
+  });
+}
+
+int rdb_op_im2col(int device, int prec, const void* x, int n, int h, int w, int c, int ld, int kh, int kw, int sh, int sw, int pt, int pl, int oh, int ow,
+                  void* out, void* stream) {
+  return op_guard([&] {
+    RDB_CHECK(x && out && n > 0, "im2col: bad argument");
+    rdb::DeviceGuard g(device);
+    const long long total = (long long)n * oh * ow * kh * kw * c;
+    if (prec == RDB_PREC_FP32)
+      rdb::ops::im2col_kernel<float><<<rdb::ops::grid_for(total), 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(x), n, h, w, c, ld, kh, kw, sh, sw, pt, pl, oh, ow, static_cast<float*>(out));
+    else
+      rdb::ops::im2col_kernel<__half><<<rdb::ops::grid_for(total), 256, 0, (cudaStream_t)stream>>>(static_cast<const __half*>(x), n, h, w, c, ld, kh, kw, sh, sw, pt, pl, oh, ow, static_cast<__half*>(out));
+    RDB_LAUNCH_CHECK();
+  });
+}
+
+int rdb_op_dwconv(int device, int prec, const void* x, int n, int h, int w, int c, int ld_in, int k, int stride, const float* wt, const float* bias, int relu,
+                  void* out, int oh, int ow, int ld_out, int c_off, void* stream) {
+  return op_guard([&] {
+    RDB_CHECK(x && out && wt && bias && n > 0 && (k & 1), "dwconv: bad argument");
+    rdb::DeviceGuard g(device);
+    const long long total = (long long)n * oh * ow * c;
+    if (prec == RDB_PREC_FP32)
+      rdb::ops::dwconv_generic_kernel<float><<<rdb::ops::grid_for(total), 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(x), n, h, w, c, ld_in, k, stride, wt, bias, relu, static_cast<float*>(out), oh, ow, ld_out, c_off);
+    else
+      rdb::ops::dwconv_generic_kernel<__half><<<rdb::ops::grid_for(total), 256, 0, (cudaStream_t)stream>>>(static_cast<const __half*>(x), n, h, w, c, ld_in, k, stride, wt, bias, relu, static_cast<__half*>(out), oh, ow, ld_out, c_off);
+    RDB_LAUNCH_CHECK();
+  });
+}
+
+int rdb_op_maxpool2x2s1(int device, int prec, const void* x, int n, int h, int w, int c, int ld_in, void* out, int ld_out, int c_off, void* stream) {
+  return op_guard([&] {
+    RDB_CHECK(x && out && n > 0, "maxpool: bad argument");
+    rdb::DeviceGuard g(device);
+    const long long total = (long long)n * h * w * c;
+    if (prec == RDB_PREC_FP32)
+      rdb::ops::maxpool2x2s1_kernel<float><<<rdb::ops::grid_for(total), 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(x), n, h, w, c, ld_in, static_cast<float*>(out), ld_out, c_off);
+    else
+      rdb::ops::maxpool2x2s1_kernel<__half><<<rdb::ops::grid_for(total), 256, 0, (cudaStream_t)stream>>>(static_cast<const __half*>(x), n, h, w, c, ld_in, static_cast<__half*>(out), ld_out, c_off);
+    RDB_LAUNCH_CHECK();
+  });
+}
+
+/* src_prec / dst_prec: 0 fp32, 1 fp16 */
+int rdb_op_copy_cols(int device, int src_prec, int dst_prec, const void* x, long long rows, int c, int ld_in, void* out, int ld_out, int c_off, void* stream) {
+  return op_guard([&] {
+    RDB_CHECK(x && out && rows > 0 && c > 0, "copy_cols: bad argument");
+    rdb::DeviceGuard g(device);
+    const int grid = rdb::ops::grid_for(rows * c);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (src_prec == 0 && dst_prec == 0) rdb::ops::copy_cols_kernel<float, float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), rows, c, ld_in, static_cast<float*>(out), ld_out, c_off);
+    else if (src_prec == 0) rdb::ops::copy_cols_kernel<float, __half><<<grid, 256, 0, st>>>(static_cast<const float*>(x), rows, c, ld_in, static_cast<__half*>(out), ld_out, c_off);
+    else if (dst_prec == 0) rdb::ops::copy_cols_kernel<__half, float><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), rows, c, ld_in, static_cast<float*>(out), ld_out, c_off);
+    else rdb::ops::copy_cols_kernel<__half, __half><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), rows, c, ld_in, static_cast<__half*>(out), ld_out, c_off);
+    RDB_LAUNCH_CHECK();
+  });
+}
+
+int rdb_op_layernorm(int device, const float* x, long long rows, int c, const float* gamma, const float* beta, float eps, float* out, void* stream) {
+  return op_guard([&] {
+    RDB_CHECK(x && out && gamma && beta && rows > 0, "layernorm: bad argument");
+    rdb::DeviceGuard g(device);
+    rdb::layernorm_kernel<float><<<rdb::cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, rows, c, gamma, beta, eps, nullptr, out);
+    RDB_LAUNCH_CHECK();
+  });
+}
+
+int rdb_op_embed(int device, const int64_t* ids, int batch, int dim, const float* tok, float scale, const float* pos_tab, int pos, float* out, void* stream) {
+  return op_guard([&] {
+    RDB_CHECK(ids && tok && pos_tab && out && batch > 0, "embed: bad argument");
+    rdb::DeviceGuard g(device);
+    rdb::ops::embed_kernel<<<rdb::cdiv((long long)batch * dim, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(ids), batch, dim, tok, scale, pos_tab, pos, out);
+    RDB_LAUNCH_CHECK();
+  });
+}
+
+int rdb_op_attn_decode(int device, const float* q, const float* k, const float* v, int batch, int t, int t_cap, int heads, int head_dim, float* out,
+                       void* stream) {
+  return op_guard([&] {
+    RDB_CHECK(q && k && v && out && batch > 0 && t > 0 && t <= t_cap, "attn_decode: bad argument");
+    RDB_CHECK((size_t)t * 4 <= 200 * 1024, "attn_decode: sequence too long for the score buffer");
+    rdb::DeviceGuard g(device);
+    auto kern = rdb::ops::attn_decode_kernel;
+    const size_t sm = (size_t)t * sizeof(float);
+    if (sm > 48 * 1024) RDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    kern<<<batch * heads, 128, sm, (cudaStream_t)stream>>>(q, k, v, t, t_cap, heads, head_dim, out);
+    RDB_LAUNCH_CHECK();
+  });
+}
+
+int rdb_op_add(int device, const float* a, const float* b, float* out, long long n, void* stream) {
+  return op_guard([&] {
+    RDB_CHECK(a && b && out && n > 0, "add: bad argument");
+    rdb::DeviceGuard g(device);
+    rdb::ops::add_kernel<<<rdb::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n);
+    RDB_LAUNCH_CHECK();
+  });
+}
+
+int rdb_op_greedy_step(int device, const int32_t* argmax, int batch, int force_eos, int eos, int pad, int64_t* next, int32_t* unfinished, int32_t* has_eos,
+                       int32_t* all_done, void* stream) {
+  return op_guard([&] {
+    RDB_CHECK(argmax && next && unfinished && has_eos && all_done && batch > 0 && batch <= 1024, "greedy_step: bad argument");
+    rdb::DeviceGuard g(device);
+    rdb::ops::greedy_step_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(argmax, batch, force_eos, eos, pad, reinterpret_cast<long long*>(next), unfinished, has_eos, all_done);
+    RDB_LAUNCH_CHECK();
+  });
+}
+
+}  // extern "C"
