@@ -196,6 +196,7 @@ int rdb_op_gemm(int device, int prec, const void* A, int lda, long long M, int K
     rdb::DeviceGuard g(device);
     cudaStream_t st = (cudaStream_t)stream;
     if (prec == RDB_PREC_FP32) {
+      RDB_CHECK(K % 4 == 0 && lda % 4 == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "gemm fp32: K and lda must be multiples of 4, A and W 16-byte aligned (vector loads)");
       rdb::GemmArgs a{};
       a.A = A; a.lda = lda; a.W = static_cast<const float*>(W); a.bias = bias; a.res = res; a.ldr = ldr; a.out = out; a.ldc = ldc; a.c_off = c_off;
       a.M = (int)M; a.N = N; a.K = K; a.act = act;

@@ -187,9 +187,11 @@ class FormulaEngine:
         self._pack(state_dict)
 
     # ---------------------------------------------------------------- weights
-    def _fold(self, sd, name, depthwise=False):
+    def _fold(self, sd, name, depthwise=False, pad_cin=0):
         torch = self.torch
         w = sd[name + ".conv.weight"].double()
+        if pad_cin and w.shape[1] < pad_cin:            # zero input channels: keeps GEMM rows 16-byte aligned (K = kh*kw*cin)
+            w = torch.cat([w, torch.zeros(w.shape[0], pad_cin - w.shape[1], w.shape[2], w.shape[3], dtype=w.dtype)], 1)
         g, b = sd[name + ".bn.weight"].double(), sd[name + ".bn.bias"].double()
         m, v = sd[name + ".bn.running_mean"].double(), sd[name + ".bn.running_var"].double()
         s = g / torch.sqrt(v + 1e-5)
@@ -218,7 +220,7 @@ class FormulaEngine:
     def _pack(self, sd):
         a = self.arch
         p = "backbone.pphgnet_b6."
-        self.stem = {k: self._fold(sd, f"{p}stem.{k}") for k in ("stem1", "stem2a", "stem2b", "stem3", "stem4")}
+        self.stem = {k: self._fold(sd, f"{p}stem.{k}", pad_cin=4 if k == "stem1" else 0) for k in ("stem1", "stem2a", "stem2b", "stem3", "stem4")}
         self.stages = []
         for si, (cin, mid, cout, blocks, down, light, k, layers) in enumerate(a["stages"]):
             sp = f"{p}stages.{si}."
@@ -309,15 +311,15 @@ class FormulaEngine:
             assert c == 1 and H % 32 == 0 and W % 32 == 0
             es, adt, st = self._esz(), self.adt, self.stem
             # gray -> 3 channels (torch.repeat_interleave in the reference), NHWC fp32: stem1 always runs in fp32 (K = 27)
-            x3 = torch.empty((B * H * W, 3), dtype=torch.float32, device=self.dev)
+            x3 = torch.zeros((B * H * W, 4), dtype=torch.float32, device=self.dev)      # 4th channel = zero pad (K = 36, 16-byte rows)
             for ch in range(3):
                 self.launches += 1
-                _lib.check_op(self.lib.rdb_op_copy_cols(self.device, 0, 0, x.data_ptr(), B * H * W, 1, 1, x3.data_ptr(), 3, ch, self._st()))
+                _lib.check_op(self.lib.rdb_op_copy_cols(self.device, 0, 0, x.data_ptr(), B * H * W, 1, 1, x3.data_ptr(), 4, ch, self._st()))
             h1, w1 = H // 2, W // 2
             P1 = B * h1 * w1
             c1 = st["stem1"].cout
             e1f = torch.empty((P1, c1), dtype=torch.float32, device=self.dev)
-            self._conv(st["stem1"], x3.data_ptr(), B, H, W, 3, 2, 1, e1f.data_ptr(), c1, 0, ACT_RELU, prec=_lib.PREC_FP32)
+            self._conv(st["stem1"], x3.data_ptr(), B, H, W, 4, 2, 1, e1f.data_ptr(), c1, 0, ACT_RELU, prec=_lib.PREC_FP32)
             if self.prec == _lib.PREC_FP16:
                 e1 = torch.empty((P1, c1), dtype=adt, device=self.dev)
                 self.launches += 1

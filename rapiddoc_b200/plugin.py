@@ -72,6 +72,32 @@ def install(device=0, precision=None, devices=None):
     return orig
 
 
+def install_window():
+    """Seam 2b: rebind the two OCR callers of the batch scheduler (backend/pipeline/analyze_utils.py:105-292, imported by name
+    into backend/pipeline/batch_analyze.py) to the window-level restatements of rapiddoc_b200/window.py: same data contract,
+    but each size bucket is detected as one window.  Returns the original pair."""
+    from rapid_doc.backend.pipeline import analyze_utils as au
+    from rapid_doc.backend.pipeline.model_list import AtomicModel
+    from . import window
+    orig = (au._run_ocr_det_batch, au._run_ocr_rec_postprocess)
+
+    def det(ocr_res_all_page, atom_model_manager, ocr_config):
+        return window.run_ocr_det_batch(ocr_res_all_page, lambda lang: atom_model_manager.get_atom_model(
+            atom_model_name=AtomicModel.OCR, lang=lang, ocr_config=ocr_config), ocr_config)
+
+    def rec(images_layout_res, ocr_config):
+        mgr = au.AtomModelSingleton()
+        return window.run_ocr_rec_postprocess(images_layout_res, lambda lang: mgr.get_atom_model(
+            atom_model_name=AtomicModel.OCR, lang=lang, ocr_config=ocr_config), ocr_config)
+    au._run_ocr_det_batch, au._run_ocr_rec_postprocess = det, rec
+    try:
+        from rapid_doc.backend.pipeline import batch_analyze as ba
+        ba._run_ocr_det_batch, ba._run_ocr_rec_postprocess = det, rec
+    except Exception:
+        pass
+    return orig
+
+
 def session_for(cfg):
     """Seam 3: pick the B200 session from the configured model file (det vs rec)."""
     from .engine import B200DetSession, B200RecSession
