@@ -44,6 +44,8 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     "pipeline": dict(name="ocr_pipeline_b64_1024x1024", batch=64, h=1024, w=1024, unit="pages/s", metric="pages/sec (full det+rec pipeline)"),
+    "formula": dict(name="formula_ppformulanet_plus_m_b32_384", batch=32, h=384, w=384, unit="crops/s",
+                    metric="formula crops/sec (PP-FormulaNet_plus-M: PPHGNetV2-B6 encoder + 64 greedy MBart tokens)"),
     "det": dict(name="det_dbnet_b64_1024x1024", batch=64, h=1024, w=1024, unit="pages/s", metric="pages/sec (DBNet text-detection hot path)"),
     "rec": dict(name="rec_svtr_ctc_b512_48x320", batch=512, h=48, w=320, unit="crops/s", metric="SVTR text-line crops/sec"),
 }
@@ -483,6 +485,121 @@ def secondary_numbers(model, dev_pages, B, H, Wd, steps=5):
     return out
 
 
+# ------------------------------------------------------------------------------- formula workload
+FORMULA_TOKENS = 64
+ENC_GFLOP_PER_CROP = 98.94          # BASELINE.md section 2 (FlopCounterMode on the reference module, 1x1x384x384)
+
+
+def formula_inputs(n, seed=4):
+    rng = np.random.default_rng(seed)
+    x = np.zeros((n, 1, 384, 384), np.float32)
+    for i in range(n):
+        lvl, amp = rng.uniform(-3.0, 1.19), rng.uniform(0.2, 2.0)
+        x[i, 0] = (lvl + amp * np.kron(rng.standard_normal((12, 12)), np.ones((32, 32))) + 0.3 * rng.standard_normal((384, 384))).astype(np.float32)
+    return x
+
+
+def run_formula(args, wl):
+    """F3/F4 workload: 32 synthetic 384x384 formula crops per step through FormulaEngine (seeded synthetic weights of the exact
+    PP-FormulaNet_plus-M architecture: the trained checkpoint is not available offline), encoder + 64 greedy tokens."""
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from rapiddoc_b200 import PREC_FP16, PREC_FP32, formula as FM
+    prec = PREC_FP16 if args.precision == "fp16" else PREC_FP32
+    sd = FM.synthetic_state_dict(seed=0)
+    eng = FM.FormulaEngine(sd, device=local, precision=prec, max_new_tokens=FORMULA_TOKENS, sync_every=64)
+    B = wl["batch"]
+    x_host = torch.from_numpy(formula_inputs(B, seed=4 + rank)).pin_memory()
+    x_dev = x_host.cuda()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def mx(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    for _ in range(max(args.warmup, 3)):
+        ids = eng(x_dev)
+    sampler = ClockSampler(local)
+    sampler.start()
+    sampler.wait_first()
+    barrier()
+    eng.launches = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        eng(x_dev)
+    e1.record()
+    barrier()
+    clocks = sampler.stop(t_begin, time.time())
+    ms = mx(e0.elapsed_time(e1))
+    launches = eng.launches
+    value = world * B * args.steps / (ms / 1e3)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ids = eng(x_host.numpy())          # host float32 crops in, ids out
+    torch.cuda.synchronize()
+    dt = mx(time.perf_counter() - t0)
+    e2e = world * B * args.steps / dt
+    if rank == 0:
+        # encoder alone: the dense-contraction part (tensor roofline)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(3):
+            enc = eng.encode(x_dev)
+        a1.record()
+        torch.cuda.synchronize()
+        enc_ms = a0.elapsed_time(a1) / 3
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("bf16_tflops_sustained", 1400.0) if prec == PREC_FP16 else None
+        ach = ENC_GFLOP_PER_CROP * B / enc_ms        # GFLOP / ms = TFLOP/s
+        roofline = {"kernel": "PPHGNetV2-B6 encoder (im2col + gemm_tc, all layers)" if prec == PREC_FP16 else "encoder (fp32 SIMT GEMM)", "bound": "tensor",
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if peak else None, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured; fp16 and bf16 share the tcgen05 rate)" if peaks else "fallback",
+                    "encoder_ms_per_step": enc_ms, "decoder_ms_per_step": ms / args.steps - enc_ms, "algorithmic_gflop_per_crop": ENC_GFLOP_PER_CROP}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import formula_net as FN
+            import torch as _t
+            _t.set_num_threads(min(os.cpu_count(), 32))
+            sample = 2
+            t0 = time.perf_counter()
+            want, _ = FN.forward(x_host.numpy()[:sample], sd, FM.ARCH_M, FORMULA_TOKENS)
+            dt_cpu = time.perf_counter() - t0
+            n = min(want.shape[1], ids.shape[1])
+            cpu = {"value": sample / dt_cpu, "unit": wl["unit"], "cores": min(os.cpu_count(), 32), "host_cores": os.cpu_count(), "kind": "port",
+                   "sample": f"{sample} crops of this step's batch through the CPU oracle (torch fp32, BN unfolded, {FORMULA_TOKENS} greedy tokens), {dt_cpu:.1f}s",
+                   "token_mismatch_vs_oracle": int((want[:, :n] != ids[:sample, :n]).sum()), "tokens_compared": int(want[:, :n].size)}
+        line = {"metric": wl["metric"], "value": value, "unit": wl["unit"], "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f16" if prec == PREC_FP16 else "f32", "data": "synthetic",
+                "config": {"workload": wl["name"], "batch_per_gpu": B, "h": 384, "w": 384, "precision": args.precision, "greedy_tokens": FORMULA_TOKENS,
+                           "weights": "seeded synthetic weights of the exact architecture (trained checkpoint unavailable offline)",
+                           "l2": "activations per step (GBs) exceed the 126 MB L2", "parallelism": f"crop-parallel replicas x{world}"},
+                "clocks": clocks, "e2e": {"value": e2e, "unit": wl["unit"], "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(ids.size * 8)},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        barrier()
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------- main arms
 def run_reference(args, wl_key, wl):
     """Reference arm: the reference's own CPU implementation of the path.  RapidDoc is pure
@@ -493,6 +610,26 @@ def run_reference(args, wl_key, wl):
     if rank != 0:
         return
     from rapiddoc_b200 import synth
+    if wl_key == "formula":
+        from oracle import formula_net as FN
+        from rapiddoc_b200 import formula as FM
+        import torch
+        torch.set_num_threads(min(os.cpu_count(), 32))
+        sd = FM.synthetic_state_dict(seed=0)
+        x = formula_inputs(2)
+        for _ in range(min(args.warmup, 1)):
+            FN.forward(x[:1], sd, FM.ARCH_M, 4)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            FN.forward(x, sd, FM.ARCH_M, FORMULA_TOKENS)
+        dt = time.perf_counter() - t0
+        v = 2 * args.steps / dt
+        print(json.dumps({"impl": "reference", "metric": wl["metric"], "value": v, "unit": wl["unit"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": wl["name"], "sample": "2 of the 32 per step", "engine": "torch CPU fp32 (oracle port of the reference module)"},
+                          "cpu_baseline": {"value": v, "unit": wl["unit"], "cores": min(os.cpu_count(), 32), "host_cores": os.cpu_count(), "kind": "port", "sample": f"2 crops per step x {args.steps} steps"},
+                          "e2e": {"value": v, "unit": wl["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
     sample = {"det": 4, "rec": 64, "pipeline": 2}[wl_key]
     data = synth.rec_crops(sample, wl["h"], wl["w"], seed=2) if wl_key == "rec" else synth.det_pages(sample, wl["h"], wl["w"], seed=1)
     fn = {"det": cpu_step_det, "rec": cpu_step_rec, "pipeline": lambda d: cpu_step_pipeline(d, args.rec_batch)}[wl_key]
@@ -524,6 +661,8 @@ def main():
         return run_reference(args, wl_key, wl)
     if wl_key == "pipeline":
         return run_pipeline(args, wl)
+    if wl_key == "formula":
+        return run_formula(args, wl)
 
     import torch
     import torch.distributed as dist

@@ -176,9 +176,11 @@ int rdb_argmax_rows(int device, const float* x, long long rows, int vocab, int32
  * exact-parity mode) or RDB_PREC_FP16 (fp16 storage, tcgen05 GEMMs).  act: 0 none, 1 ReLU, 2 GELU(erf). */
 const char* rdb_ops_last_error(void);
 /* out[M, c_off : c_off+N] (row pitch ldc) = act(A[M,K] (pitch lda) * W[N,K]^T + bias) (+ res [M,N] pitch ldr): every conv1x1 /
- * nn.Linear, and every dense k x k conv after rdb_op_im2col.  W fp32 (prec 0) or fp16 (prec 1); bias fp32. */
+ * nn.Linear, and every dense k x k conv after rdb_op_im2col.  W fp32 (prec 0) or fp16 (prec 1); bias fp32.
+ * fp32 with M <= 32 rows (one decode step of a batch) runs a weight-streaming kernel; there out_step (device counter, may be
+ * NULL) shifts the output by *out_step * out_step_stride elements — the k / v projections append to their KV-cache row. */
 int rdb_op_gemm(int device, int prec, const void* A, int lda, long long M, int K, const void* W, int N, const float* bias, int act,
-                const void* res, int ldr, void* out, int ldc, int c_off, void* stream);
+                const void* res, int ldr, void* out, int ldc, int c_off, void* stream, const int32_t* out_step, long long out_step_stride);
 /* x [n,h,w,c] (pixel pitch ld) -> out [n*oh*ow, kh*kw*c], K order (ky, kx, c) = the packed conv weight order */
 int rdb_op_im2col(int device, int prec, const void* x, int n, int h, int w, int c, int ld, int kh, int kw, int sh, int sw, int pt, int pl,
                   int oh, int ow, void* out, void* stream);
@@ -193,18 +195,21 @@ int rdb_op_copy_cols(int device, int src_prec, int dst_prec, const void* x, long
                      int c_off, void* stream);
 int rdb_op_layernorm(int device, const float* x, long long rows, int c, const float* gamma, const float* beta, float eps, float* out,
                      void* stream);
-/* embed_tokens[id] * scale + embed_positions[pos + 2]  (MBartLearnedPositionalEmbedding, offset 2) */
+/* embed_tokens[id] * scale + embed_positions[pos + 2]  (MBartLearnedPositionalEmbedding, offset 2).
+ * step (device counter, may be NULL): pos = *step and the ids are row *step of a [steps+1, batch] token table — the form every
+ * decode-step op takes so that ONE captured CUDA graph replays for all steps. */
 int rdb_op_embed(int device, const int64_t* ids, int batch, int dim, const float* tok, float scale, const float* pos_tab, int pos,
-                 float* out, void* stream);
+                 float* out, void* stream, const int32_t* step);
 /* softmax(q k^T) v for ONE new query per row against t cached positions: q [B, heads*head_dim] (already scaled),
  * k / v caches [B, t_cap, heads*head_dim] (MBartAttention.forward with tgt_len 1) */
 int rdb_op_attn_decode(int device, const float* q, const float* k, const float* v, int batch, int t, int t_cap, int heads, int head_dim,
-                       float* out, void* stream);
+                       float* out, void* stream, const int32_t* step /* t = *step + 1 */);
 int rdb_op_add(int device, const float* a, const float* b, float* out, long long n, void* stream);
 /* one greedy step of generate_export (rec_ppformulanet_head.py:1118-1160) on the device: next token = argmax (eos when force_eos),
  * finished rows emit pad, a row finishes on eos; *all_done = every row has produced an eos */
 int rdb_op_greedy_step(int device, const int32_t* argmax, int batch, int force_eos, int eos, int pad, int64_t* next, int32_t* unfinished,
-                       int32_t* has_eos, int32_t* all_done, void* stream);
+                       int32_t* has_eos, int32_t* all_done, void* stream, int32_t* step /* token-table row + counter, incremented */,
+                       int forced_len);
 
 /* ---- text recognition ----------------------------------------------------------------- */
 int rdb_rec_create(const void* weights, size_t nbytes, int device, int precision, rdb_rec_t** out);

@@ -42,16 +42,16 @@ SYMBOLS = {
     "rdb_layout_containment": (_i, [_i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "rdb_argmax_rows": (_i, [_i, _vp, C.c_longlong, _i, _vp, _vp, _vp]),
     "rdb_ops_last_error": (C.c_char_p, []),
-    "rdb_op_gemm": (_i, [_i, _i, _vp, _i, C.c_longlong, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp]),
+    "rdb_op_gemm": (_i, [_i, _i, _vp, _i, C.c_longlong, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, C.c_longlong]),
     "rdb_op_im2col": (_i, [_i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "rdb_op_dwconv": (_i, [_i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "rdb_op_maxpool2x2s1": (_i, [_i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "rdb_op_copy_cols": (_i, [_i, _i, _i, _vp, C.c_longlong, _i, _i, _vp, _i, _i, _vp]),
     "rdb_op_layernorm": (_i, [_i, _vp, C.c_longlong, _i, _vp, _vp, _f, _vp, _vp]),
-    "rdb_op_embed": (_i, [_i, _vp, _i, _i, _vp, _f, _vp, _i, _vp, _vp]),
-    "rdb_op_attn_decode": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "rdb_op_embed": (_i, [_i, _vp, _i, _i, _vp, _f, _vp, _i, _vp, _vp, _vp]),
+    "rdb_op_attn_decode": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "rdb_op_add": (_i, [_i, _vp, _vp, _vp, C.c_longlong, _vp]),
-    "rdb_op_greedy_step": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "rdb_op_greedy_step": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "rdb_debug_cubic_tab": (_i, [_vp]),
     "rdb_clipper_offset": (_i, [C.POINTER(C.c_double), _i, C.c_double, C.POINTER(C.c_int64), _i]),
     "rdb_clipper_offset_batch": (_i, [_vp, _i, _vp, _vp, _i, _vp]),

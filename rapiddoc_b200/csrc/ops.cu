@@ -34,6 +34,57 @@ __global__ void im2col_kernel(const T* __restrict__ x, int n, int H, int W, int 
   }
 }
 
+// the same gather with 8 channels per thread (C % 8 == 0, ld % 8 == 0, 16-byte aligned base): 128-bit loads / stores
+template <typename T>
+__global__ void im2col_vec8_kernel(const T* __restrict__ x, int n, int H, int W, int C, int ld, int KH, int KW, int sh, int sw, int pt, int pl, int OH, int OW,
+                                   T* __restrict__ out) {
+  const int C8 = C / 8;
+  const long long K8 = (long long)KH * KW * C8;
+  const long long total = (long long)n * OH * OW * K8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / K8;
+    const int k = (int)(i % K8);
+    const int c8 = k % C8, tap = k / C8, kx = tap % KW, ky = tap / KW;
+    const int ox = (int)(row % OW), oy = (int)((row / OW) % OH), b = (int)(row / ((long long)OW * OH));
+    const int iy = oy * sh - pt + ky, ix = ox * sw - pl + kx;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) Vec8<T>::load(x + ((long long)(b * H + iy) * W + ix) * ld + c8 * 8, v);
+    Vec8<T>::store(out + i * 8, v);
+  }
+}
+
+// depthwise k x k, 8 channels per thread (C % 8 == 0, pitches % 8 == 0)
+template <typename T>
+__global__ void dwconv_vec8_kernel(const T* __restrict__ x, int n, int H, int W, int C, int ld_in, int K, int s, const float* __restrict__ w,
+                                   const float* __restrict__ bias, int relu, T* __restrict__ out, int OH, int OW, int ld_out, int c_off) {
+  const int C8 = C / 8, p = (K - 1) / 2;
+  const long long total = (long long)n * OH * OW * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8) * 8;
+    const long long px = i / C8;
+    const int ox = (int)(px % OW), oy = (int)((px / OW) % OH), b = (int)(px / ((long long)OW * OH));
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int ky = 0; ky < K; ++ky) {
+      const int iy = oy * s - p + ky;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < K; ++kx) {
+        const int ix = ox * s - p + kx;
+        if (ix < 0 || ix >= W) continue;
+        float v[8], wv[8];
+        Vec8<T>::load(x + ((long long)(b * H + iy) * W + ix) * ld_in + c, v);
+        Vec8<float>::load(w + (ky * K + kx) * C + c, wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], wv[j], acc[j]);
+      }
+    }
+    float bv[8];
+    Vec8<float>::load(bias + c, bv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[j] += bv[j]; if (relu) acc[j] = fmaxf(acc[j], 0.f); }
+    Vec8<T>::store(out + px * ld_out + c_off + c, acc);
+  }
+}
+
 // depthwise k x k, pad (k-1)/2, stride s, weights [k][k][C] fp32, bias [C]; in pitch ld_in, out pitch ld_out (+ c_off)
 template <typename T>
 __global__ void dwconv_generic_kernel(const T* __restrict__ x, int n, int H, int W, int C, int ld_in, int K, int s, const float* __restrict__ w,
@@ -93,18 +144,20 @@ __global__ void copy_cols_kernel(const TI* __restrict__ x, long long rows, int C
 // MBart decoder input (rec_unimernet_head.py:440-456, rec_ppformulanet_head.py:449-486): embed_tokens[id] * embed_scale +
 // embed_positions[pos + 2]
 __global__ void embed_kernel(const long long* __restrict__ ids, int B, int D, const float* __restrict__ tok, float scale, const float* __restrict__ pos_tab,
-                             int pos, float* __restrict__ out) {
+                             int pos, float* __restrict__ out, const int* __restrict__ step) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * D) return;
   const int b = i / D, d = i % D;
+  if (step) { pos = *step; ids += (long long)pos * B; }        // device-side step counter: ids = row `step` of the token table
   out[i] = tok[ids[b] * D + d] * scale + pos_tab[(long long)(pos + 2) * D + d];
 }
 
 // one query per (batch row, head) against T cached keys / values: q [B, H*HD] (already scaled), k / v [B, Tcap, H*HD]
 // softmax(q k^T) v in fp32 (MBartAttention.forward, rec_unimernet_head.py:541-633, tgt_len = 1, no mask needed)
 __global__ void attn_decode_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int T, int Tcap, int H, int HD,
-                                   float* __restrict__ out) {
+                                   float* __restrict__ out, const int* __restrict__ step) {
   extern __shared__ float sc[];          // scores [T]
+  if (step) T = *step + 1;
   const int b = blockIdx.x / H, h = blockIdx.x % H, D = H * HD;
   const float* qp = q + (long long)b * D + h * HD;
   const float* kp = k + (long long)b * Tcap * D + h * HD;
@@ -138,6 +191,56 @@ __global__ void attn_decode_kernel(const float* __restrict__ q, const float* __r
   }
 }
 
+// out[m, n] = act(A[m,:] . W[n,:] + bias[n]) (+ res[m,n]) for M <= 32 rows (one decode step of the whole batch): a GEMM this
+// thin is a weight-streaming problem (HBM-bound, 4 B/MAC/32 rows), so each warp owns 2 output columns, reads their two weight
+// rows exactly once with 128-bit loads, and the 32 activation rows of the current 128-wide K chunk sit in shared memory.
+// out_step: optional device counter; the output rows are then written at out + *out_step * out_step_stride (KV-cache append).
+template <int ACT>
+__global__ void __launch_bounds__(128) skinny_gemm_kernel(const float* __restrict__ A, int lda, int M, int K, const float* __restrict__ W, int N,
+                                                          const float* __restrict__ bias, const float* __restrict__ res, int ldr, float* __restrict__ out,
+                                                          int ldc, const int* __restrict__ out_step, long long out_step_stride) {
+  __shared__ float4 As[32][32];            // [row][k4] of the current chunk (128 k)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = (blockIdx.x * 4 + warp) * 2;
+  float acc0[32], acc1[32];
+#pragma unroll
+  for (int m = 0; m < 32; ++m) { acc0[m] = 0.f; acc1[m] = 0.f; }
+  const bool v0 = n0 < N, v1 = n0 + 1 < N;
+  for (int k0 = 0; k0 < K; k0 += 128) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * 32; i += 128) {
+      const int m = i >> 5, k4 = i & 31;
+      As[m][k4] = m < M ? *reinterpret_cast<const float4*>(A + (long long)m * lda + k0 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    const float4 w0 = v0 ? *reinterpret_cast<const float4*>(W + (long long)n0 * K + k0 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 w1 = v1 ? *reinterpret_cast<const float4*>(W + (long long)(n0 + 1) * K + k0 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int m = 0; m < 32; ++m) {
+      const float4 a = As[m][lane];
+      acc0[m] = fmaf(a.x, w0.x, fmaf(a.y, w0.y, fmaf(a.z, w0.z, fmaf(a.w, w0.w, acc0[m]))));
+      acc1[m] = fmaf(a.x, w1.x, fmaf(a.y, w1.y, fmaf(a.z, w1.z, fmaf(a.w, w1.w, acc1[m]))));
+    }
+  }
+  // lane m ends up with the totals of row m: butterfly over the 32 rows
+#pragma unroll
+  for (int m = 0; m < 32; ++m) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      acc0[m] += __shfl_xor_sync(0xffffffffu, acc0[m], o);
+      acc1[m] += __shfl_xor_sync(0xffffffffu, acc1[m], o);
+    }
+  }
+  float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+  for (int m = 0; m < 32; ++m) if (lane == m) { r0 = acc0[m]; r1 = acc1[m]; }
+  if (lane < M) {
+    float* o = out + (out_step ? (long long)(*out_step) * out_step_stride : 0) + (long long)lane * ldc;
+    if (v0) { float y = apply_act<ACT>(r0 + (bias ? bias[n0] : 0.f)); if (res) y += res[(long long)lane * ldr + n0]; o[n0] = y; }
+    if (v1) { float y = apply_act<ACT>(r1 + (bias ? bias[n0 + 1] : 0.f)); if (res) y += res[(long long)lane * ldr + n0 + 1]; o[n0 + 1] = y; }
+  }
+}
+
 __global__ void add_kernel(const float* a, const float* b, float* out, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = a[i] + b[i];
@@ -146,8 +249,10 @@ __global__ void add_kernel(const float* a, const float* b, float* out, long long
 // greedy step bookkeeping of PPFormulaNet_Head.generate_export (rec_ppformulanet_head.py:1118-1160): next = argmax (or eos when
 // the forced-EOS length is reached), finished rows emit pad; a row finishes when it emits eos.  all_done: every row has an eos.
 __global__ void greedy_step_kernel(const int* __restrict__ arg, int B, int force_eos, int eos, int pad, long long* __restrict__ next, int* __restrict__ unfinished,
-                                   int* __restrict__ has_eos, int* __restrict__ all_done) {
+                                   int* __restrict__ has_eos, int* __restrict__ all_done, int* __restrict__ step, int forced_len) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int st = step ? *step : 0;
+  if (step) { next += (long long)(st + 1) * B; all_done += st + 1; force_eos = (st + 1) == forced_len - 1; }
   if (b < B) {
     long long t = force_eos ? eos : arg[b];
     t = unfinished[b] ? t : pad;
@@ -155,10 +260,11 @@ __global__ void greedy_step_kernel(const int* __restrict__ arg, int B, int force
     if (t == eos) { unfinished[b] = 0; has_eos[b] = 1; }
   }
   __syncthreads();
-  if (blockIdx.x == 0 && threadIdx.x == 0) {   // B <= blockDim.x * gridDim.x with gridDim.x == 1 (checked by the launcher)
+  if (blockIdx.x == 0 && threadIdx.x == 0) {   // single block (B <= 1024, checked by the launcher)
     int d = 1;
     for (int i = 0; i < B; ++i) d &= has_eos[i];
     *all_done = d;
+    if (step) *step = st + 1;
   }
 }
 
@@ -190,19 +296,33 @@ extern "C" {
 const char* rdb_ops_last_error(void) { return g_ops_err.c_str(); }
 
 int rdb_op_gemm(int device, int prec, const void* A, int lda, long long M, int K, const void* W, int N, const float* bias, int act, const void* res,
-                int ldr, void* out, int ldc, int c_off, void* stream) {
+                int ldr, void* out, int ldc, int c_off, void* stream, const int32_t* out_step, long long out_step_stride) {
   return op_guard([&] {
     RDB_CHECK(A && W && out && M > 0 && K > 0 && N > 0, "gemm: bad argument");
     rdb::DeviceGuard g(device);
     cudaStream_t st = (cudaStream_t)stream;
     if (prec == RDB_PREC_FP32) {
       RDB_CHECK(K % 4 == 0 && lda % 4 == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "gemm fp32: K and lda must be multiples of 4, A and W 16-byte aligned (vector loads)");
+      if (M <= 32 && K % 128 == 0 && (act == rdb::ACT_NONE || act == rdb::ACT_GELU || act == rdb::ACT_RELU)) {   // decode step: weight-streaming kernel
+        const float* Af = static_cast<const float*>(A);
+        const float* Wf = static_cast<const float*>(W);
+        const float* Rf = static_cast<const float*>(res);
+        float* Of = static_cast<float*>(out) + c_off;
+        const int grid = (N + 7) / 8;
+        if (act == rdb::ACT_GELU) rdb::ops::skinny_gemm_kernel<rdb::ACT_GELU><<<grid, 128, 0, st>>>(Af, lda, (int)M, K, Wf, N, bias, Rf, ldr, Of, ldc, out_step, out_step_stride);
+        else if (act == rdb::ACT_RELU) rdb::ops::skinny_gemm_kernel<rdb::ACT_RELU><<<grid, 128, 0, st>>>(Af, lda, (int)M, K, Wf, N, bias, Rf, ldr, Of, ldc, out_step, out_step_stride);
+        else rdb::ops::skinny_gemm_kernel<rdb::ACT_NONE><<<grid, 128, 0, st>>>(Af, lda, (int)M, K, Wf, N, bias, Rf, ldr, Of, ldc, out_step, out_step_stride);
+        RDB_LAUNCH_CHECK();
+        return;
+      }
+      RDB_CHECK(out_step == nullptr, "gemm: out_step is only supported on the decode (M <= 32, K % 128 == 0) path");
       rdb::GemmArgs a{};
       a.A = A; a.lda = lda; a.W = static_cast<const float*>(W); a.bias = bias; a.res = res; a.ldr = ldr; a.out = out; a.ldc = ldc; a.c_off = c_off;
       a.M = (int)M; a.N = N; a.K = K; a.act = act;
       RDB_CHECK(M < (1ll << 31), "gemm: M too large");
       rdb::launch_gemm_simt<float, float>(a, st);
     } else {
+      RDB_CHECK(out_step == nullptr, "gemm fp16: out_step not supported");
       RDB_CHECK(K % 8 == 0 && lda % 8 == 0 && c_off % 8 == 0 && ldc % 8 == 0, "gemm fp16: K, lda, ldc, c_off must be multiples of 8 (16-byte TMA rows)");
       rdb::Ctx cx;
       cx.st = st; cx.pool = &ops_pool(device); cx.precision = 1; cx.use_tc = true; cx.num_sms = sm_count(device);
@@ -218,6 +338,14 @@ int rdb_op_im2col(int device, int prec, const void* x, int n, int h, int w, int 
     RDB_CHECK(x && out && n > 0, "im2col: bad argument");
     rdb::DeviceGuard g(device);
     const long long total = (long long)n * oh * ow * kh * kw * c;
+    if (c % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x % 16) == 0) {
+      if (prec == RDB_PREC_FP32)
+        rdb::ops::im2col_vec8_kernel<float><<<rdb::ops::grid_for(total / 8), 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(x), n, h, w, c, ld, kh, kw, sh, sw, pt, pl, oh, ow, static_cast<float*>(out));
+      else
+        rdb::ops::im2col_vec8_kernel<__half><<<rdb::ops::grid_for(total / 8), 256, 0, (cudaStream_t)stream>>>(static_cast<const __half*>(x), n, h, w, c, ld, kh, kw, sh, sw, pt, pl, oh, ow, static_cast<__half*>(out));
+      RDB_LAUNCH_CHECK();
+      return;
+    }
     if (prec == RDB_PREC_FP32)
       rdb::ops::im2col_kernel<float><<<rdb::ops::grid_for(total), 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(x), n, h, w, c, ld, kh, kw, sh, sw, pt, pl, oh, ow, static_cast<float*>(out));
     else
@@ -232,6 +360,14 @@ int rdb_op_dwconv(int device, int prec, const void* x, int n, int h, int w, int 
     RDB_CHECK(x && out && wt && bias && n > 0 && (k & 1), "dwconv: bad argument");
     rdb::DeviceGuard g(device);
     const long long total = (long long)n * oh * ow * c;
+    if (c % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && c_off % 8 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0) {
+      if (prec == RDB_PREC_FP32)
+        rdb::ops::dwconv_vec8_kernel<float><<<rdb::ops::grid_for(total / 8), 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(x), n, h, w, c, ld_in, k, stride, wt, bias, relu, static_cast<float*>(out), oh, ow, ld_out, c_off);
+      else
+        rdb::ops::dwconv_vec8_kernel<__half><<<rdb::ops::grid_for(total / 8), 256, 0, (cudaStream_t)stream>>>(static_cast<const __half*>(x), n, h, w, c, ld_in, k, stride, wt, bias, relu, static_cast<__half*>(out), oh, ow, ld_out, c_off);
+      RDB_LAUNCH_CHECK();
+      return;
+    }
     if (prec == RDB_PREC_FP32)
       rdb::ops::dwconv_generic_kernel<float><<<rdb::ops::grid_for(total), 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(x), n, h, w, c, ld_in, k, stride, wt, bias, relu, static_cast<float*>(out), oh, ow, ld_out, c_off);
     else
@@ -277,25 +413,27 @@ int rdb_op_layernorm(int device, const float* x, long long rows, int c, const fl
   });
 }
 
-int rdb_op_embed(int device, const int64_t* ids, int batch, int dim, const float* tok, float scale, const float* pos_tab, int pos, float* out, void* stream) {
+int rdb_op_embed(int device, const int64_t* ids, int batch, int dim, const float* tok, float scale, const float* pos_tab, int pos, float* out, void* stream,
+                 const int32_t* step) {
   return op_guard([&] {
     RDB_CHECK(ids && tok && pos_tab && out && batch > 0, "embed: bad argument");
     rdb::DeviceGuard g(device);
-    rdb::ops::embed_kernel<<<rdb::cdiv((long long)batch * dim, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(ids), batch, dim, tok, scale, pos_tab, pos, out);
+    rdb::ops::embed_kernel<<<rdb::cdiv((long long)batch * dim, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(ids), batch, dim, tok, scale, pos_tab, pos, out, step);
     RDB_LAUNCH_CHECK();
   });
 }
 
 int rdb_op_attn_decode(int device, const float* q, const float* k, const float* v, int batch, int t, int t_cap, int heads, int head_dim, float* out,
-                       void* stream) {
+                       void* stream, const int32_t* step) {
   return op_guard([&] {
     RDB_CHECK(q && k && v && out && batch > 0 && t > 0 && t <= t_cap, "attn_decode: bad argument");
+    if (step) t = t_cap;                     // score buffer sized for the whole cache when the length lives on the device
     RDB_CHECK((size_t)t * 4 <= 200 * 1024, "attn_decode: sequence too long for the score buffer");
     rdb::DeviceGuard g(device);
     auto kern = rdb::ops::attn_decode_kernel;
     const size_t sm = (size_t)t * sizeof(float);
     if (sm > 48 * 1024) RDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    kern<<<batch * heads, 128, sm, (cudaStream_t)stream>>>(q, k, v, t, t_cap, heads, head_dim, out);
+    kern<<<batch * heads, 128, sm, (cudaStream_t)stream>>>(q, k, v, t, t_cap, heads, head_dim, out, step);
     RDB_LAUNCH_CHECK();
   });
 }
@@ -310,11 +448,11 @@ int rdb_op_add(int device, const float* a, const float* b, float* out, long long
 }
 
 int rdb_op_greedy_step(int device, const int32_t* argmax, int batch, int force_eos, int eos, int pad, int64_t* next, int32_t* unfinished, int32_t* has_eos,
-                       int32_t* all_done, void* stream) {
+                       int32_t* all_done, void* stream, int32_t* step, int forced_len) {
   return op_guard([&] {
     RDB_CHECK(argmax && next && unfinished && has_eos && all_done && batch > 0 && batch <= 1024, "greedy_step: bad argument");
     rdb::DeviceGuard g(device);
-    rdb::ops::greedy_step_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(argmax, batch, force_eos, eos, pad, reinterpret_cast<long long*>(next), unfinished, has_eos, all_done);
+    rdb::ops::greedy_step_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(argmax, batch, force_eos, eos, pad, reinterpret_cast<long long*>(next), unfinished, has_eos, all_done, step, forced_len);
     RDB_LAUNCH_CHECK();
   });
 }

@@ -172,7 +172,7 @@ class _Conv:
 class FormulaEngine:
     """state_dict (reference key layout) -> token ids.  x: [B,1,H,W] float32 (numpy or device tensor), H = W = 384 for -M."""
 
-    def __init__(self, state_dict, device=0, precision=_lib.PREC_FP32, arch=ARCH_M, max_new_tokens=None, sync_every=8):
+    def __init__(self, state_dict, device=0, precision=_lib.PREC_FP32, arch=ARCH_M, max_new_tokens=None, sync_every=8, use_graph=True):
         import torch
         self.lib = _lib.load()
         if self.lib.rdb_device_count() <= int(device):
@@ -182,6 +182,8 @@ class FormulaEngine:
         self.dev = torch.device("cuda", self.device)
         self.max_new = int(max_new_tokens if max_new_tokens is not None else arch["max_new_tokens"])
         self.sync_every = sync_every
+        self.use_graph = use_graph
+        self._dec = {}
         self.launches = 0
         self.adt = torch.float16 if self.prec == _lib.PREC_FP16 else torch.float32
         self._pack(state_dict)
@@ -264,9 +266,10 @@ class FormulaEngine:
     def _st(self):
         return self.torch.cuda.current_stream(self.dev).cuda_stream or None
 
-    def _gemm(self, prec, A, lda, M, K, W, N, bias, act, res, ldr, out, ldc, c_off):
+    def _gemm(self, prec, A, lda, M, K, W, N, bias, act, res, ldr, out, ldc, c_off, out_step=None, out_step_stride=0):
         self.launches += 1
-        _lib.check_op(self.lib.rdb_op_gemm(self.device, prec, A, lda, M, K, _lib.ptr(W), N, _lib.ptr(bias), act, res, ldr, out, ldc, c_off, self._st()))
+        _lib.check_op(self.lib.rdb_op_gemm(self.device, prec, A, lda, M, K, _lib.ptr(W), N, _lib.ptr(bias), act, res, ldr, out, ldc, c_off, self._st(),
+                                           out_step, out_step_stride))
 
     def _esz(self):
         return 2 if self.prec == _lib.PREC_FP16 else 4
@@ -394,78 +397,112 @@ class FormulaEngine:
         self._gemm(self.prec, src.data_ptr(), cin, P, cin, W, cv.cout, cv.b, ACT_RELU, res, ldr, out_ptr, ldc, c_off)
 
     # ---------------------------------------------------------------- decoder
+    def _decoder_state(self, B, S):
+        """Per (batch, encoder length) buffers + the captured CUDA graph of ONE decode step.  Every step-dependent quantity
+        (position, cache row, attention length, token-table row) is read from a device counter, so the same graph replays
+        for every step: ~100 kernel launches per token cost one graph launch."""
+        key = (B, S)
+        if key in self._dec:
+            return self._dec[key]
+        torch, a = self.torch, self.arch
+        d, V = a["d_model"], a["vocab"]
+        new = lambda *s: torch.empty(s, dtype=torch.float32, device=self.dev)      # noqa: E731
+        cap = self.max_new + 1
+        st = dict(cap=cap, encp=new(B * S, d), cross=[(new(B * S, d), new(B * S, d)) for _ in self.layers],
+                  kc=[new(B, cap, d) for _ in self.layers], vc=[new(B, cap, d) for _ in self.layers],
+                  toks=torch.zeros((cap, B), dtype=torch.int64, device=self.dev), unfinished=torch.ones(B, dtype=torch.int32, device=self.dev),
+                  has_eos=torch.zeros(B, dtype=torch.int32, device=self.dev), done=torch.zeros(cap, dtype=torch.int32, device=self.dev),
+                  step=torch.zeros(1, dtype=torch.int32, device=self.dev), h=new(B, d), x=new(B, d), q=new(B, d), att=new(B, d), r1=new(B, d),
+                  f=new(B, a["ffn"]), logits=new(B, V), arg=torch.empty(B, dtype=torch.int32, device=self.dev), val=new(B), graph=None)
+        # the attention kernel's dynamic shared memory attribute must be set outside capture
+        _lib.check_op(self.lib.rdb_op_attn_decode(self.device, st["q"].data_ptr(), st["kc"][0].data_ptr(), st["vc"][0].data_ptr(), B, 1, cap, a["heads"],
+                                                  d // a["heads"], st["att"].data_ptr(), self._st(), st["step"].data_ptr()))
+        self._decode_step(st, B, S)                # eager warm-up of every kernel on scratch state (no lazy init inside the capture)
+        torch.cuda.synchronize(self.dev)
+        if self.use_graph:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._decode_step(st, B, S)
+            st["graph"] = g
+        self._dec[key] = st
+        return st
+
+    def _decode_step(self, st, B, S):
+        """One greedy step for the whole batch (MBartDecoderLayer x N, rec_unimernet_head.py:666-748; lm_head; argmax; bookkeeping)."""
+        a, lib, dv, stm = self.arch, self.lib, self.device, self._st()
+        d, H, V = a["d_model"], a["heads"], a["vocab"]
+        hd, f32, cap = d // H, _lib.PREC_FP32, st["cap"]
+        sp = st["step"].data_ptr()
+        h, x, q, att, r1, f = st["h"], st["x"], st["q"], st["att"], st["r1"], st["f"]
+        _lib.check_op(lib.rdb_op_embed(dv, st["toks"].data_ptr(), B, d, self.tok.data_ptr(), math.sqrt(d), self.pos.data_ptr(), 0, x.data_ptr(), stm, sp))
+        _lib.check_op(lib.rdb_op_layernorm(dv, x.data_ptr(), B, d, self.ln_emb[0].data_ptr(), self.ln_emb[1].data_ptr(), 1e-5, h.data_ptr(), stm))
+        for li, L in enumerate(self.layers):
+            # self attention (pre-LN); k / v append to cache row `step`
+            _lib.check_op(lib.rdb_op_layernorm(dv, h.data_ptr(), B, d, L["sln"][0].data_ptr(), L["sln"][1].data_ptr(), 1e-5, x.data_ptr(), stm))
+            self._gemm(f32, x.data_ptr(), d, B, d, L["sq"][0], d, L["sq"][1], ACT_NONE, None, 0, q.data_ptr(), d, 0)
+            self._gemm(f32, x.data_ptr(), d, B, d, L["sk"][0], d, L["sk"][1], ACT_NONE, None, 0, st["kc"][li].data_ptr(), cap * d, 0, sp, d)
+            self._gemm(f32, x.data_ptr(), d, B, d, L["sv"][0], d, L["sv"][1], ACT_NONE, None, 0, st["vc"][li].data_ptr(), cap * d, 0, sp, d)
+            _lib.check_op(lib.rdb_op_attn_decode(dv, q.data_ptr(), st["kc"][li].data_ptr(), st["vc"][li].data_ptr(), B, 1, cap, H, hd, att.data_ptr(), stm, sp))
+            self._gemm(f32, att.data_ptr(), d, B, d, L["so"][0], d, L["so"][1], ACT_NONE, h.data_ptr(), d, r1.data_ptr(), d, 0)
+            # cross attention over the encoder tokens (K / V computed once per batch)
+            _lib.check_op(lib.rdb_op_layernorm(dv, r1.data_ptr(), B, d, L["cln"][0].data_ptr(), L["cln"][1].data_ptr(), 1e-5, x.data_ptr(), stm))
+            self._gemm(f32, x.data_ptr(), d, B, d, L["cq"][0], d, L["cq"][1], ACT_NONE, None, 0, q.data_ptr(), d, 0)
+            _lib.check_op(lib.rdb_op_attn_decode(dv, q.data_ptr(), st["cross"][li][0].data_ptr(), st["cross"][li][1].data_ptr(), B, S, S, H, hd, att.data_ptr(), stm, None))
+            self._gemm(f32, att.data_ptr(), d, B, d, L["co"][0], d, L["co"][1], ACT_NONE, r1.data_ptr(), d, h.data_ptr(), d, 0)
+            # feed forward
+            _lib.check_op(lib.rdb_op_layernorm(dv, h.data_ptr(), B, d, L["ln3"][0].data_ptr(), L["ln3"][1].data_ptr(), 1e-5, x.data_ptr(), stm))
+            self._gemm(f32, x.data_ptr(), d, B, d, L["fc1"][0], a["ffn"], L["fc1"][1], ACT_GELU, None, 0, f.data_ptr(), a["ffn"], 0)
+            self._gemm(f32, f.data_ptr(), a["ffn"], B, a["ffn"], L["fc2"][0], d, L["fc2"][1], ACT_NONE, h.data_ptr(), d, r1.data_ptr(), d, 0)
+            h, r1 = r1, h
+        _lib.check_op(lib.rdb_op_layernorm(dv, h.data_ptr(), B, d, self.ln_out[0].data_ptr(), self.ln_out[1].data_ptr(), 1e-5, x.data_ptr(), stm))
+        self._gemm(f32, x.data_ptr(), d, B, d, self.lm_head, V, None, ACT_NONE, None, 0, st["logits"].data_ptr(), V, 0)
+        _lib.check(lib.rdb_argmax_rows(dv, st["logits"].data_ptr(), B, V, st["arg"].data_ptr(), st["val"].data_ptr(), stm))
+        _lib.check_op(lib.rdb_op_greedy_step(dv, st["arg"].data_ptr(), B, 0, a["eos"], a["pad"], st["toks"].data_ptr(), st["unfinished"].data_ptr(),
+                                             st["has_eos"].data_ptr(), st["done"].data_ptr(), stm, sp, a["forced_eos_len"]))
+
     def generate(self, enc):
         """enc [B,S,enc_dim] float32 device tensor -> ids [B, L] int64 numpy (start token first), as generate_export returns."""
         torch, a = self.torch, self.arch
         with torch.cuda.device(self.dev):
             B, S, E = enc.shape
-            d, H, V = a["d_model"], a["heads"], a["vocab"]
-            hd = d // H
+            assert B <= 32, "decode batches are at most 32 rows (split larger batches)"
+            d = a["d_model"]
             f32 = _lib.PREC_FP32
-            new = lambda *s: torch.empty(s, dtype=torch.float32, device=self.dev)      # noqa: E731
-            encp = new(B * S, d)
-            self._gemm(f32, enc.data_ptr(), E, B * S, E, self.proj[0], d, self.proj[1], ACT_NONE, None, 0, encp.data_ptr(), d, 0)
-            cross = []
-            for L in self.layers:
-                ck, cv_ = new(B * S, d), new(B * S, d)
-                self._gemm(f32, encp.data_ptr(), d, B * S, d, L["ck"][0], d, L["ck"][1], ACT_NONE, None, 0, ck.data_ptr(), d, 0)
-                self._gemm(f32, encp.data_ptr(), d, B * S, d, L["cv"][0], d, L["cv"][1], ACT_NONE, None, 0, cv_.data_ptr(), d, 0)
-                cross.append((ck, cv_))
-            cap = self.max_new + 1
-            kc = [new(B, cap, d) for _ in self.layers]
-            vc = [new(B, cap, d) for _ in self.layers]
-            ids = torch.full((B,), a["start"], dtype=torch.int64, device=self.dev)
-            toks = torch.empty((self.max_new + 1, B), dtype=torch.int64, device=self.dev)
-            toks[0] = ids
-            unfinished = torch.ones(B, dtype=torch.int32, device=self.dev)
-            has_eos = torch.zeros(B, dtype=torch.int32, device=self.dev)
-            done = torch.zeros(self.max_new + 1, dtype=torch.int32, device=self.dev)
-            h, x, q, att, r1, f = new(B, d), new(B, d), new(B, d), new(B, d), new(B, d), new(B, a["ffn"])
-            logits = new(B, V)
-            arg = torch.empty(B, dtype=torch.int32, device=self.dev)
-            val = new(B)
-            st, lib, dv = self._st(), self.lib, self.device
+            st = self._decoder_state(B, S)
+            self._gemm(f32, enc.data_ptr(), E, B * S, E, self.proj[0], d, self.proj[1], ACT_NONE, None, 0, st["encp"].data_ptr(), d, 0)
+            for L, (ck, cv_) in zip(self.layers, st["cross"]):
+                self._gemm(f32, st["encp"].data_ptr(), d, B * S, d, L["ck"][0], d, L["ck"][1], ACT_NONE, None, 0, ck.data_ptr(), d, 0)
+                self._gemm(f32, st["encp"].data_ptr(), d, B * S, d, L["cv"][0], d, L["cv"][1], ACT_NONE, None, 0, cv_.data_ptr(), d, 0)
+            st["toks"].zero_()
+            st["toks"][0] = a["start"]
+            st["unfinished"].fill_(1)
+            st["has_eos"].zero_()
+            st["done"].zero_()
+            st["step"].zero_()
             steps = 0
-            for step in range(self.max_new):
-                self.launches += 2
-                _lib.check_op(lib.rdb_op_embed(dv, toks[step].data_ptr(), B, d, self.tok.data_ptr(), math.sqrt(d), self.pos.data_ptr(), step, x.data_ptr(), st))
-                _lib.check_op(lib.rdb_op_layernorm(dv, x.data_ptr(), B, d, self.ln_emb[0].data_ptr(), self.ln_emb[1].data_ptr(), 1e-5, h.data_ptr(), st))
-                for li, L in enumerate(self.layers):
-                    # self attention (pre-LN), k / v written straight into cache row `step`
-                    _lib.check_op(lib.rdb_op_layernorm(dv, h.data_ptr(), B, d, L["sln"][0].data_ptr(), L["sln"][1].data_ptr(), 1e-5, x.data_ptr(), st))
-                    self._gemm(f32, x.data_ptr(), d, B, d, L["sq"][0], d, L["sq"][1], ACT_NONE, None, 0, q.data_ptr(), d, 0)
-                    self._gemm(f32, x.data_ptr(), d, B, d, L["sk"][0], d, L["sk"][1], ACT_NONE, None, 0, kc[li].data_ptr() + step * d * 4, cap * d, 0)
-                    self._gemm(f32, x.data_ptr(), d, B, d, L["sv"][0], d, L["sv"][1], ACT_NONE, None, 0, vc[li].data_ptr() + step * d * 4, cap * d, 0)
-                    _lib.check_op(lib.rdb_op_attn_decode(dv, q.data_ptr(), kc[li].data_ptr(), vc[li].data_ptr(), B, step + 1, cap, H, hd, att.data_ptr(), st))
-                    self._gemm(f32, att.data_ptr(), d, B, d, L["so"][0], d, L["so"][1], ACT_NONE, h.data_ptr(), d, r1.data_ptr(), d, 0)
-                    # cross attention over the encoder tokens
-                    _lib.check_op(lib.rdb_op_layernorm(dv, r1.data_ptr(), B, d, L["cln"][0].data_ptr(), L["cln"][1].data_ptr(), 1e-5, x.data_ptr(), st))
-                    self._gemm(f32, x.data_ptr(), d, B, d, L["cq"][0], d, L["cq"][1], ACT_NONE, None, 0, q.data_ptr(), d, 0)
-                    _lib.check_op(lib.rdb_op_attn_decode(dv, q.data_ptr(), cross[li][0].data_ptr(), cross[li][1].data_ptr(), B, S, S, H, hd, att.data_ptr(), st))
-                    self._gemm(f32, att.data_ptr(), d, B, d, L["co"][0], d, L["co"][1], ACT_NONE, r1.data_ptr(), d, h.data_ptr(), d, 0)
-                    # feed forward
-                    _lib.check_op(lib.rdb_op_layernorm(dv, h.data_ptr(), B, d, L["ln3"][0].data_ptr(), L["ln3"][1].data_ptr(), 1e-5, x.data_ptr(), st))
-                    self._gemm(f32, x.data_ptr(), d, B, d, L["fc1"][0], a["ffn"], L["fc1"][1], ACT_GELU, None, 0, f.data_ptr(), a["ffn"], 0)
-                    self._gemm(f32, f.data_ptr(), a["ffn"], B, a["ffn"], L["fc2"][0], d, L["fc2"][1], ACT_NONE, h.data_ptr(), d, r1.data_ptr(), d, 0)
-                    h, r1 = r1, h
-                    self.launches += 5
-                _lib.check_op(lib.rdb_op_layernorm(dv, h.data_ptr(), B, d, self.ln_out[0].data_ptr(), self.ln_out[1].data_ptr(), 1e-5, x.data_ptr(), st))
-                self._gemm(f32, x.data_ptr(), d, B, d, self.lm_head, V, None, ACT_NONE, None, 0, logits.data_ptr(), V, 0)
-                _lib.check(lib.rdb_argmax_rows(dv, logits.data_ptr(), B, V, arg.data_ptr(), val.data_ptr(), st))
-                force = 1 if (step + 1) == a["forced_eos_len"] - 1 else 0
-                _lib.check_op(lib.rdb_op_greedy_step(dv, arg.data_ptr(), B, force, a["eos"], a["pad"], toks[step + 1].data_ptr(), unfinished.data_ptr(),
-                                                     has_eos.data_ptr(), done[step + 1:].data_ptr(), st))
-                self.launches += 3
-                steps = step + 1
-                if steps % self.sync_every == 0 and bool(done[steps].item()):
+            per_step = 15 * len(self.layers) + 5
+            while steps < self.max_new:
+                if st["graph"] is not None:
+                    st["graph"].replay()
+                else:
+                    self._decode_step(st, B, S)
+                self.launches += per_step
+                steps += 1
+                if steps % self.sync_every == 0 and bool(st["done"][steps].item()):
                     break
-            dn = done[:steps + 1].cpu().numpy()
+            dn = st["done"][:steps + 1].cpu().numpy()
             first = np.nonzero(dn)[0]
             L_out = int(first[0]) if len(first) else steps          # generate_export stops right after the step that completed every row
-            return toks[:L_out + 1].t().contiguous().cpu().numpy()
+            return st["toks"][:L_out + 1].t().contiguous().cpu().numpy()
 
     def __call__(self, x):
-        return self.generate(self.encode(x))
+        """x [B,1,H,W] -> ids; batches larger than 32 are decoded 32 rows at a time (ragged tails padded by the caller's batching)."""
+        n = x.shape[0]
+        if n <= 32:
+            return self.generate(self.encode(x))
+        outs = [self.generate(self.encode(x[i:i + 32])) for i in range(0, n, 32)]
+        L = max(o.shape[1] for o in outs)
+        return np.concatenate([np.pad(o, ((0, 0), (0, L - o.shape[1])), constant_values=self.arch["pad"]) for o in outs], 0)
 
 
 class B200FormulaSession:
