@@ -210,11 +210,12 @@ __global__ void __launch_bounds__(128) skinny_gemm_kernel(const float* __restric
     __syncthreads();
     for (int i = threadIdx.x; i < 32 * 32; i += 128) {
       const int m = i >> 5, k4 = i & 31;
-      As[m][k4] = m < M ? *reinterpret_cast<const float4*>(A + (long long)m * lda + k0 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      As[m][k4] = (m < M && k0 + k4 * 4 < K) ? *reinterpret_cast<const float4*>(A + (long long)m * lda + k0 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
-    const float4 w0 = v0 ? *reinterpret_cast<const float4*>(W + (long long)n0 * K + k0 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 w1 = v1 ? *reinterpret_cast<const float4*>(W + (long long)(n0 + 1) * K + k0 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool kin = k0 + lane * 4 < K;         // K % 4 == 0: a float4 is either fully inside or fully outside
+    const float4 w0 = (v0 && kin) ? *reinterpret_cast<const float4*>(W + (long long)n0 * K + k0 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 w1 = (v1 && kin) ? *reinterpret_cast<const float4*>(W + (long long)(n0 + 1) * K + k0 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int m = 0; m < 32; ++m) {
       const float4 a = As[m][lane];
@@ -303,7 +304,7 @@ int rdb_op_gemm(int device, int prec, const void* A, int lda, long long M, int K
     cudaStream_t st = (cudaStream_t)stream;
     if (prec == RDB_PREC_FP32) {
       RDB_CHECK(K % 4 == 0 && lda % 4 == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "gemm fp32: K and lda must be multiples of 4, A and W 16-byte aligned (vector loads)");
-      if (M <= 32 && K % 128 == 0 && (act == rdb::ACT_NONE || act == rdb::ACT_GELU || act == rdb::ACT_RELU)) {   // decode step: weight-streaming kernel
+      if (M <= 32 && (act == rdb::ACT_NONE || act == rdb::ACT_GELU || act == rdb::ACT_RELU)) {   // decode step: weight-streaming kernel
         const float* Af = static_cast<const float*>(A);
         const float* Wf = static_cast<const float*>(W);
         const float* Rf = static_cast<const float*>(res);
@@ -315,7 +316,7 @@ int rdb_op_gemm(int device, int prec, const void* A, int lda, long long M, int K
         RDB_LAUNCH_CHECK();
         return;
       }
-      RDB_CHECK(out_step == nullptr, "gemm: out_step is only supported on the decode (M <= 32, K % 128 == 0) path");
+      RDB_CHECK(out_step == nullptr, "gemm: out_step is only supported on the decode (M <= 32 rows) path");
       rdb::GemmArgs a{};
       a.A = A; a.lda = lda; a.W = static_cast<const float*>(W); a.bias = bias; a.res = res; a.ldr = ldr; a.out = out; a.ldc = ldc; a.c_off = c_off;
       a.M = (int)M; a.N = N; a.K = K; a.act = act;
