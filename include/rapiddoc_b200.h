@@ -130,6 +130,18 @@ int rdb_rec_set_pool_cap_bytes(rdb_rec_t* h, size_t bytes);
 long long rdb_det_pool_bytes(rdb_det_t* h);
 long long rdb_rec_pool_bytes(rdb_rec_t* h);
 
+/* cv2.findContours(bitmap, RETR_LIST, CHAIN_APPROX_SIMPLE) for n same-size {0, non-zero} uint8 bitmaps on host threads (no GIL):
+ * the contour source of DBPostProcess.boxes_from_bitmap (rapidocr, called from rapid_doc/model/ocr/ocr_patch.py:236-239).
+ * Same contours, same order, same points as OpenCV (Suzuki-Abe border following, reverse discovery order).  Host-only.
+ *   rdb_contours_trace   traces every page (max_threads <= 0: all hardware threads) and returns a handle
+ *   rdb_contours_counts  per_page [n] contour counts, totals
+ *   rdb_contours_fetch   contour_sizes [total_contours] (page after page, cv2 order), points_xy [total_points][2] int32 */
+typedef struct rdb_contours rdb_contours_t;
+int rdb_contours_trace(const uint8_t* bitmaps, int n, int hgt, int wid, int max_threads, rdb_contours_t** out);
+int rdb_contours_counts(rdb_contours_t* c, int32_t* per_page, int64_t* total_contours, int64_t* total_points);
+int rdb_contours_fetch(rdb_contours_t* c, int32_t* contour_sizes, int32_t* points_xy);
+void rdb_contours_free(rdb_contours_t* c);
+
 /* DBPostProcess binarise (+ optional cv2.dilate 2x2) on an existing prob map [n,h,w]:
  * rapid_doc/model/ocr/ocr_patch.py:228-235. */
 int rdb_db_bitmap(int device, const float* prob, int n, int hgt, int wid, float thresh, int use_dilation,

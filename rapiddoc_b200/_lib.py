@@ -52,6 +52,10 @@ SYMBOLS = {
     "rdb_op_attn_decode": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "rdb_op_add": (_i, [_i, _vp, _vp, _vp, C.c_longlong, _vp]),
     "rdb_op_greedy_step": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "rdb_contours_trace": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_vp)]),
+    "rdb_contours_counts": (_i, [_vp, _vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "rdb_contours_fetch": (_i, [_vp, _vp, _vp]),
+    "rdb_contours_free": (None, [_vp]),
     "rdb_debug_cubic_tab": (_i, [_vp]),
     "rdb_clipper_offset": (_i, [C.POINTER(C.c_double), _i, C.c_double, C.POINTER(C.c_int64), _i]),
     "rdb_clipper_offset_batch": (_i, [_vp, _i, _vp, _vp, _i, _vp]),

@@ -23,8 +23,10 @@ struct ScratchCarver {
   T* take(size_t n) { T* p = reinterpret_cast<T*>(base + off); off += (n * sizeof(T) + 255) / 256 * 256; return p; }
 };
 inline uint8_t* device_scratch(int device, size_t bytes) {
-  static uint8_t* buf[64] = {};
-  static size_t cap[64] = {};
+  // per host thread: the detection stage of one window and the recognition stage of the previous one may run on two
+  // threads at once (B200OcrModel.ocr_pages_stream); each keeps its own grow-only scratch
+  static thread_local uint8_t* buf[64] = {};
+  static thread_local size_t cap[64] = {};
   RDB_CHECK(device >= 0 && device < 64, "scratch: device index");
   if (cap[device] < bytes) {
     if (buf[device]) { RDB_CUDA(cudaDeviceSynchronize()); cudaFree(buf[device]); buf[device] = nullptr; cap[device] = 0; }

@@ -110,6 +110,27 @@ def order_points_clockwise(boxes):
     return np.stack([left[:, 0], right[:, 0], right[:, 1], left[:, 1]], axis=1).astype(np.float32)
 
 
+def find_contours_window(bitmaps, max_threads=0):
+    """cv2.findContours(bm, RETR_LIST, CHAIN_APPROX_SIMPLE) for every page of a window in one native call (host threads, no GIL;
+    rdb_contours_*: same contours, order and points as OpenCV).  bitmaps [n,h,w] uint8 C-contiguous.
+    Returns (per_page counts [n], sizes [total], points [total_points, 1, 2] int32)."""
+    lib = _lib.load()
+    bitmaps = np.ascontiguousarray(bitmaps, np.uint8)
+    n, h, w = bitmaps.shape
+    hnd = C.c_void_p()
+    _lib.check(lib.rdb_contours_trace(_lib.ptr(bitmaps), n, h, w, int(max_threads), C.byref(hnd)))
+    try:
+        per_page = np.zeros(n, np.int32)
+        tc, tp = C.c_int64(), C.c_int64()
+        _lib.check(lib.rdb_contours_counts(hnd, _lib.ptr(per_page), C.byref(tc), C.byref(tp)))
+        sizes = np.zeros(max(1, tc.value), np.int32)
+        pts = np.zeros((max(1, tp.value), 1, 2), np.int32)
+        _lib.check(lib.rdb_contours_fetch(hnd, _lib.ptr(sizes), _lib.ptr(pts)))
+    finally:
+        lib.rdb_contours_free(hnd)
+    return per_page, sizes[:tc.value], pts[:tp.value]
+
+
 def clipper_offset_batch(boxes, distances):
     """rdb_clipper_offset for every box of a window in one C call.  Returns (points int32 [total,1,2], starts int64 [m+1])."""
     m = len(boxes)
@@ -136,29 +157,33 @@ def window_boxes(bitmaps, ori_shapes, score_fn, box_thresh=0.5, unclip_ratio=1.6
     """DBPostProcess for every page of a window.  bitmaps [n,h,w] uint8 (host), ori_shapes n x (src_h, src_w).
     Returns [(boxes [k,4,2] f32, scores)] per page, identical to running the reference's per-page loop.
 
-    Only cv2.findContours runs on the worker pool (it releases the GIL and is the one heavy call); the per-contour
-    cv2.minAreaRect / cv2.boxPoints calls stay on the calling thread (microseconds each — threads would only fight over the
-    GIL), and all array arithmetic is done ONCE for the boxes of the whole window."""
+    Contours come from the native border follower (rdb_contours_*, host threads, no GIL, identical to cv2.findContours); the
+    per-contour cv2.minAreaRect / cv2.boxPoints calls stay on the calling thread (microseconds each — Python threads would only
+    fight over the GIL), and all array arithmetic is done ONCE for the boxes of the whole window."""
     n = len(bitmaps)
     height, width = bitmaps[0].shape
     if len(set(tuple(s) for s in ori_shapes)) != 1:      # mixed source sizes: page by page (the reference's own loop)
         return [window_boxes(bitmaps[i:i + 1], ori_shapes[i:i + 1], _shift_pages(score_fn, i), box_thresh, unclip_ratio, max_candidates,
                              min_size, False)[0] for i in range(n)]
     src_h, src_w = ori_shapes[0]
-    find = lambda bm: cv2.findContours(bm, cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)      # noqa: E731
-    futs = [pool().submit(find, bm) for bm in bitmaps] if (parallel and n > 1) else None
-    with timed("det.findContours+minAreaRect"):
-        # pages are consumed in order while the pool is still tracing the later ones: the per-contour cv2 calls on this thread
-        # (GIL held) overlap cv2.findContours on the workers (GIL released)
+    with timed("det.findContours(native)"):
+        # every page of the window traced by the native border follower on host threads (no GIL): same contours, order and
+        # points as cv2.findContours(RETR_LIST, CHAIN_APPROX_SIMPLE) (tests/test_contours.py)
+        per_page, sizes, cpts = find_contours_window(bitmaps, 0 if parallel else 1)
+    with timed("det.minAreaRect"):
         pts, ss, page_idx = [], [], []
+        so = po = 0
         for i in range(n):
-            res = futs[i].result() if futs else find(bitmaps[i])
-            contours = res[0] if len(res) == 2 else res[1]
-            for c in contours[:max_candidates]:
-                r = cv2.minAreaRect(c)
-                ss.append(min(r[1]))
-                pts.append(cv2.boxPoints(r))
-                page_idx.append(i)
+            k = int(per_page[i])
+            for j in range(k):
+                m = int(sizes[so + j])
+                if j < max_candidates:
+                    r = cv2.minAreaRect(cpts[po: po + m])
+                    ss.append(min(r[1]))
+                    pts.append(cv2.boxPoints(r))
+                    page_idx.append(i)
+                po += m
+            so += k
     empty = (np.zeros((0, 4, 2), np.float32), [])
     if not pts:
         return [empty for _ in range(n)]

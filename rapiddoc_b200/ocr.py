@@ -373,8 +373,10 @@ class B200TextDetector:
         bitmaps = self._pin_bm.numpy()[:need].reshape(n, rh, rw)
         probs = torch.empty((n, rh, rw), dtype=torch.float32, device=dev)
 
+        st_outer = torch.cuda.current_stream(dev)       # the caller's stream: the worker thread below has its own default
+
         def gpu(lo, hi):
-            with torch.cuda.device(dev):
+            with torch.cuda.device(dev), torch.cuda.stream(st_outer):
                 if host is not None:
                     pages_dev[lo:hi].copy_(torch.from_numpy(host[lo:hi]), non_blocking=True)
                 self.engine.infer_u8(pages_dev[lo:hi], thresh=po.thresh, use_dilation=po.use_dilation, mean=self.mean, std=self.std,
@@ -742,83 +744,144 @@ class B200OcrModel:
             return None, None
         return [np.asarray(b, np.float32) for b, _ in res], [r for _, r in res]
 
-    def ocr_pages(self, pages, mfd_res_list=None, drop_score=None):
-        """det + rec for a WINDOW of pages — the fused equivalent of the reference's window flow
-        (`_run_ocr_det_batch` analyze_utils.py:105-212 then `_run_ocr_rec_postprocess` :216-292, or `__call__`
-        rapid_ocr.py:351-401 per page): det on all pages -> sorted/merged boxes -> every text-line crop of the window
-        warped on the GPU from the resident pages (get_rotate_crop_image, bit-exact) -> one recognition pass over all crops.
-        Returns per page: None (no boxes) or [[box (4x2 list), (text, score)], ...] with score >= drop_score."""
-        import torch
-        drop = self.drop_score if drop_score is None else drop_score
+    def _windows(self, pages):
+        """Same-size groups cut into windows of det_window pages: [(indices, h, w, sub-batch)]."""
         n = len(pages)
-        out = [None] * n
         groups = {}
         for i, im in enumerate(pages):
             groups.setdefault((int(im.shape[0]), int(im.shape[1])), []).append(i)
-        dev_index = self.text_detector.engine.device
+        out = []
         for (h, w), idxs in groups.items():
             for c0 in range(0, len(idxs), self.det_window):
                 part = idxs[c0: c0 + self.det_window]
-                whole = len(part) == n
-                if whole:
+                if len(part) == n:
                     sub = pages
                 elif hasattr(pages, "is_cuda"):
                     sub = pages[part[0]: part[-1] + 1] if part == list(range(part[0], part[-1] + 1)) else pages[part]
                 else:
                     sub = [pages[i] for i in part]
-                with dbpost.timed("pages.det_window"):
-                    res, pages_dev = self.text_detector.detect_window(sub, keep_pages=True)
-                t_geo = dbpost.timed("pages.sort/merge+crop_geometry")
-                t_geo.__enter__()
-                boxes_per_page, flat, page_idx = [], [], []
-                for k, (i, (boxes, _)) in enumerate(zip(part, res)):
-                    if boxes is None or len(boxes) == 0:
-                        boxes_per_page.append([])
-                        continue
-                    # the detector sorts its boxes (TextDetector.sorted_boxes), __call__ sorts them again (rapid_ocr.py:372)
-                    bl = self._post_boxes(np.array(sorted_boxes(boxes)), mfd_res_list[i] if mfd_res_list else None)
-                    boxes_per_page.append(bl)
-                    flat.extend(bl)
-                    page_idx.extend([k] * len(bl))
-                keep, sizes, minv, rot = crop_geometry_batch(flat)
-                if len(keep) != len(flat):      # degenerate quads (the reference's warp would fail on them too) are dropped
-                    alive = set(int(v) for v in keep)
-                    q, pruned = 0, []
-                    for bl in boxes_per_page:
-                        pruned.append([b for j, b in enumerate(bl) if (q + j) in alive])
-                        q += len(bl)
-                    boxes_per_page = pruned
-                    page_idx = [page_idx[int(v)] for v in keep]
-                t_geo.__exit__()
-                if len(keep) == 0:
-                    continue
-                pidx = np.asarray(page_idx, np.int32)          # named: the array must outlive the ctypes call
-                minv = np.ascontiguousarray(minv)
-                sizes = np.ascontiguousarray(sizes)
-                nbytes = sizes[:, 0].astype(np.int64) * sizes[:, 1] * 3
-                offs = np.concatenate([[0], np.cumsum(nbytes)[:-1]]).astype(np.int64)
-                dev = torch.device("cuda", dev_index)
-                with torch.cuda.device(dev):
-                    buf = torch.empty(int(nbytes.sum()), dtype=torch.uint8, device=dev)
-                    _lib.check(_lib.load().rdb_warp_crops_batch(dev_index, _lib.ptr(pages_dev), len(part), h, w, len(keep),
-                                                                _lib.ptr(pidx), _lib.ptr(minv), _lib.ptr(sizes),
-                                                                _lib.ptr(rot), _lib.ptr(buf), _lib.ptr(offs), int(buf.numel()),
-                                                                torch.cuda.current_stream(dev).cuda_stream or None))
-                self.text_recognizer.stats["launches"] += 1                        # warp_cubic
-                self.text_recognizer.stats["h2d_bytes"] += len(keep) * 104
-                shapes = [((int(cw), int(ch)) if r else (int(ch), int(cw))) for (cw, ch), r in zip(sizes, rot)]
-                with dbpost.timed("pages.rec"):
-                    rec = self.text_recognizer(DeviceCrops(buf, offs, shapes, dev_index))
-                q = 0
-                for k, i in enumerate(part):
-                    page_res = []
-                    for b in boxes_per_page[k]:
-                        t, sc = rec.txts[q], rec.scores[q]
-                        q += 1
-                        if sc >= drop:
-                            page_res.append([np.asarray(b).tolist(), (t, sc)])
-                    out[i] = page_res or None
+                out.append((part, h, w, sub))
         return out
+
+    def _window_crops(self, part, h, w, sub, mfd_res_list):
+        """Stage A of one window: det -> sorted / merged boxes -> crop geometry -> every text-line crop warped on the GPU from
+        the resident pages.  Returns (boxes per page, DeviceCrops or None, event recorded after the warp)."""
+        import torch
+        dev_index = self.text_detector.engine.device
+        with dbpost.timed("pages.det_window"):
+            res, pages_dev = self.text_detector.detect_window(sub, keep_pages=True)
+        t_geo = dbpost.timed("pages.sort/merge+crop_geometry")
+        t_geo.__enter__()
+        boxes_per_page, flat, page_idx = [], [], []
+        for k, (i, (boxes, _)) in enumerate(zip(part, res)):
+            if boxes is None or len(boxes) == 0:
+                boxes_per_page.append([])
+                continue
+            # the detector sorts its boxes (TextDetector.sorted_boxes), __call__ sorts them again (rapid_ocr.py:372)
+            bl = self._post_boxes(np.array(sorted_boxes(boxes)), mfd_res_list[i] if mfd_res_list else None)
+            boxes_per_page.append(bl)
+            flat.extend(bl)
+            page_idx.extend([k] * len(bl))
+        keep, sizes, minv, rot = crop_geometry_batch(flat)
+        if len(keep) != len(flat):      # degenerate quads (the reference's warp would fail on them too) are dropped
+            alive = set(int(v) for v in keep)
+            q, pruned = 0, []
+            for bl in boxes_per_page:
+                pruned.append([b for j, b in enumerate(bl) if (q + j) in alive])
+                q += len(bl)
+            boxes_per_page = pruned
+            page_idx = [page_idx[int(v)] for v in keep]
+        t_geo.__exit__()
+        if len(keep) == 0:
+            return boxes_per_page, None, None
+        pidx = np.asarray(page_idx, np.int32)          # named: the array must outlive the ctypes call
+        minv = np.ascontiguousarray(minv)
+        sizes = np.ascontiguousarray(sizes)
+        nbytes = sizes[:, 0].astype(np.int64) * sizes[:, 1] * 3
+        offs = np.concatenate([[0], np.cumsum(nbytes)[:-1]]).astype(np.int64)
+        dev = torch.device("cuda", dev_index)
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev)
+            buf = torch.empty(int(nbytes.sum()), dtype=torch.uint8, device=dev)
+            _lib.check(_lib.load().rdb_warp_crops_batch(dev_index, _lib.ptr(pages_dev), len(part), h, w, len(keep), _lib.ptr(pidx), _lib.ptr(minv),
+                                                        _lib.ptr(sizes), _lib.ptr(rot), _lib.ptr(buf), _lib.ptr(offs), int(buf.numel()),
+                                                        st.cuda_stream or None))
+            ev = torch.cuda.Event()
+            ev.record(st)
+        self.text_recognizer.stats["launches"] += 1                        # warp_cubic
+        self.text_recognizer.stats["h2d_bytes"] += len(keep) * 104
+        shapes = [((int(cw), int(ch)) if r else (int(ch), int(cw))) for (cw, ch), r in zip(sizes, rot)]
+        return boxes_per_page, DeviceCrops(buf, offs, shapes, dev_index), ev
+
+    def _window_texts(self, part, boxes_per_page, dc, ev, drop, out):
+        """Stage B of one window: one recognition pass over all its crops, results written into out[page index]."""
+        import torch
+        if dc is None:
+            return
+        cur = torch.cuda.current_stream(dc.buf.device)
+        if ev is not None:
+            cur.wait_event(ev)                 # the crops may have been produced on another stream (ocr_pages_stream)
+            dc.buf.record_stream(cur)
+        with dbpost.timed("pages.rec"):
+            rec = self.text_recognizer(dc)
+        q = 0
+        for k, i in enumerate(part):
+            page_res = []
+            for b in boxes_per_page[k]:
+                t, sc = rec.txts[q], rec.scores[q]
+                q += 1
+                if sc >= drop:
+                    page_res.append([np.asarray(b).tolist(), (t, sc)])
+            out[i] = page_res or None
+
+    def ocr_pages(self, pages, mfd_res_list=None, drop_score=None):
+        """det + rec for a WINDOW of pages — the fused equivalent of the reference's window flow
+        (`_run_ocr_det_batch` analyze_utils.py:105-212 then `_run_ocr_rec_postprocess` :216-292, or `__call__`
+        rapid_ocr.py:351-401 per page): det on all pages -> sorted/merged boxes -> every text-line crop of the window
+        warped on the GPU from the resident pages (get_rotate_crop_image, bit-exact) -> one recognition pass over all crops.
+        Returns per page: None (no boxes) or [[box (4x2 list), (text, score)], ...] with score >= drop_score.
+        More than `det_window` pages (or mixed sizes) are processed window by window; each window is its own recognition
+        window (its crops are batched together, as the reference batches the crops of one `ocr(det=False)` call)."""
+        drop = self.drop_score if drop_score is None else drop_score
+        out = [None] * len(pages)
+        for part, h, w, sub in self._windows(pages):
+            boxes_per_page, dc, ev = self._window_crops(part, h, w, sub, mfd_res_list)
+            self._window_texts(part, boxes_per_page, dc, ev, drop, out)
+        return out
+
+    def ocr_pages_stream(self, batches, drop_score=None):
+        """Generator over an iterable of page batches: yields `ocr_pages(batch)` for each, with the detection stage of the next
+        window running on a worker thread (own CUDA stream) while this thread recognises the current one — the host half of
+        detection (contours, boxes, crop geometry) hides behind the recogniser's GPU time and vice versa.  Results are
+        identical to calling `ocr_pages` on each batch (same windows, same recognition batches)."""
+        import torch
+        from concurrent.futures import ThreadPoolExecutor
+        drop = self.drop_score if drop_score is None else drop_score
+        dev = torch.device("cuda", self.text_detector.engine.device)
+        if getattr(self, "_stage_a", None) is None:
+            self._stage_a = ThreadPoolExecutor(max_workers=1)
+            self._stream_a = torch.cuda.Stream(dev)
+
+        def stage_a(pages):
+            with torch.cuda.device(dev), torch.cuda.stream(self._stream_a):
+                return [(part, self._window_crops(part, h, w, sub, None)) for part, h, w, sub in self._windows(pages)]
+        it = iter(batches)
+        try:
+            cur_pages = next(it)
+        except StopIteration:
+            return
+        fut = self._stage_a.submit(stage_a, cur_pages)
+        while fut is not None:
+            staged, n_cur = fut.result(), len(cur_pages)
+            try:
+                cur_pages = next(it)
+                fut = self._stage_a.submit(stage_a, cur_pages)
+            except StopIteration:
+                fut = None
+            out = [None] * n_cur
+            for part, (boxes_per_page, dc, ev) in staged:
+                self._window_texts(part, boxes_per_page, dc, ev, drop, out)
+            yield out
 
     # ---- rapid_ocr.py:225-299
     def ocr(self, img, det=True, rec=True, mfd_res=None, tqdm_enable=False, tqdm_desc="OCR-rec Predict", return_word_box=False,

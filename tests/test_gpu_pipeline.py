@@ -151,6 +151,16 @@ def test_ocr_pages_vs_oracle_pipeline(prec):
         assert same >= len([1 for _, (t, sc) in zip(boxes0, rec) if sc >= 0.5]) - 1
 
 
+def test_ocr_pages_stream_equals_ocr_pages():
+    pages_a = list(synth.det_pages(3, 384, 640, seed=5, lines=8))
+    pages_b = list(synth.det_pages(2, 256, 512, seed=6, lines=5))
+    model = B200OcrModel(det_db_box_thresh=0.3, det_db_unclip_ratio=1.8, precision=PREC_FP16)
+    want = [model.ocr_pages(p) for p in (pages_a, pages_b, pages_a)]
+    got = list(model.ocr_pages_stream([pages_a, pages_b, pages_a]))
+    assert got == want
+    assert list(model.ocr_pages_stream([])) == []
+
+
 def test_recognizer_window_path_on_golden_lines(golden_dir):
     g = np.load(os.path.join(golden_dir, "rec_real_6lines.npz"))
     crops = [g[f"crop{i}"] for i in range(6)]
