@@ -179,12 +179,30 @@ inline void db_box_scores(int device, const float* prob, int n, int H, int W, in
   int* df = sc.take<int>(m);
   const float* dp = prob;
   if (!p_dev) { float* t = sc.take<float>((size_t)n * H * W); RDB_CUDA(cudaMemcpyAsync(t, prob, prob_b, cudaMemcpyHostToDevice, st)); dp = t; }
-  RDB_CUDA(cudaMemcpyAsync(dq, hq.data(), sizeof(ScoreQuad) * m, cudaMemcpyHostToDevice, st));
+  static const bool dbg = std::getenv("RDB_SCORE_TIMING") != nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+  if (dbg) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventRecord(e0, st); }
+  HostCarver hcv{pinned_scratch(pad256(sizeof(ScoreQuad) * m) + pad256(sizeof(double) * m) + pad256(sizeof(int) * m))};
+  ScoreQuad* hqp = hcv.take<ScoreQuad>(m);
+  double* hsp = hcv.take<double>(m);
+  int* hfp = hcv.take<int>(m);
+  std::memcpy(hqp, hq.data(), sizeof(ScoreQuad) * m);
+  RDB_CUDA(cudaMemcpyAsync(dq, hqp, sizeof(ScoreQuad) * m, cudaMemcpyHostToDevice, st));
+  if (dbg) cudaEventRecord(e1, st);
   box_score_kernel<<<m, 256, 0, st>>>(dp, H, W, dq, ds, df);
   RDB_LAUNCH_CHECK();
-  RDB_CUDA(cudaMemcpyAsync(scores, ds, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
-  RDB_CUDA(cudaMemcpyAsync(flags, df, sizeof(int) * m, cudaMemcpyDeviceToHost, st));
+  if (dbg) cudaEventRecord(e2, st);
+  RDB_CUDA(cudaMemcpyAsync(hsp, ds, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+  RDB_CUDA(cudaMemcpyAsync(hfp, df, sizeof(int) * m, cudaMemcpyDeviceToHost, st));
   RDB_CUDA(cudaStreamSynchronize(st));
+  std::memcpy(scores, hsp, sizeof(double) * m);
+  std::memcpy(flags, hfp, sizeof(int) * m);
+  if (dbg) {
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b, e1, e2);
+    fprintf(stderr, "[box_scores] m=%d h2d %.3f ms kernel %.3f ms\n", m, a, b);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  }
 }
 
 // host-only: the mask quad_row_intervals produces (tests pin it against cv2.fillPoly without a GPU)

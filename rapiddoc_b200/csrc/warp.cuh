@@ -39,6 +39,28 @@ inline uint8_t* device_scratch(int device, size_t bytes) {
 }
 inline size_t pad256(size_t b) { return (b + 255) / 256 * 256; }
 
+// Grow-only PINNED host staging per host thread.  Small descriptor tables / results go through it instead of pageable memory:
+// a pageable cudaMemcpyAsync is a blocking call inside the driver, and two of them from different threads serialise — with the
+// two-stage window pipeline the box scorer of window k+1 was observed waiting 13 ms per call behind the recogniser's
+// (pageable) result copy of window k.  Pinned copies are truly asynchronous; the caller synchronises its own stream.
+struct HostCarver {
+  uint8_t* base; size_t off = 0;
+  template <typename T>
+  T* take(size_t n) { T* p = reinterpret_cast<T*>(base + off); off += (n * sizeof(T) + 255) / 256 * 256; return p; }
+};
+inline uint8_t* pinned_scratch(size_t bytes) {
+  static thread_local uint8_t* buf = nullptr;
+  static thread_local size_t cap = 0;
+  if (cap < bytes) {
+    if (buf) cudaFreeHost(buf);
+    size_t want = bytes + bytes / 2;
+    if (want < (size_t)1 << 20) want = (size_t)1 << 20;
+    RDB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&buf), want, cudaHostAllocDefault));
+    cap = want;
+  }
+  return buf;
+}
+
 struct WarpCrop {
   double m[9];          // dst -> src homography (cv::invert of getPerspectiveTransform)
   int w, h;             // warp output size (before rotation)
@@ -165,7 +187,9 @@ inline void warp_crops(int device, const uint8_t* page, int H, int W, int n, con
   WarpCrop* dc = sc.take<WarpCrop>(n);
   if (!p_dev) { dp = sc.take<uint8_t>(page_b); RDB_CUDA(cudaMemcpyAsync(dp, page, page_b, cudaMemcpyHostToDevice, st)); }
   if (!o_dev) dout = sc.take<uint8_t>((size_t)out_bytes);
-  RDB_CUDA(cudaMemcpyAsync(dc, hc.data(), sizeof(WarpCrop) * n, cudaMemcpyHostToDevice, st));
+  WarpCrop* hp = reinterpret_cast<WarpCrop*>(pinned_scratch(sizeof(WarpCrop) * n));
+  std::memcpy(hp, hc.data(), sizeof(WarpCrop) * n);
+  RDB_CUDA(cudaMemcpyAsync(dc, hp, sizeof(WarpCrop) * n, cudaMemcpyHostToDevice, st));
   dim3 grid((unsigned)((max_px + 255) / 256), (unsigned)n);
   warp_cubic_kernel<<<grid, 256, 0, st>>>(dp, H, W, dc, dev_tab[device], dout);
   RDB_LAUNCH_CHECK();
@@ -320,7 +344,9 @@ inline void resize_pack_slots(int device, const uint8_t* src, long long src_byte
   }
   ScratchCarver sc{device_scratch(device, pad256(sizeof(ResizeSlot) * n))};
   ResizeSlot* ds = sc.take<ResizeSlot>(n);
-  RDB_CUDA(cudaMemcpyAsync(ds, hs.data(), sizeof(ResizeSlot) * n, cudaMemcpyHostToDevice, st));
+  ResizeSlot* hp = reinterpret_cast<ResizeSlot*>(pinned_scratch(sizeof(ResizeSlot) * n));
+  std::memcpy(hp, hs.data(), sizeof(ResizeSlot) * n);
+  RDB_CUDA(cudaMemcpyAsync(ds, hp, sizeof(ResizeSlot) * n, cudaMemcpyHostToDevice, st));
   for (int i0 = 0; i0 < n; i0 += 32768) {     // grid.y limit
     const int m = n - i0 < 32768 ? n - i0 : 32768;
     dim3 grid((unsigned)((dh * max_pitch + 255) / 256), (unsigned)m);

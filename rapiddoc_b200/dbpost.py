@@ -270,8 +270,10 @@ def gpu_score_fn(device, prob_dev, n, h, w, stream=None):
         m = len(quads)
         scores = np.zeros(m, np.float64)
         flags = np.zeros(m, np.int32)
-        _lib.check(lib.rdb_db_box_scores(int(device), _lib.ptr(prob_dev), int(n), int(h), int(w), m, _lib.ptr(quads), _lib.ptr(page_idx),
-                                         _lib.ptr(scores), _lib.ptr(flags), stream))
+        with timed("det.box_scores.ccall"):
+            rc = lib.rdb_db_box_scores(int(device), _lib.ptr(prob_dev), int(n), int(h), int(w), m, _lib.ptr(quads), _lib.ptr(page_idx),
+                                       _lib.ptr(scores), _lib.ptr(flags), stream)
+        _lib.check(rc)
         bad = np.nonzero(flags)[0]
         if len(bad):
             one = cv2_score_fn(None).score_one

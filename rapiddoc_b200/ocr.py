@@ -393,7 +393,9 @@ class B200TextDetector:
             if k + 1 < len(cuts):
                 fut = dbpost.pool().submit(gpu, *cuts[k + 1])
             if getattr(self, "_post_stream", None) is None:
-                self._post_stream = torch.cuda.Stream(dev)
+                # high priority: when another window's recogniser keeps the GPU busy (ocr_pages_stream) the tiny scorer
+                # kernel must not queue behind its launches
+                self._post_stream = torch.cuda.Stream(dev, priority=-1)
             score_fn = dbpost.gpu_score_fn(self.engine.device, probs[lo:hi], hi - lo, rh, rw, self._post_stream.cuda_stream)
             res = dbpost.window_boxes(bitmaps[lo:hi], [(h, w)] * (hi - lo), score_fn, po.box_thresh,
                                       po.unclip_ratio, po.max_candidates, po.min_size)
@@ -596,7 +598,11 @@ class B200TextRecognizer:
             _lib.check(_lib.load().rdb_resize_pack_slots(dc.device, _lib.ptr(dc.buf), int(dc.buf.numel()), n, _lib.ptr(src_offs), _lib.ptr(sizes),
                                                          _lib.ptr(dst_w), _lib.ptr(dst_offs), _lib.ptr(pitch), _lib.ptr(packed), int(base), ih,
                                                          st.cuda_stream or None))
-            vw_dev = torch.from_numpy(dst_w).to(dev)
+            vw_dev = torch.empty(n, dtype=torch.int32, device=dev)
+            if getattr(self, "_pin_vw", None) is None or self._pin_vw.numel() < n:
+                self._pin_vw = torch.empty(n + 1024, dtype=torch.int32).pin_memory()
+            self._pin_vw[:n].copy_(torch.from_numpy(dst_w))
+            vw_dev.copy_(self._pin_vw[:n], non_blocking=True)
             ids_all = torch.empty(toks, dtype=torch.int32, device=dev)
             probs_all = torch.empty(toks, dtype=torch.float32, device=dev)
             t_l = dbpost.timed("rec.launch")
@@ -611,8 +617,16 @@ class B200TextRecognizer:
             self.stats["d2h_bytes"] += toks * 8
             self.stats["crops"] += n
             with dbpost.timed("rec.sync+d2h"):
-                ids_h = ids_all.cpu().numpy()
-                probs_h = probs_all.cpu().numpy()
+                # pinned destination + stream synchronise: a pageable `.cpu()` is a blocking driver call that also stalls the
+                # small copies of the other pipeline stage (see pinned_scratch in csrc/warp.cuh)
+                if getattr(self, "_pin_out", None) is None or self._pin_out.numel() < 2 * toks:
+                    self._pin_out = torch.empty(2 * toks + 4096, dtype=torch.int32).pin_memory()
+                pi, pp = self._pin_out[:toks], self._pin_out[toks: 2 * toks].view(torch.float32)
+                pi.copy_(ids_all, non_blocking=True)
+                pp.copy_(probs_all, non_blocking=True)
+                st.synchronize()
+                ids_h = pi.numpy().copy()
+                probs_h = pp.numpy().copy()
         if getattr(self, "keep_ids", False):      # diagnostics (bench parity report): per-crop argmax ids in input order
             self.last_ids = [None] * n
             for (lo, hi, imgW, _mx), to in zip(batches, tok_off):
@@ -860,7 +874,7 @@ class B200OcrModel:
         dev = torch.device("cuda", self.text_detector.engine.device)
         if getattr(self, "_stage_a", None) is None:
             self._stage_a = ThreadPoolExecutor(max_workers=1)
-            self._stream_a = torch.cuda.Stream(dev)
+            self._stream_a = torch.cuda.Stream(dev, priority=-1)      # detection stage ahead of the running recogniser
 
         def stage_a(pages):
             with torch.cuda.device(dev), torch.cuda.stream(self._stream_a):
@@ -870,7 +884,18 @@ class B200OcrModel:
             cur_pages = next(it)
         except StopIteration:
             return
+        # two Python threads share the GIL: with the default 5 ms switch interval every return from a C call in one stage can
+        # wait that long for the other stage's pure-Python loop; a short interval keeps both stages moving
+        import sys
+        old_switch = sys.getswitchinterval()
+        sys.setswitchinterval(min(old_switch, 2e-4))
         fut = self._stage_a.submit(stage_a, cur_pages)
+        try:
+            yield from self._stream_loop(fut, it, cur_pages, stage_a, drop)
+        finally:
+            sys.setswitchinterval(old_switch)
+
+    def _stream_loop(self, fut, it, cur_pages, stage_a, drop):
         while fut is not None:
             staged, n_cur = fut.result(), len(cur_pages)
             try:
