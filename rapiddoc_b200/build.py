@@ -10,7 +10,10 @@ SOURCES = ["api.cu", "det.cu", "rec.cu", "ops.cu", "contours.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--use_fast_math" if os.environ.get("RDB_FAST_MATH") else "-DRDB_NO_FAST_MATH", "-cudart", "static"]
-if os.environ.get("RDB_SMEM_BASE") == "shared":      # build-time experiment, see gemm_tc.cuh RDB_ALIGNED_SMEM
+# aligned dynamic-smem base derived without leaving the shared address space: LDS/STS instead of generic LD/ST in the fused
+# kernels (gemm_tc.cuh RDB_ALIGNED_SMEM).  A/B on a B200 (profiles/r02_ab_smem_base.txt): det 5908 -> 6109 pages/s, rec 97.6 ->
+# 98.8 k crops/s, parity tests green; RDB_SMEM_BASE=generic builds the round-1 variant.
+if os.environ.get("RDB_SMEM_BASE") != "generic":
     FLAGS.append("-DRDB_SMEM_SHARED_BASE")
 
 

@@ -199,6 +199,9 @@ void RecEngine::infer_impl(const RecInput& in0, int n, int W, const RecOutput& o
   const bool in_dev = is_device_ptr(src);
   int chunk = chunk_crops_;
   if (chunk > n) chunk = n;
+  // a batch that fits one chunk is still cut in two when it is large enough: the two compute lanes overlap each other's
+  // small kernels (SE FCs, LightSVTR) — the recogniser of a window is called with one <= rec_batch_num batch at a time
+  if (chunk == n && (long long)n * W >= 64ll * 320 && n >= 8 && !env_is("RDB_REC_SPLIT", "0")) chunk = (n + 1) / 2;
   // two compute lanes (stream + pool each), chunks alternate (see DetEngine::infer)
   const int n_chunks = (n + chunk - 1) / chunk;
   const int lanes = (n_chunks >= 2 && !env_is("RDB_LANES", "1")) ? 2 : 1;
