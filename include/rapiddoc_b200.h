@@ -142,6 +142,12 @@ int rdb_contours_counts(rdb_contours_t* c, int32_t* per_page, int64_t* total_con
 int rdb_contours_fetch(rdb_contours_t* c, int32_t* contour_sizes, int32_t* points_xy);
 void rdb_contours_free(rdb_contours_t* c);
 
+/* sorted_boxes (applied twice: TextDetector + caller) and, with merge != 0, merge_det_boxes for every page of a window
+ * (rapid_doc/utils/ocr_utils.py:105-127, 257-317), float32 like the NumPy scalars of the reference.  boxes [total][4][2] f32
+ * delimited by page_offsets [n_pages+1]; out (capacity = total boxes) / out_offsets [n_pages+1]; returns the output count.
+ * Host-only. */
+int rdb_lines_sort_merge(const float* boxes, const int32_t* page_offsets, int n_pages, int merge, float* out, int32_t* out_offsets);
+
 /* DBPostProcess binarise (+ optional cv2.dilate 2x2) on an existing prob map [n,h,w]:
  * rapid_doc/model/ocr/ocr_patch.py:228-235. */
 int rdb_db_bitmap(int device, const float* prob, int n, int hgt, int wid, float thresh, int use_dilation,

@@ -56,6 +56,7 @@ SYMBOLS = {
     "rdb_contours_counts": (_i, [_vp, _vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "rdb_contours_fetch": (_i, [_vp, _vp, _vp]),
     "rdb_contours_free": (None, [_vp]),
+    "rdb_lines_sort_merge": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "rdb_debug_cubic_tab": (_i, [_vp]),
     "rdb_clipper_offset": (_i, [C.POINTER(C.c_double), _i, C.c_double, C.POINTER(C.c_int64), _i]),
     "rdb_clipper_offset_batch": (_i, [_vp, _i, _vp, _vp, _i, _vp]),

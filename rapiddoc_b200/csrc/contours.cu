@@ -181,3 +181,106 @@ int rdb_contours_fetch(rdb_contours_t* c, int32_t* contour_sizes, int32_t* point
 void rdb_contours_free(rdb_contours_t* c) { delete c; }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// sorted_boxes (twice: detector + caller) and merge_det_boxes for every page of a window, in float32 like the NumPy scalars the
+// reference computes with (rapid_doc/utils/ocr_utils.py:105-127, 257-317 with merge_spans_to_line :16-38,
+// _is_overlaps_y_exceeds_threshold :40-52, merge_overlapping_spans :219-254, calculate_is_angle :478-485).  The Python
+// restatement (rapiddoc_b200/lines.py, pinned against the reference's functions) stays the specification; this is the same
+// logic off the interpreter: 64 pages x 25 boxes cost 14 ms of GIL time in Python.
+namespace {
+
+struct Box { float p[8]; };   // x0,y0,x1,y1,x2,y2,x3,y3
+
+void sort_boxes(std::vector<Box>& b) {
+  std::stable_sort(b.begin(), b.end(), [](const Box& a, const Box& c) { return a.p[1] < c.p[1] || (a.p[1] == c.p[1] && a.p[0] < c.p[0]); });
+  const int n = (int)b.size();
+  for (int i = 0; i < n - 1; ++i)
+    for (int j = i; j >= 0; --j) {
+      const float d = b[j + 1].p[1] - b[j].p[1];
+      if ((d < 0 ? -d : d) < 10.f && b[j + 1].p[0] < b[j].p[0]) std::swap(b[j], b[j + 1]);
+      else break;
+    }
+}
+
+bool is_angle(const Box& b) {
+  const float height = ((b.p[7] - b.p[1]) + (b.p[5] - b.p[3])) / 2.f;
+  const float dy = b.p[5] - b.p[1];
+  return !(0.8f * height <= dy && dy <= 1.2f * height);
+}
+
+struct Span { float x0, y0, x1, y1; };
+
+bool y_overlap_exceeds(const Span& a, const Span& b, float thr) {
+  const float lo = a.y0 > b.y0 ? a.y0 : b.y0, hi = a.y1 < b.y1 ? a.y1 : b.y1;
+  float overlap = hi - lo;
+  if (!(overlap > 0.f)) overlap = 0.f;                       // max(0, .)
+  const float h1 = a.y1 - a.y0, h2 = b.y1 - b.y0, mh = h1 < h2 ? h1 : h2;
+  return mh > 0.f ? (overlap / mh) > thr : false;
+}
+
+void put_span(const Span& s, std::vector<Box>& out) {
+  out.push_back(Box{{s.x0, s.y0, s.x1, s.y0, s.x1, s.y1, s.x0, s.y1}});
+}
+
+void merge_boxes(const std::vector<Box>& in, std::vector<Box>& out) {
+  std::vector<Span> spans;
+  std::vector<Box> angled;
+  for (const Box& b : in) {
+    if (is_angle(b)) angled.push_back(b);
+    else spans.push_back(Span{b.p[0], b.p[1], b.p[2], b.p[5]});
+  }
+  std::stable_sort(spans.begin(), spans.end(), [](const Span& a, const Span& b) { return a.y0 < b.y0; });
+  std::vector<std::vector<Span>> lines;
+  for (const Span& s : spans) {
+    if (lines.empty() || !y_overlap_exceeds(s, lines.back().back(), 0.6f)) lines.emplace_back();
+    lines.back().push_back(s);
+  }
+  for (auto& line : lines) {
+    float mnx = line[0].x0, mxx = line[0].x1, mny = line[0].y0, mxy = line[0].y1;
+    for (const Span& s : line) {
+      mnx = s.x0 < mnx ? s.x0 : mnx; mxx = s.x1 > mxx ? s.x1 : mxx;
+      mny = s.y0 < mny ? s.y0 : mny; mxy = s.y1 > mxy ? s.y1 : mxy;
+    }
+    if ((mxx - mnx) > (mxy - mny) * 4.f) {
+      std::stable_sort(line.begin(), line.end(), [](const Span& a, const Span& b) { return a.x0 < b.x0; });
+      std::vector<Span> merged;
+      for (const Span& s : line) {
+        if (merged.empty() || merged.back().x1 < s.x0) merged.push_back(s);
+        else {
+          Span& m = merged.back();
+          m.x0 = m.x0 < s.x0 ? m.x0 : s.x0; m.y0 = m.y0 < s.y0 ? m.y0 : s.y0;
+          m.x1 = m.x1 > s.x1 ? m.x1 : s.x1; m.y1 = m.y1 > s.y1 ? m.y1 : s.y1;
+        }
+      }
+      for (const Span& s : merged) put_span(s, out);
+    } else {
+      for (const Span& s : line) put_span(s, out);
+    }
+  }
+  for (const Box& b : angled) out.push_back(b);
+}
+
+}  // namespace
+
+extern "C" int rdb_lines_sort_merge(const float* boxes, const int32_t* page_offsets, int n_pages, int merge, float* out, int32_t* out_offsets) {
+  if (!boxes || !page_offsets || !out || !out_offsets || n_pages < 0) return RDB_ERR_INVALID;
+  try {
+    int total = 0;
+    out_offsets[0] = 0;
+    for (int p = 0; p < n_pages; ++p) {
+      std::vector<Box> b(page_offsets[p + 1] - page_offsets[p]);
+      if (!b.empty()) std::memcpy(b.data(), boxes + (size_t)page_offsets[p] * 8, b.size() * sizeof(Box));
+      sort_boxes(b);          // TextDetector.sorted_boxes
+      sort_boxes(b);          // the caller's sorted_boxes on the sorted result (rapid_ocr.py:372 / analyze_utils.py:194)
+      std::vector<Box> res;
+      if (merge) merge_boxes(b, res); else res = b;
+      if (!res.empty()) std::memcpy(out + (size_t)total * 8, res.data(), res.size() * sizeof(Box));
+      total += (int)res.size();
+      out_offsets[p + 1] = total;
+    }
+    return total;
+  } catch (...) {
+    return RDB_ERR_INVALID;
+  }
+}

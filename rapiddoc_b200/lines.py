@@ -114,3 +114,21 @@ def update_det_boxes(dt_boxes, mfd_res):
             out.append(_points([lo, tb[1], hi, tb[3]]))
     out.extend(angled)
     return out
+
+
+def sort_merge_window(boxes_per_page, merge=True):
+    """sorted_boxes (detector) -> sorted_boxes (caller) -> merge_det_boxes for every page of a window in one native call
+    (rdb_lines_sort_merge: the logic above in float32, off the interpreter).  boxes_per_page: list of [k,4,2] arrays (or empty).
+    Returns a list of [k',4,2] float32 arrays."""
+    from . import _lib
+    counts = [len(b) for b in boxes_per_page]
+    offs = np.zeros(len(counts) + 1, np.int32)
+    offs[1:] = np.cumsum(counts)
+    total = int(offs[-1])
+    if total == 0:
+        return [np.zeros((0, 4, 2), np.float32) for _ in counts]
+    flat = np.ascontiguousarray(np.concatenate([np.asarray(b, np.float32).reshape(-1, 8) for b in boxes_per_page if len(b)]), np.float32)
+    out = np.empty((total, 8), np.float32)
+    out_offs = np.zeros(len(counts) + 1, np.int32)
+    _lib.check(_lib.load().rdb_lines_sort_merge(_lib.ptr(flat), _lib.ptr(offs), len(counts), int(bool(merge)), _lib.ptr(out), _lib.ptr(out_offs)))
+    return [out[out_offs[p]: out_offs[p + 1]].reshape(-1, 4, 2) for p in range(len(counts))]

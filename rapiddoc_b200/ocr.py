@@ -787,15 +787,25 @@ class B200OcrModel:
         t_geo = dbpost.timed("pages.sort/merge+crop_geometry")
         t_geo.__enter__()
         boxes_per_page, flat, page_idx = [], [], []
-        for k, (i, (boxes, _)) in enumerate(zip(part, res)):
-            if boxes is None or len(boxes) == 0:
-                boxes_per_page.append([])
-                continue
-            # the detector sorts its boxes (TextDetector.sorted_boxes), __call__ sorts them again (rapid_ocr.py:372)
-            bl = self._post_boxes(np.array(sorted_boxes(boxes)), mfd_res_list[i] if mfd_res_list else None)
-            boxes_per_page.append(bl)
-            flat.extend(bl)
-            page_idx.extend([k] * len(bl))
+        if not mfd_res_list or not any(mfd_res_list[i] for i in part):
+            # sorted_boxes (detector) -> sorted_boxes (caller, rapid_ocr.py:372) -> merge_det_boxes for the whole window in one
+            # native call (lines.sort_merge_window == the Python functions below, tests/test_lines.py)
+            from .lines import sort_merge_window
+            merged = sort_merge_window([b if b is not None else [] for b, _ in res], self.enable_merge_det_boxes)
+            for k, bl in enumerate(merged):
+                bl = list(bl)
+                boxes_per_page.append(bl)
+                flat.extend(bl)
+                page_idx.extend([k] * len(bl))
+        else:
+            for k, (i, (boxes, _)) in enumerate(zip(part, res)):
+                if boxes is None or len(boxes) == 0:
+                    boxes_per_page.append([])
+                    continue
+                bl = self._post_boxes(np.array(sorted_boxes(boxes)), mfd_res_list[i])
+                boxes_per_page.append(bl)
+                flat.extend(bl)
+                page_idx.extend([k] * len(bl))
         keep, sizes, minv, rot = crop_geometry_batch(flat)
         if len(keep) != len(flat):      # degenerate quads (the reference's warp would fail on them too) are dropped
             alive = set(int(v) for v in keep)
