@@ -273,6 +273,8 @@ int rdb_debug_gemm(int device, int use_tc, int mode, const float* A, const float
  * {"kernel": [total_ms, launches], ...} and returns the bytes needed. */
 /* host-only: the 1024 x 16 int16 bicubic weight table rdb_warp_crops uses (OpenCV initInterTab2D(INTER_CUBIC, fixpt)) */
 int rdb_debug_cubic_tab(int16_t* out);
+/* the RDB_* A/B switches are read from the environment once per process; call this after changing one */
+int rdb_switches_reload(void);
 int rdb_profile_enable(int on);
 int rdb_profile_reset(void);
 int rdb_profile_dump(char* buf, size_t cap);

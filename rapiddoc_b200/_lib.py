@@ -69,6 +69,7 @@ SYMBOLS = {
     "rdb_det_last_launches": (C.c_longlong, [_vp]),
     "rdb_rec_last_launches": (C.c_longlong, [_vp]),
     "rdb_debug_gemm": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "rdb_switches_reload": (_i, []),
     "rdb_profile_enable": (_i, [_i]),
     "rdb_profile_reset": (_i, []),
     "rdb_profile_dump": (_i, [C.c_char_p, C.c_size_t]),

@@ -432,7 +432,7 @@ int rdb_debug_gemm(int device, int use_tc, int mode, const float* A, const float
       __half* dO = pool.alloc_t<__half>((size_t)M * N);
       float* dOf = pool.alloc_t<float>((size_t)M * N);
       if (use_tc) {
-        const char* reps_env = getenv("RDB_DEBUG_GEMM_REPS");   // timing aid: repeat the launch (see rdb_profile_*)
+        const char* reps_env = rdb::sw_get("RDB_DEBUG_GEMM_REPS");   // timing aid: repeat the launch (see rdb_profile_*)
         const int reps = reps_env ? atoi(reps_env) : 1;
         for (int r = 0; r < (reps > 1 ? reps : 1); ++r) rdb::launch_gemm_tc(cx, dAh, K, M, K, dWh, N, dB, act, dRh, N, dO, N, 0);
       } else {
@@ -467,6 +467,11 @@ int rdb_debug_gemm(int device, int use_tc, int mode, const float* A, const float
     RDB_CUDA(cudaDeviceSynchronize());
     if (rdb::Profiler::global().on) rdb::Profiler::global().resolve();
   });
+}
+
+int rdb_switches_reload(void) {
+  rdb::Switches::get().reload();
+  return RDB_OK;
 }
 
 int rdb_profile_enable(int on) {

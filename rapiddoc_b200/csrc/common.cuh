@@ -5,8 +5,12 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 
 namespace rdb {
 
@@ -40,6 +44,34 @@ inline bool first_on_device(bool (&flags)[kMaxDevices]) {
   flags[d] = true;
   return true;
 }
+
+// A/B switches (RDB_*): read from the environment ONCE per process and cached — the hot path never calls getenv.  Tests that
+// flip a switch between calls use rdb_switches_reload().  Switches that exist only to measure what a stage costs (and give
+// wrong results by design, e.g. RDB_SE_SKIP) or that print debug marks compile in only with -DRDB_DEBUG_SWITCHES.
+struct Switches {
+  std::unordered_map<std::string, std::string> vals;   // name -> value for the names that are set
+  std::unordered_map<std::string, bool> seen;
+  std::mutex mu;
+  static Switches& get() { static Switches s; return s; }
+  const char* lookup(const char* name) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = seen.find(name);
+    if (it == seen.end()) {
+      const char* e = std::getenv(name);
+      seen[name] = e != nullptr;
+      if (e) vals[name] = e;
+      return e ? vals[name].c_str() : nullptr;
+    }
+    return it->second ? vals[name].c_str() : nullptr;
+  }
+  void reload() { std::lock_guard<std::mutex> lk(mu); vals.clear(); seen.clear(); }
+};
+inline const char* sw_get(const char* name) { return Switches::get().lookup(name); }
+#ifdef RDB_DEBUG_SWITCHES
+inline const char* sw_debug(const char* name) { return sw_get(name); }
+#else
+inline const char* sw_debug(const char*) { return nullptr; }
+#endif
 
 // Every C-ABI entry point selects its engine's device; the caller's current device (torch's, for instance) is put back on exit.
 struct DeviceGuard {

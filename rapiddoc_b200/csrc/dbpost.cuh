@@ -179,7 +179,7 @@ inline void db_box_scores(int device, const float* prob, int n, int H, int W, in
   int* df = sc.take<int>(m);
   const float* dp = prob;
   if (!p_dev) { float* t = sc.take<float>((size_t)n * H * W); RDB_CUDA(cudaMemcpyAsync(t, prob, prob_b, cudaMemcpyHostToDevice, st)); dp = t; }
-  static const bool dbg = std::getenv("RDB_SCORE_TIMING") != nullptr;
+  static const bool dbg = sw_debug("RDB_SCORE_TIMING") != nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
   if (dbg) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventRecord(e0, st); }
   HostCarver hcv{pinned_scratch(pad256(sizeof(ScoreQuad) * m) + pad256(sizeof(double) * m) + pad256(sizeof(int) * m))};

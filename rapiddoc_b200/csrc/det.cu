@@ -264,7 +264,7 @@ void DetEngine::infer_impl(const DetInput& in_host_or_dev, int n, int H, int W, 
   const bool any_host = !in_dev || (prob && !prob_dev) || (bitmap && !bm_dev);
   const int n_chunks = (n + chunk - 1) / chunk;
   int lanes = 2;
-  if (const char* e = std::getenv("RDB_LANES")) lanes = std::atoi(e);
+  if (const char* e = sw_get("RDB_LANES")) lanes = std::atoi(e);
   if (lanes > kMaxLanes) lanes = kMaxLanes;
   if (lanes > n_chunks) lanes = n_chunks;
   if (lanes < 1) lanes = 1;
@@ -311,7 +311,7 @@ void DetEngine::infer_impl(const DetInput& in_host_or_dev, int n, int H, int W, 
   {
     int rest = n;
     int ramp = (any_host && chunk >= 4 && n >= 2 * chunk) ? 1 : 0;    // 1: one half-size chunk at each end; 2: quarter + half
-    if (const char* e = std::getenv("RDB_RAMP")) ramp = (any_host && chunk >= 4 && n >= 2 * chunk) ? std::atoi(e) : 0;
+    if (const char* e = sw_get("RDB_RAMP")) ramp = (any_host && chunk >= 4 && n >= 2 * chunk) ? std::atoi(e) : 0;
     std::vector<int> head;
     if (ramp >= 2) head.push_back(chunk / 4);
     if (ramp >= 1) head.push_back(chunk / 2);

@@ -590,7 +590,7 @@ struct Plan {
 inline int pick_aw(int K) {
   // TMA cost is per box row ("segment"), not per byte (profiles/r01_tma_microbench.txt): use the widest span (64 halves =
   // 128 B) as soon as K > 32 even when the last block is only partly valid (K = 48, 96, 120, 240 ...)
-  const char* e = std::getenv("RDB_TC_AW");
+  const char* e = sw_get("RDB_TC_AW");
   if (e != nullptr && e[0] == 'n') {            // RDB_TC_AW=narrow: previous rule (largest span dividing K), for A/B runs
     if (K % 64 == 0) return 64;
     if (K % 32 == 0) return 32;
@@ -623,7 +623,7 @@ inline void finish_plan(Plan& p, int num_sms) {
   const size_t budget = 200 * 1024;
   if (a.b_blocks == 0) a.b_blocks = a.k_blocks;
   const size_t b_res = (size_t)a.b_blocks * b_bytes;
-  const char* e = std::getenv("RDB_TC_RESIDENT");
+  const char* e = sw_get("RDB_TC_RESIDENT");
   const bool allow = !(e != nullptr && e[0] == '0');
   int min_stages = a.k_blocks < 3 ? a.k_blocks + 2 : 4;
   if (allow && a.tiles_n <= num_sms && b_res + (size_t)min_stages * a_bytes <= budget) {
@@ -723,7 +723,7 @@ inline Plan make_conv_plan_wide(int n, int H, int W, int C, int N, int KH, int K
 }
 
 inline Plan make_conv_plan(int n, int H, int W, int C, int N, int KH, int KW, int sh, int sw, int pt, int pl, int OH, int OW, int num_sms) {
-  const char* e = std::getenv("RDB_TC_PATCH");
+  const char* e = sw_get("RDB_TC_PATCH");
   const bool allow = !(e != nullptr && e[0] == '0');
   if (allow && sh == 1 && sw == 1 && OW >= 8) {
     Plan p = make_conv_plan_mode(n, H, W, C, N, KH, KW, sh, sw, pt, pl, OH, OW, num_sms, true);

@@ -264,7 +264,7 @@ inline void launch_head_planar(Ctx& cx, const Weights& w, const __half* const* f
   a.w_up = w.get("head.up.w").h; a.b_up = w.get("head.up.b").d;
   a.w_fin = w.get("head.final.w").d; a.b_fin = w.get("head.final.b").d;
   a.thresh = thresh; a.prob = prob; a.seg = seg;
-  if (const char* e = std::getenv("RDB_HEAD_DBG")) a.dbg = std::atoi(e);
+  if (const char* e = sw_debug("RDB_HEAD_DBG")) a.dbg = std::atoi(e);
   a.tiles_x = (W + S::TW - 1) / S::TW; a.tiles_y = (H + S::TH - 1) / S::TH; a.tiles = n * a.tiles_x * a.tiles_y;
   auto k = head_planar_kernel;
   static bool attr_done[rdb::kMaxDevices] = {};

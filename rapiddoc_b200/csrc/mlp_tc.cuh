@@ -528,8 +528,8 @@ inline void launch_mlp_big(Ctx& cx, const Weights& wts, const std::string& name,
     RDB_CUDA(cudaStreamSynchronize(cx.st));   // first use only: the other compute lane (another stream) reads the same images
   }
   a.w1p = w1p; a.w2p = w2p;
-  a.dbg = std::getenv("RDB_MLPBIG_DBG") != nullptr;
-  static const bool want_marks = std::getenv("RDB_MLPBIG_MARKS") != nullptr;
+  a.dbg = sw_debug("RDB_MLPBIG_DBG") != nullptr;
+  static const bool want_marks = sw_debug("RDB_MLPBIG_MARKS") != nullptr;
   if (want_marks) { RDB_CUDA(cudaMalloc(&a.marks, 256 * sizeof(long long))); RDB_CUDA(cudaMemset(a.marks, 0, 256 * sizeof(long long))); }
   const int grid = a.tiles < cx.num_sms ? a.tiles : cx.num_sms;
   cx.begin("mlp_tc[M=" + std::to_string(M) + ",C=" + std::to_string(C) + ",N=" + std::to_string(COUT) + ",res=" + (res ? "1" : "0") + "]");

@@ -433,7 +433,7 @@ inline void launch_stem_fused(Ctx& cx, const Weights& w, const __half* e1, int n
   static bool attr_done[rdb::kMaxDevices] = {};
   if (rdb::first_on_device(attr_done)) { RDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmem)); }
   const int grid = a.tiles < cx.num_sms ? a.tiles : cx.num_sms;
-  static const bool dbg = std::getenv("RDB_STEM_DBG") != nullptr;
+  static const bool dbg = sw_debug("RDB_STEM_DBG") != nullptr;
   if (dbg) { RDB_CUDA(cudaMalloc(&a.dbg, 3 * 128 * sizeof(long long))); RDB_CUDA(cudaMemset(a.dbg, 0, 3 * 128 * sizeof(long long))); }
   cx.begin("stem_fused[P=" + std::to_string((long long)n * H2 * W2) + "]");
   k<<<grid, kStemThreads + 32, S::kSmem, cx.st>>>(a);

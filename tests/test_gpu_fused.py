@@ -6,6 +6,8 @@ import os
 import numpy as np
 import pytest
 
+from rapiddoc_b200 import _lib
+
 from oracle import nets, ocr_post as P
 from rapiddoc_b200 import PREC_FP16
 from rapiddoc_b200.engine import DetEngine, RecEngine
@@ -39,10 +41,12 @@ def test_det_fused_paths_match_unfused_and_oracle(det, shape):
     assert np.array_equal(bm, np.stack([P.db_bitmap(p, 0.3, True) for p in prob]))
     for name, val in SWITCHES:
         os.environ[name] = val
+        _lib.load().rdb_switches_reload()        # switches are cached per process
         try:
             alt, alt_bm = det.infer_u8(pages, thresh=0.3, use_dilation=True)
         finally:
             del os.environ[name]
+            _lib.load().rdb_switches_reload()
         assert np.abs(alt - want).max() <= 3e-2, (name, val)
         assert np.abs(alt - prob).max() <= 2e-2, (name, val)          # same math, different rounding points
         flips = (alt > 0.3) != (prob > 0.3)
@@ -69,8 +73,10 @@ def test_rec_fused_paths_match_unfused():
     assert not ((base["ids"] != logits.argmax(2)) & (margin > 0.25)).any()
     for name, val in [("RDB_MLP", "unfused"), ("RDB_STEM1", "simt"), ("RDB_GELU", "exact")]:
         os.environ[name] = val
+        _lib.load().rdb_switches_reload()
         try:
             alt = rec.infer_f32(x)
         finally:
             del os.environ[name]
+            _lib.load().rdb_switches_reload()
         assert not ((alt["ids"] != base["ids"]) & (margin > 0.25)).any(), (name, val)
