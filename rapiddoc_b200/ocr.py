@@ -127,19 +127,20 @@ class DeviceCrops:
     The recogniser resizes / packs them on the device (rdb_resize_pack_u8); `numpy(i)` fetches one crop for host-side users."""
 
     def __init__(self, buf, offsets, shapes, device):
-        self.buf, self.offsets, self.shapes, self.device = buf, np.asarray(offsets, np.int64), list(shapes), int(device)
+        self.buf, self.offsets, self.device = buf, np.asarray(offsets, np.int64), int(device)
+        self.shapes = np.asarray(shapes, np.int64).reshape(-1, 2)       # stored (h, w) per crop
 
     def __len__(self):
         return len(self.shapes)
 
     def numpy(self, i):
-        h, w = self.shapes[i]
+        h, w = (int(v) for v in self.shapes[i])
         o = int(self.offsets[i])
         return self.buf[o: o + h * w * 3].cpu().numpy().reshape(h, w, 3)
 
     def to_list(self):
         host = self.buf.cpu().numpy()
-        return [host[int(o): int(o) + h * w * 3].reshape(h, w, 3) for o, (h, w) in zip(self.offsets, self.shapes)]
+        return [host[int(o): int(o) + int(h) * int(w) * 3].reshape(int(h), int(w), 3) for o, (h, w) in zip(self.offsets, self.shapes)]
 
 
 def get_rotate_crop_images_gpu(img, boxes, device=0, keep_on_device=False):
@@ -552,13 +553,15 @@ class B200TextRecognizer:
         """text_recognizer_call's batching (rapid_ocr.py:411-440): crops sorted by w/h, consecutive batches of rec_batch_num,
         every batch padded to int(48 * max(320/48, its widest ratio)).  Returns (order, ratios, [(lo, hi, imgW, max_ratio)])."""
         _, ih, iw = self.rec_image_shape
-        ratios = [w / float(h) for h, w in shapes]
-        order = np.argsort(np.array(ratios))
+        sh = np.asarray(shapes, np.float64).reshape(-1, 2)
+        ratios = sh[:, 1] / sh[:, 0]                         # w / float(h), the same IEEE division
+        order = np.argsort(ratios)
+        sorted_r = ratios[order]
         batches = []
-        for b0 in range(0, len(shapes), self.rec_batch_num):
-            idx = order[b0: b0 + self.rec_batch_num]
-            mx = max([iw / ih] + [ratios[i] for i in idx])
-            batches.append((b0, b0 + len(idx), int(ih * mx), mx))
+        for b0 in range(0, len(sh), self.rec_batch_num):
+            b1 = min(len(sh), b0 + self.rec_batch_num)
+            mx = max(iw / ih, float(sorted_r[b0:b1].max()))
+            batches.append((b0, b1, int(ih * mx), mx))
         return order, ratios, batches
 
     def __call__(self, img_list, return_word_box=False):
@@ -578,7 +581,7 @@ class B200TextRecognizer:
         order, ratios, batches = self.plan(dc.shapes)
         dev = dc.buf.device
         # slot table in batch order
-        sizes = np.array([[dc.shapes[i][1], dc.shapes[i][0]] for i in order], np.int32)            # (w, h)
+        sizes = np.ascontiguousarray(np.asarray(dc.shapes, np.int32).reshape(-1, 2)[order][:, ::-1])   # (w, h)
         src_offs = np.ascontiguousarray(dc.offsets[order], np.int64)
         dst_w = np.empty(n, np.int32)
         pitch = np.empty(n, np.int32)
@@ -834,7 +837,7 @@ class B200OcrModel:
             ev.record(st)
         self.text_recognizer.stats["launches"] += 1                        # warp_cubic
         self.text_recognizer.stats["h2d_bytes"] += len(keep) * 104
-        shapes = [((int(cw), int(ch)) if r else (int(ch), int(cw))) for (cw, ch), r in zip(sizes, rot)]
+        shapes = np.where(rot[:, None] != 0, sizes, sizes[:, ::-1]).astype(np.int64)      # stored (h, w): rot90 swaps them
         return boxes_per_page, DeviceCrops(buf, offs, shapes, dev_index), ev
 
     def _window_texts(self, part, boxes_per_page, dc, ev, drop, out):
@@ -849,13 +852,14 @@ class B200OcrModel:
         with dbpost.timed("pages.rec"):
             rec = self.text_recognizer(dc)
         q = 0
+        txts, scores = rec.txts, rec.scores
         for k, i in enumerate(part):
-            page_res = []
-            for b in boxes_per_page[k]:
-                t, sc = rec.txts[q], rec.scores[q]
-                q += 1
-                if sc >= drop:
-                    page_res.append([np.asarray(b).tolist(), (t, sc)])
+            bl = boxes_per_page[k]
+            if len(bl) == 0:
+                continue
+            quads = np.asarray(bl).tolist()                 # one conversion per page instead of one per box
+            page_res = [[quads[j], (txts[q + j], scores[q + j])] for j in range(len(bl)) if scores[q + j] >= drop]
+            q += len(bl)
             out[i] = page_res or None
 
     def ocr_pages(self, pages, mfd_res_list=None, drop_score=None):
