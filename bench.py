@@ -574,6 +574,18 @@ def run_formula(args, wl):
         a1.record()
         torch.cuda.synchronize()
         enc_ms = a0.elapsed_time(a1) / 3
+        if args.profile_out:
+            from rapiddoc_b200 import _lib
+            _lib.profile(True)
+            _lib.profile_reset()
+            eng.encode(x_dev)
+            torch.cuda.synchronize()
+            prof = _lib.profile_dump()           # synchronises and resolves the pending event pairs
+            _lib.profile(False)
+            tot = sum(v[0] for v in prof.values()) or 1.0
+            json.dump({"workload": wl["name"], "precision": args.precision, "encoder_total_ms": tot,
+                       "kernels": [{"kernel": k, "total_ms": v[0], "launches": v[1], "share": v[0] / tot} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])]},
+                      open(args.profile_out, "w"), indent=1)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -199,6 +199,11 @@ const char* rdb_ops_last_error(void);
  * NULL) shifts the output by *out_step * out_step_stride elements — the k / v projections append to their KV-cache row. */
 int rdb_op_gemm(int device, int prec, const void* A, int lda, long long M, int K, const void* W, int N, const float* bias, int act,
                 const void* res, int ldr, void* out, int ldc, int c_off, void* stream, const int32_t* out_step, long long out_step_stride);
+/* dense kh x kw conv as a tcgen05 IMPLICIT GEMM (fp16): x [n,h,w,c] with pixel pitch ld (a channel slice of a wider buffer is
+ * fine) read through a 4-D TMA map — padding = TMA out-of-bounds zero fill, stride = element strides, no im2col buffer;
+ * wt [cout][kh][kw][c] fp16; out channel slice (ldc, c_off) = act(conv + bias).  ConvBNAct of PPHGNetV2 (rec_pphgnetv2.py:858-913). */
+int rdb_op_conv_tc(int device, const void* x, int n, int h, int w, int c, int ld, const void* wt, int cout, const float* bias, int act,
+                   int kh, int kw, int sh, int sw, int pt, int pl, void* out, int oh, int ow, int ldc, int c_off, void* stream);
 /* x [n,h,w,c] (pixel pitch ld) -> out [n*oh*ow, kh*kw*c], K order (ky, kx, c) = the packed conv weight order */
 int rdb_op_im2col(int device, int prec, const void* x, int n, int h, int w, int c, int ld, int kh, int kw, int sh, int sw, int pt, int pl,
                   int oh, int ow, void* out, void* stream);

@@ -484,6 +484,10 @@ int rdb_profile_reset(void) {
 }
 // JSON object {"kernel name": [total_ms, launches], ...}; returns bytes needed (incl. NUL)
 int rdb_profile_dump(char* buf, size_t cap) {
+  if (!rdb::Profiler::global().recs.empty()) {      // op-level records (rdb_op_*) are resolved here
+    cudaDeviceSynchronize();
+    try { rdb::Profiler::global().resolve(); } catch (...) {}
+  }
   std::string s = "{";
   bool first = true;
   for (auto& kv : rdb::Profiler::global().acc) {

@@ -314,15 +314,16 @@ inline void launch_gemm_tc(Ctx& cx, const __half* A, int lda, long long M, int K
 // mode (the KW horizontal taps are one K range).  out_wp > 0: the output is written with that row pitch.
 inline void launch_conv_tc(Ctx& cx, const char* name, const __half* in, int n, int H, int W, int C, const __half* Wh, int N, const float* bias,
                            int act, int KH, int KW, int sh, int sw, int pt, int pl, __half* out, int OH, int OW, int ldc, int c_off,
-                           int in_wp = 0, int out_wp = 0) {
+                           int in_wp = 0, int out_wp = 0, int in_ld = 0) {
   const bool wide = in_wp > 0 && sh == 1 && sw == 1;
+  RDB_CHECK(!(wide && in_ld > 0), "conv_tc: a pixel pitch and the wide-row mode exclude each other");
   tc::Plan p = wide ? tc::make_conv_plan_wide(n, H, W, C, N, KH, KW, pt, OH, OW, cx.num_sms)
                     : tc::make_conv_plan(n, H, W, C, N, KH, KW, sh, sw, pt, pl, OH, OW, cx.num_sms);
   tc::Args& a = p.a;
   RDB_CHECK(!wide || (a.patch && a.resident), "conv_tc: wide-row mode needs the weights resident");
   a.bias = bias; a.res = nullptr; a.ldr = 0; a.out = out; a.ldc = ldc; a.c_off = c_off; a.act = act; a.out_wp = out_wp;
   CUtensorMap mA = wide ? tc::make_map_wide(in, n, H, W, in_wp, C, KW, a.AW, a.TH + a.KH - 1)
-                        : tc::make_map_nhwc(in, n, H, in_wp > 0 ? in_wp : W, C, a.AW, a.patch ? a.TH + a.KH - 1 : a.TH, a.TW, sh, sw);
+                        : tc::make_map_nhwc(in, n, H, in_wp > 0 ? in_wp : W, C, a.AW, a.patch ? a.TH + a.KH - 1 : a.TH, a.TW, sh, sw, in_ld);
   CUtensorMap mB = tc::make_map(Wh, N, KH * KW * C, KH * KW * C, a.AW, a.BN);
   cx.begin(std::string(name) + (wide ? "_tcw[P=" : (a.patch ? "_tcp[P=" : "_tc[P=")) + std::to_string((long long)n * OH * OW) + ",C=" + std::to_string(C) + ",N=" + std::to_string(N) + "]");
   launch_tc_store(p, mA, mB, act, cx.st);

@@ -548,14 +548,17 @@ inline CUtensorMap make_map(const void* base, long long rows, int cols, int ld, 
 }
 
 // 4-D fp16 NHWC tensor {C, W, H, n}; box {aw, TW*sw, TH*sh, 1} traversed with element strides {1, sw, sh, 1}
-inline CUtensorMap make_map_nhwc(const void* base, int n, int H, int W, int C, int aw, int TH, int TW, int sh, int sw) {
+// ld: pixel pitch in elements (0 = C): a channel SLICE of a wider NHWC buffer (the formula encoder's dense-concat buffers) is a
+// valid conv input — dims[0] = C bounds the slice, channels beyond it are zero-filled by TMA
+inline CUtensorMap make_map_nhwc(const void* base, int n, int H, int W, int C, int aw, int TH, int TW, int sh, int sw, int ld = 0) {
   CUtensorMap m;
+  const cuuint64_t P = ld > 0 ? ld : C;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint64_t strides[3] = {P * 2, (cuuint64_t)W * P * 2, (cuuint64_t)H * W * P * 2};
   cuuint32_t box[4] = {(cuuint32_t)aw, (cuuint32_t)(TW * sw), (cuuint32_t)(TH * sh), 1};
   cuuint32_t es[4] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1};
   CUtensorMapSwizzle swz = aw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (aw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  RDB_CHECK(((uintptr_t)base & 15) == 0 && (C * 2) % 16 == 0, "tma: NHWC base/channel pitch must be 16-byte aligned");
+  RDB_CHECK(((uintptr_t)base & 15) == 0 && (P * 2) % 16 == 0, "tma: NHWC base/channel pitch must be 16-byte aligned");
   CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw Error("cuda: cuTensorMapEncodeTiled(4d) failed, code " + std::to_string((int)r));

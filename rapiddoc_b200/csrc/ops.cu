@@ -85,6 +85,59 @@ __global__ void dwconv_vec8_kernel(const T* __restrict__ x, int n, int H, int W,
   }
 }
 
+// stride-1 depthwise k x k with a 4-pixel strip per thread: the k + 3 input vectors of a kernel row are loaded once and
+// reused by the four outputs (k = 5: 40 vector loads per strip instead of 100)
+template <typename T, int K>
+__global__ void dwconv_strip4_kernel(const T* __restrict__ x, int n, int H, int W, int C, int ld_in, const float* __restrict__ w,
+                                     const float* __restrict__ bias, int relu, T* __restrict__ out, int ld_out, int c_off) {
+  constexpr int P = (K - 1) / 2;
+  const int C8 = C / 8, W4 = (W + 3) / 4;
+  const long long total = (long long)n * H * W4 * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8) * 8;
+    const long long t = i / C8;
+    const int ox0 = (int)(t % W4) * 4, oy = (int)((t / W4) % H), b = (int)(t / ((long long)W4 * H));
+    float acc[4][8];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
+    for (int ky = 0; ky < K; ++ky) {
+      const int iy = oy - P + ky;
+      if (iy < 0 || iy >= H) continue;
+      const T* row = x + ((long long)(b * H + iy) * W) * ld_in + c;
+      float v[K + 3][8];
+#pragma unroll
+      for (int q = 0; q < K + 3; ++q) {
+        const int ix = ox0 - P + q;
+        if (ix >= 0 && ix < W) Vec8<T>::load(row + (long long)ix * ld_in, v[q]);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[q][j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        float wv[8];
+        Vec8<float>::load(w + (ky * K + kx) * C + c, wv);
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(v[kx + p][j], wv[j], acc[p][j]);
+      }
+    }
+    float bv[8];
+    Vec8<float>::load(bias + c, bv);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      if (ox0 + p >= W) break;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc[p][j] += bv[j]; if (relu) acc[p][j] = fmaxf(acc[p][j], 0.f); }
+      Vec8<T>::store(out + ((long long)(b * H + oy) * W + ox0 + p) * ld_out + c_off + c, acc[p]);
+    }
+  }
+}
+
 // depthwise k x k, pad (k-1)/2, stride s, weights [k][k][C] fp32, bias [C]; in pitch ld_in, out pitch ld_out (+ c_off)
 template <typename T>
 __global__ void dwconv_generic_kernel(const T* __restrict__ x, int n, int H, int W, int C, int ld_in, int K, int s, const float* __restrict__ w,
@@ -285,6 +338,12 @@ rdb::Pool& ops_pool(int device) {       // gemm_tc needs no workspace; the pool 
   static rdb::Pool pools[rdb::kMaxDevices];
   return pools[device];
 }
+// per-kernel timing of the simple ops through the same profiler the engines use (rdb_profile_*)
+struct OpTimer {
+  rdb::Ctx cx;
+  OpTimer(const std::string& name, cudaStream_t st) { cx.st = st; cx.begin(name); }
+  ~OpTimer() { rdb::Profiler& p = rdb::Profiler::global(); if (p.on && !p.recs.empty()) cudaEventRecord(p.recs.back().b, cx.st); }
+};
 int sm_count(int device) {
   static int n[rdb::kMaxDevices] = {};
   if (!n[device]) RDB_CUDA(cudaDeviceGetAttribute(&n[device], cudaDevAttrMultiProcessorCount, device));
@@ -321,6 +380,7 @@ int rdb_op_gemm(int device, int prec, const void* A, int lda, long long M, int K
       a.A = A; a.lda = lda; a.W = static_cast<const float*>(W); a.bias = bias; a.res = res; a.ldr = ldr; a.out = out; a.ldc = ldc; a.c_off = c_off;
       a.M = (int)M; a.N = N; a.K = K; a.act = act;
       RDB_CHECK(M < (1ll << 31), "gemm: M too large");
+      OpTimer tm("gemm_simt_op[M=" + std::to_string(M) + ",K=" + std::to_string(K) + ",N=" + std::to_string(N) + "]", st);
       rdb::launch_gemm_simt<float, float>(a, st);
     } else {
       RDB_CHECK(out_step == nullptr, "gemm fp16: out_step not supported");
@@ -333,12 +393,26 @@ int rdb_op_gemm(int device, int prec, const void* A, int lda, long long M, int K
   });
 }
 
+int rdb_op_conv_tc(int device, const void* x, int n, int h, int w, int c, int ld, const void* wt, int cout, const float* bias, int act, int kh, int kw,
+                   int sh, int sw, int pt, int pl, void* out, int oh, int ow, int ldc, int c_off, void* stream) {
+  return op_guard([&] {
+    RDB_CHECK(x && wt && out && n > 0, "conv_tc: bad argument");
+    RDB_CHECK(c % 8 == 0 && ld % 8 == 0 && ldc % 8 == 0 && c_off % 8 == 0, "conv_tc: channel counts / pitches must be multiples of 8");
+    rdb::DeviceGuard g(device);
+    rdb::Ctx cx;
+    cx.st = (cudaStream_t)stream; cx.pool = &ops_pool(device); cx.precision = 1; cx.use_tc = true; cx.num_sms = sm_count(device);
+    rdb::launch_conv_tc(cx, "conv_op", static_cast<const __half*>(x), n, h, w, c, static_cast<const __half*>(wt), cout, bias, act, kh, kw, sh, sw, pt, pl,
+                        static_cast<__half*>(out), oh, ow, ldc, c_off, 0, 0, ld == c ? 0 : ld);
+  });
+}
+
 int rdb_op_im2col(int device, int prec, const void* x, int n, int h, int w, int c, int ld, int kh, int kw, int sh, int sw, int pt, int pl, int oh, int ow,
                   void* out, void* stream) {
   return op_guard([&] {
     RDB_CHECK(x && out && n > 0, "im2col: bad argument");
     rdb::DeviceGuard g(device);
     const long long total = (long long)n * oh * ow * kh * kw * c;
+    OpTimer tm("im2col[P=" + std::to_string((long long)n * oh * ow) + ",K=" + std::to_string(kh * kw * c) + "]", (cudaStream_t)stream);
     if (c % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x % 16) == 0) {
       if (prec == RDB_PREC_FP32)
         rdb::ops::im2col_vec8_kernel<float><<<rdb::ops::grid_for(total / 8), 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(x), n, h, w, c, ld, kh, kw, sh, sw, pt, pl, oh, ow, static_cast<float*>(out));
@@ -361,7 +435,23 @@ int rdb_op_dwconv(int device, int prec, const void* x, int n, int h, int w, int 
     RDB_CHECK(x && out && wt && bias && n > 0 && (k & 1), "dwconv: bad argument");
     rdb::DeviceGuard g(device);
     const long long total = (long long)n * oh * ow * c;
-    if (c % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && c_off % 8 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0) {
+    OpTimer tm("dwconv_op[P=" + std::to_string((long long)n * oh * ow) + ",C=" + std::to_string(c) + ",k=" + std::to_string(k) + "]", (cudaStream_t)stream);
+    const bool vec = c % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && c_off % 8 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0;
+    if (vec && stride == 1 && (k == 5 || k == 3) && oh == h && ow == w) {
+      const long long strips = (long long)n * h * ((w + 3) / 4) * (c / 8);
+      const int grid = rdb::ops::grid_for(strips);
+      cudaStream_t st = (cudaStream_t)stream;
+      if (prec == RDB_PREC_FP32) {
+        if (k == 5) rdb::ops::dwconv_strip4_kernel<float, 5><<<grid, 256, 0, st>>>(static_cast<const float*>(x), n, h, w, c, ld_in, wt, bias, relu, static_cast<float*>(out), ld_out, c_off);
+        else rdb::ops::dwconv_strip4_kernel<float, 3><<<grid, 256, 0, st>>>(static_cast<const float*>(x), n, h, w, c, ld_in, wt, bias, relu, static_cast<float*>(out), ld_out, c_off);
+      } else {
+        if (k == 5) rdb::ops::dwconv_strip4_kernel<__half, 5><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), n, h, w, c, ld_in, wt, bias, relu, static_cast<__half*>(out), ld_out, c_off);
+        else rdb::ops::dwconv_strip4_kernel<__half, 3><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), n, h, w, c, ld_in, wt, bias, relu, static_cast<__half*>(out), ld_out, c_off);
+      }
+      RDB_LAUNCH_CHECK();
+      return;
+    }
+    if (vec) {
       if (prec == RDB_PREC_FP32)
         rdb::ops::dwconv_vec8_kernel<float><<<rdb::ops::grid_for(total / 8), 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(x), n, h, w, c, ld_in, k, stride, wt, bias, relu, static_cast<float*>(out), oh, ow, ld_out, c_off);
       else

@@ -172,7 +172,7 @@ class _Conv:
 class FormulaEngine:
     """state_dict (reference key layout) -> token ids.  x: [B,1,H,W] float32 (numpy or device tensor), H = W = 384 for -M."""
 
-    def __init__(self, state_dict, device=0, precision=_lib.PREC_FP32, arch=ARCH_M, max_new_tokens=None, sync_every=8, use_graph=True):
+    def __init__(self, state_dict, device=0, precision=_lib.PREC_FP32, arch=ARCH_M, max_new_tokens=None, sync_every=8, use_graph=True, implicit_conv=True):
         import torch
         self.lib = _lib.load()
         if self.lib.rdb_device_count() <= int(device):
@@ -183,6 +183,7 @@ class FormulaEngine:
         self.max_new = int(max_new_tokens if max_new_tokens is not None else arch["max_new_tokens"])
         self.sync_every = sync_every
         self.use_graph = use_graph
+        self.implicit_conv = implicit_conv       # fp16: dense k x k convs through rdb_op_conv_tc instead of im2col + GEMM
         self._dec = {}
         self.launches = 0
         self.adt = torch.float16 if self.prec == _lib.PREC_FP16 else torch.float32
@@ -287,6 +288,13 @@ class FormulaEngine:
         M = n * oh * ow
         if k == 1 and stride == 1:
             self._gemm(prec, x_ptr, ld, M, cv.cin, W, cv.cout, cv.b, act, res, ldr, out_ptr, ldc, c_off)
+            return oh, ow
+        if prec == _lib.PREC_FP16 and self.implicit_conv and cv.cin % 8 == 0:
+            # tcgen05 implicit GEMM: the taps are TMA boxes of the NHWC input (zero fill = padding), no im2col buffer
+            self.launches += 1
+            _lib.check_op(self.lib.rdb_op_conv_tc(self.device, x_ptr, n, h, w, cv.cin, ld, _lib.ptr(W), cv.cout, _lib.ptr(cv.b), act, k, k, stride, stride,
+                                                  pt, pt, out_ptr, oh, ow, ldc, c_off, self._st()))
+            assert res is None
             return oh, ow
         K = k * k * cv.cin
         col = self.torch.empty((M, K), dtype=self.torch.float16 if prec == _lib.PREC_FP16 else self.torch.float32, device=self.dev)
