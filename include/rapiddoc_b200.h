@@ -196,11 +196,9 @@ const char* rdb_ops_last_error(void);
 /* out[M, c_off : c_off+N] (row pitch ldc) = act(A[M,K] (pitch lda) * W[N,K]^T + bias) (+ res [M,N] pitch ldr): every conv1x1 /
  * nn.Linear, and every dense k x k conv after rdb_op_im2col.  W fp32 (prec 0) or fp16 (prec 1); bias fp32.
  * fp32 with M <= 32 rows (one decode step of a batch) runs a weight-streaming kernel; there out_step (device counter, may be
- * NULL) shifts the output by *out_step * out_step_stride elements — the k / v projections append to their KV-cache row — and
- * ln_gamma / ln_beta (may be NULL; K <= 512) layer-normalise the rows of A first (pre-LN decoder: no separate LayerNorm launch). */
+ * NULL) shifts the output by *out_step * out_step_stride elements — the k / v projections append to their KV-cache row. */
 int rdb_op_gemm(int device, int prec, const void* A, int lda, long long M, int K, const void* W, int N, const float* bias, int act,
-                const void* res, int ldr, void* out, int ldc, int c_off, void* stream, const int32_t* out_step, long long out_step_stride,
-                const float* ln_gamma, const float* ln_beta, float ln_eps);
+                const void* res, int ldr, void* out, int ldc, int c_off, void* stream, const int32_t* out_step, long long out_step_stride);
 /* dense kh x kw conv as a tcgen05 IMPLICIT GEMM (fp16): x [n,h,w,c] with pixel pitch ld (a channel slice of a wider buffer is
  * fine) read through a 4-D TMA map — padding = TMA out-of-bounds zero fill, stride = element strides, no im2col buffer;
  * wt [cout][kh][kw][c] fp16; out channel slice (ldc, c_off) = act(conv + bias).  ConvBNAct of PPHGNetV2 (rec_pphgnetv2.py:858-913). */

@@ -42,7 +42,7 @@ SYMBOLS = {
     "rdb_layout_containment": (_i, [_i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "rdb_argmax_rows": (_i, [_i, _vp, C.c_longlong, _i, _vp, _vp, _vp]),
     "rdb_ops_last_error": (C.c_char_p, []),
-    "rdb_op_gemm": (_i, [_i, _i, _vp, _i, C.c_longlong, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, C.c_longlong, _vp, _vp, _f]),
+    "rdb_op_gemm": (_i, [_i, _i, _vp, _i, C.c_longlong, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, C.c_longlong]),
     "rdb_op_conv_tc": (_i, [_i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),
     "rdb_op_im2col": (_i, [_i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "rdb_op_dwconv": (_i, [_i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),

@@ -237,91 +237,43 @@ __global__ void attn_decode_kernel(const float* __restrict__ q, const float* __r
   sum = 0.f;
   for (int i = 0; i < (blockDim.x + 31) / 32; ++i) sum += red[i];
   const float inv = 1.f / sum;
-  // value pass: thread (d, part) sums every (blockDim / HD)-th key, the parts are folded through shared memory
-  __shared__ float part[128];
-  const int parts = blockDim.x / HD;
-  if (parts >= 2 && HD <= 64) {
-    const int d = threadIdx.x % HD, pi = threadIdx.x / HD;
+  for (int d = threadIdx.x; d < HD; d += blockDim.x) {
     float acc = 0.f;
-    if (pi < parts)
-      for (int t = pi; t < T; t += parts) acc = fmaf(sc[t], vp[(long long)t * D + d], acc);
-    part[threadIdx.x] = acc;
-    __syncthreads();
-    if (threadIdx.x < HD) {
-      float tot = 0.f;
-      for (int q = 0; q < parts; ++q) tot += part[q * HD + threadIdx.x];
-      out[(long long)b * D + h * HD + threadIdx.x] = tot * inv;
-    }
-  } else {
-    for (int d = threadIdx.x; d < HD; d += blockDim.x) {
-      float acc = 0.f;
-      for (int t = 0; t < T; ++t) acc = fmaf(sc[t], vp[(long long)t * D + d], acc);
-      out[(long long)b * D + h * HD + d] = acc * inv;
-    }
+    for (int t = 0; t < T; ++t) acc = fmaf(sc[t], vp[(long long)t * D + d], acc);
+    out[(long long)b * D + h * HD + d] = acc * inv;
   }
 }
 
-// out[m, n] = act(LN?(A)[m,:] . W[n,:] + bias[n]) (+ res[m,n]) for M <= 32 rows (one decode step of the whole batch): a GEMM
-// this thin is a weight-streaming problem (HBM-bound, 4 B per MAC per 32 rows).  Each warp owns 2 output columns and reads
-// their two weight rows exactly once with 128-bit loads; the activation rows sit in shared memory in chunks of KC <= 512
-// columns loaded with one burst of independent 128-bit loads (one memory latency per chunk instead of one per 128 columns).
-// ln_g / ln_b != null (K <= KC): the rows are layer-normalised in shared memory first (pre-LN decoder: the LayerNorm
-// launches in front of q/k/v, fc1 and the lm head disappear; every block normalises its own copy of the 32 x K tile).
-// out_step: optional device counter; output rows are written at out + *out_step * out_step_stride (KV-cache append).
-constexpr int SK_KC = 512;
+// out[m, n] = act(A[m,:] . W[n,:] + bias[n]) (+ res[m,n]) for M <= 32 rows (one decode step of the whole batch): a GEMM this
+// thin is a weight-streaming problem (HBM-bound, 4 B/MAC/32 rows), so each warp owns 2 output columns, reads their two weight
+// rows exactly once with 128-bit loads, and the 32 activation rows of the current 128-wide K chunk sit in shared memory.
+// out_step: optional device counter; the output rows are then written at out + *out_step * out_step_stride (KV-cache append).
 template <int ACT>
 __global__ void __launch_bounds__(128) skinny_gemm_kernel(const float* __restrict__ A, int lda, int M, int K, const float* __restrict__ W, int N,
                                                           const float* __restrict__ bias, const float* __restrict__ res, int ldr, float* __restrict__ out,
-                                                          int ldc, const int* __restrict__ out_step, long long out_step_stride,
-                                                          const float* __restrict__ ln_g, const float* __restrict__ ln_b, float ln_eps) {
-  extern __shared__ float4 As[];           // [32][kc / 4]
+                                                          int ldc, const int* __restrict__ out_step, long long out_step_stride) {
+  __shared__ float4 As[32][32];            // [row][k4] of the current chunk (128 k)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = (blockIdx.x * 4 + warp) * 2;
   float acc0[32], acc1[32];
 #pragma unroll
   for (int m = 0; m < 32; ++m) { acc0[m] = 0.f; acc1[m] = 0.f; }
   const bool v0 = n0 < N, v1 = n0 + 1 < N;
-  for (int k0 = 0; k0 < K; k0 += SK_KC) {
-    const int kc = K - k0 < SK_KC ? K - k0 : SK_KC, kc4 = kc / 4;
+  for (int k0 = 0; k0 < K; k0 += 128) {
     __syncthreads();
-    for (int i = threadIdx.x; i < 32 * kc4; i += 128) {
-      const int m = i / kc4, k4 = i - m * kc4;
-      As[m * kc4 + k4] = m < M ? *reinterpret_cast<const float4*>(A + (long long)m * lda + k0 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = threadIdx.x; i < 32 * 32; i += 128) {
+      const int m = i >> 5, k4 = i & 31;
+      As[m][k4] = (m < M && k0 + k4 * 4 < K) ? *reinterpret_cast<const float4*>(A + (long long)m * lda + k0 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
-    if (ln_g != nullptr) {                 // LayerNorm of the rows (host guarantees K <= SK_KC): warp w takes rows w, w+4, ...
-      for (int m = warp; m < M; m += 4) {
-        float sum = 0.f;
-        for (int k4 = lane; k4 < kc4; k4 += 32) { const float4 a = As[m * kc4 + k4]; sum += a.x + a.y + a.z + a.w; }
-        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        const float mean = sum / kc;
-        float var = 0.f;
-        for (int k4 = lane; k4 < kc4; k4 += 32) {
-          const float4 a = As[m * kc4 + k4];
-          const float d0 = a.x - mean, d1 = a.y - mean, d2 = a.z - mean, d3 = a.w - mean;
-          var += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
-        }
-        for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
-        const float rstd = rsqrtf(var / kc + ln_eps);
-        for (int k4 = lane; k4 < kc4; k4 += 32) {
-          float4 a = As[m * kc4 + k4];
-          const float4 g = *reinterpret_cast<const float4*>(ln_g + k4 * 4), bb = *reinterpret_cast<const float4*>(ln_b + k4 * 4);
-          a.x = (a.x - mean) * rstd * g.x + bb.x; a.y = (a.y - mean) * rstd * g.y + bb.y;
-          a.z = (a.z - mean) * rstd * g.z + bb.z; a.w = (a.w - mean) * rstd * g.w + bb.w;
-          As[m * kc4 + k4] = a;
-        }
-      }
-      __syncthreads();
-    }
-    for (int k4 = lane; k4 < kc4; k4 += 32) {
-      const float4 w0 = v0 ? *reinterpret_cast<const float4*>(W + (long long)n0 * K + k0 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 w1 = v1 ? *reinterpret_cast<const float4*>(W + (long long)(n0 + 1) * K + k0 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool kin = k0 + lane * 4 < K;         // K % 4 == 0: a float4 is either fully inside or fully outside
+    const float4 w0 = (v0 && kin) ? *reinterpret_cast<const float4*>(W + (long long)n0 * K + k0 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 w1 = (v1 && kin) ? *reinterpret_cast<const float4*>(W + (long long)(n0 + 1) * K + k0 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int m = 0; m < 32; ++m) {
-        const float4 a = As[m * kc4 + k4];
-        acc0[m] = fmaf(a.x, w0.x, fmaf(a.y, w0.y, fmaf(a.z, w0.z, fmaf(a.w, w0.w, acc0[m]))));
-        acc1[m] = fmaf(a.x, w1.x, fmaf(a.y, w1.y, fmaf(a.z, w1.z, fmaf(a.w, w1.w, acc1[m]))));
-      }
+    for (int m = 0; m < 32; ++m) {
+      const float4 a = As[m][lane];
+      acc0[m] = fmaf(a.x, w0.x, fmaf(a.y, w0.y, fmaf(a.z, w0.z, fmaf(a.w, w0.w, acc0[m]))));
+      acc1[m] = fmaf(a.x, w1.x, fmaf(a.y, w1.y, fmaf(a.z, w1.z, fmaf(a.w, w1.w, acc1[m]))));
     }
   }
   // lane m ends up with the totals of row m: butterfly over the 32 rows
@@ -404,36 +356,25 @@ extern "C" {
 const char* rdb_ops_last_error(void) { return g_ops_err.c_str(); }
 
 int rdb_op_gemm(int device, int prec, const void* A, int lda, long long M, int K, const void* W, int N, const float* bias, int act, const void* res,
-                int ldr, void* out, int ldc, int c_off, void* stream, const int32_t* out_step, long long out_step_stride, const float* ln_g, const float* ln_b,
-                float ln_eps) {
+                int ldr, void* out, int ldc, int c_off, void* stream, const int32_t* out_step, long long out_step_stride) {
   return op_guard([&] {
     RDB_CHECK(A && W && out && M > 0 && K > 0 && N > 0, "gemm: bad argument");
     rdb::DeviceGuard g(device);
     cudaStream_t st = (cudaStream_t)stream;
     if (prec == RDB_PREC_FP32) {
       RDB_CHECK(K % 4 == 0 && lda % 4 == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "gemm fp32: K and lda must be multiples of 4, A and W 16-byte aligned (vector loads)");
-      if (M <= 32 && K % 4 == 0 && (act == rdb::ACT_NONE || act == rdb::ACT_GELU || act == rdb::ACT_RELU)) {   // decode step: weight-streaming kernel
+      if (M <= 32 && (act == rdb::ACT_NONE || act == rdb::ACT_GELU || act == rdb::ACT_RELU)) {   // decode step: weight-streaming kernel
         const float* Af = static_cast<const float*>(A);
         const float* Wf = static_cast<const float*>(W);
         const float* Rf = static_cast<const float*>(res);
         float* Of = static_cast<float*>(out) + c_off;
-        RDB_CHECK(ln_g == nullptr || K <= rdb::ops::SK_KC, "gemm: fused LayerNorm needs K <= 512");
         const int grid = (N + 7) / 8;
-        const size_t sm = (size_t)32 * (K < rdb::ops::SK_KC ? K : rdb::ops::SK_KC) * sizeof(float);
-        static bool attr[rdb::kMaxDevices] = {};
-        if (rdb::first_on_device(attr)) {
-          RDB_CUDA(cudaFuncSetAttribute(rdb::ops::skinny_gemm_kernel<rdb::ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * rdb::ops::SK_KC * 4));
-          RDB_CUDA(cudaFuncSetAttribute(rdb::ops::skinny_gemm_kernel<rdb::ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * rdb::ops::SK_KC * 4));
-          RDB_CUDA(cudaFuncSetAttribute(rdb::ops::skinny_gemm_kernel<rdb::ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * rdb::ops::SK_KC * 4));
-        }
-        OpTimer tm("skinny_gemm[M=" + std::to_string(M) + ",K=" + std::to_string(K) + ",N=" + std::to_string(N) + (ln_g ? ",ln" : "") + "]", st);
-        if (act == rdb::ACT_GELU) rdb::ops::skinny_gemm_kernel<rdb::ACT_GELU><<<grid, 128, sm, st>>>(Af, lda, (int)M, K, Wf, N, bias, Rf, ldr, Of, ldc, out_step, out_step_stride, ln_g, ln_b, ln_eps);
-        else if (act == rdb::ACT_RELU) rdb::ops::skinny_gemm_kernel<rdb::ACT_RELU><<<grid, 128, sm, st>>>(Af, lda, (int)M, K, Wf, N, bias, Rf, ldr, Of, ldc, out_step, out_step_stride, ln_g, ln_b, ln_eps);
-        else rdb::ops::skinny_gemm_kernel<rdb::ACT_NONE><<<grid, 128, sm, st>>>(Af, lda, (int)M, K, Wf, N, bias, Rf, ldr, Of, ldc, out_step, out_step_stride, ln_g, ln_b, ln_eps);
+        if (act == rdb::ACT_GELU) rdb::ops::skinny_gemm_kernel<rdb::ACT_GELU><<<grid, 128, 0, st>>>(Af, lda, (int)M, K, Wf, N, bias, Rf, ldr, Of, ldc, out_step, out_step_stride);
+        else if (act == rdb::ACT_RELU) rdb::ops::skinny_gemm_kernel<rdb::ACT_RELU><<<grid, 128, 0, st>>>(Af, lda, (int)M, K, Wf, N, bias, Rf, ldr, Of, ldc, out_step, out_step_stride);
+        else rdb::ops::skinny_gemm_kernel<rdb::ACT_NONE><<<grid, 128, 0, st>>>(Af, lda, (int)M, K, Wf, N, bias, Rf, ldr, Of, ldc, out_step, out_step_stride);
         RDB_LAUNCH_CHECK();
         return;
       }
-      RDB_CHECK(ln_g == nullptr, "gemm: fused LayerNorm is only supported on the decode (M <= 32 rows) path");
       RDB_CHECK(out_step == nullptr, "gemm: out_step is only supported on the decode (M <= 32 rows) path");
       rdb::GemmArgs a{};
       a.A = A; a.lda = lda; a.W = static_cast<const float*>(W); a.bias = bias; a.res = res; a.ldr = ldr; a.out = out; a.ldc = ldc; a.c_off = c_off;
@@ -442,7 +383,7 @@ int rdb_op_gemm(int device, int prec, const void* A, int lda, long long M, int K
       OpTimer tm("gemm_simt_op[M=" + std::to_string(M) + ",K=" + std::to_string(K) + ",N=" + std::to_string(N) + "]", st);
       rdb::launch_gemm_simt<float, float>(a, st);
     } else {
-      RDB_CHECK(out_step == nullptr && ln_g == nullptr, "gemm fp16: out_step / fused LayerNorm not supported");
+      RDB_CHECK(out_step == nullptr, "gemm fp16: out_step not supported");
       RDB_CHECK(K % 8 == 0 && lda % 8 == 0 && c_off % 8 == 0 && ldc % 8 == 0, "gemm fp16: K, lda, ldc, c_off must be multiples of 8 (16-byte TMA rows)");
       rdb::Ctx cx;
       cx.st = st; cx.pool = &ops_pool(device); cx.precision = 1; cx.use_tc = true; cx.num_sms = sm_count(device);
@@ -558,7 +499,6 @@ int rdb_op_layernorm(int device, const float* x, long long rows, int c, const fl
   return op_guard([&] {
     RDB_CHECK(x && out && gamma && beta && rows > 0, "layernorm: bad argument");
     rdb::DeviceGuard g(device);
-    OpTimer tm("layernorm_op", (cudaStream_t)stream);
     rdb::layernorm_kernel<float><<<rdb::cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, rows, c, gamma, beta, eps, nullptr, out);
     RDB_LAUNCH_CHECK();
   });
@@ -584,7 +524,6 @@ int rdb_op_attn_decode(int device, const float* q, const float* k, const float* 
     auto kern = rdb::ops::attn_decode_kernel;
     const size_t sm = (size_t)t * sizeof(float);
     if (sm > 48 * 1024) RDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    OpTimer tm(step ? "attn_decode_self" : "attn_decode_cross", (cudaStream_t)stream);
     kern<<<batch * heads, 128, sm, (cudaStream_t)stream>>>(q, k, v, t, t_cap, heads, head_dim, out, step);
     RDB_LAUNCH_CHECK();
   });

@@ -267,10 +267,10 @@ class FormulaEngine:
     def _st(self):
         return self.torch.cuda.current_stream(self.dev).cuda_stream or None
 
-    def _gemm(self, prec, A, lda, M, K, W, N, bias, act, res, ldr, out, ldc, c_off, out_step=None, out_step_stride=0, ln=None):
+    def _gemm(self, prec, A, lda, M, K, W, N, bias, act, res, ldr, out, ldc, c_off, out_step=None, out_step_stride=0):
         self.launches += 1
         _lib.check_op(self.lib.rdb_op_gemm(self.device, prec, A, lda, M, K, _lib.ptr(W), N, _lib.ptr(bias), act, res, ldr, out, ldc, c_off, self._st(),
-                                           out_step, out_step_stride, _lib.ptr(ln[0]) if ln else None, _lib.ptr(ln[1]) if ln else None, 1e-5))
+                                           out_step, out_step_stride))
 
     def _esz(self):
         return 2 if self.prec == _lib.PREC_FP16 else 4
@@ -445,21 +445,25 @@ class FormulaEngine:
         _lib.check_op(lib.rdb_op_embed(dv, st["toks"].data_ptr(), B, d, self.tok.data_ptr(), math.sqrt(d), self.pos.data_ptr(), 0, x.data_ptr(), stm, sp))
         _lib.check_op(lib.rdb_op_layernorm(dv, x.data_ptr(), B, d, self.ln_emb[0].data_ptr(), self.ln_emb[1].data_ptr(), 1e-5, h.data_ptr(), stm))
         for li, L in enumerate(self.layers):
-            # self attention (pre-LN fused into the projections' A staging); k / v append to cache row `step`
-            self._gemm(f32, h.data_ptr(), d, B, d, L["sq"][0], d, L["sq"][1], ACT_NONE, None, 0, q.data_ptr(), d, 0, ln=L["sln"])
-            self._gemm(f32, h.data_ptr(), d, B, d, L["sk"][0], d, L["sk"][1], ACT_NONE, None, 0, st["kc"][li].data_ptr(), cap * d, 0, sp, d, ln=L["sln"])
-            self._gemm(f32, h.data_ptr(), d, B, d, L["sv"][0], d, L["sv"][1], ACT_NONE, None, 0, st["vc"][li].data_ptr(), cap * d, 0, sp, d, ln=L["sln"])
+            # self attention (pre-LN); k / v append to cache row `step`
+            _lib.check_op(lib.rdb_op_layernorm(dv, h.data_ptr(), B, d, L["sln"][0].data_ptr(), L["sln"][1].data_ptr(), 1e-5, x.data_ptr(), stm))
+            self._gemm(f32, x.data_ptr(), d, B, d, L["sq"][0], d, L["sq"][1], ACT_NONE, None, 0, q.data_ptr(), d, 0)
+            self._gemm(f32, x.data_ptr(), d, B, d, L["sk"][0], d, L["sk"][1], ACT_NONE, None, 0, st["kc"][li].data_ptr(), cap * d, 0, sp, d)
+            self._gemm(f32, x.data_ptr(), d, B, d, L["sv"][0], d, L["sv"][1], ACT_NONE, None, 0, st["vc"][li].data_ptr(), cap * d, 0, sp, d)
             _lib.check_op(lib.rdb_op_attn_decode(dv, q.data_ptr(), st["kc"][li].data_ptr(), st["vc"][li].data_ptr(), B, 1, cap, H, hd, att.data_ptr(), stm, sp))
             self._gemm(f32, att.data_ptr(), d, B, d, L["so"][0], d, L["so"][1], ACT_NONE, h.data_ptr(), d, r1.data_ptr(), d, 0)
             # cross attention over the encoder tokens (K / V computed once per batch)
-            self._gemm(f32, r1.data_ptr(), d, B, d, L["cq"][0], d, L["cq"][1], ACT_NONE, None, 0, q.data_ptr(), d, 0, ln=L["cln"])
+            _lib.check_op(lib.rdb_op_layernorm(dv, r1.data_ptr(), B, d, L["cln"][0].data_ptr(), L["cln"][1].data_ptr(), 1e-5, x.data_ptr(), stm))
+            self._gemm(f32, x.data_ptr(), d, B, d, L["cq"][0], d, L["cq"][1], ACT_NONE, None, 0, q.data_ptr(), d, 0)
             _lib.check_op(lib.rdb_op_attn_decode(dv, q.data_ptr(), st["cross"][li][0].data_ptr(), st["cross"][li][1].data_ptr(), B, S, S, H, hd, att.data_ptr(), stm, None))
             self._gemm(f32, att.data_ptr(), d, B, d, L["co"][0], d, L["co"][1], ACT_NONE, r1.data_ptr(), d, h.data_ptr(), d, 0)
             # feed forward
-            self._gemm(f32, h.data_ptr(), d, B, d, L["fc1"][0], a["ffn"], L["fc1"][1], ACT_GELU, None, 0, f.data_ptr(), a["ffn"], 0, ln=L["ln3"])
+            _lib.check_op(lib.rdb_op_layernorm(dv, h.data_ptr(), B, d, L["ln3"][0].data_ptr(), L["ln3"][1].data_ptr(), 1e-5, x.data_ptr(), stm))
+            self._gemm(f32, x.data_ptr(), d, B, d, L["fc1"][0], a["ffn"], L["fc1"][1], ACT_GELU, None, 0, f.data_ptr(), a["ffn"], 0)
             self._gemm(f32, f.data_ptr(), a["ffn"], B, a["ffn"], L["fc2"][0], d, L["fc2"][1], ACT_NONE, h.data_ptr(), d, r1.data_ptr(), d, 0)
             h, r1 = r1, h
-        self._gemm(f32, h.data_ptr(), d, B, d, self.lm_head, V, None, ACT_NONE, None, 0, st["logits"].data_ptr(), V, 0, ln=self.ln_out)
+        _lib.check_op(lib.rdb_op_layernorm(dv, h.data_ptr(), B, d, self.ln_out[0].data_ptr(), self.ln_out[1].data_ptr(), 1e-5, x.data_ptr(), stm))
+        self._gemm(f32, x.data_ptr(), d, B, d, self.lm_head, V, None, ACT_NONE, None, 0, st["logits"].data_ptr(), V, 0)
         _lib.check(lib.rdb_argmax_rows(dv, st["logits"].data_ptr(), B, V, st["arg"].data_ptr(), st["val"].data_ptr(), stm))
         _lib.check_op(lib.rdb_op_greedy_step(dv, st["arg"].data_ptr(), B, 0, a["eos"], a["pad"], st["toks"].data_ptr(), st["unfinished"].data_ptr(),
                                              st["has_eos"].data_ptr(), st["done"].data_ptr(), stm, sp, a["forced_eos_len"]))
@@ -484,7 +488,7 @@ class FormulaEngine:
             st["done"].zero_()
             st["step"].zero_()
             steps = 0
-            per_step = 12 * len(self.layers) + 5
+            per_step = 15 * len(self.layers) + 5
             while steps < self.max_new:
                 if st["graph"] is not None:
                     st["graph"].replay()
