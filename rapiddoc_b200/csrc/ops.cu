@@ -237,10 +237,27 @@ __global__ void attn_decode_kernel(const float* __restrict__ q, const float* __r
   sum = 0.f;
   for (int i = 0; i < (blockDim.x + 31) / 32; ++i) sum += red[i];
   const float inv = 1.f / sum;
-  for (int d = threadIdx.x; d < HD; d += blockDim.x) {
+  // value pass: thread (d, part) sums every (blockDim / HD)-th key, the parts are folded through shared memory
+  __shared__ float part[128];
+  const int parts = blockDim.x / HD;
+  if (parts >= 2 && HD <= 64) {
+    const int d = threadIdx.x % HD, pi = threadIdx.x / HD;
     float acc = 0.f;
-    for (int t = 0; t < T; ++t) acc = fmaf(sc[t], vp[(long long)t * D + d], acc);
-    out[(long long)b * D + h * HD + d] = acc * inv;
+    if (pi < parts)
+      for (int t = pi; t < T; t += parts) acc = fmaf(sc[t], vp[(long long)t * D + d], acc);
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < HD) {
+      float tot = 0.f;
+      for (int q = 0; q < parts; ++q) tot += part[q * HD + threadIdx.x];
+      out[(long long)b * D + h * HD + threadIdx.x] = tot * inv;
+    }
+  } else {
+    for (int d = threadIdx.x; d < HD; d += blockDim.x) {
+      float acc = 0.f;
+      for (int t = 0; t < T; ++t) acc = fmaf(sc[t], vp[(long long)t * D + d], acc);
+      out[(long long)b * D + h * HD + d] = acc * inv;
+    }
   }
 }
 
@@ -369,6 +386,7 @@ int rdb_op_gemm(int device, int prec, const void* A, int lda, long long M, int K
         const float* Rf = static_cast<const float*>(res);
         float* Of = static_cast<float*>(out) + c_off;
         const int grid = (N + 7) / 8;
+        OpTimer tm("skinny_gemm[M=" + std::to_string(M) + ",K=" + std::to_string(K) + ",N=" + std::to_string(N) + "]", st);
         if (act == rdb::ACT_GELU) rdb::ops::skinny_gemm_kernel<rdb::ACT_GELU><<<grid, 128, 0, st>>>(Af, lda, (int)M, K, Wf, N, bias, Rf, ldr, Of, ldc, out_step, out_step_stride);
         else if (act == rdb::ACT_RELU) rdb::ops::skinny_gemm_kernel<rdb::ACT_RELU><<<grid, 128, 0, st>>>(Af, lda, (int)M, K, Wf, N, bias, Rf, ldr, Of, ldc, out_step, out_step_stride);
         else rdb::ops::skinny_gemm_kernel<rdb::ACT_NONE><<<grid, 128, 0, st>>>(Af, lda, (int)M, K, Wf, N, bias, Rf, ldr, Of, ldc, out_step, out_step_stride);
@@ -499,6 +517,7 @@ int rdb_op_layernorm(int device, const float* x, long long rows, int c, const fl
   return op_guard([&] {
     RDB_CHECK(x && out && gamma && beta && rows > 0, "layernorm: bad argument");
     rdb::DeviceGuard g(device);
+    OpTimer tm("layernorm_op", (cudaStream_t)stream);
     rdb::layernorm_kernel<float><<<rdb::cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, rows, c, gamma, beta, eps, nullptr, out);
     RDB_LAUNCH_CHECK();
   });
@@ -524,6 +543,7 @@ int rdb_op_attn_decode(int device, const float* q, const float* k, const float* 
     auto kern = rdb::ops::attn_decode_kernel;
     const size_t sm = (size_t)t * sizeof(float);
     if (sm > 48 * 1024) RDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    OpTimer tm(step ? "attn_decode_self" : "attn_decode_cross", (cudaStream_t)stream);
     kern<<<batch * heads, 128, sm, (cudaStream_t)stream>>>(q, k, v, t, t_cap, heads, head_dim, out, step);
     RDB_LAUNCH_CHECK();
   });
