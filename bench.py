@@ -315,7 +315,8 @@ def run_pipeline(args, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from rapiddoc_b200 import _lib, PREC_FP16, PREC_FP32, synth, weights as W
-    from rapiddoc_b200.parallel import broadcast_blob
+    from rapiddoc_b200.parallel import broadcast_blob, pin_rank_to_cores
+    cores = pin_rank_to_cores(local, world) if world > 1 else None
     prec = PREC_FP16 if args.precision == "fp16" else PREC_FP32
     esz = 2 if prec == PREC_FP16 else 4
     blobs = (broadcast_blob(W.det_blob() if rank == 0 else None, local), broadcast_blob(W.rec_blob() if rank == 0 else None, local))
@@ -449,7 +450,8 @@ def run_pipeline(args, wl):
                            "rec_batch_num": args.rec_batch, "text_lines_per_step": int(lines_per_step),
                            "issue": "step by step (ocr_pages)" if args.no_stream else "streaming API (ocr_pages_stream): detection stage of step k+1 overlaps recognition of step k; every step's results are materialised on the host inside the timed region", "crops_per_step": crops_per_step,
                            "l2": f"inputs {host.numel() / 1e6:.0f} MB + activations per step exceed the 126 MB L2 (no explicit flush)",
-                           "parallelism": f"page-parallel replicas x{world}, NCCL weight broadcast at init only"},
+                           "parallelism": f"page-parallel replicas x{world}, NCCL weight broadcast at init only",
+                           "host_cores_per_rank": len(cores) if cores else os.cpu_count()},
                 "clocks": clocks, "e2e": {"value": e2e, "unit": wl["unit"], "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "fp32_exact": fp32, "secondary": secondary,
                 "skipped": SKIPPED_CONFIGS}

@@ -39,11 +39,20 @@ class timed:
         TIMES[self.name] = TIMES.get(self.name, 0.0) + time.perf_counter() - self.t
 
 
+def host_threads():
+    """Host threads this process may use: its CPU affinity (one process per GPU under torchrun gets its share of the box),
+    not the machine's core count."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 8
+
+
 def pool():
     """Process-wide worker pool for the per-page OpenCV calls."""
     global _POOL
     if _POOL is None:
-        _POOL = ThreadPoolExecutor(max_workers=max(2, min(32, (os.cpu_count() or 8))))
+        _POOL = ThreadPoolExecutor(max_workers=max(2, min(32, host_threads())))
     return _POOL
 
 
@@ -118,7 +127,7 @@ def find_contours_window(bitmaps, max_threads=0):
     bitmaps = np.ascontiguousarray(bitmaps, np.uint8)
     n, h, w = bitmaps.shape
     hnd = C.c_void_p()
-    _lib.check(lib.rdb_contours_trace(_lib.ptr(bitmaps), n, h, w, int(max_threads), C.byref(hnd)))
+    _lib.check(lib.rdb_contours_trace(_lib.ptr(bitmaps), n, h, w, int(max_threads) if max_threads > 0 else host_threads(), C.byref(hnd)))
     try:
         per_page = np.zeros(n, np.int32)
         tc, tp = C.c_int64(), C.c_int64()

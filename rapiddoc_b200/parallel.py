@@ -58,3 +58,21 @@ def gather_objects(obj):
     out = [None] * dist.get_world_size()
     dist.all_gather_object(out, obj)
     return out
+
+
+def pin_rank_to_cores(local_rank: int, local_world: int):
+    """One process per GPU on one box: give every rank a contiguous, equal share of the cores this job may use (core numbering
+    is node-contiguous on the usual 2-socket hosts, so ranks 0..N/2-1 land on NUMA node 0 with GPUs 0..N/2-1).  The host half
+    of the pipeline (contours, Clipper, staging copies) then sizes its thread pools from the affinity mask instead of
+    oversubscribing the whole machine N times.  Returns the core list (or None where affinity is not supported)."""
+    import os
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
+    per = len(cores) // max(1, local_world)
+    if per < 1:
+        return cores
+    mine = cores[local_rank * per: (local_rank + 1) * per]
+    os.sched_setaffinity(0, mine)
+    return mine

@@ -50,3 +50,22 @@ def test_gloo_world2_broadcast_and_gather():
     [p.join(30) for p in ps]
     assert out[0][1] == out[1][1] > 0 and out[0][2] == out[1][2] == b"RDW1"
     assert out[0][3] == out[1][3] == 11 and out[0][4] == list(range(11))
+
+
+def test_pin_rank_to_cores_partitions_the_affinity_mask():
+    import os
+    from rapiddoc_b200.parallel import pin_rank_to_cores
+    if not hasattr(os, "sched_getaffinity"):
+        return
+    before = sorted(os.sched_getaffinity(0))
+    try:
+        shares = []
+        for r in range(2):
+            os.sched_setaffinity(0, before)
+            shares.append(pin_rank_to_cores(r, 2))
+        if len(before) >= 2:
+            assert not set(shares[0]) & set(shares[1]) and len(shares[0]) == len(shares[1]) == len(before) // 2
+            from rapiddoc_b200 import dbpost
+            assert dbpost.host_threads() == len(shares[1])
+    finally:
+        os.sched_setaffinity(0, before)
