@@ -75,16 +75,54 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self._stop = index, [], None, None, False
 
     def start(self):
+        """In-process NVML polling (one cheap query every 25 ms; a looping `nvidia-smi -lms` process costs the host-bound pipeline
+        real CPU time and driver-lock contention); `nvidia-smi` is the fallback when pynvml cannot initialise."""
+        if os.environ.get("RDB_BENCH_CLOCKS", "nvml") == "nvml":
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                phys = self.index
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                    phys = int(vis.split(",")[self.index])
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+                self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+                pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+                self.nvml = pynvml
+                self.t = threading.Thread(target=self._poll, daemon=True)
+                self.t.start()
+                return
+            except Exception:
+                self.nvml = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv = self.nvml
+        bits = [(0x8, 2), (0x40, 3), (0x20, 4), (0x4, 5)]        # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap (NVML reason masks)
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                row = [str(sm), str(self.max_sm), "Not Active", "Not Active", "Not Active", "Not Active"]
+                for bit, col in bits:
+                    if mask & bit:
+                        row[col] = "Active"
+                self.rows.append((time.time(), row))
+            except Exception:
+                pass
+            time.sleep(0.025)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -93,15 +131,19 @@ class ClockSampler:
     def wait_first(self, timeout=5.0):
         """nvidia-smi needs ~100+ ms to start: block until the first sample is in."""
         t0 = time.time()
-        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+        while (self.proc is not None or self.nvml is not None) and not self.rows and time.time() - t0 < timeout:
             time.sleep(0.01)
 
     def stop(self, t_begin=None, t_end=None):
         """Summarise the samples taken inside [t_begin, t_end] (the timed region)."""
-        if self.proc is None:
+        if self.proc is None and self.nvml is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.05)
-        self.proc.terminate()
+        if self.nvml is not None:
+            self._stop = True
+            self.t.join(timeout=1.0)
+        else:
+            self.proc.terminate()
         inside = [r for t, r in self.rows if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end + 0.03)]
         self.rows = inside if inside else [r for _, r in self.rows[-3:]]
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
@@ -112,7 +154,7 @@ class ClockSampler:
                 if v == "Active":
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------- roofline model

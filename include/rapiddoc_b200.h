@@ -228,6 +228,22 @@ int rdb_op_embed(int device, const int64_t* ids, int batch, int dim, const float
 int rdb_op_attn_decode(int device, const float* q, const float* k, const float* v, int batch, int t, int t_cap, int heads, int head_dim,
                        float* out, void* stream, const int32_t* step /* t = *step + 1 */);
 int rdb_op_add(int device, const float* a, const float* b, float* out, long long n, void* stream);
+/* ---- ops of the small ONNX CNNs RapidDoc ships (rapid_orientation.onnx: RapidOrientation.__call__,
+ * rapid_doc/model/orientation/rapid_orientation/rapid_orientation.py:43-56; pp-ocrv4_mobile_seal_det.onnx), NHWC fp32.
+ * rdb_op_chain applies up to 8 per-element steps in one launch; kinds: 0 x*a+b, 1 x*va[c]+vb[c] (either pointer may be NULL:
+ * folded BatchNormalization / conv bias), 2 Relu, 3 HardSigmoid(alpha=a, beta=b), 4 x*HardSigmoid(x) (HardSwish: a=1/6, b=.5),
+ * 5 Sigmoid.  va / vb are host arrays of n_steps device pointers. */
+int rdb_op_chain(int device, const float* x, long long rows, int c, int ld_in, const int32_t* kinds, const float* a, const float* b,
+                 const float* const* va, const float* const* vb, int n_steps, float* out, int ld_out, int c_off, void* stream);
+int rdb_op_global_avgpool(int device, const float* x, int n, int hw, int c, int ld, float* out /* [n,c] */, void* stream);
+/* squeeze-excite scaling out[n,p,c] = x[n,p,c] * gate[n,c] */
+int rdb_op_mul_gate(int device, const float* x, const float* gate, int n, int hw, int c, int ld_in, float* out, int ld_out, void* stream);
+/* Resize(nearest, asymmetric, floor) by an integer factor, into a channel slice */
+int rdb_op_resize_nearest(int device, const float* x, int n, int h, int w, int c, int ld_in, int scale, float* out, int ld_out, int c_off,
+                          void* stream);
+/* ConvTranspose(kernel = stride = scale) = rdb_op_gemm to [n*h*w, scale*scale*c] (columns dy, dx, c) + this pixel shuffle */
+int rdb_op_depth_to_space(int device, const float* g, int n, int h, int w, int c, int scale, float* out, void* stream);
+int rdb_op_softmax_rows(int device, const float* x, long long rows, int c, float* out, void* stream);
 /* one greedy step of generate_export (rec_ppformulanet_head.py:1118-1160) on the device: next token = argmax (eos when force_eos),
  * finished rows emit pad, a row finishes on eos; *all_done = every row has produced an eos */
 int rdb_op_greedy_step(int device, const int32_t* argmax, int batch, int force_eos, int eos, int pad, int64_t* next, int32_t* unfinished,

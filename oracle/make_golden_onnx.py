@@ -1,0 +1,47 @@
+"""Generates tests/golden/onnx_cases.npz: outputs of OpenCV's DNN importer (cv2.dnn.readNetFromONNX — an implementation
+independent of both oracle/onnx_ref.py and the CUDA executor) on the two ONNX files of weights/, for seeded inputs that the tests
+regenerate.  Run in the build container:  python oracle/make_golden_onnx.py"""
+import os
+import sys
+
+import cv2
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from rapiddoc_b200 import synth                      # noqa: E402
+from oracle import onnx_ref                          # noqa: E402
+
+
+def orientation_inputs():
+    """Four 224x224 network inputs: a synthetic text page in its four rotations, through the reference preprocessing."""
+    page = synth.det_pages(1, 640, 480, seed=11, lines=24)[0]
+    rots = [page, cv2.rotate(page, cv2.ROTATE_90_COUNTERCLOCKWISE), cv2.rotate(page, cv2.ROTATE_180), cv2.rotate(page, cv2.ROTATE_90_CLOCKWISE)]
+    return rots, np.stack([onnx_ref.orientation_preprocess(r) for r in rots])
+
+
+def seal_input(seed=0, size=320):
+    img = synth.seal_image(seed, size)
+    mean = np.array([0.485, 0.456, 0.406], np.float32)
+    std = np.array([0.229, 0.224, 0.225], np.float32)
+    return np.ascontiguousarray(((img.astype(np.float32) / 255.0 - mean) / std).transpose(2, 0, 1)[None], np.float32)
+
+
+def main():
+    out = {}
+    net = cv2.dnn.readNetFromONNX(os.path.join(ROOT, "weights", "rapid_orientation.onnx"))
+    _, xs = orientation_inputs()
+    ys = []
+    for x in xs:                                     # the importer bakes batch 1 into the flatten
+        net.setInput(x[None])
+        ys.append(net.forward().copy())
+    out["orientation_scores"] = np.concatenate(ys)
+    net = cv2.dnn.readNetFromONNX(os.path.join(ROOT, "weights", "pp-ocrv4_mobile_seal_det.onnx"))
+    net.setInput(seal_input())
+    out["seal_prob"] = net.forward().copy()[0, 0].astype(np.float16)      # fp16 storage: the tests compare at 2e-3
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "onnx_cases.npz"), **out)
+    print({k: (v.shape, v.dtype) for k, v in out.items()}, out["orientation_scores"].round(3))
+
+
+if __name__ == "__main__":
+    main()

@@ -52,6 +52,12 @@ SYMBOLS = {
     "rdb_op_embed": (_i, [_i, _vp, _i, _i, _vp, _f, _vp, _i, _vp, _vp, _vp]),
     "rdb_op_attn_decode": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "rdb_op_add": (_i, [_i, _vp, _vp, _vp, C.c_longlong, _vp]),
+    "rdb_op_chain": (_i, [_i, _vp, C.c_longlong, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp]),
+    "rdb_op_global_avgpool": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "rdb_op_mul_gate": (_i, [_i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    "rdb_op_resize_nearest": (_i, [_i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
+    "rdb_op_depth_to_space": (_i, [_i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "rdb_op_softmax_rows": (_i, [_i, _vp, C.c_longlong, _i, _vp, _vp]),
     "rdb_op_greedy_step": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "rdb_contours_trace": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_vp)]),
     "rdb_contours_counts": (_i, [_vp, _vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

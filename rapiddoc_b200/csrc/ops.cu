@@ -339,6 +339,103 @@ __global__ void greedy_step_kernel(const int* __restrict__ arg, int B, int force
   }
 }
 
+// ---- elementwise / reshaping ops of the small ONNX CNNs (orientation classifier, seal detector), NHWC fp32 -------------------
+// one launch applies a short chain of per-element steps: BatchNorm / bias / learnable-affine (scalar or per channel), ReLU,
+// HardSigmoid(alpha, beta), x * HardSigmoid (HardSwish with the graph's own alpha), Sigmoid
+struct ChainStep { int kind; float a, b; const float* va; const float* vb; };
+struct Chain { int n; ChainStep s[8]; };
+enum { CH_AFFINE = 0, CH_AFFINE_VEC = 1, CH_RELU = 2, CH_HSIG = 3, CH_HSWISH = 4, CH_SIGMOID = 5 };
+
+__global__ void chain_kernel(const float* __restrict__ x, long long rows, int C, int ld_in, float* __restrict__ out, int ld_out, int c_off, Chain ch) {
+  const long long total = rows * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C;
+    const int c = (int)(i % C);
+    float v = x[r * ld_in + c];
+    for (int k = 0; k < ch.n; ++k) {
+      const ChainStep& s = ch.s[k];
+      switch (s.kind) {
+        case CH_AFFINE: v = __fadd_rn(__fmul_rn(v, s.a), s.b); break;
+        case CH_AFFINE_VEC: {
+          if (s.va) v = __fmul_rn(v, s.va[c]);
+          if (s.vb) v = __fadd_rn(v, s.vb[c]);
+        } break;
+        case CH_RELU: v = fmaxf(v, 0.f); break;
+        case CH_HSIG: v = fminf(fmaxf(__fadd_rn(__fmul_rn(s.a, v), s.b), 0.f), 1.f); break;
+        case CH_HSWISH: v = __fmul_rn(v, fminf(fmaxf(__fadd_rn(__fmul_rn(s.a, v), s.b), 0.f), 1.f)); break;
+        case CH_SIGMOID: v = 1.f / (1.f + expf(-v)); break;
+      }
+    }
+    out[r * ld_out + c_off + c] = v;
+  }
+}
+
+// GlobalAveragePool: x [n, hw, C] (pitch ld) -> out [n, C]; block (32 channels x 8 row lanes)
+__global__ void global_avgpool_kernel(const float* __restrict__ x, int hw, int C, int ld, float* __restrict__ out) {
+  __shared__ float part[8][33];
+  const int b = blockIdx.x, c = blockIdx.y * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < C)
+    for (int r = threadIdx.y; r < hw; r += 8) acc += x[((long long)b * hw + r) * ld + c];
+  part[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += part[j][threadIdx.x];
+    out[(long long)b * C + c] = s / (float)hw;
+  }
+}
+
+// squeeze-excite scaling: out[n, p, c] = x[n, p, c] * gate[n, c]
+__global__ void mul_gate_kernel(const float* __restrict__ x, const float* __restrict__ gate, long long rows, int rows_per_image, int C, int ld_in,
+                                float* __restrict__ out, int ld_out) {
+  const long long total = rows * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C;
+    const int c = (int)(i % C);
+    out[r * ld_out + c] = x[r * ld_in + c] * gate[(r / rows_per_image) * C + c];
+  }
+}
+
+// Resize(mode nearest, asymmetric, floor) by an integer factor into a channel slice: out[n, oy, ox] = x[n, oy / s, ox / s]
+__global__ void resize_nearest_kernel(const float* __restrict__ x, int n, int H, int W, int C, int ld_in, int s, float* __restrict__ out, int ld_out, int c_off) {
+  const int OH = H * s, OW = W * s;
+  const long long total = (long long)n * OH * OW * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long px = i / C;
+    const int ox = (int)(px % OW), oy = (int)((px / OW) % OH), b = (int)(px / ((long long)OW * OH));
+    out[px * ld_out + c_off + c] = x[((long long)(b * H + oy / s) * W + ox / s) * ld_in + c];
+  }
+}
+
+// ConvTranspose(k = stride = s) after its GEMM: g [n*H*W, s*s*C] with columns (dy, dx, c) -> out [n, s*H, s*W, C]
+__global__ void depth_to_space_kernel(const float* __restrict__ g, int n, int H, int W, int C, int s, float* __restrict__ out) {
+  const int OH = H * s, OW = W * s;
+  const long long total = (long long)n * OH * OW * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long px = i / C;
+    const int ox = (int)(px % OW), oy = (int)((px / OW) % OH), b = (int)(px / ((long long)OW * OH));
+    out[i] = g[((long long)(b * H + oy / s) * W + ox / s) * (s * s * C) + ((oy % s) * s + ox % s) * C + c];
+  }
+}
+
+// Softmax over the last axis, one warp per row
+__global__ void softmax_rows_kernel(const float* __restrict__ x, long long rows, int C, float* __restrict__ out) {
+  const long long r = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (r >= rows) return;
+  float m = -INFINITY;
+  for (int c = lane; c < C; c += 32) m = fmaxf(m, x[r * C + c]);
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += expf(x[r * C + c] - m);
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int c = lane; c < C; c += 32) out[r * C + c] = expf(x[r * C + c] - m) / s;
+}
+
 inline int grid_for(long long total) { long long g = (total + 255) / 256; return (int)(g > 148 * 32 ? 148 * 32 : (g < 1 ? 1 : g)); }
 
 }  // namespace ops
@@ -545,6 +642,73 @@ int rdb_op_attn_decode(int device, const float* q, const float* k, const float* 
     if (sm > 48 * 1024) RDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     OpTimer tm(step ? "attn_decode_self" : "attn_decode_cross", (cudaStream_t)stream);
     kern<<<batch * heads, 128, sm, (cudaStream_t)stream>>>(q, k, v, t, t_cap, heads, head_dim, out, step);
+    RDB_LAUNCH_CHECK();
+  });
+}
+
+int rdb_op_chain(int device, const float* x, long long rows, int c, int ld_in, const int32_t* kinds, const float* a, const float* b,
+                 const float* const* va, const float* const* vb, int n_steps, float* out, int ld_out, int c_off, void* stream) {
+  return op_guard([&] {
+    RDB_CHECK(x && out && rows > 0 && c > 0 && n_steps >= 0 && n_steps <= 8 && (n_steps == 0 || (kinds && a && b)), "chain: bad argument (at most 8 steps)");
+    rdb::DeviceGuard g(device);
+    rdb::ops::Chain ch{};
+    ch.n = n_steps;
+    for (int i = 0; i < n_steps; ++i) {
+      RDB_CHECK(kinds[i] >= rdb::ops::CH_AFFINE && kinds[i] <= rdb::ops::CH_SIGMOID, "chain: unknown step kind");
+      ch.s[i] = rdb::ops::ChainStep{kinds[i], a[i], b[i], va ? va[i] : nullptr, vb ? vb[i] : nullptr};
+    }
+    OpTimer tm("chain_op[n=" + std::to_string(n_steps) + "]", (cudaStream_t)stream);
+    rdb::ops::chain_kernel<<<rdb::ops::grid_for(rows * c), 256, 0, (cudaStream_t)stream>>>(x, rows, c, ld_in, out, ld_out, c_off, ch);
+    RDB_LAUNCH_CHECK();
+  });
+}
+
+int rdb_op_global_avgpool(int device, const float* x, int n, int hw, int c, int ld, float* out, void* stream) {
+  return op_guard([&] {
+    RDB_CHECK(x && out && n > 0 && hw > 0 && c > 0, "global_avgpool: bad argument");
+    rdb::DeviceGuard g(device);
+    OpTimer tm("global_avgpool_op", (cudaStream_t)stream);
+    rdb::ops::global_avgpool_kernel<<<dim3(n, (c + 31) / 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(x, hw, c, ld, out);
+    RDB_LAUNCH_CHECK();
+  });
+}
+
+int rdb_op_mul_gate(int device, const float* x, const float* gate, int n, int hw, int c, int ld_in, float* out, int ld_out, void* stream) {
+  return op_guard([&] {
+    RDB_CHECK(x && gate && out && n > 0 && hw > 0 && c > 0, "mul_gate: bad argument");
+    rdb::DeviceGuard g(device);
+    OpTimer tm("mul_gate_op", (cudaStream_t)stream);
+    rdb::ops::mul_gate_kernel<<<rdb::ops::grid_for((long long)n * hw * c), 256, 0, (cudaStream_t)stream>>>(x, gate, (long long)n * hw, hw, c, ld_in, out, ld_out);
+    RDB_LAUNCH_CHECK();
+  });
+}
+
+int rdb_op_resize_nearest(int device, const float* x, int n, int h, int w, int c, int ld_in, int scale, float* out, int ld_out, int c_off, void* stream) {
+  return op_guard([&] {
+    RDB_CHECK(x && out && n > 0 && h > 0 && w > 0 && c > 0 && scale >= 1, "resize_nearest: bad argument");
+    rdb::DeviceGuard g(device);
+    OpTimer tm("resize_nearest_op", (cudaStream_t)stream);
+    rdb::ops::resize_nearest_kernel<<<rdb::ops::grid_for((long long)n * h * scale * w * scale * c), 256, 0, (cudaStream_t)stream>>>(x, n, h, w, c, ld_in, scale, out, ld_out, c_off);
+    RDB_LAUNCH_CHECK();
+  });
+}
+
+int rdb_op_depth_to_space(int device, const float* g_in, int n, int h, int w, int c, int scale, float* out, void* stream) {
+  return op_guard([&] {
+    RDB_CHECK(g_in && out && n > 0 && h > 0 && w > 0 && c > 0 && scale >= 1, "depth_to_space: bad argument");
+    rdb::DeviceGuard g(device);
+    OpTimer tm("depth_to_space_op", (cudaStream_t)stream);
+    rdb::ops::depth_to_space_kernel<<<rdb::ops::grid_for((long long)n * h * scale * w * scale * c), 256, 0, (cudaStream_t)stream>>>(g_in, n, h, w, c, scale, out);
+    RDB_LAUNCH_CHECK();
+  });
+}
+
+int rdb_op_softmax_rows(int device, const float* x, long long rows, int c, float* out, void* stream) {
+  return op_guard([&] {
+    RDB_CHECK(x && out && rows > 0 && c > 0, "softmax_rows: bad argument");
+    rdb::DeviceGuard g(device);
+    OpTimer tm("softmax_rows_op", (cudaStream_t)stream);
+    rdb::ops::softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, rows, c, out);
     RDB_LAUNCH_CHECK();
   });
 }

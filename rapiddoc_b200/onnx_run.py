@@ -1,0 +1,350 @@
+"""A B200 executor for the small CNN graphs RapidDoc ships as ONNX files and runs through onnxruntime on the CPU:
+
+  rapid_orientation.onnx          PP-LCNet x1.0, 4-way table-orientation classifier  — `OrtInferSession.__call__`
+                                  (rapid_doc/model/orientation/rapid_orientation/utils.py:47-52, called rapid_orientation.py:48)
+  pp-ocrv4_mobile_seal_det.onnx   PP-LCNetV3 + RSE-FPN + DB head of the seal-text detector
+
+The graph is read by `onnx_lite` (no onnx / onnxruntime package), compiled once into a launch plan over the C-ABI ops of
+include/rapiddoc_b200.h (NHWC fp32: rdb_op_gemm / rdb_op_im2col / rdb_op_dwconv for the convolutions, rdb_op_chain for every
+run of BatchNormalization / bias / learnable-affine / activation nodes between two convolutions — ONE launch per run instead
+of one per node — rdb_op_global_avgpool + rdb_op_mul_gate for squeeze-excite, rdb_op_resize_nearest, rdb_op_depth_to_space for
+ConvTranspose, rdb_op_softmax_rows) and executed on the caller's CUDA stream.  There is no CPU path: without the CUDA library
+`_lib.load()` raises.  tests/test_onnx_run.py compares it with `oracle/onnx_ref.py` (torch CPU), which is itself pinned to
+OpenCV's DNN importer on the same files.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib, onnx_lite
+
+CH_AFFINE, CH_AFFINE_VEC, CH_RELU, CH_HSIG, CH_HSWISH, CH_SIGMOID = range(6)
+MAX_STEPS = 8
+ACT_NONE = 0
+
+
+class _T:
+    """A device activation: buf [rows, ld] fp32 NHWC (rows = n*h*w) + a pending chain of per-element steps not yet applied."""
+    __slots__ = ("buf", "n", "h", "w", "c", "steps")
+
+    def __init__(self, buf, n, h, w, c, steps=()):
+        self.buf, self.n, self.h, self.w, self.c, self.steps = buf, n, h, w, c, tuple(steps)
+
+    @property
+    def rows(self):
+        return self.n * self.h * self.w
+
+
+class OnnxCnn:
+    def __init__(self, path, device=0):
+        import torch
+        self.torch, self.device, self.lib = torch, int(device), _lib.load()
+        self.dev = torch.device("cuda", self.device)
+        g = onnx_lite.load(path)
+        self.graph, self.path = g, path
+        self.meta = getattr(g, "meta", {})
+        self.launches = 0
+        self._const = {}          # name -> numpy constant (initializers + folded shape arithmetic)
+        self._dev = {}            # cache key -> device tensor (weights / per-channel vectors)
+        self._alias = {}
+        self.nodes = self._rewrite(g)
+        self.input_name, self.output_name = g.inputs[0], g.outputs[0]
+
+    # ---------------------------------------------------------------- compile
+    def _rewrite(self, g):
+        """Drop Identity nodes; fuse Mul(HardSigmoid(y), y) into one HardSwish-with-(alpha, beta) node."""
+        alias = {}
+        nodes = []
+        for n in g.nodes:
+            if n.op == "Identity":
+                alias[n.outputs[0]] = alias.get(n.inputs[0], n.inputs[0])
+            else:
+                nodes.append(onnx_lite.Node(n.op, [alias.get(i, i) for i in n.inputs], list(n.outputs), dict(n.attrs), n.name))
+        self._alias = alias
+        uses = {}
+        for n in nodes:
+            for i in n.inputs:
+                uses[i] = uses.get(i, 0) + 1
+        prod = {o: n for n in nodes for o in n.outputs}
+        dead = set()
+        for n in nodes:
+            if n.op != "Mul" or len(n.inputs) != 2:
+                continue
+            for a, b in (n.inputs, n.inputs[::-1]):
+                p = prod.get(a)
+                if p is not None and p.op == "HardSigmoid" and p.inputs[0] == b and uses.get(a, 0) == 1:
+                    n.op, n.inputs = "HardSwishAB", [b]
+                    n.attrs = {"alpha": p.attrs.get("alpha", 0.2), "beta": p.attrs.get("beta", 0.5)}
+                    dead.add(id(p))
+                    break
+        return [n for n in nodes if id(n) not in dead]
+
+    def _weight(self, key, make):
+        t = self._dev.get(key)
+        if t is None:
+            t = self.torch.from_numpy(np.ascontiguousarray(make(), np.float32)).to(self.dev)
+            self._dev[key] = t
+        return t
+
+    # ---------------------------------------------------------------- launch helpers
+    def _st(self):
+        return self.torch.cuda.current_stream(self.dev).cuda_stream or None
+
+    def _new(self, rows, c):
+        return self.torch.empty((rows, c), dtype=self.torch.float32, device=self.dev)
+
+    def _chain(self, t, out=None, ld_out=None, c_off=0):
+        """Apply t's pending steps (possibly none: a strided copy) into `out` (a new [rows, c] buffer by default)."""
+        if out is None:
+            out, ld_out = self._new(t.rows, t.c), t.c
+        n = len(t.steps)
+        kinds = (ctypes.c_int32 * max(n, 1))(*[s[0] for s in t.steps])
+        a = (ctypes.c_float * max(n, 1))(*[s[1] for s in t.steps])
+        b = (ctypes.c_float * max(n, 1))(*[s[2] for s in t.steps])
+        va = (ctypes.c_void_p * max(n, 1))(*[s[3].data_ptr() if s[3] is not None else None for s in t.steps])
+        vb = (ctypes.c_void_p * max(n, 1))(*[s[4].data_ptr() if s[4] is not None else None for s in t.steps])
+        self.launches += 1
+        _lib.check_op(self.lib.rdb_op_chain(self.device, t.buf.data_ptr(), t.rows, t.c, t.buf.shape[1], kinds, a, b, va, vb, n, out.data_ptr(), ld_out, c_off,
+                                            self._st()))
+        return out
+
+    def _mat(self, t):
+        """The activation with its pending steps applied (materialised)."""
+        if not t.steps:
+            return t
+        return _T(self._chain(t), t.n, t.h, t.w, t.c)
+
+    def _push(self, t, step):
+        if len(t.steps) >= MAX_STEPS:
+            t = self._mat(t)
+        return _T(t.buf, t.n, t.h, t.w, t.c, t.steps + (step,))
+
+    def _gemm(self, A, lda, M, K, W, N, bias, out, ldc, c_off=0):
+        self.launches += 1
+        _lib.check_op(self.lib.rdb_op_gemm(self.device, _lib.PREC_FP32, A, lda, M, K, W.data_ptr(), N, bias.data_ptr() if bias is not None else None, ACT_NONE,
+                                           None, 0, out, ldc, c_off, self._st(), None, 0))
+
+    # ---------------------------------------------------------------- ops
+    def _conv(self, node, x):
+        g = self.graph
+        wname = node.inputs[1]
+        W = g.init[wname]
+        co, cig, kh, kw = W.shape
+        group = node.attrs.get("group", 1)
+        sh, sw = node.attrs.get("strides", [1, 1])
+        pads = node.attrs.get("pads", [0, 0, 0, 0])
+        assert kh == kw and sh == sw and len(set(pads)) == 1 and set(node.attrs.get("dilations", [1, 1])) == {1}, f"unsupported conv geometry {node}"
+        p = pads[0]
+        bias = self._weight(("b", node.inputs[2]), lambda: g.init[node.inputs[2]]) if len(node.inputs) > 2 and node.inputs[2] else None
+        x = self._mat(x)
+        oh, ow = (x.h + 2 * p - kh) // sh + 1, (x.w + 2 * p - kw) // sw + 1
+        if group == 1:
+            cin = x.c                                       # the network input is stored with its channels padded to 4
+            assert cig <= cin and cin % 4 == 0 and x.buf.shape[1] % 4 == 0
+
+            def pack():
+                w = np.zeros((co, kh, kw, cin), np.float32)
+                w[..., :cig] = W.transpose(0, 2, 3, 1)
+                return w.reshape(co, kh * kw * cin)
+            Wd = self._weight(("w", wname, cin), pack)
+            out = self._new(x.n * oh * ow, co)
+            M = x.n * oh * ow
+            if kh == 1 and sh == 1 and p == 0:
+                self._gemm(x.buf.data_ptr(), x.buf.shape[1], M, cin, Wd, co, bias, out.data_ptr(), co)
+            else:
+                K = kh * kw * cin
+                col = self._new(M, K)
+                self.launches += 1
+                _lib.check_op(self.lib.rdb_op_im2col(self.device, _lib.PREC_FP32, x.buf.data_ptr(), x.n, x.h, x.w, cin, x.buf.shape[1], kh, kw, sh, sw, p, p, oh, ow,
+                                                     col.data_ptr(), self._st()))
+                self._gemm(col.data_ptr(), K, M, K, Wd, co, bias, out.data_ptr(), co)
+            return _T(out, x.n, oh, ow, co)
+        assert group == x.c == co and cig == 1 and p == (kh - 1) // 2 and (kh & 1), f"only depthwise grouped convs are supported: {node}"
+        Wd = self._weight(("dw", wname), lambda: W.reshape(co, kh * kw).T)
+        if bias is None:
+            bias = self._weight(("zeros", co), lambda: np.zeros(co, np.float32))
+        out = self._new(x.n * oh * ow, co)
+        self.launches += 1
+        _lib.check_op(self.lib.rdb_op_dwconv(self.device, _lib.PREC_FP32, x.buf.data_ptr(), x.n, x.h, x.w, co, x.buf.shape[1], kh, sh, Wd.data_ptr(), bias.data_ptr(),
+                                             0, out.data_ptr(), oh, ow, co, 0, self._st()))
+        return _T(out, x.n, oh, ow, co)
+
+    def _conv_transpose(self, node, x):
+        g = self.graph
+        W = g.init[node.inputs[1]] if node.inputs[1] in g.init else self._const[node.inputs[1]]
+        ci, co, kh, kw = W.shape
+        s = node.attrs.get("strides", [1, 1])
+        assert kh == kw == s[0] == s[1] and set(node.attrs.get("pads", [0, 0, 0, 0])) == {0} and node.attrs.get("group", 1) == 1, f"unsupported ConvTranspose {node}"
+        k = kh
+        x = self._mat(x)
+        assert ci == x.c and ci % 4 == 0
+        Wd = self._weight(("wt", node.inputs[1]), lambda: W.transpose(2, 3, 1, 0).reshape(k * k * co, ci))
+        bias = None
+        if len(node.inputs) > 2 and node.inputs[2]:
+            bias = self._weight(("bt", node.inputs[2]), lambda: np.tile(self._const_of(node.inputs[2]).reshape(-1), k * k))
+        M = x.rows
+        tmp = self._new(M, k * k * co)
+        self._gemm(x.buf.data_ptr(), x.buf.shape[1], M, ci, Wd, k * k * co, bias, tmp.data_ptr(), k * k * co)
+        out = self._new(M * k * k, co)
+        self.launches += 1
+        _lib.check_op(self.lib.rdb_op_depth_to_space(self.device, tmp.data_ptr(), x.n, x.h, x.w, co, k, out.data_ptr(), self._st()))
+        return _T(out, x.n, x.h * k, x.w * k, co)
+
+    def _const_of(self, name):
+        if name in self.graph.init:
+            return self.graph.init[name]
+        return self._const.get(name)
+
+    def _affine_const(self, t, c, mul):
+        """x * c or x + c for a constant c: scalar, or per channel ([C], [1,C,1,1])."""
+        c = np.asarray(c, np.float32)
+        if c.size == 1:
+            v = float(c.reshape(-1)[0])
+            return self._push(t, (CH_AFFINE, v, 0.0, None, None) if mul else (CH_AFFINE, 1.0, v, None, None))
+        assert c.size == t.c and (c.ndim == 1 or (c.ndim == 4 and c.shape[1] == t.c)), f"unsupported broadcast {c.shape} on C={t.c}"
+        vec = self._weight(("vec", c.tobytes()), lambda: c.reshape(-1))
+        return self._push(t, (CH_AFFINE_VEC, 0.0, 0.0, vec, None) if mul else (CH_AFFINE_VEC, 0.0, 0.0, None, vec))
+
+    def _binary(self, node, env, mul):
+        a, b = node.inputs
+        ca, cb = self._const_of(a), self._const_of(b)
+        if ca is not None and cb is not None:
+            self._const[node.outputs[0]] = ca * cb if mul else ca + cb
+            return None
+        if ca is not None or cb is not None:
+            t, c = (env[b], ca) if ca is not None else (env[a], cb)
+            return self._affine_const(t, c, mul)
+        ta, tb = env[a], env[b]
+        if mul:
+            gate, x = (ta, tb) if ta.h * ta.w == 1 and tb.h * tb.w > 1 else (tb, ta)
+            assert gate.h * gate.w == 1 and gate.c == x.c and gate.n == x.n, f"unsupported Mul of two activations: {node}"
+            gate, x = self._mat(gate), self._mat(x)
+            assert gate.buf.shape[1] == gate.c
+            out = self._new(x.rows, x.c)
+            self.launches += 1
+            _lib.check_op(self.lib.rdb_op_mul_gate(self.device, x.buf.data_ptr(), gate.buf.data_ptr(), x.n, x.h * x.w, x.c, x.buf.shape[1], out.data_ptr(), x.c,
+                                                   self._st()))
+            return _T(out, x.n, x.h, x.w, x.c)
+        ta, tb = self._mat(ta), self._mat(tb)
+        assert (ta.n, ta.h, ta.w, ta.c) == (tb.n, tb.h, tb.w, tb.c) and ta.buf.shape[1] == ta.c and tb.buf.shape[1] == tb.c, f"Add of unequal shapes: {node}"
+        out = self._new(ta.rows, ta.c)
+        self.launches += 1
+        _lib.check_op(self.lib.rdb_op_add(self.device, ta.buf.data_ptr(), tb.buf.data_ptr(), out.data_ptr(), ta.rows * ta.c, self._st()))
+        return _T(out, ta.n, ta.h, ta.w, ta.c)
+
+    def _bn(self, node, x):
+        g = self.graph
+        gamma, beta, mean, var = (g.init[i].astype(np.float64) for i in node.inputs[1:5])
+        eps = float(node.attrs.get("epsilon", 1e-5))
+        key = ("bn", node.inputs[1])
+        scale = self._weight(key + ("s",), lambda: gamma / np.sqrt(var + eps))
+        shift = self._weight(key + ("t",), lambda: beta - mean * gamma / np.sqrt(var + eps))
+        return self._push(x, (CH_AFFINE_VEC, 0.0, 0.0, scale, shift))
+
+    # ---------------------------------------------------------------- run
+    def __call__(self, x):
+        """x [n, 3, h, w] float32 (numpy or a CUDA tensor) -> numpy output of the graph (NCHW / [n, classes])."""
+        torch = self.torch
+        with torch.cuda.device(self.dev):
+            if isinstance(x, np.ndarray):
+                x = torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(self.dev, non_blocking=False)
+            n, c, h, w = x.shape
+            cp = (c + 3) // 4 * 4
+            xin = torch.zeros((n, h, w, cp), dtype=torch.float32, device=self.dev)
+            xin[..., :c] = x.permute(0, 2, 3, 1)
+            env = {self.input_name: _T(xin.view(n * h * w, cp), n, h, w, cp)}
+            self._const, self._flat_out = {}, False
+            for node in self.nodes:
+                out = self._run_node(node, env)
+                if out is not None:
+                    env[node.outputs[0]] = out
+            name = self._alias.get(self.output_name, self.output_name)
+            t = self._mat(env[name])
+            y = t.buf.view(t.n, t.h, t.w, t.buf.shape[1])[..., :t.c]
+            y = y.permute(0, 3, 1, 2).contiguous().cpu().numpy()
+            return y.reshape(t.n, t.c) if self._flat_out and t.h * t.w == 1 else y
+
+    def _run_node(self, node, env):
+        op = node.op
+        if op == "Conv":
+            return self._conv(node, env[node.inputs[0]])
+        if op == "ConvTranspose":
+            return self._conv_transpose(node, env[node.inputs[0]])
+        if op == "BatchNormalization":
+            return self._bn(node, env[node.inputs[0]])
+        if op == "Relu":
+            return self._push(env[node.inputs[0]], (CH_RELU, 0.0, 0.0, None, None))
+        if op == "Sigmoid":
+            return self._push(env[node.inputs[0]], (CH_SIGMOID, 0.0, 0.0, None, None))
+        if op == "HardSigmoid":
+            return self._push(env[node.inputs[0]], (CH_HSIG, float(node.attrs.get("alpha", 0.2)), float(node.attrs.get("beta", 0.5)), None, None))
+        if op == "HardSwish":
+            return self._push(env[node.inputs[0]], (CH_HSWISH, 1.0 / 6.0, 0.5, None, None))
+        if op == "HardSwishAB":
+            return self._push(env[node.inputs[0]], (CH_HSWISH, float(node.attrs["alpha"]), float(node.attrs["beta"]), None, None))
+        if op in ("Add", "Mul"):
+            return self._binary(node, env, op == "Mul")
+        if op == "GlobalAveragePool":
+            x = self._mat(env[node.inputs[0]])
+            out = self._new(x.n, x.c)
+            self.launches += 1
+            _lib.check_op(self.lib.rdb_op_global_avgpool(self.device, x.buf.data_ptr(), x.n, x.h * x.w, x.c, x.buf.shape[1], out.data_ptr(), self._st()))
+            return _T(out, x.n, 1, 1, x.c)
+        if op == "Resize":
+            assert node.attrs.get("mode") == "nearest" and node.attrs.get("coordinate_transformation_mode") == "asymmetric" \
+                and node.attrs.get("nearest_mode", "floor") == "floor", f"unsupported Resize {node.attrs}"
+            scales = self._const_of(node.inputs[2])
+            s = int(scales[2])
+            assert scales[0] == scales[1] == 1 and scales[2] == scales[3] == s
+            x = self._mat(env[node.inputs[0]])
+            out = self._new(x.rows * s * s, x.c)
+            self.launches += 1
+            _lib.check_op(self.lib.rdb_op_resize_nearest(self.device, x.buf.data_ptr(), x.n, x.h, x.w, x.c, x.buf.shape[1], s, out.data_ptr(), x.c, 0, self._st()))
+            return _T(out, x.n, x.h * s, x.w * s, x.c)
+        if op == "Concat":
+            if all(self._const_of(i) is not None for i in node.inputs):
+                self._const[node.outputs[0]] = np.concatenate([np.atleast_1d(self._const_of(i)) for i in node.inputs], axis=node.attrs.get("axis", 0))
+                return None
+            assert node.attrs.get("axis") == 1, "only channel Concat is supported"
+            parts = [env[i] for i in node.inputs]
+            ctot = sum(p.c for p in parts)
+            p0 = parts[0]
+            out = self._new(p0.rows, ctot)
+            off = 0
+            for p in parts:
+                assert (p.n, p.h, p.w) == (p0.n, p0.h, p0.w)
+                self._chain(p, out, ctot, off)              # pending steps (or a plain copy) straight into the channel slice
+                off += p.c
+            return _T(out, p0.n, p0.h, p0.w, ctot)
+        if op == "Shape":
+            t = env[node.inputs[0]]
+            self._const[node.outputs[0]] = np.array([t.n, t.c, t.h, t.w], np.int64)
+            return None
+        if op == "Slice":
+            data, starts, ends = (self._const_of(i) for i in node.inputs[:3])
+            axes = self._const_of(node.inputs[3]) if len(node.inputs) > 3 else np.array([0])
+            assert data is not None and int(np.asarray(axes).reshape(-1)[0]) == 0, "Slice is only supported on shape vectors"
+            self._const[node.outputs[0]] = data[int(starts.reshape(-1)[0]): int(ends.reshape(-1)[0])]
+            return None
+        if op == "Reshape":
+            t = env[node.inputs[0]]
+            shape = self._const_of(node.inputs[1])
+            assert t.h * t.w == 1 and len(shape) == 2, "Reshape is only supported as the [n,C,1,1] -> [n,C] flatten"
+            self._flat_out = True
+            return t
+        if op == "MatMul":
+            t = self._mat(env[node.inputs[0]])
+            W = self._const_of(node.inputs[1])
+            assert t.h * t.w == 1 and W.shape[0] == t.c and t.c % 4 == 0
+            Wd = self._weight(("mm", node.inputs[1]), lambda: W.T)
+            out = self._new(t.n, W.shape[1])
+            self._gemm(t.buf.data_ptr(), t.buf.shape[1], t.n, t.c, Wd, W.shape[1], None, out.data_ptr(), W.shape[1])
+            return _T(out, t.n, 1, 1, W.shape[1])
+        if op == "Softmax":
+            t = self._mat(env[node.inputs[0]])
+            assert t.h * t.w == 1 and node.attrs.get("axis", -1) in (-1, 1) and t.buf.shape[1] == t.c
+            out = self._new(t.n, t.c)
+            self.launches += 1
+            _lib.check_op(self.lib.rdb_op_softmax_rows(self.device, t.buf.data_ptr(), t.n, t.c, out.data_ptr(), self._st()))
+            return _T(out, t.n, 1, 1, t.c)
+        raise NotImplementedError(f"ONNX op {op} is not supported by the B200 executor ({node})")

@@ -55,3 +55,27 @@ def rec_crop(rng, h=48, w=320):
 def rec_crops(n, h=48, w=320, seed=2):
     rng = np.random.default_rng(seed)
     return np.stack([rec_crop(rng, h, w) for _ in range(n)])
+
+
+def seal_image(seed=0, size=320, text="RAPIDDOCSEALTEXT2026"):
+    """A synthetic round seal (BGR uint8): red ring, glyphs set along an arc, one straight line in the middle — the curved-text
+    input of the seal detector (pp-ocrv4_mobile_seal_det.onnx)."""
+    import cv2
+    rng = np.random.RandomState(seed)
+    img = np.full((size, size, 3), 255, np.uint8)
+    c = size // 2
+    cv2.circle(img, (c, c), int(size * 0.45), (0, 0, 255), 3)
+    start = 1.15 + 0.1 * rng.rand()
+    for k, ch in enumerate(text):
+        ang = np.pi * (start + 1.4 * k / len(text))
+        r = size * 0.36
+        x, y = int(c + r * np.cos(ang)), int(c + r * np.sin(ang))
+        glyph = np.full((40, 40, 3), 255, np.uint8)
+        cv2.putText(glyph, ch, (8, 30), cv2.FONT_HERSHEY_SIMPLEX, 1.0, (0, 0, 255), 2, cv2.LINE_AA)
+        M = cv2.getRotationMatrix2D((20, 20), -np.degrees(ang) - 90, 1.0)
+        glyph = cv2.warpAffine(glyph, M, (40, 40), borderValue=(255, 255, 255))
+        y0, x0 = y - 20, x - 20
+        if 0 <= y0 and y0 + 40 <= size and 0 <= x0 and x0 + 40 <= size:
+            img[y0:y0 + 40, x0:x0 + 40] = np.minimum(img[y0:y0 + 40, x0:x0 + 40], glyph)
+    cv2.putText(img, "CONTRACT SEAL", (c - 90, c + 10), cv2.FONT_HERSHEY_SIMPLEX, 0.8, (0, 0, 255), 2, cv2.LINE_AA)
+    return img

@@ -1,0 +1,133 @@
+"""The ONNX CNNs of the orientation classifier and the seal detector: reader, CPU oracle pinned to
+OpenCV's DNN importer, and the CUDA executor against the oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import make_golden_onnx as MG          # noqa: E402
+from oracle import onnx_ref                        # noqa: E402
+from rapiddoc_b200 import onnx_lite                # noqa: E402
+
+ORI = os.path.join(ROOT, "weights", "rapid_orientation.onnx")
+SEAL = os.path.join(ROOT, "weights", "pp-ocrv4_mobile_seal_det.onnx")
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "onnx_cases.npz"))
+
+
+def test_reader_sees_the_whole_graph():
+    g = onnx_lite.load(ORI)
+    assert g.inputs == ["x"] and g.outputs == ["fetch_name_0"] and len(g.nodes) == 115
+    assert g.meta["character"].splitlines() == ["0", "90", "180", "270"]
+    assert sum(n.op == "Conv" for n in g.nodes) == 32 and g.init["linear_0.w_0_deepcopy_144"].shape == (1280, 4)
+    conv = g.nodes[0]
+    assert conv.attrs["strides"] == [2, 2] and conv.attrs["pads"] == [1, 1, 1, 1] and conv.attrs["group"] == 1
+    s = onnx_lite.load(SEAL)
+    assert len(s.nodes) == 526 and sum(n.op == "ConvTranspose" for n in s.nodes) == 2
+    hs = {round(n.attrs["alpha"], 4) for n in s.nodes if n.op == "HardSigmoid"}
+    assert hs == {0.1667, 0.2}
+    assert abs(sum(a.size for a in s.init.values()) - 1171745) < 10
+
+
+def test_oracle_matches_the_cv2_dnn_golden():
+    _, xs = MG.orientation_inputs()
+    y = onnx_ref.run(ORI, xs)                                   # batch 4 in one run; the golden was made one image at a time
+    assert np.abs(y - GOLD["orientation_scores"]).max() < 2e-6
+    assert list(np.argmax(y, 1)) == [0, 3, 2, 1]                # page rotated by 0 / 90ccw / 180 / 90cw
+    p = onnx_ref.run(SEAL, MG.seal_input())[0, 0]
+    assert np.abs(p - GOLD["seal_prob"].astype(np.float32)).max() < 1e-3      # fp16 storage of the golden
+    assert (p > 0.2).sum() > 5000
+
+
+def test_oracle_matches_cv2_dnn_live():
+    cv2 = pytest.importorskip("cv2")
+    x = np.random.RandomState(3).randn(1, 3, 224, 224).astype(np.float32)
+    net = cv2.dnn.readNetFromONNX(ORI)
+    net.setInput(x)
+    assert np.abs(onnx_ref.run(ORI, x) - net.forward()).max() < 2e-6
+    x = MG.seal_input(seed=1, size=256)
+    net = cv2.dnn.readNetFromONNX(SEAL)
+    net.setInput(x)
+    assert np.abs(onnx_ref.run(SEAL, x) - net.forward()).max() < 3e-4        # cv2.dnn fuses / reorders the fp32 sums
+
+
+def test_orientation_label_follows_the_reference_preprocess():
+    rots, _ = MG.orientation_inputs()
+    labels = [onnx_ref.orientation(ORI, r)[0] for r in rots]
+    assert labels == ["0", "270", "180", "90"]
+
+
+def test_executor_plan_fuses_elementwise_runs():
+    """Compile only (no GPU work): Identity nodes vanish, Mul(HardSigmoid(y), y) pairs become one step."""
+    from rapiddoc_b200.onnx_run import OnnxCnn
+    s = OnnxCnn.__new__(OnnxCnn)
+    s._alias = {}
+    nodes = s._rewrite(onnx_lite.load(SEAL))
+    ops = [n.op for n in nodes]
+    assert "Identity" not in ops and ops.count("HardSwishAB") >= 20
+    assert ops.count("HardSigmoid") == 34 - ops.count("HardSwishAB")          # the rest are squeeze-excite gates
+
+
+# ------------------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+def test_orientation_executor_matches_the_oracle():
+    from rapiddoc_b200.onnx_run import OnnxCnn
+    rots, xs = MG.orientation_inputs()
+    net = OnnxCnn(ORI, 0)
+    y = net(xs)
+    ref = onnx_ref.run(ORI, xs)
+    assert y.shape == (4, 4)
+    assert np.abs(y - ref).max() < 1e-4, np.abs(y - ref).max()               # fp32 both sides, different summation order
+    assert np.abs(y - GOLD["orientation_scores"]).max() < 1e-4
+    assert net.launches < 160                                               # 115 graph nodes -> fused launches
+    y1 = net(xs[:1])                                                        # batch 1 = the reference's own call shape
+    assert np.abs(y1 - ref[:1]).max() < 1e-4
+
+
+@pytest.mark.gpu
+def test_orientation_model_interface():
+    from rapiddoc_b200.orientation import B200Orientation, B200OrientationModel
+    import cv2
+    rots, _ = MG.orientation_inputs()
+    eng = B200Orientation(device=0)
+    assert [eng(r)[0] for r in rots] == ["0", "270", "180", "90"]
+    assert np.abs(eng.scores(rots) - GOLD["orientation_scores"]).max() < 1e-4
+    m = B200OrientationModel(device=0)
+    portrait = cv2.cvtColor(rots[0], cv2.COLOR_BGR2RGB)                     # 640 x 480 portrait
+    assert m.predict(portrait) == onnx_ref.orientation(ORI, portrait)[0]
+    assert m.predict(cv2.cvtColor(rots[1], cv2.COLOR_BGR2RGB)) == "0"       # landscape: the classifier is not run
+    flat = [[[0, 0], [100, 0], [100, 20], [0, 20]]] * 5
+    assert m.predict(portrait, flat) == "0"                                 # portrait but horizontal text boxes
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size", [320, 256])
+def test_seal_detector_executor_matches_the_oracle(size):
+    from rapiddoc_b200.onnx_run import OnnxCnn
+    x = MG.seal_input(seed=0 if size == 320 else 1, size=size)
+    net = OnnxCnn(SEAL, 0)
+    p = net(x)
+    ref = onnx_ref.run(SEAL, x)
+    assert p.shape == ref.shape == (1, 1, size, size)
+    d = np.abs(p - ref)
+    assert d.max() < 2e-3 and d.mean() < 1e-5, (d.max(), d.mean())          # sigmoid of fp32 sums in another order
+    assert ((p > 0.2) != (ref > 0.2)).sum() <= 2                            # the bitmap at the seal threshold
+    if size == 320:
+        assert np.abs(p[0, 0] - GOLD["seal_prob"].astype(np.float32)).max() < 3e-3
+    assert net.launches < 330                                               # 526 graph nodes
+
+
+@pytest.mark.gpu
+def test_seal_detector_interface():
+    from rapiddoc_b200 import synth
+    from rapiddoc_b200.orientation import B200SealDetector, sort_poly_boxes
+    det = B200SealDetector(device=0)
+    img = synth.seal_image(0, 320)
+    prob, bitmap = det(img)
+    assert prob.shape == (736, 736) and bitmap.dtype == np.uint8             # short side scaled up to 736 (limit_type 'min')
+    ref = onnx_ref.run(SEAL, det.preprocess(img))[0, 0]
+    assert ((prob > 0.2) != (ref > 0.2)).mean() < 1e-4
+    polys = [np.array([[0, 30], [5, 40], [9, 31]]), np.array([[0, 3], [5, 4], [9, 9]]), np.array([[0, 13], [5, 14]])]
+    assert [int(p[0, 1]) for p in sort_poly_boxes(polys)] == [3, 13, 30]
