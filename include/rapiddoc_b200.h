@@ -244,6 +244,29 @@ int rdb_op_resize_nearest(int device, const float* x, int n, int h, int w, int c
 /* ConvTranspose(kernel = stride = scale) = rdb_op_gemm to [n*h*w, scale*scale*c] (columns dy, dx, c) + this pixel shuffle */
 int rdb_op_depth_to_space(int device, const float* g, int n, int h, int w, int c, int scale, float* out, void* stream);
 int rdb_op_softmax_rows(int device, const float* x, long long rows, int c, float* out, void* stream);
+
+/* ---- table structure: SLANet head ---------------------------------------------------------
+ * The GRU-attention decode loop of SLAHead (the `Loop` node of slanet-1m.onnx / SLANet_plus, executed by onnxruntime inside
+ * OrtInferSession.__call__, rapid_doc/model/table/rapid_table_self/inference_engine/onnxruntime/main.py:70-76; caller
+ * PPTableStructurer.__call__, table_structure/pp_structure/main.py:41-51) as ONE persistent launch, one CTA per table image.
+ * All matrices fp32 on the device, stored [in][out]; the GRU matrices transposed to [in][3*hidden] (gate order r, z, c). */
+typedef struct rdb_sla_weights {
+  int hidden;                              /* 256 */
+  const float *Wh, *bh;                    /* h2h   [hidden][hidden], [hidden]            (linear_1) */
+  const float *ws;                         /* score [hidden]                              (linear_2) */
+  const float *WihT, *WhhT, *bih, *bhh;    /* GRUCell: [C+classes][3h], [h][3h], [3h], [3h] */
+  const float *W3, *b3, *W4, *b4;          /* structure generator: [h][h], [h][classes]   (linear_3, linear_4) */
+  const float *W5, *b5, *W6, *b6;          /* box generator: [h][h], [h][loc] + sigmoid   (linear_5, linear_6) */
+} rdb_sla_weights_t;
+const char* rdb_sla_last_error(void);
+/* feat [batch, hw, c] (the neck output, NHWC) and feat_proj = feat * Wi2h [batch, hw, hidden] (hoisted out of the loop);
+ * logits / probs [batch, max_steps, classes], loc [batch, max_steps, loc_dim], ids [batch, max_steps]: rows >= *total_steps read
+ * as the reference's untouched rows (probability 1/classes, box 0).  *total_steps = steps the reference loop would run: first
+ * step after which every image has emitted `eos` (or max_steps); the caller keeps min(total_steps + 1, max_steps) rows, as the
+ * graph's final Slice does.  sync_words: 2 int32 of device scratch; steps_run [batch] (diagnostic). */
+int rdb_sla_decode(int device, const float* feat, const float* feat_proj, int batch, int hw, int c, const rdb_sla_weights_t* w, int classes,
+                   int loc_dim, int max_steps, int eos, float* logits, float* probs, float* loc, int32_t* ids, int32_t* sync_words,
+                   int32_t* steps_run, int32_t* total_steps, void* stream);
 /* one greedy step of generate_export (rec_ppformulanet_head.py:1118-1160) on the device: next token = argmax (eos when force_eos),
  * finished rows emit pad, a row finishes on eos; *all_done = every row has produced an eos */
 int rdb_op_greedy_step(int device, const int32_t* argmax, int batch, int force_eos, int eos, int pad, int64_t* next, int32_t* unfinished,

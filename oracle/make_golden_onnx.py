@@ -27,6 +27,14 @@ def seal_input(seed=0, size=320):
     return np.ascontiguousarray(((img.astype(np.float32) / 255.0 - mean) / std).transpose(2, 0, 1)[None], np.float32)
 
 
+def table_inputs():
+    """Three synthetic table crops (4x3 ruled, 6x4 ruled, 3x2 borderless) through TablePreprocess (T3)."""
+    from rapiddoc_b200 import table
+    imgs = [synth.table_image(0, 4, 3), synth.table_image(1, 6, 4, 360, 520), synth.table_image(2, 3, 2, 200, 300, lines=False)]
+    x, shapes = table.TablePreprocess()(imgs)
+    return imgs, np.asarray(x, np.float32), shapes
+
+
 def main():
     out = {}
     net = cv2.dnn.readNetFromONNX(os.path.join(ROOT, "weights", "rapid_orientation.onnx"))
@@ -39,6 +47,13 @@ def main():
     net = cv2.dnn.readNetFromONNX(os.path.join(ROOT, "weights", "pp-ocrv4_mobile_seal_det.onnx"))
     net.setInput(seal_input())
     out["seal_prob"] = net.forward().copy()[0, 0].astype(np.float16)      # fp16 storage: the tests compare at 2e-3
+    # SLANet: cv2.dnn cannot import the graph (dynamic shapes + Loop), so these rows come from oracle/onnx_ref.py itself — a
+    # regression fixture for the literal node-by-node execution of the file, not an independent pin
+    _, x, _ = table_inputs()
+    loc, probs = onnx_ref.run(os.path.join(ROOT, "weights", "slanet-1m.onnx"), x)
+    out["slanet_ids"] = probs.argmax(-1).astype(np.int16)
+    out["slanet_loc"] = loc.astype(np.float16)
+    out["slanet_pmax"] = probs.max(-1).astype(np.float16)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "onnx_cases.npz"), **out)
     print({k: (v.shape, v.dtype) for k, v in out.items()}, out["orientation_scores"].round(3))
 

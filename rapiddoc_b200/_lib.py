@@ -58,6 +58,8 @@ SYMBOLS = {
     "rdb_op_resize_nearest": (_i, [_i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "rdb_op_depth_to_space": (_i, [_i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "rdb_op_softmax_rows": (_i, [_i, _vp, C.c_longlong, _i, _vp, _vp]),
+    "rdb_sla_last_error": (C.c_char_p, []),
+    "rdb_sla_decode": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rdb_op_greedy_step": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "rdb_contours_trace": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_vp)]),
     "rdb_contours_counts": (_i, [_vp, _vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

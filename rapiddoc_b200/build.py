@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librapiddoc_b200.so")
-SOURCES = ["api.cu", "det.cu", "rec.cu", "ops.cu", "contours.cu"]
+SOURCES = ["api.cu", "det.cu", "rec.cu", "ops.cu", "contours.cu", "table.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--use_fast_math" if os.environ.get("RDB_FAST_MATH") else "-DRDB_NO_FAST_MATH", "-cudart", "static"]

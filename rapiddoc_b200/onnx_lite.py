@@ -85,6 +85,8 @@ def _attr(b):
             val = bytes(v).decode("utf-8", "replace")
         elif f == 5:
             val = _tensor(v)[1]
+        elif f == 6:
+            val = _graph(v)
         elif f == 7:
             floats += list(np.frombuffer(bytes(v), np.float32)) if w == 2 else [struct.unpack("<f", v)[0]]
         elif f == 8:
@@ -111,16 +113,7 @@ class Graph:
         self.nodes, self.init, self.inputs, self.outputs, self.meta = nodes, init, inputs, outputs, meta or {}
 
 
-def load(path):
-    data = memoryview(open(path, "rb").read())
-    graph, meta = None, {}
-    for f, w, v in _fields(data):
-        if f == 7:
-            graph = v
-        elif f == 14:                                   # metadata_props: StringStringEntryProto {1: key, 2: value}
-            kv = {g: bytes(x).decode("utf-8", "replace") for g, _, x in _fields(v) if g in (1, 2)}
-            meta[kv.get(1, "")] = kv.get(2, "")
-    assert graph is not None, "no graph in the model file"
+def _graph(graph, meta=None):
     nodes, init, inputs, outputs = [], {}, [], []
     for f, w, v in _fields(graph):
         if f == 1:
@@ -147,3 +140,16 @@ def load(path):
                     (inputs if f == 11 else outputs).append(bytes(x).decode())
     inputs = [i for i in inputs if i not in init]
     return Graph(nodes, init, inputs, outputs, meta)
+
+
+def load(path):
+    data = memoryview(open(path, "rb").read())
+    graph, meta = None, {}
+    for f, w, v in _fields(data):
+        if f == 7:
+            graph = v
+        elif f == 14:                                   # metadata_props: StringStringEntryProto {1: key, 2: value}
+            kv = {g: bytes(x).decode("utf-8", "replace") for g, _, x in _fields(v) if g in (1, 2)}
+            meta[kv.get(1, "")] = kv.get(2, "")
+    assert graph is not None, "no graph in the model file"
+    return _graph(graph, meta)

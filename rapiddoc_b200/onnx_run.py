@@ -46,7 +46,11 @@ class OnnxCnn:
         self.launches = 0
         self._const = {}          # name -> numpy constant (initializers + folded shape arithmetic)
         self._dev = {}            # cache key -> device tensor (weights / per-channel vectors)
-        self._alias = {}
+        self._alias, self._plans = {}, {}
+        self.consts = dict(g.init)                    # initializers + Constant nodes (Paddle2ONNX exports the weights either way)
+        for n in g.nodes:
+            if n.op == "Constant":
+                self.consts[n.outputs[0]] = np.asarray(n.attrs["value"])
         self.nodes = self._rewrite(g)
         self.input_name, self.output_name = g.inputs[0], g.outputs[0]
 
@@ -58,6 +62,8 @@ class OnnxCnn:
         for n in g.nodes:
             if n.op == "Identity":
                 alias[n.outputs[0]] = alias.get(n.inputs[0], n.inputs[0])
+            elif n.op == "Constant":
+                continue
             else:
                 nodes.append(onnx_lite.Node(n.op, [alias.get(i, i) for i in n.inputs], list(n.outputs), dict(n.attrs), n.name))
         self._alias = alias
@@ -128,18 +134,23 @@ class OnnxCnn:
     def _conv(self, node, x):
         g = self.graph
         wname = node.inputs[1]
-        W = g.init[wname]
+        W = self.consts[wname]
         co, cig, kh, kw = W.shape
         group = node.attrs.get("group", 1)
         sh, sw = node.attrs.get("strides", [1, 1])
         pads = node.attrs.get("pads", [0, 0, 0, 0])
         assert kh == kw and sh == sw and len(set(pads)) == 1 and set(node.attrs.get("dilations", [1, 1])) == {1}, f"unsupported conv geometry {node}"
         p = pads[0]
-        bias = self._weight(("b", node.inputs[2]), lambda: g.init[node.inputs[2]]) if len(node.inputs) > 2 and node.inputs[2] else None
+        bias = self._weight(("b", node.inputs[2]), lambda: self.consts[node.inputs[2]]) if len(node.inputs) > 2 and node.inputs[2] else None
         x = self._mat(x)
         oh, ow = (x.h + 2 * p - kh) // sh + 1, (x.w + 2 * p - kw) // sw + 1
         if group == 1:
-            cin = x.c                                       # the network input is stored with its channels padded to 4
+            if x.c % 4 or x.buf.shape[1] % 4:               # the GEMM reads 16-byte vectors: pad the channels to a multiple of 4
+                cp = (x.c + 3) // 4 * 4
+                padded = self.torch.zeros((x.rows, cp), dtype=self.torch.float32, device=self.dev)
+                self._chain(x, padded, cp, 0)
+                x = _T(padded, x.n, x.h, x.w, cp)
+            cin = x.c                                       # (the network input is stored padded the same way)
             assert cig <= cin and cin % 4 == 0 and x.buf.shape[1] % 4 == 0
 
             def pack():
@@ -171,7 +182,7 @@ class OnnxCnn:
 
     def _conv_transpose(self, node, x):
         g = self.graph
-        W = g.init[node.inputs[1]] if node.inputs[1] in g.init else self._const[node.inputs[1]]
+        W = self._const_of(node.inputs[1])
         ci, co, kh, kw = W.shape
         s = node.attrs.get("strides", [1, 1])
         assert kh == kw == s[0] == s[1] and set(node.attrs.get("pads", [0, 0, 0, 0])) == {0} and node.attrs.get("group", 1) == 1, f"unsupported ConvTranspose {node}"
@@ -191,8 +202,8 @@ class OnnxCnn:
         return _T(out, x.n, x.h * k, x.w * k, co)
 
     def _const_of(self, name):
-        if name in self.graph.init:
-            return self.graph.init[name]
+        if name in self.consts:
+            return self.consts[name]
         return self._const.get(name)
 
     def _affine_const(self, t, c, mul):
@@ -234,7 +245,7 @@ class OnnxCnn:
 
     def _bn(self, node, x):
         g = self.graph
-        gamma, beta, mean, var = (g.init[i].astype(np.float64) for i in node.inputs[1:5])
+        gamma, beta, mean, var = (self.consts[i].astype(np.float64) for i in node.inputs[1:5])
         eps = float(node.attrs.get("epsilon", 1e-5))
         key = ("bn", node.inputs[1])
         scale = self._weight(key + ("s",), lambda: gamma / np.sqrt(var + eps))
@@ -242,18 +253,51 @@ class OnnxCnn:
         return self._push(x, (CH_AFFINE_VEC, 0.0, 0.0, scale, shift))
 
     # ---------------------------------------------------------------- run
+    def _closure(self, targets):
+        """The nodes (in graph order) the named tensors depend on."""
+        prod = {o: n for n in self.nodes for o in n.outputs}
+        need, stack = set(), [self._alias.get(t, t) for t in targets]
+        while stack:
+            t = stack.pop()
+            n = prod.get(t)
+            if n is None or id(n) in need:
+                continue
+            need.add(id(n))
+            stack.extend(i for i in n.inputs if i)
+        return [n for n in self.nodes if id(n) in need]
+
+    def features(self, x, name):
+        """Run only what the tensor `name` needs and return it on the device as (buffer [n*h*w, C] NHWC fp32, n, h, w, C)."""
+        torch = self.torch
+        with torch.cuda.device(self.dev):
+            env = self._feed(x)
+            plan = self._plans.get(name)
+            if plan is None:
+                plan = self._plans[name] = self._closure([name])
+            for node in plan:
+                out = self._run_node(node, env)
+                if out is not None:
+                    env[node.outputs[0]] = out
+            t = self._mat(env[self._alias.get(name, name)])
+            assert t.buf.shape[1] == t.c
+            return t.buf, t.n, t.h, t.w, t.c
+
+    def _feed(self, x):
+        torch = self.torch
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(self.dev, non_blocking=False)
+        n, c, h, w = x.shape
+        cp = (c + 3) // 4 * 4
+        xin = torch.zeros((n, h, w, cp), dtype=torch.float32, device=self.dev)
+        xin[..., :c] = x.permute(0, 2, 3, 1)
+        self._const, self._flat_out = {}, False
+        return {self.input_name: _T(xin.view(n * h * w, cp), n, h, w, cp)}
+
     def __call__(self, x):
         """x [n, 3, h, w] float32 (numpy or a CUDA tensor) -> numpy output of the graph (NCHW / [n, classes])."""
         torch = self.torch
         with torch.cuda.device(self.dev):
-            if isinstance(x, np.ndarray):
-                x = torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(self.dev, non_blocking=False)
-            n, c, h, w = x.shape
-            cp = (c + 3) // 4 * 4
-            xin = torch.zeros((n, h, w, cp), dtype=torch.float32, device=self.dev)
-            xin[..., :c] = x.permute(0, 2, 3, 1)
-            env = {self.input_name: _T(xin.view(n * h * w, cp), n, h, w, cp)}
-            self._const, self._flat_out = {}, False
+            env = self._feed(x)
             for node in self.nodes:
                 out = self._run_node(node, env)
                 if out is not None:
@@ -264,8 +308,47 @@ class OnnxCnn:
             y = y.permute(0, 3, 1, 2).contiguous().cpu().numpy()
             return y.reshape(t.n, t.c) if self._flat_out and t.h * t.w == 1 else y
 
+    def _host_fold(self, node, env):
+        """Shape arithmetic on the host: nodes whose inputs are all constants (or `Shape` of an activation)."""
+        op, a = node.op, node.attrs
+        if op == "Shape":
+            t = env.get(node.inputs[0])
+            if t is None:
+                return False
+            self._const[node.outputs[0]] = np.array([t.n, t.c, t.h, t.w], np.int64)
+            return True
+        if op not in ("Cast", "Slice", "Squeeze", "Unsqueeze", "Reshape", "Concat", "Gather"):
+            return False
+        vals = [self._const_of(i) if i else None for i in node.inputs]
+        if any(v is None and i for v, i in zip(vals, node.inputs)):
+            return False
+        v = [np.asarray(x) if x is not None else None for x in vals]
+        if op == "Cast":
+            y = v[0].astype({1: np.float32, 6: np.int32, 7: np.int64, 9: np.bool_, 11: np.float64}[a["to"]])
+        elif op == "Slice":
+            axes = v[3].reshape(-1) if len(v) > 3 and v[3] is not None else range(v[1].size)
+            y = v[0]
+            for st, en, ax in zip(v[1].reshape(-1), v[2].reshape(-1), axes):
+                y = np.take(y, range(*slice(int(st), int(en)).indices(y.shape[int(ax)])), axis=int(ax))
+        elif op == "Squeeze":
+            y = np.squeeze(v[0], axis=tuple(int(x) for x in v[1].reshape(-1)) if len(v) > 1 and v[1] is not None else None)
+        elif op == "Unsqueeze":
+            y = v[0]
+            for ax in sorted(int(x) for x in v[1].reshape(-1)):
+                y = np.expand_dims(y, ax)
+        elif op == "Reshape":
+            y = v[0].reshape([int(x) for x in v[1].reshape(-1)])
+        elif op == "Gather":
+            y = np.take(v[0], v[1].astype(np.int64), axis=a.get("axis", 0))
+        else:
+            y = np.concatenate([np.atleast_1d(x) for x in v], axis=a.get("axis", 0))
+        self._const[node.outputs[0]] = y
+        return True
+
     def _run_node(self, node, env):
         op = node.op
+        if self._host_fold(node, env):
+            return None
         if op == "Conv":
             return self._conv(node, env[node.inputs[0]])
         if op == "ConvTranspose":
@@ -293,10 +376,16 @@ class OnnxCnn:
         if op == "Resize":
             assert node.attrs.get("mode") == "nearest" and node.attrs.get("coordinate_transformation_mode") == "asymmetric" \
                 and node.attrs.get("nearest_mode", "floor") == "floor", f"unsupported Resize {node.attrs}"
-            scales = self._const_of(node.inputs[2])
-            s = int(scales[2])
-            assert scales[0] == scales[1] == 1 and scales[2] == scales[3] == s
             x = self._mat(env[node.inputs[0]])
+            sizes = self._const_of(node.inputs[3]) if len(node.inputs) > 3 and node.inputs[3] else None
+            if sizes is not None and np.asarray(sizes).size == 4:
+                oh, ow = (int(v) for v in np.asarray(sizes).reshape(-1)[2:])
+                s = oh // x.h
+                assert oh == x.h * s and ow == x.w * s, "Resize: only integer factors are supported"
+            else:
+                scales = self._const_of(node.inputs[2])
+                s = int(scales[2])
+                assert scales[0] == scales[1] == 1 and scales[2] == scales[3] == s
             out = self._new(x.rows * s * s, x.c)
             self.launches += 1
             _lib.check_op(self.lib.rdb_op_resize_nearest(self.device, x.buf.data_ptr(), x.n, x.h, x.w, x.c, x.buf.shape[1], s, out.data_ptr(), x.c, 0, self._st()))

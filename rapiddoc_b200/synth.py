@@ -79,3 +79,23 @@ def seal_image(seed=0, size=320, text="RAPIDDOCSEALTEXT2026"):
             img[y0:y0 + 40, x0:x0 + 40] = np.minimum(img[y0:y0 + 40, x0:x0 + 40], glyph)
     cv2.putText(img, "CONTRACT SEAL", (c - 90, c + 10), cv2.FONT_HERSHEY_SIMPLEX, 0.8, (0, 0, 255), 2, cv2.LINE_AA)
     return img
+
+
+def table_image(seed=0, rows=4, cols=3, h=300, w=400, lines=True):
+    """A synthetic table crop (BGR uint8): a ruled (or borderless) grid with short cell texts — the input of the table
+    structure model (SLANet)."""
+    import cv2
+    rng = np.random.RandomState(seed)
+    img = np.full((h, w, 3), 255, np.uint8)
+    x0, y0, x1, y1 = 10, 20, w - 10, h - 40
+    ch, cw = (y1 - y0) // rows, (x1 - x0) // cols
+    if lines:
+        for r in range(rows + 1):
+            cv2.line(img, (x0, y0 + r * ch), (x0 + cols * cw, y0 + r * ch), (0, 0, 0), 1)
+        for c in range(cols + 1):
+            cv2.line(img, (x0 + c * cw, y0), (x0 + c * cw, y0 + rows * ch), (0, 0, 0), 1)
+    for r in range(rows):
+        for c in range(cols):
+            txt = "".join(chr(ord("a") + int(v)) for v in rng.randint(0, 26, 3)) + str(int(rng.randint(0, 100)))
+            cv2.putText(img, txt, (x0 + c * cw + 8, y0 + r * ch + int(ch * 0.65)), cv2.FONT_HERSHEY_SIMPLEX, 0.6, (0, 0, 0), 2)
+    return img

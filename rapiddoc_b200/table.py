@@ -173,3 +173,114 @@ def needs_orientation_cls(img_shape, det_res):
         if (bw / bh if bh > 0 else 1.0) < 0.8:
             vertical += 1
     return vertical >= len(det_res) * 0.28 and vertical >= 3
+
+
+class SlaNetSession:
+    """T4: the SLANet ONNX graph on the B200 — what `OrtInferSession.__call__` returns for it
+    (rapid_table_self/inference_engine/onnxruntime/main.py:70-76): (bbox_preds [B,T,loc], struct_probs [B,T,classes]).
+    Backbone + CSP-PAN (77 convolutions) run through `onnx_run.OnnxCnn`; the SLAHead `Loop` (GRU attention, <= 501 sequential
+    steps) is ONE persistent kernel launch (rdb_sla_decode, csrc/table.cu).  Tensor names are those of the Paddle2ONNX export
+    (slanet-1m.onnx; SLANet_plus is exported by the same tool from the same head class)."""
+    MAX_BATCH = 128          # one CTA per image, all co-resident (148 SMs)
+
+    def __init__(self, model_path, device=0):
+        import ctypes
+        import torch
+        from .onnx_run import OnnxCnn
+        self.torch, self.device = torch, int(device)
+        self.net = OnnxCnn(model_path, device)
+        self.lib = self.net.lib
+        g, c = self.net.graph, self.net.consts
+        loop = [n for n in g.nodes if n.op == "Loop"]
+        assert len(loop) == 1, "not a SLANet export: no Loop node"
+        body = loop[0].attrs["body"]
+        bconst = {n.outputs[0]: np.asarray(n.attrs["value"]) for n in body.nodes if n.op == "Constant"}
+        prod = {o: n for n in g.nodes for o in n.outputs}
+        feat_t = [i for i in loop[0].inputs if i in prod and prod[i].op == "Transpose"]
+        assert len(feat_t) == 1
+        self.feature_name = prod[prod[feat_t[0]].inputs[0]].inputs[0]            # Transpose <- Reshape <- neck output
+        onehot = [n for n in body.nodes if n.op == "OneHot"][0]
+        self.classes = int(bconst[onehot.inputs[1]].reshape(-1)[0])
+        eq = [n for n in body.nodes if n.op == "Equal"][0]
+        self.eos = int([bconst[i] for i in eq.inputs if i in bconst][0].reshape(-1)[0])
+        self.max_steps = int(np.asarray(c["assign_0.tmp_0.0"]).reshape(-1)[0]) + 1
+        dev = self.net.dev
+
+        def up(a):
+            return torch.from_numpy(np.ascontiguousarray(a, np.float32)).to(dev)
+        self.Wi_t = up(c["linear_0.w_0"].T)                                       # [hidden, C] = the [N, K] layout rdb_op_gemm takes
+        self.hidden, self.C = self.Wi_t.shape
+        self.loc_dim = int(c["linear_6.w_0"].shape[1])
+        assert c["gru_cell_0.w_0"].shape == (3 * self.hidden, self.C + self.classes) and c["linear_4.w_0"].shape[1] == self.classes
+        self._w = dict(Wh=up(c["linear_1.w_0"]), bh=up(c["linear_1.b_0"]), ws=up(c["linear_2.w_0"].reshape(-1)),
+                       WihT=up(c["gru_cell_0.w_0"].T), WhhT=up(c["gru_cell_0.w_1"].T), bih=up(c["gru_cell_0.b_0"]), bhh=up(c["gru_cell_0.b_1"]),
+                       W3=up(c["linear_3.w_0"]), b3=up(c["linear_3.b_0"]), W4=up(c["linear_4.w_0"]), b4=up(c["linear_4.b_0"]),
+                       W5=up(c["linear_5.w_0"]), b5=up(c["linear_5.b_0"]), W6=up(c["linear_6.w_0"]), b6=up(c["linear_6.b_0"]))
+
+        class W(ctypes.Structure):
+            _fields_ = [("hidden", ctypes.c_int)] + [(k, ctypes.c_void_p) for k in
+                                                     ("Wh", "bh", "ws", "WihT", "WhhT", "bih", "bhh", "W3", "b3", "W4", "b4", "W5", "b5", "W6", "b6")]
+        self._wstruct = W(self.hidden, *[self._w[k].data_ptr() for k in ("Wh", "bh", "ws", "WihT", "WhhT", "bih", "bhh", "W3", "b3", "W4", "b4", "W5", "b5", "W6", "b6")])
+        self._ctypes = ctypes
+        self.launches = 0
+        self.last_steps = 0
+
+    def get_character_list(self, key="character"):
+        return self.net.meta[key].splitlines()
+
+    def __call__(self, imgs):
+        """imgs [B,3,H,W] float32 -> (bbox_preds [B,T,loc], struct_probs [B,T,classes]) numpy, T as the graph's final Slice."""
+        torch, ct = self.torch, self._ctypes
+        imgs = np.asarray(imgs, np.float32)
+        outs = []
+        for b0 in range(0, len(imgs), self.MAX_BATCH):
+            x = imgs[b0:b0 + self.MAX_BATCH]
+            with torch.cuda.device(self.net.dev):
+                l0 = self.net.launches
+                feat, n, h, w, c = self.net.features(x, self.feature_name)
+                assert c == self.C
+                st = torch.cuda.current_stream(self.net.dev).cuda_stream or None
+                dev, hw, S, V, L = self.net.dev, h * w, self.max_steps, self.classes, self.loc_dim
+                proj = torch.empty((n * hw, self.hidden), dtype=torch.float32, device=dev)
+                _lib.check_op(self.lib.rdb_op_gemm(self.device, _lib.PREC_FP32, feat.data_ptr(), c, n * hw, c, self.Wi_t.data_ptr(), self.hidden, None, 0, None, 0,
+                                                   proj.data_ptr(), self.hidden, 0, st, None, 0))
+                logits = torch.zeros((n, S, V), dtype=torch.float32, device=dev)
+                probs = torch.empty((n, S, V), dtype=torch.float32, device=dev)
+                loc = torch.zeros((n, S, L), dtype=torch.float32, device=dev)
+                ids = torch.zeros((n, S), dtype=torch.int32, device=dev)
+                sync = torch.zeros(2 + n + 1, dtype=torch.int32, device=dev)
+                rc = self.lib.rdb_sla_decode(self.device, feat.data_ptr(), proj.data_ptr(), n, hw, c, ct.byref(self._wstruct), V, L, S, self.eos, logits.data_ptr(),
+                                             probs.data_ptr(), loc.data_ptr(), ids.data_ptr(), sync.data_ptr(), sync[2:].data_ptr(), sync[2 + n:].data_ptr(), st)
+                if rc < 0:
+                    raise _lib.B200Error(f"rdb_sla_decode: {self.lib.rdb_sla_last_error().decode('utf-8', 'replace')}")
+                self.launches += self.net.launches - l0 + 3
+                total = int(sync[2 + n].item())
+                self.last_steps = total
+                T = min(total + 1, S)
+                outs.append((loc[:, :T].cpu().numpy(), probs[:, :T].cpu().numpy()))
+        if len(outs) == 1:
+            return outs[0]
+        T = max(o[0].shape[1] for o in outs)                 # batches decoded separately stop at their own step: pad with untouched rows
+
+        def pad(a, fill):
+            return np.concatenate([a, np.full((a.shape[0], T - a.shape[1], a.shape[2]), fill, np.float32)], 1) if a.shape[1] < T else a
+        return (np.concatenate([pad(o[0], 0.0) for o in outs]), np.concatenate([pad(o[1], 1.0 / self.classes) for o in outs]))
+
+
+class B200TableStructurer:
+    """Mirror of `PPTableStructurer` (table_structure/pp_structure/main.py:25-51) for ModelType.SLANET1M (the weights RapidDoc
+    ships, rapid_table_self/main.py:38-40) — preprocess (T3) -> SLANet (T4) -> TableLabelDecode (T5)."""
+
+    def __init__(self, model_path=None, model_type="slanet_1m", device=0):
+        import os
+        from .weights import WEIGHTS_DIR
+        if model_path is None:
+            model_path = os.path.join(WEIGHTS_DIR, "slanet-1m.onnx")
+        self.session = SlaNetSession(model_path, device)
+        self.preprocess_op = TablePreprocess()
+        self.postprocess_op = TableLabelDecode(self.session.get_character_list(), slanet_plus=(model_type == "slanet_plus"), device=device)
+
+    def __call__(self, ori_imgs):
+        imgs, shape_lists = self.preprocess_op(ori_imgs)
+        bbox_preds, struct_probs = self.session(np.asarray(imgs).copy())
+        return self.postprocess_op(bbox_preds, struct_probs, shape_lists, ori_imgs)

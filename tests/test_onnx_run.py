@@ -131,3 +131,81 @@ def test_seal_detector_interface():
     assert ((prob > 0.2) != (ref > 0.2)).mean() < 1e-4
     polys = [np.array([[0, 30], [5, 40], [9, 31]]), np.array([[0, 3], [5, 4], [9, 9]]), np.array([[0, 13], [5, 14]])]
     assert [int(p[0, 1]) for p in sort_poly_boxes(polys)] == [3, 13, 30]
+
+
+# ------------------------------------------------------------------------------------------------------- SLANet (T4)
+SLANET = os.path.join(ROOT, "weights", "slanet-1m.onnx")
+
+
+def test_slanet_oracle_runs_the_loop_of_the_file():
+    """The node-by-node interpreter executes the Loop / If subgraphs literally; structure of three synthetic tables."""
+    imgs, x, _ = MG.table_inputs()
+    loc, probs = onnx_ref.run(SLANET, x[:1])
+    ids = probs.argmax(-1)[0]
+    g = GOLD["slanet_ids"][0]
+    T = len(ids)
+    assert T == 26 and list(ids) == list(g[:T])                 # batch 1 stops at its own eos (+ the untouched row)
+    assert ids[24] == 29 and ids[25] == 0 and np.allclose(probs[0, 25], 1 / 30) and np.all(loc[0, 25] == 0)
+    assert np.abs(loc[0, :T - 1] - GOLD["slanet_loc"][0, :T - 1].astype(np.float32)).max() < 2e-3   # (in the batch-3 golden this row decodes on)
+    chars = onnx_lite.load(SLANET).meta["character"].splitlines()
+    from rapiddoc_b200 import table
+    dec = table.TableLabelDecode(chars, slanet_plus=False)
+    assert dec.character[29] == "eos" and dec.character[28] == "<td></td>"
+    toks = [dec.character[i] for i in ids[:24]]
+    assert toks.count("<tr>") == 4 and toks.count("<td></td>") == 12
+
+
+def test_slanet_session_reads_the_head_from_the_graph():
+    from rapiddoc_b200.table import SlaNetSession
+    s = SlaNetSession.__new__(SlaNetSession)
+    g = onnx_lite.load(SLANET)
+    loop = [n for n in g.nodes if n.op == "Loop"][0]
+    body = loop.attrs["body"]
+    assert len(body.nodes) == 235 and sum(n.op == "MatMul" for n in body.nodes) == 10
+    assert [n for n in body.nodes if n.op == "If"][0].attrs["then_branch"].outputs
+
+
+@pytest.mark.gpu
+def test_slanet_backbone_matches_the_oracle():
+    from rapiddoc_b200.onnx_run import OnnxCnn
+    _, x, _ = MG.table_inputs()
+    net = OnnxCnn(SLANET, 0)
+    feat, n, h, w, c = net.features(x, "hardswish_72.tmp_0")
+    ref, = onnx_ref.run(SLANET, x, outputs=["hardswish_72.tmp_0"])
+    assert (n, c, h, w) == ref.shape == (3, 96, 16, 16)
+    got = feat.view(n, h, w, c).permute(0, 3, 1, 2).cpu().numpy()
+    assert np.abs(got - ref).max() < 1e-4 * max(1.0, np.abs(ref).max()), np.abs(got - ref).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch", [1, 3])
+def test_slanet_session_matches_the_oracle(batch):
+    """One persistent launch for the whole decode loop: same stop step, same tokens, probabilities / boxes to fp32 rounding.
+    batch 3 = three tables with different lengths: every row keeps decoding until the LAST one has emitted eos."""
+    from rapiddoc_b200.table import SlaNetSession
+    _, x, _ = MG.table_inputs()
+    x = x[:batch]
+    s = SlaNetSession(SLANET, 0)
+    loc, probs = s(x)
+    rloc, rprobs = onnx_ref.run(SLANET, x)
+    assert loc.shape == rloc.shape and probs.shape == rprobs.shape, (loc.shape, rloc.shape)
+    assert np.array_equal(probs.argmax(-1), rprobs.argmax(-1))
+    assert np.abs(probs - rprobs).max() < 2e-4 and np.abs(loc - rloc).max() < 2e-4, (np.abs(probs - rprobs).max(), np.abs(loc - rloc).max())
+    if batch == 3:
+        assert np.array_equal(probs.argmax(-1), GOLD["slanet_ids"]) and loc.shape[1] == 42
+    assert s.launches < 250                                       # 830 graph nodes + <= 501 loop iterations
+
+
+@pytest.mark.gpu
+def test_table_structurer_interface():
+    from rapiddoc_b200.table import B200TableStructurer, TableLabelDecode
+    imgs, x, shapes = MG.table_inputs()
+    ts = B200TableStructurer(device=0)
+    structs, cells = ts(imgs)
+    rloc, rprobs = onnx_ref.run(SLANET, x)
+    dec = TableLabelDecode(onnx_lite.load(SLANET).meta["character"].splitlines(), slanet_plus=False, device=0)
+    rstructs, rcells = dec(rloc, rprobs, shapes, imgs)
+    for (tok, score), (rtok, rscore), cb, rcb, (rows, cols) in zip(structs, rstructs, cells, rcells, [(4, 3), (6, 4), (3, 2)]):
+        assert tok == rtok and abs(score - rscore) < 1e-4
+        assert tok.count("<tr>") == rows and tok.count("<td></td>") == rows * cols
+        assert cb.shape == rcb.shape == (rows * cols, 4) and np.abs(cb - rcb).max() < 0.1        # pixels
