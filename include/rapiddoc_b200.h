@@ -238,8 +238,8 @@ int rdb_op_chain(int device, const float* x, long long rows, int c, int ld_in, c
 int rdb_op_global_avgpool(int device, const float* x, int n, int hw, int c, int ld, float* out /* [n,c] */, void* stream);
 /* squeeze-excite scaling out[n,p,c] = x[n,p,c] * gate[n,c] */
 int rdb_op_mul_gate(int device, const float* x, const float* gate, int n, int hw, int c, int ld_in, float* out, int ld_out, void* stream);
-/* Resize(nearest, asymmetric, floor) by an integer factor, into a channel slice */
-int rdb_op_resize_nearest(int device, const float* x, int n, int h, int w, int c, int ld_in, int scale, float* out, int ld_out, int c_off,
+/* Resize(nearest, asymmetric, floor) to oh x ow, into a channel slice: src = min(floor(dst / (out/in)), in - 1) in float32 */
+int rdb_op_resize_nearest(int device, const float* x, int n, int h, int w, int c, int ld_in, int oh, int ow, float* out, int ld_out, int c_off,
                           void* stream);
 /* ConvTranspose(kernel = stride = scale) = rdb_op_gemm to [n*h*w, scale*scale*c] (columns dy, dx, c) + this pixel shuffle */
 int rdb_op_depth_to_space(int device, const float* g, int n, int h, int w, int c, int scale, float* out, void* stream);

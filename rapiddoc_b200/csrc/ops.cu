@@ -398,15 +398,17 @@ __global__ void mul_gate_kernel(const float* __restrict__ x, const float* __rest
   }
 }
 
-// Resize(mode nearest, asymmetric, floor) by an integer factor into a channel slice: out[n, oy, ox] = x[n, oy / s, ox / s]
-__global__ void resize_nearest_kernel(const float* __restrict__ x, int n, int H, int W, int C, int ld_in, int s, float* __restrict__ out, int ld_out, int c_off) {
-  const int OH = H * s, OW = W * s;
+// Resize(mode nearest, coordinate_transformation_mode asymmetric, nearest_mode floor) into a channel slice:
+// src = min(floor(dst / scale), in - 1) with scale = out / in in float32, as the ONNX definition (and onnxruntime) evaluate it
+__global__ void resize_nearest_kernel(const float* __restrict__ x, int n, int H, int W, int C, int ld_in, int OH, int OW, float sy, float sx,
+                                      float* __restrict__ out, int ld_out, int c_off) {
   const long long total = (long long)n * OH * OW * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const long long px = i / C;
     const int ox = (int)(px % OW), oy = (int)((px / OW) % OH), b = (int)(px / ((long long)OW * OH));
-    out[px * ld_out + c_off + c] = x[((long long)(b * H + oy / s) * W + ox / s) * ld_in + c];
+    const int iy = min((int)floorf(__fdiv_rn((float)oy, sy)), H - 1), ix = min((int)floorf(__fdiv_rn((float)ox, sx)), W - 1);
+    out[px * ld_out + c_off + c] = x[((long long)(b * H + iy) * W + ix) * ld_in + c];
   }
 }
 
@@ -683,12 +685,13 @@ int rdb_op_mul_gate(int device, const float* x, const float* gate, int n, int hw
   });
 }
 
-int rdb_op_resize_nearest(int device, const float* x, int n, int h, int w, int c, int ld_in, int scale, float* out, int ld_out, int c_off, void* stream) {
+int rdb_op_resize_nearest(int device, const float* x, int n, int h, int w, int c, int ld_in, int oh, int ow, float* out, int ld_out, int c_off, void* stream) {
   return op_guard([&] {
-    RDB_CHECK(x && out && n > 0 && h > 0 && w > 0 && c > 0 && scale >= 1, "resize_nearest: bad argument");
+    RDB_CHECK(x && out && n > 0 && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0, "resize_nearest: bad argument");
     rdb::DeviceGuard g(device);
     OpTimer tm("resize_nearest_op", (cudaStream_t)stream);
-    rdb::ops::resize_nearest_kernel<<<rdb::ops::grid_for((long long)n * h * scale * w * scale * c), 256, 0, (cudaStream_t)stream>>>(x, n, h, w, c, ld_in, scale, out, ld_out, c_off);
+    rdb::ops::resize_nearest_kernel<<<rdb::ops::grid_for((long long)n * oh * ow * c), 256, 0, (cudaStream_t)stream>>>(x, n, h, w, c, ld_in, oh, ow, (float)oh / (float)h,
+                                                                                                                   (float)ow / (float)w, out, ld_out, c_off);
     RDB_LAUNCH_CHECK();
   });
 }

@@ -380,16 +380,14 @@ class OnnxCnn:
             sizes = self._const_of(node.inputs[3]) if len(node.inputs) > 3 and node.inputs[3] else None
             if sizes is not None and np.asarray(sizes).size == 4:
                 oh, ow = (int(v) for v in np.asarray(sizes).reshape(-1)[2:])
-                s = oh // x.h
-                assert oh == x.h * s and ow == x.w * s, "Resize: only integer factors are supported"
             else:
-                scales = self._const_of(node.inputs[2])
-                s = int(scales[2])
-                assert scales[0] == scales[1] == 1 and scales[2] == scales[3] == s
-            out = self._new(x.rows * s * s, x.c)
+                scales = np.asarray(self._const_of(node.inputs[2]), np.float32)
+                assert scales[0] == scales[1] == 1
+                oh, ow = int(x.h * scales[2]), int(x.w * scales[3])
+            out = self._new(x.n * oh * ow, x.c)
             self.launches += 1
-            _lib.check_op(self.lib.rdb_op_resize_nearest(self.device, x.buf.data_ptr(), x.n, x.h, x.w, x.c, x.buf.shape[1], s, out.data_ptr(), x.c, 0, self._st()))
-            return _T(out, x.n, x.h * s, x.w * s, x.c)
+            _lib.check_op(self.lib.rdb_op_resize_nearest(self.device, x.buf.data_ptr(), x.n, x.h, x.w, x.c, x.buf.shape[1], oh, ow, out.data_ptr(), x.c, 0, self._st()))
+            return _T(out, x.n, oh, ow, x.c)
         if op == "Concat":
             if all(self._const_of(i) is not None for i in node.inputs):
                 self._const[node.outputs[0]] = np.concatenate([np.atleast_1d(self._const_of(i)) for i in node.inputs], axis=node.attrs.get("axis", 0))

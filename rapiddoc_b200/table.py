@@ -231,7 +231,8 @@ class SlaNetSession:
     def __call__(self, imgs):
         """imgs [B,3,H,W] float32 -> (bbox_preds [B,T,loc], struct_probs [B,T,classes]) numpy, T as the graph's final Slice."""
         torch, ct = self.torch, self._ctypes
-        imgs = np.asarray(imgs, np.float32)
+        if not torch.is_tensor(imgs):                       # a CUDA tensor (already preprocessed, resident) is taken as it is
+            imgs = np.asarray(imgs, np.float32)
         outs = []
         for b0 in range(0, len(imgs), self.MAX_BATCH):
             x = imgs[b0:b0 + self.MAX_BATCH]

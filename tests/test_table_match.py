@@ -1,0 +1,121 @@
+"""T7 / T1 (wireless tables): TableMatch restatement against the reference's own class (imported by path in the build container)
+and against invariants that hold everywhere."""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from rapiddoc_b200 import table_match as TM       # noqa: E402
+
+REF = "/root/reference/rapid_doc/model/table/rapid_table_self/table_matcher"
+
+
+def _ref_matcher():
+    if not os.path.isdir(REF):
+        pytest.skip("reference tree not mounted")
+    import types
+    pkg = types.ModuleType("ref_tm")
+    pkg.__path__ = [REF]
+    sys.modules["ref_tm"] = pkg
+    for name in ("utils", "main"):
+        spec = importlib.util.spec_from_file_location(f"ref_tm.{name}", os.path.join(REF, f"{name}.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[f"ref_tm.{name}"] = mod
+        spec.loader.exec_module(mod)
+    return sys.modules["ref_tm.main"].TableMatch()
+
+
+def _case(seed, rows=5, cols=4, spans=False):
+    rng = np.random.RandomState(seed)
+    W, H = 600, 300
+    xs, ys = np.linspace(10, W - 10, cols + 1), np.linspace(40, H - 10, rows + 1)
+    tokens, cells = ["<html>", "<body>", "<table>", "<thead>"], []
+    for r in range(rows):
+        tokens.append("<tr>")
+        c = 0
+        while c < cols:
+            span = 2 if spans and c + 1 < cols and rng.rand() < 0.25 else 1
+            if span == 1:
+                tokens.append("<td></td>")
+            else:
+                tokens += ["<td", f' colspan="{span}"', ">", "</td>"]
+            cells.append([xs[c] + rng.randn(), ys[r] + rng.randn(), xs[c + span] + rng.randn(), ys[r + 1] + rng.randn()])
+            c += span
+        tokens.append("</tr>")
+        if r == 0:
+            tokens += ["</thead>", "<tbody>"]
+    tokens += ["</tbody>", "</table>", "</body>", "</html>"]
+    cells = np.array(cells)
+    dt, rec = [], []
+    for k, cb in enumerate(cells):
+        n = rng.randint(0, 3)
+        for j in range(n):
+            w = (cb[2] - cb[0]) / max(n, 1)
+            dt.append([cb[0] + j * w + 2, cb[1] + 3, cb[0] + (j + 1) * w - 2, cb[3] - 3])
+            txt = f" t{k}_{j} " if rng.rand() < 0.3 else f"t{k}_{j}"
+            if j == 0 and rng.rand() < 0.2:
+                txt = "<b>" + txt + "</b>"
+            rec.append((txt, float(rng.rand())))
+    dt.append([5, 2, 100, 20]); rec.append(("title above the table", 0.9))          # filtered: ends above the first cell
+    dt.append([W + 50, H + 50, W + 90, H + 70]); rec.append(("outside", 0.9))        # no intersection with any cell
+    dt.append([xs[1] - 5, ys[1] - 4, xs[1] + 5, ys[1] + 4]); rec.append(("corner", 0.8))   # touches four cells: tie-breaks
+    return (tokens, 0.9), cells, np.array(dt, np.float64), rec
+
+
+@pytest.mark.parametrize("seed,spans", [(0, False), (1, True), (2, True), (3, False)])
+def test_table_match_equals_the_reference(seed, spans):
+    ref = _ref_matcher()
+    struct, cells, dt, rec = _case(seed, spans=spans)
+    mine = TM.TableMatch()
+    assert mine([struct], [cells], [dt], [rec]) == ref([struct], [cells], [dt], [rec])
+    f_dt, f_rec = mine.filter_ocr_result(cells, dt, rec)
+    r_dt, r_rec = ref.filter_ocr_result(cells, dt, rec)
+    assert np.array_equal(f_dt, r_dt) and f_rec == r_rec
+    assert mine.match_result(cells, f_dt) == ref.match_result(cells, r_dt)
+    assert np.array_equal(mine.decode_logic_points([struct])[0], ref.decode_logic_points([struct])[0])
+    cells8 = np.stack([cells[:, 0], cells[:, 1], cells[:, 2], cells[:, 1], cells[:, 2], cells[:, 3], cells[:, 0], cells[:, 3]], 1)
+    assert mine.match_result(cells8, f_dt) == ref.match_result(cells8, r_dt)
+    assert mine([struct], [cells], [None], [None]) == [None]
+
+
+def test_table_match_invariants():
+    struct, cells, dt, rec = _case(5)
+    m = TM.TableMatch()
+    html = m.process_one(struct, cells, dt, rec)
+    assert html.startswith("<html><body><table><tr><td>") and html.endswith("</table></body></html>")
+    assert "<thead>" not in html and "title above the table" not in html and "outside" not in html
+    assert html.count("<td>") == len(cells) and html.count("<tr>") == 5
+    matched = m.match_result(cells, m.filter_ocr_result(cells, dt, rec)[0])
+    assert sorted(i for v in matched.values() for i in v) == sorted(set(i for v in matched.values() for i in v))   # each box once
+    lp = m.decode_one_logic_points(["<tr>", "<td", ' rowspan="2"', ">", "</td>", "<td></td>", "</tr>", "<tr>", "<td></td>", "</tr>"])
+    assert lp == [[0, 1, 0, 0], [0, 0, 1, 1], [1, 1, 1, 1]]
+    assert m.match_result(np.zeros((0, 4)), dt) == {} and m.match_result(cells, np.zeros((0, 4))) == {}
+
+
+def test_format_ocr_results_clips_to_the_image():
+    boxes = [[[-5, 3], [50, 3], [50, 20], [-5, 20]], [[90, 40], [130, 40], [130, 70], [90, 70]]]
+    dt, rec = TM.format_ocr_results((boxes, ("a", "b"), (0.9, 0.8)), 60, 120)
+    assert dt.tolist() == [[0, 3, 50, 20], [90, 40, 120, 60]] and rec == [("a", 0.9), ("b", 0.8)]
+
+
+@pytest.mark.gpu
+def test_rapid_table_end_to_end_on_synthetic_tables():
+    """image + OCR results -> html through the CUDA structure model; every cell's text lands in its own <td>."""
+    from rapiddoc_b200 import synth
+    imgs = [synth.table_image(0, 4, 3), synth.table_image(1, 6, 4, 360, 520)]
+    rt = TM.B200RapidTable(device=0)
+    plain = rt(imgs)
+    assert plain.pred_htmls == [] and [len(c) for c in plain.cell_bboxes] == [12, 24]
+    assert plain.logic_points[0].tolist()[:4] == [[0, 0, 0, 0], [0, 0, 1, 1], [0, 0, 2, 2], [1, 1, 0, 0]]
+    ocr = []
+    for cells in plain.cell_bboxes:                   # one OCR box inside every predicted cell, text = its index
+        boxes = [[[c[0] + 4, c[1] + 4], [c[2] - 4, c[1] + 4], [c[2] - 4, c[3] - 4], [c[0] + 4, c[3] - 4]] for c in cells]
+        ocr.append((boxes, tuple(f"c{k}" for k in range(len(cells))), tuple(0.9 for _ in cells)))
+    out = rt(imgs, ocr)
+    for html, cells in zip(out.pred_htmls, out.cell_bboxes):
+        got = [t.split("</td>")[0] for t in html.split("<td>")[1:]]
+        assert got == [f"c{k}" for k in range(len(cells))]

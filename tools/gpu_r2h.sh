@@ -32,3 +32,5 @@ tot = sum(v[0] for v in prof.values())
 print("profiled ops total %.2f ms" % tot)
 for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:12]: print("  %-50s %8.3f ms x%d" % (k, v[0], v[1]))
 PY
+python bench.py --workload table --steps 5 --warmup 3 --profile-out gpurun_out/r2h_prof_table.json > gpurun_out/r2h_bench_table.json 2> gpurun_out/r2h_bench_table.err
+echo "table bench exit $?"; head -c 2500 gpurun_out/r2h_bench_table.json; echo; tail -3 gpurun_out/r2h_bench_table.err
