@@ -39,6 +39,8 @@ class OnnxCnn:
     def __init__(self, path, device=0):
         import torch
         self.torch, self.device, self.lib = torch, int(device), _lib.load()
+        if self.lib.rdb_device_count() <= self.device:
+            raise _lib.B200Error(f"no sm_100 CUDA device {self.device} for the ONNX executor (there is no CPU fallback)")
         self.dev = torch.device("cuda", self.device)
         g = onnx_lite.load(path)
         self.graph, self.path = g, path

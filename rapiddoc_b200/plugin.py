@@ -98,6 +98,34 @@ def install_window():
     return orig
 
 
+def install_orientation(device=0):
+    """Seam 2 for SURVEY T8: rebind the table-orientation classifier factory (`img_orientation_cls_model_init`,
+    rapid_doc/backend/pipeline/model_init.py:32-34, -> RapidOrientationModel) to the CUDA classifier.  Returns the original."""
+    from rapid_doc.backend.pipeline import model_init as mi
+    from .orientation import B200OrientationModel
+    orig = mi.img_orientation_cls_model_init
+    mi.img_orientation_cls_model_init = lambda: B200OrientationModel(device=device)
+    mi.AtomModelSingleton._models.clear()
+    return orig
+
+
+def install_table_structure(device=0):
+    """Seam 3 for SURVEY T4: `RapidTable._init_table_structer` (rapid_table_self/main.py:64-76) returns the CUDA structurer for
+    ModelType.SLANET1M — the wireless-table model RapidDoc ships — and the reference's own object for every other model type.
+    Returns the original method."""
+    from rapid_doc.model.table.rapid_table_self import main as rt
+    from .table import B200TableStructurer
+    orig = rt.RapidTable._init_table_structer
+
+    def init_structurer(self):
+        mt = getattr(self.cfg.model_type, "value", self.cfg.model_type)
+        if mt == "slanet_1m":
+            return B200TableStructurer(model_path=self.cfg.model_dir_or_path, model_type=mt, device=device)
+        return orig(self)
+    rt.RapidTable._init_table_structer = init_structurer
+    return orig
+
+
 def session_for(cfg):
     """Seam 3: pick the B200 session from the configured model file (det vs rec)."""
     from .engine import B200DetSession, B200RecSession

@@ -172,6 +172,45 @@ def test_plugin_install_hooks_against_stub_modules(monkeypatch):
             rt.TorchInferSession({"model_path": os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "weights", "ch_PP-OCRv6_rec_small.safetensors")})
 
 
+def test_plugin_table_and_orientation_hooks_against_stub_modules(monkeypatch):
+    from rapiddoc_b200 import B200Error, _lib, plugin
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__path__ = []
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        monkeypatch.setitem(sys.modules, name, m)
+        return m
+
+    class Singleton:
+        _models = {"cached": 1}
+
+    class RapidTable:
+        def __init__(self, model_type, path=None):
+            self.cfg = types.SimpleNamespace(model_type=types.SimpleNamespace(value=model_type), model_dir_or_path=path)
+            self.table_structure = self._init_table_structer()
+
+        def _init_table_structer(self):
+            return "reference-structurer"
+    stub("rapid_doc"), stub("rapid_doc.backend"), stub("rapid_doc.model"), stub("rapid_doc.model.table")
+    mi = stub("rapid_doc.backend.pipeline.model_init", img_orientation_cls_model_init=lambda: "reference-orientation", AtomModelSingleton=Singleton)
+    stub("rapid_doc.backend.pipeline", model_init=mi)
+    rt = stub("rapid_doc.model.table.rapid_table_self.main", RapidTable=RapidTable)
+    stub("rapid_doc.model.table.rapid_table_self", main=rt)
+    assert plugin.install_orientation(device=0)() == "reference-orientation" and Singleton._models == {}
+    plugin.install_table_structure(device=0)
+    assert RapidTable("unet").table_structure == "reference-structurer"          # other model types keep the reference object
+    if _lib.load().rdb_device_count() == 0:
+        with pytest.raises(B200Error):                                            # no silent CPU fallback
+            mi.img_orientation_cls_model_init()
+        with pytest.raises(B200Error):
+            RapidTable("slanet_1m", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "weights", "slanet-1m.onnx"))
+    else:
+        assert type(RapidTable("slanet_1m").table_structure).__name__ == "B200TableStructurer"
+        assert type(mi.img_orientation_cls_model_init()).__name__ == "B200OrientationModel"
+
+
 def test_multi_gpu_dispatch_with_stand_in_models():
     """B200OcrPool: pages round-robin, whole reference rec batches dealt round-robin, results in input order."""
     from rapiddoc_b200.multi import B200OcrPool
