@@ -191,7 +191,7 @@ int rdb_argmax_rows(int device, const float* x, long long rows, int vocab, int32
  * `InferSession.__call__` (rapid_formula_self/inference_engine/torch.py:25-131); here the host side
  * (rapiddoc_b200/formula.py) walks the network and enqueues these ops on DEVICE buffers (NHWC activations = [pixels, C]
  * matrices with a row pitch).  All pointers are device pointers; nothing synchronises; prec = RDB_PREC_FP32 (fp32 SIMT,
- * exact-parity mode) or RDB_PREC_FP16 (fp16 storage, tcgen05 GEMMs).  act: 0 none, 1 ReLU, 2 GELU(erf). */
+ * exact-parity mode) or RDB_PREC_FP16 (fp16 storage, tcgen05 GEMMs).  act: 0 none, 1 ReLU, 2 GELU(erf), 6 HardSwish (fp32 path). */
 const char* rdb_ops_last_error(void);
 /* out[M, c_off : c_off+N] (row pitch ldc) = act(A[M,K] (pitch lda) * W[N,K]^T + bias) (+ res [M,N] pitch ldr): every conv1x1 /
  * nn.Linear, and every dense k x k conv after rdb_op_im2col.  W fp32 (prec 0) or fp16 (prec 1); bias fp32.
@@ -207,7 +207,8 @@ int rdb_op_conv_tc(int device, const void* x, int n, int h, int w, int c, int ld
 /* x [n,h,w,c] (pixel pitch ld) -> out [n*oh*ow, kh*kw*c], K order (ky, kx, c) = the packed conv weight order */
 int rdb_op_im2col(int device, int prec, const void* x, int n, int h, int w, int c, int ld, int kh, int kw, int sh, int sw, int pt, int pl,
                   int oh, int ow, void* out, void* stream);
-/* depthwise k x k conv + folded BN (+ ReLU): LightConvBNAct.conv2 and the stage downsample (rec_pphgnetv2.py:916-959,1177-1187) */
+/* depthwise k x k conv + folded BN + activation (`relu`: 0 none, 1 ReLU, 6 HardSwish — the act codes of rdb_op_gemm):
+ * LightConvBNAct.conv2 and the stage downsample (rec_pphgnetv2.py:916-959,1177-1187), the depthwise layers of PP-LCNet */
 int rdb_op_dwconv(int device, int prec, const void* x, int n, int h, int w, int c, int ld_in, int k, int stride, const float* wt,
                   const float* bias, int relu, void* out, int oh, int ow, int ld_out, int c_off, void* stream);
 /* PaddingSameAsPaddleMaxPool2d(2, stride 1) (rec_pphgnetv2.py:962-976) into a channel slice */
@@ -244,6 +245,11 @@ int rdb_op_resize_nearest(int device, const float* x, int n, int h, int w, int c
 /* ConvTranspose(kernel = stride = scale) = rdb_op_gemm to [n*h*w, scale*scale*c] (columns dy, dx, c) + this pixel shuffle */
 int rdb_op_depth_to_space(int device, const float* g, int n, int h, int w, int c, int scale, float* out, void* stream);
 int rdb_op_softmax_rows(int device, const float* x, long long rows, int c, float* out, void* stream);
+/* Image normalisation of TablePreprocess (rapid_table_self/table_structure/pp_structure/pre_process.py) on the device:
+ * img [n,h,w,3] uint8 canvases whose top-left valid_hw[i] = (rh, rw) region holds the resized image; out [n,h,w,4] fp32 NHWC
+ * (4th channel and the padding = 0); lut [3][256] fp32 = the reference's numpy expression evaluated for every byte value. */
+int rdb_op_lut_u8_nhwc4(int device, const uint8_t* img, const int32_t* valid_hw, const float* lut, int n, int h, int w, float* out,
+                        void* stream);
 
 /* ---- table structure: SLANet head ---------------------------------------------------------
  * The GRU-attention decode loop of SLAHead (the `Loop` node of slanet-1m.onnx / SLANet_plus, executed by onnxruntime inside

@@ -83,7 +83,7 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SILU = 3, ACT_SIGMOID = 4, ACT_GELUF = 5 };
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SILU = 3, ACT_SIGMOID = 4, ACT_GELUF = 5, ACT_HSWISH = 6 };
 
 // erf-GELU for the fp16 path, 11 issue slots instead of erff's ~24 (the GELU GEMM epilogues are issue-bound):
 // gelu(x) = x * Phi(x) with Phi(x) = sigmoid(x * h(x^2)), h = degree-4 least-max fit of logit(Phi(x)) / x on |x| <= 8
@@ -109,6 +109,7 @@ __device__ __forceinline__ float apply_act(float x) {
   if (ACT == ACT_GELUF) return gelu_fast(x);
   if (ACT == ACT_SILU) return x / (1.f + __expf(-x));
   if (ACT == ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
+  if (ACT == ACT_HSWISH) return x * fminf(fmaxf(fmaf(x, 1.f / 6.f, 0.5f), 0.f), 1.f);   // ONNX HardSwish: x * max(0, min(1, x/6 + 0.5))
   return x;
 }
 
@@ -119,6 +120,7 @@ __device__ __forceinline__ float apply_act_rt(float x, int act) {
     case ACT_GELUF: return apply_act<ACT_GELUF>(x);
     case ACT_SILU: return apply_act<ACT_SILU>(x);
     case ACT_SIGMOID: return apply_act<ACT_SIGMOID>(x);
+    case ACT_HSWISH: return apply_act<ACT_HSWISH>(x);
     default: return x;
   }
 }

@@ -145,6 +145,7 @@ void launch_gemm_simt(const GemmArgs& g, cudaStream_t st) {
     case ACT_RELU: gemm_simt_kernel<TA, TO, ACT_RELU, false><<<grid, 256, 0, st>>>(g); break;
     case ACT_GELU: gemm_simt_kernel<TA, TO, ACT_GELU, false><<<grid, 256, 0, st>>>(g); break;
     case ACT_SILU: gemm_simt_kernel<TA, TO, ACT_SILU, false><<<grid, 256, 0, st>>>(g); break;
+    case ACT_HSWISH: gemm_simt_kernel<TA, TO, ACT_HSWISH, false><<<grid, 256, 0, st>>>(g); break;
     default: throw Error("gemm_simt: bad act");
   }
   RDB_LAUNCH_CHECK();

@@ -80,7 +80,7 @@ __global__ void dwconv_vec8_kernel(const T* __restrict__ x, int n, int H, int W,
     float bv[8];
     Vec8<float>::load(bias + c, bv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { acc[j] += bv[j]; if (relu) acc[j] = fmaxf(acc[j], 0.f); }
+    for (int j = 0; j < 8; ++j) acc[j] = rdb::apply_act_rt(acc[j] + bv[j], relu);
     Vec8<T>::store(out + px * ld_out + c_off + c, acc);
   }
 }
@@ -132,7 +132,7 @@ __global__ void dwconv_strip4_kernel(const T* __restrict__ x, int n, int H, int 
     for (int p = 0; p < 4; ++p) {
       if (ox0 + p >= W) break;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { acc[p][j] += bv[j]; if (relu) acc[p][j] = fmaxf(acc[p][j], 0.f); }
+      for (int j = 0; j < 8; ++j) acc[p][j] = rdb::apply_act_rt(acc[p][j] + bv[j], relu);
       Vec8<T>::store(out + ((long long)(b * H + oy) * W + ox0 + p) * ld_out + c_off + c, acc[p]);
     }
   }
@@ -159,7 +159,7 @@ __global__ void dwconv_generic_kernel(const T* __restrict__ x, int n, int H, int
       }
     }
     acc += bias[c];
-    if (relu) acc = fmaxf(acc, 0.f);
+    acc = rdb::apply_act_rt(acc, relu);
     out[px * ld_out + c_off + c] = from_f32<T>(acc);
   }
 }
@@ -438,6 +438,26 @@ __global__ void softmax_rows_kernel(const float* __restrict__ x, long long rows,
   for (int c = lane; c < C; c += 32) out[r * C + c] = expf(x[r * C + c] - m) / s;
 }
 
+// uint8 HWC images (one padded canvas per image, valid region rh x rw at the top-left) -> normalised fp32 NHWC with the channels
+// padded to 4: out = lut[c][v] inside the valid region, 0 outside.  The 3 x 256 table is built by the caller with the very numpy
+// expression of the reference preprocessing, so the result is bit-identical to it by construction.
+__global__ void lut_u8_nhwc4_kernel(const uint8_t* __restrict__ img, const int* __restrict__ valid, const float* __restrict__ lut, int n, int H, int W,
+                                    float4* __restrict__ out) {
+  __shared__ float t[3 * 256];
+  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) t[i] = lut[i];
+  __syncthreads();
+  const long long total = (long long)n * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)((i / W) % H), b = (int)(i / ((long long)W * H));
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y < valid[2 * b] && x < valid[2 * b + 1]) {
+      const uint8_t* p = img + i * 3;
+      v = make_float4(t[p[0]], t[256 + p[1]], t[512 + p[2]], 0.f);
+    }
+    out[i] = v;
+  }
+}
+
 inline int grid_for(long long total) { long long g = (total + 255) / 256; return (int)(g > 148 * 32 ? 148 * 32 : (g < 1 ? 1 : g)); }
 
 }  // namespace ops
@@ -712,6 +732,16 @@ int rdb_op_softmax_rows(int device, const float* x, long long rows, int c, float
     rdb::DeviceGuard g(device);
     OpTimer tm("softmax_rows_op", (cudaStream_t)stream);
     rdb::ops::softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, rows, c, out);
+    RDB_LAUNCH_CHECK();
+  });
+}
+
+int rdb_op_lut_u8_nhwc4(int device, const uint8_t* img, const int32_t* valid_hw, const float* lut, int n, int h, int w, float* out, void* stream) {
+  return op_guard([&] {
+    RDB_CHECK(img && valid_hw && lut && out && n > 0 && h > 0 && w > 0 && ((uintptr_t)out % 16) == 0, "lut_u8_nhwc4: bad argument");
+    rdb::DeviceGuard g(device);
+    OpTimer tm("lut_u8_nhwc4_op", (cudaStream_t)stream);
+    rdb::ops::lut_u8_nhwc4_kernel<<<rdb::ops::grid_for((long long)n * h * w), 256, 0, (cudaStream_t)stream>>>(img, valid_hw, lut, n, h, w, reinterpret_cast<float4*>(out));
     RDB_LAUNCH_CHECK();
   });
 }

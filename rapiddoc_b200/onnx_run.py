@@ -36,19 +36,21 @@ class _T:
 
 
 class OnnxCnn:
-    def __init__(self, path, device=0):
+    def __init__(self, path, device=0, compile_only=False):
+        """compile_only: read the file and build the launch plan without touching a device (plan inspection in CPU tests)."""
         import torch
         self.torch, self.device, self.lib = torch, int(device), _lib.load()
-        if self.lib.rdb_device_count() <= self.device:
-            raise _lib.B200Error(f"no sm_100 CUDA device {self.device} for the ONNX executor (there is no CPU fallback)")
-        self.dev = torch.device("cuda", self.device)
+        if not compile_only:
+            if self.lib.rdb_device_count() <= self.device:
+                raise _lib.B200Error(f"no sm_100 CUDA device {self.device} for the ONNX executor (there is no CPU fallback)")
+            self.dev = torch.device("cuda", self.device)
         g = onnx_lite.load(path)
         self.graph, self.path = g, path
         self.meta = getattr(g, "meta", {})
         self.launches = 0
         self._const = {}          # name -> numpy constant (initializers + folded shape arithmetic)
         self._dev = {}            # cache key -> device tensor (weights / per-channel vectors)
-        self._alias, self._plans = {}, {}
+        self._alias, self._plans, self._folded = {}, {}, {}
         self.consts = dict(g.init)                    # initializers + Constant nodes (Paddle2ONNX exports the weights either way)
         for n in g.nodes:
             if n.op == "Constant":
@@ -85,6 +87,49 @@ class OnnxCnn:
                     n.attrs = {"alpha": p.attrs.get("alpha", 0.2), "beta": p.attrs.get("beta", 0.5)}
                     dead.add(id(p))
                     break
+        nodes = [n for n in nodes if id(n) not in dead]
+        return self._fuse_conv_epilogues(nodes)
+
+    def _fuse_conv_epilogues(self, nodes):
+        """Conv -> BatchNormalization -> (HardSwish | Relu), and Conv -> Add(per-channel constant) -> Relu, collapse into the conv
+        launch: BN scale folded into the packed weights, shift / bias into the GEMM bias, the activation into its epilogue."""
+        uses = {}
+        for n in nodes:
+            for i in n.inputs:
+                uses[i] = uses.get(i, 0) + 1
+        for o in self.graph.outputs:
+            uses[o] = uses.get(o, 0) + 1
+        consumer = {}
+        for n in nodes:
+            for i in n.inputs:
+                consumer.setdefault(i, n)
+        dead = set()
+        for n in nodes:
+            if n.op != "Conv":
+                continue
+            def only_next(ops):
+                out = n.outputs[0]
+                m = consumer.get(out)
+                return m if m is not None and uses.get(out, 0) == 1 and m.op in ops and m.inputs[0] == out and id(m) not in dead else None
+            m = only_next(("BatchNormalization",))
+            if m is not None:
+                n.attrs["fold_bn"] = (list(m.inputs[1:5]), float(m.attrs.get("epsilon", 1e-5)))
+                n.outputs = list(m.outputs)
+                dead.add(id(m))
+            else:
+                m = only_next(("Add",))
+                if m is not None and len(n.inputs) < 3:
+                    c = self.consts.get(m.inputs[1])
+                    co = self.consts[n.inputs[1]].shape[0]
+                    if c is not None and np.asarray(c).size == co:
+                        n.attrs["fold_bias"] = m.inputs[1]
+                        n.outputs = list(m.outputs)
+                        dead.add(id(m))
+            m = only_next(("HardSwish", "Relu"))
+            if m is not None:
+                n.attrs["fold_act"] = 6 if m.op == "HardSwish" else 1
+                n.outputs = list(m.outputs)
+                dead.add(id(m))
         return [n for n in nodes if id(n) not in dead]
 
     def _weight(self, key, make):
@@ -127,9 +172,9 @@ class OnnxCnn:
             t = self._mat(t)
         return _T(t.buf, t.n, t.h, t.w, t.c, t.steps + (step,))
 
-    def _gemm(self, A, lda, M, K, W, N, bias, out, ldc, c_off=0):
+    def _gemm(self, A, lda, M, K, W, N, bias, out, ldc, c_off=0, act=ACT_NONE):
         self.launches += 1
-        _lib.check_op(self.lib.rdb_op_gemm(self.device, _lib.PREC_FP32, A, lda, M, K, W.data_ptr(), N, bias.data_ptr() if bias is not None else None, ACT_NONE,
+        _lib.check_op(self.lib.rdb_op_gemm(self.device, _lib.PREC_FP32, A, lda, M, K, W.data_ptr(), N, bias.data_ptr() if bias is not None else None, act,
                                            None, 0, out, ldc, c_off, self._st(), None, 0))
 
     # ---------------------------------------------------------------- ops
@@ -143,7 +188,26 @@ class OnnxCnn:
         pads = node.attrs.get("pads", [0, 0, 0, 0])
         assert kh == kw and sh == sw and len(set(pads)) == 1 and set(node.attrs.get("dilations", [1, 1])) == {1}, f"unsupported conv geometry {node}"
         p = pads[0]
-        bias = self._weight(("b", node.inputs[2]), lambda: self.consts[node.inputs[2]]) if len(node.inputs) > 2 and node.inputs[2] else None
+        act = int(node.attrs.get("fold_act", ACT_NONE))
+        scale = None
+        if "fold_bn" in node.attrs:
+            names, eps = node.attrs["fold_bn"]
+            if ("bnb", wname) not in self._dev or wname not in self._folded:
+                gamma, beta, mean, var = (self.consts[i].astype(np.float64) for i in names)
+                scale = gamma / np.sqrt(var + eps)
+                shift = beta - mean * scale
+                if len(node.inputs) > 2 and node.inputs[2]:
+                    shift = shift + self.consts[node.inputs[2]].astype(np.float64) * scale
+            else:
+                shift = None
+            bias = self._weight(("bnb", wname), lambda: shift)
+            if wname not in self._folded:
+                self._folded[wname] = (W.astype(np.float64) * scale.reshape(-1, 1, 1, 1)).astype(np.float32)
+            W = self._folded[wname]
+        elif "fold_bias" in node.attrs:
+            bias = self._weight(("fb", node.attrs["fold_bias"]), lambda: np.asarray(self.consts[node.attrs["fold_bias"]]).reshape(-1))
+        else:
+            bias = self._weight(("b", node.inputs[2]), lambda: self.consts[node.inputs[2]]) if len(node.inputs) > 2 and node.inputs[2] else None
         x = self._mat(x)
         oh, ow = (x.h + 2 * p - kh) // sh + 1, (x.w + 2 * p - kw) // sw + 1
         if group == 1:
@@ -163,14 +227,14 @@ class OnnxCnn:
             out = self._new(x.n * oh * ow, co)
             M = x.n * oh * ow
             if kh == 1 and sh == 1 and p == 0:
-                self._gemm(x.buf.data_ptr(), x.buf.shape[1], M, cin, Wd, co, bias, out.data_ptr(), co)
+                self._gemm(x.buf.data_ptr(), x.buf.shape[1], M, cin, Wd, co, bias, out.data_ptr(), co, act=act)
             else:
                 K = kh * kw * cin
                 col = self._new(M, K)
                 self.launches += 1
                 _lib.check_op(self.lib.rdb_op_im2col(self.device, _lib.PREC_FP32, x.buf.data_ptr(), x.n, x.h, x.w, cin, x.buf.shape[1], kh, kw, sh, sw, p, p, oh, ow,
                                                      col.data_ptr(), self._st()))
-                self._gemm(col.data_ptr(), K, M, K, Wd, co, bias, out.data_ptr(), co)
+                self._gemm(col.data_ptr(), K, M, K, Wd, co, bias, out.data_ptr(), co, act=act)
             return _T(out, x.n, oh, ow, co)
         assert group == x.c == co and cig == 1 and p == (kh - 1) // 2 and (kh & 1), f"only depthwise grouped convs are supported: {node}"
         Wd = self._weight(("dw", wname), lambda: W.reshape(co, kh * kw).T)
@@ -179,7 +243,7 @@ class OnnxCnn:
         out = self._new(x.n * oh * ow, co)
         self.launches += 1
         _lib.check_op(self.lib.rdb_op_dwconv(self.device, _lib.PREC_FP32, x.buf.data_ptr(), x.n, x.h, x.w, co, x.buf.shape[1], kh, sh, Wd.data_ptr(), bias.data_ptr(),
-                                             0, out.data_ptr(), oh, ow, co, 0, self._st()))
+                                             act, out.data_ptr(), oh, ow, co, 0, self._st()))
         return _T(out, x.n, oh, ow, co)
 
     def _conv_transpose(self, node, x):
@@ -268,11 +332,17 @@ class OnnxCnn:
             stack.extend(i for i in n.inputs if i)
         return [n for n in self.nodes if id(n) in need]
 
-    def features(self, x, name):
-        """Run only what the tensor `name` needs and return it on the device as (buffer [n*h*w, C] NHWC fp32, n, h, w, C)."""
+    def features(self, x, name, nhwc4=None):
+        """Run only what the tensor `name` needs and return it on the device as (buffer [n*h*w, C] NHWC fp32, n, h, w, C).
+        nhwc4=(n, h, w): `x` is already the network input on the device as [n*h*w, 4] fp32 NHWC (3 channels + a zero one)."""
         torch = self.torch
         with torch.cuda.device(self.dev):
-            env = self._feed(x)
+            if nhwc4 is not None:
+                n, h, w = nhwc4
+                self._const, self._flat_out = {}, False
+                env = {self.input_name: _T(x.view(n * h * w, 4), n, h, w, 4)}
+            else:
+                env = self._feed(x)
             plan = self._plans.get(name)
             if plan is None:
                 plan = self._plans[name] = self._closure([name])

@@ -26,6 +26,7 @@ class TablePreprocess:
 
     def __init__(self, max_len=488):
         self.max_len = max_len
+        self._stage, self._lut, self._lut_dev = {}, None, {}
 
     def __call__(self, img_list):
         if isinstance(img_list, np.ndarray):
@@ -44,6 +45,48 @@ class TablePreprocess:
             imgs.append(pad.transpose((2, 0, 1)))
             shapes.append([h, w, ratio, ratio, self.max_len, self.max_len])
         return imgs, np.array(shapes)
+
+    def device_batch(self, img_list, device=0):
+        """The same preprocessing with only the uint8 resize on the host (cv2, threaded): the resized images are packed into one
+        pinned uint8 canvas batch, uploaded once, and normalised / padded on the device by table lookup (rdb_op_lut_u8_nhwc4; the
+        256-entry table per channel is produced by the numpy expression of __call__, so every float equals the host path's).
+        -> (CUDA tensor [B, max_len, max_len, 4] fp32 NHWC, shapes as __call__)"""
+        import torch
+        from .dbpost import pool
+        L = self.max_len
+        imgs = [im for im in ([img_list] if isinstance(img_list, np.ndarray) else img_list) if im is not None]
+        B = len(imgs)
+        stage = self._stage.get(B)
+        if stage is None:
+            stage = self._stage[B] = (torch.zeros((B, L, L, 3), dtype=torch.uint8).pin_memory(), torch.zeros((B, 2), dtype=torch.int32).pin_memory())
+        canvas, valid = stage
+        cnp, vnp = canvas.numpy(), valid.numpy()
+        shapes = []
+
+        def one(i):
+            h, w = imgs[i].shape[:2]
+            ratio = L / (max(h, w) * 1.0)
+            rh, rw = int(h * ratio), int(w * ratio)
+            cnp[i, :rh, :rw] = cv2.resize(imgs[i], (rw, rh))
+            vnp[i] = (rh, rw)
+            return [h, w, ratio, ratio, L, L]
+        shapes = list(pool().map(one, range(B)))
+        if self._lut is None:
+            v = np.arange(256, dtype=np.uint8).reshape(256, 1, 1).repeat(3, axis=2)              # [256,1,3]: value v in every channel
+            lut = np.zeros((256, 1, 3), np.float32)
+            lut[:] = (v.astype("float32") * (1 / 255.0) - IMAGENET_MEAN) / IMAGENET_STD          # the expression of __call__
+            self._lut = np.ascontiguousarray(lut[:, 0, :].T)                                     # [3][256]
+        dev = torch.device("cuda", int(device))
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream or None
+            if device not in self._lut_dev:
+                self._lut_dev[device] = torch.from_numpy(self._lut).to(dev)
+            d_img, d_valid = canvas.to(dev, non_blocking=True), valid.to(dev, non_blocking=True)
+            out = torch.empty((B, L, L, 4), dtype=torch.float32, device=dev)
+            _lib.check_op(_lib.load().rdb_op_lut_u8_nhwc4(int(device), d_img.data_ptr(), d_valid.data_ptr(), self._lut_dev[device].data_ptr(), B, L, L,
+                                                          out.data_ptr(), st))
+            torch.cuda.current_stream(dev).synchronize()          # the pinned canvases are reused by the next call
+        return out, np.array(shapes)
 
 
 def cls_preprocess_paddle(imgs, resize_short=256, size=224):
@@ -228,8 +271,10 @@ class SlaNetSession:
     def get_character_list(self, key="character"):
         return self.net.meta[key].splitlines()
 
-    def __call__(self, imgs):
-        """imgs [B,3,H,W] float32 -> (bbox_preds [B,T,loc], struct_probs [B,T,classes]) numpy, T as the graph's final Slice."""
+    def __call__(self, imgs, nhwc4=None, device_out=False):
+        """imgs [B,3,H,W] float32 -> (bbox_preds [B,T,loc], struct_probs [B,T,classes]) numpy, T as the graph's final Slice.
+        nhwc4=(H, W): imgs is a CUDA tensor [B,H,W,4] already normalised (TablePreprocess.device_batch).  device_out: the two
+        results stay on the device (torch tensors)."""
         torch, ct = self.torch, self._ctypes
         if not torch.is_tensor(imgs):                       # a CUDA tensor (already preprocessed, resident) is taken as it is
             imgs = np.asarray(imgs, np.float32)
@@ -238,7 +283,10 @@ class SlaNetSession:
             x = imgs[b0:b0 + self.MAX_BATCH]
             with torch.cuda.device(self.net.dev):
                 l0 = self.net.launches
-                feat, n, h, w, c = self.net.features(x, self.feature_name)
+                if nhwc4 is not None:
+                    feat, n, h, w, c = self.net.features(x.contiguous(), self.feature_name, nhwc4=(len(x), nhwc4[0], nhwc4[1]))
+                else:
+                    feat, n, h, w, c = self.net.features(x, self.feature_name)
                 assert c == self.C
                 st = torch.cuda.current_stream(self.net.dev).cuda_stream or None
                 dev, hw, S, V, L = self.net.dev, h * w, self.max_steps, self.classes, self.loc_dim
@@ -258,9 +306,11 @@ class SlaNetSession:
                 total = int(sync[2 + n].item())
                 self.last_steps = total
                 T = min(total + 1, S)
-                outs.append((loc[:, :T].cpu().numpy(), probs[:, :T].cpu().numpy()))
+                outs.append((loc[:, :T], probs[:, :T]) if device_out else (loc[:, :T].cpu().numpy(), probs[:, :T].cpu().numpy()))
         if len(outs) == 1:
             return outs[0]
+        if device_out:
+            outs = [(o[0].cpu().numpy(), o[1].cpu().numpy()) for o in outs]
         T = max(o[0].shape[1] for o in outs)                 # batches decoded separately stop at their own step: pad with untouched rows
 
         def pad(a, fill):
@@ -282,6 +332,11 @@ class B200TableStructurer:
         self.postprocess_op = TableLabelDecode(self.session.get_character_list(), slanet_plus=(model_type == "slanet_plus"), device=device)
 
     def __call__(self, ori_imgs):
-        imgs, shape_lists = self.preprocess_op(ori_imgs)
-        bbox_preds, struct_probs = self.session(np.asarray(imgs).copy())
+        """Host crops in, (structure tokens + score, cell boxes) out.  Only the uint8 resize runs on the host; normalisation,
+        network, decode loop and the arg-max of the label decode run on the device."""
+        x, shape_lists = self.preprocess_op.device_batch(ori_imgs, self.session.device)
+        L = self.preprocess_op.max_len
+        bbox_preds, struct_probs = self.session(x, nhwc4=(L, L), device_out=len(x) <= self.session.MAX_BATCH)
+        if not isinstance(bbox_preds, np.ndarray):
+            bbox_preds = bbox_preds.cpu().numpy()
         return self.postprocess_op(bbox_preds, struct_probs, shape_lists, ori_imgs)

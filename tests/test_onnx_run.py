@@ -60,14 +60,18 @@ def test_orientation_label_follows_the_reference_preprocess():
 
 
 def test_executor_plan_fuses_elementwise_runs():
-    """Compile only (no GPU work): Identity nodes vanish, Mul(HardSigmoid(y), y) pairs become one step."""
+    """Compile only (no GPU work): Identity nodes vanish, Mul(HardSigmoid(y), y) pairs become one step, Conv + BatchNormalization
+    + activation (and Conv + bias Add + Relu) collapse into the conv launch."""
     from rapiddoc_b200.onnx_run import OnnxCnn
-    s = OnnxCnn.__new__(OnnxCnn)
-    s._alias = {}
-    nodes = s._rewrite(onnx_lite.load(SEAL))
-    ops = [n.op for n in nodes]
+    ops = [n.op for n in OnnxCnn(SEAL, compile_only=True).nodes]
     assert "Identity" not in ops and ops.count("HardSwishAB") >= 20
     assert ops.count("HardSigmoid") == 34 - ops.count("HardSwishAB")          # the rest are squeeze-excite gates
+    ori = OnnxCnn(ORI, compile_only=True).nodes
+    assert len(ori) < 50 and not any(n.op in ("BatchNormalization", "HardSwish", "Relu") for n in ori)     # 115 graph nodes
+    convs = [n for n in ori if n.op == "Conv"]
+    assert sum("fold_bn" in n.attrs and n.attrs.get("fold_act") == 6 for n in convs) == 27
+    sla = OnnxCnn(os.path.join(ROOT, "weights", "slanet-1m.onnx"), compile_only=True).nodes
+    assert sum(n.op == "Conv" and "fold_bn" in n.attrs and n.attrs.get("fold_act") == 6 for n in sla) == 73
 
 
 # ------------------------------------------------------------------------------------------------------- GPU
@@ -194,6 +198,20 @@ def test_slanet_session_matches_the_oracle(batch):
     if batch == 3:
         assert np.array_equal(probs.argmax(-1), GOLD["slanet_ids"]) and loc.shape[1] == 42
     assert s.launches < 250                                       # 830 graph nodes + <= 501 loop iterations
+
+
+@pytest.mark.gpu
+def test_table_device_preprocess_is_bit_identical_to_the_host_class():
+    import torch
+    from rapiddoc_b200.table import TablePreprocess
+    imgs, x, shapes = MG.table_inputs()
+    pre = TablePreprocess()
+    d, dshapes = pre.device_batch(imgs, 0)
+    assert d.shape == (3, 488, 488, 4) and np.array_equal(dshapes, shapes)
+    got = d.cpu().numpy()
+    assert np.array_equal(got[..., :3].transpose(0, 3, 1, 2), x) and not got[..., 3].any()
+    d2, _ = pre.device_batch(imgs[:1], 0)                                   # another batch size: its own staging canvases
+    assert torch.equal(d2[0], d[0])
 
 
 @pytest.mark.gpu
