@@ -304,23 +304,41 @@ dwconv_tiled_kernel(const T* __restrict__ in, int N, int H, int W, int C, const 
   const int c0 = cb * 8 * G;
   const int tid = threadIdx.x;
   for (int i = tid; i < K * K * 8 * G; i += blockDim.x) sw[i] = w[(i / (8 * G)) * C + c0 + i % (8 * G)];
-  for (int i = tid; i < HH * HW * G; i += blockDim.x) {
-    const int g = i % G, p = i / G;
-    const int hx = p % HW, hy = p / HW;
-    const int iy = y0 + hy - K / 2, ix = x0 + hx - K / 2;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-      if (sizeof(T) == 2) {
-        v = *reinterpret_cast<const uint4*>(in + (((long long)n * H + iy) * W + ix) * C + c0 + g * 8);
-      } else {
+  if (sizeof(T) == 2) {
+    // halo staging with every load of a thread in flight before the first shared-memory store (ncu: the per-iteration
+    // load -> store dependency left the kernel waiting on long_scoreboard 4 cycles per issued instruction)
+    constexpr int NT = G * (TW / 4) * TH, NLD = (HH * HW * G + NT - 1) / NT;
+    uint4 v[NLD];
+#pragma unroll
+    for (int u = 0; u < NLD; ++u) {
+      const int i = tid + u * NT;
+      const int g = i % G, p = i / G;
+      const int hx = p % HW, hy = p / HW;
+      const int iy = y0 + hy - K / 2, ix = x0 + hx - K / 2;
+      v[u] = make_uint4(0, 0, 0, 0);
+      if (i < HH * HW * G && iy >= 0 && iy < H && ix >= 0 && ix < W)
+        v[u] = __ldg(reinterpret_cast<const uint4*>(in + (((long long)n * H + iy) * W + ix) * C + c0 + g * 8));
+    }
+#pragma unroll
+    for (int u = 0; u < NLD; ++u) {
+      const int i = tid + u * NT;
+      if (i < HH * HW * G) *reinterpret_cast<uint4*>(tile + (i / G) * PITCH + (i % G) * 16) = v[u];
+    }
+  } else {
+    for (int i = tid; i < HH * HW * G; i += blockDim.x) {
+      const int g = i % G, p = i / G;
+      const int hx = p % HW, hy = p / HW;
+      const int iy = y0 + hy - K / 2, ix = x0 + hx - K / 2;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
         float f[8];
         Vec8<T>::load(in + (((long long)n * H + iy) * W + ix) * C + c0 + g * 8, f);
         __half2* hp = reinterpret_cast<__half2*>(&v);
 #pragma unroll
         for (int j = 0; j < 4; ++j) hp[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
       }
+      *reinterpret_cast<uint4*>(tile + (hy * HW + hx) * PITCH + g * 16) = v;
     }
-    *reinterpret_cast<uint4*>(tile + (hy * HW + hx) * PITCH + g * 16) = v;
   }
   __syncthreads();
   const int g = tid % G, xs = (tid / G) % XS, ty = tid / (G * XS);
