@@ -354,8 +354,6 @@ def run_pipeline(args, wl):
     import torch.distributed as dist
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from rapiddoc_b200 import _lib, PREC_FP16, PREC_FP32, synth, weights as W
@@ -876,6 +874,9 @@ def run_reference(args, wl_key, wl):
 
 def main():
     args = parse()
+    # NCCL prints its version banner (levels VERSION and WARN) and every debug line to stdout: route them to stderr so that
+    # stdout carries the one JSON line only
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     wl_key = args.workload
     wl = dict(WORKLOADS[wl_key])
     if args.batch:
@@ -893,8 +894,6 @@ def main():
     import torch.distributed as dist
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"        # NCCL's version banner goes to stdout: keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from rapiddoc_b200 import _lib, PREC_FP16, PREC_FP32, synth, weights as W

@@ -60,19 +60,64 @@ def gather_objects(obj):
     return out
 
 
-def pin_rank_to_cores(local_rank: int, local_world: int):
-    """One process per GPU on one box: give every rank a contiguous, equal share of the cores this job may use (core numbering
-    is node-contiguous on the usual 2-socket hosts, so ranks 0..N/2-1 land on NUMA node 0 with GPUs 0..N/2-1).  The host half
-    of the pipeline (contours, Clipper, staging copies) then sizes its thread pools from the affinity mask instead of
+def gpu_ideal_cores(local_world: int):
+    """Per local GPU, the CPU set NVML reports as closest to it (its NUMA node / PCIe root), or None when NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        import os
+        ncpu = (max(os.sched_getaffinity(0)) // 64) + 1
+        out = []
+        for g in range(local_world):
+            h = pynvml.nvmlDeviceGetHandleByIndex(g)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, max(ncpu, 1))
+            out.append({64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1})
+        return out
+    except Exception:
+        return None
+
+
+def plan_rank_cores(cores, local_world: int, ideal=None):
+    """Core lists for local ranks 0..local_world-1.  With `ideal` (per-GPU nearest-CPU sets) every rank gets an equal share of
+    the allowed cores NEAR ITS GPU — ranks whose GPUs hang off the same NUMA node split that node's cores; ranks whose ideal set
+    is empty after intersecting with the allowed cores, and the no-NVML case, fall back to contiguous equal shares."""
+    cores = sorted(cores)
+    per = len(cores) // max(1, local_world)
+    if per < 1:
+        return [list(cores) for _ in range(local_world)]
+    flat = [cores[r * per:(r + 1) * per] for r in range(local_world)]
+    if not ideal or len(ideal) < local_world:
+        return flat
+    groups = {}
+    for r in range(local_world):
+        key = tuple(sorted(set(ideal[r]) & set(cores)))
+        groups.setdefault(key, []).append(r)
+    plan = [None] * local_world
+    for key, ranks in groups.items():
+        share = len(key) // len(ranks)
+        if share < 1:
+            for r in ranks:
+                plan[r] = flat[r]
+            continue
+        share = min(share, max(per, 1) * 2)           # never starve the other node: at most twice the flat share
+        for i, r in enumerate(ranks):
+            plan[r] = list(key[i * share:(i + 1) * share])
+    return plan
+
+
+def pin_rank_to_cores(local_rank: int, local_world: int, ideal="nvml"):
+    """One process per GPU on one box: give every rank an equal share of the cores this job may use, taken from the CPUs NVML
+    reports as nearest to the rank's GPU (pinned staging buffers are then first-touched on that NUMA node, and the copy
+    engines do not cross the socket interconnect); contiguous equal shares when NVML gives nothing.  The host half of the
+    pipeline (contours, Clipper, staging copies) sizes its thread pools from the resulting affinity mask instead of
     oversubscribing the whole machine N times.  Returns the core list (or None where affinity is not supported)."""
     import os
     try:
         cores = sorted(os.sched_getaffinity(0))
     except Exception:
         return None
-    per = len(cores) // max(1, local_world)
-    if per < 1:
-        return cores
-    mine = cores[local_rank * per: (local_rank + 1) * per]
-    os.sched_setaffinity(0, mine)
+    sets = gpu_ideal_cores(local_world) if ideal == "nvml" else ideal
+    mine = plan_rank_cores(cores, local_world, sets)[local_rank]
+    if mine:
+        os.sched_setaffinity(0, mine)
     return mine

@@ -62,10 +62,27 @@ def test_pin_rank_to_cores_partitions_the_affinity_mask():
         shares = []
         for r in range(2):
             os.sched_setaffinity(0, before)
-            shares.append(pin_rank_to_cores(r, 2))
+            shares.append(pin_rank_to_cores(r, 2, ideal=None))
         if len(before) >= 2:
             assert not set(shares[0]) & set(shares[1]) and len(shares[0]) == len(shares[1]) == len(before) // 2
             from rapiddoc_b200 import dbpost
             assert dbpost.host_threads() == len(shares[1])
     finally:
         os.sched_setaffinity(0, before)
+
+
+def test_rank_core_plan_follows_gpu_numa_locality():
+    from rapiddoc_b200.parallel import plan_rank_cores
+    cores = list(range(32))
+    assert plan_rank_cores(cores, 4) == [list(range(0, 8)), list(range(8, 16)), list(range(16, 24)), list(range(24, 32))]
+    # 8 GPUs, two NUMA nodes with interleaved core numbering (even cores node 0, odd cores node 1); GPUs 0-3 on node 0
+    node0, node1 = set(range(0, 32, 2)), set(range(1, 32, 2))
+    plan = plan_rank_cores(cores, 8, [node0] * 4 + [node1] * 4)
+    assert all(len(p) == 4 for p in plan) and all(set(p) <= node0 for p in plan[:4]) and all(set(p) <= node1 for p in plan[4:])
+    assert len({c for p in plan for c in p}) == 32                                   # disjoint, all cores used
+    # the job may only use 8 cores, all on node 0: ranks on node 1 fall back to their flat share
+    plan = plan_rank_cores(list(range(0, 16, 2)), 4, [node0, node0, node1, node1])
+    assert plan[0] == [0, 2, 4, 6][:len(plan[0])] and plan[2] == [8, 10] and plan[3] == [12, 14]
+    # one GPU with every core near it: capped at twice the flat share is irrelevant for a single rank
+    assert plan_rank_cores(cores, 1, [set(cores)]) == [cores]
+    assert plan_rank_cores([0, 1], 4) == [[0, 1]] * 4                                # fewer cores than ranks: no pinning split
