@@ -503,7 +503,7 @@ def run_pipeline(args, wl):
                 "clocks": clocks, "e2e": {"value": e2e, "unit": wl["unit"], "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "fp32_exact": fp32, "secondary": secondary,
                 "skipped": SKIPPED_CONFIGS}
-        print(json.dumps(line), flush=True)
+        emit_line(json.dumps(line), flush=True)
     if world > 1:
         barrier()
         dist.destroy_process_group()
@@ -668,7 +668,7 @@ def run_formula(args, wl):
                            "l2": "activations per step (GBs) exceed the 126 MB L2", "parallelism": f"crop-parallel replicas x{world}"},
                 "clocks": clocks, "e2e": {"value": e2e, "unit": wl["unit"], "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(ids.size * 8)},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        emit_line(json.dumps(line), flush=True)
     if world > 1:
         barrier()
         dist.destroy_process_group()
@@ -758,10 +758,23 @@ def run_table(args, wl):
         except Exception:
             pass
         hbm = peaks.get("hbm_gbs_sustained", peaks.get("hbm_gbs", 6500.0))
-        # the backbone's convolutions dominate: fp32 activations, every conv input read once and output written once
-        conv_ms = sum(v[0] for k, v in fam.items() if k in ("gemm_simt_op", "im2col_op", "dwconv_op", "chain_op"))
-        roofline = {"kernel": top[0][0], "bound": "hbm", "achieved": None, "peak": hbm, "unit": "GB/s", "frac": None, "traffic": None,
-                    "share_of_step": top[0][1][0] / tot, "top5": [{"kernel": k, "ms": v[0], "launches": v[1], "share": v[0] / tot} for k, v in top[:5]],
+        # the backbone's convolutions dominate: fp32 activations; a GEMM launch must read A [M,K] and W [N,K] and write [M,N] once
+        conv_ms = sum(v[0] for k, v in fam.items() if k in ("gemm_simt_op", "im2col", "im2col_op", "dwconv_op", "chain_op"))
+        g_bytes = g_ms = 0.0
+        g_launches = 0
+        for k, v in prof.items():
+            kind, a = _kv(k)
+            if kind == "gemm_simt_op":
+                g_bytes += 4.0 * (a["M"] * a["K"] + a["M"] * a["N"] + a["N"] * a["K"]) * v[1]
+                g_ms += v[0]
+                g_launches += v[1]
+        ach = g_bytes / (g_ms * 1e-3) / 1e9 if g_ms else None
+        roofline = {"kernel": "gemm_simt_op (fp32 SIMT GEMM: the backbone's pointwise / im2col convolutions)", "bound": "hbm", "achieved": ach, "peak": hbm,
+                    "unit": "GB/s", "frac": (ach / hbm) if ach else None, "traffic": None, "launches_profiled": g_launches,
+                    "avg_launch_us": (g_ms * 1e3 / g_launches) if g_launches else None,
+                    "algorithmic_bytes_per_launch": (g_bytes / g_launches) if g_launches else None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback",
+                    "share_of_step": (g_ms / tot) if tot else None, "top5": [{"kernel": k, "ms": v[0], "launches": v[1], "share": v[0] / tot} for k, v in top[:5]],
                     "backbone_ms": conv_ms, "profiled_total_ms": tot, "decode_steps": steps_decoded,
                     "note": "fp32 SIMT path (the reference's precision); the decode loop is latency-bound (one CTA per table, sequential steps)"}
         cpu = None
@@ -788,7 +801,7 @@ def run_table(args, wl):
                 "clocks": clocks, "e2e": {"value": e2e, "unit": wl["unit"], "h2d_bytes_per_step": int(x_host.numel() * 4),
                                           "d2h_bytes_per_step": int(loc.size * 4 + probs.size * 4)},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        emit_line(json.dumps(line), flush=True)
     if world > 1:
         barrier()
         dist.destroy_process_group()
@@ -818,7 +831,7 @@ def run_reference(args, wl_key, wl):
             FN.forward(x, sd, FM.ARCH_M, FORMULA_TOKENS)
         dt = time.perf_counter() - t0
         v = 2 * args.steps / dt
-        print(json.dumps({"impl": "reference", "metric": wl["metric"], "value": v, "unit": wl["unit"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        emit_line(json.dumps({"impl": "reference", "metric": wl["metric"], "value": v, "unit": wl["unit"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": wl["name"], "sample": "2 of the 32 per step", "engine": "torch CPU fp32 (oracle port of the reference module)"},
                           "cpu_baseline": {"value": v, "unit": wl["unit"], "cores": min(os.cpu_count(), 32), "host_cores": os.cpu_count(), "kind": "port", "sample": f"2 crops per step x {args.steps} steps"},
@@ -845,7 +858,7 @@ def run_reference(args, wl_key, wl):
             step()
         dt = time.perf_counter() - t0
         v = 2 * args.steps / dt
-        print(json.dumps({"impl": "reference", "metric": wl["metric"], "value": v, "unit": wl["unit"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        emit_line(json.dumps({"impl": "reference", "metric": wl["metric"], "value": v, "unit": wl["unit"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": wl["name"], "sample": "2 of the 32 per step", "engine": "torch CPU fp32 node-by-node execution of slanet-1m.onnx (onnxruntime is not installed)"},
                           "cpu_baseline": {"value": v, "unit": wl["unit"], "cores": min(os.cpu_count(), 32), "host_cores": os.cpu_count(), "kind": "port", "sample": f"2 tables per step x {args.steps} steps"},
@@ -869,11 +882,32 @@ def run_reference(args, wl_key, wl):
                        **({"rec_batch_num": args.rec_batch} if wl_key == "pipeline" else {})},
             "cpu_baseline": {"value": v, "unit": wl["unit"], "cores": threads, "host_cores": os.cpu_count(), "kind": "port", "sample": f"{sample} {wl['unit'].split('/')[0]} per step x {args.steps} steps"},
             "e2e": {"value": v, "unit": wl["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit_line(json.dumps(line), flush=True)
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries write there too (NCCL prints its version banner to fd 1 from C).
+    Keep a private duplicate of the real stdout for the result line and point fd 1 (and Python's sys.stdout) at stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def emit_line(text, flush=True):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(text + "\n")
+    out.flush()
 
 
 def main():
     args = parse()
+    claim_stdout()
     # NCCL prints its version banner (levels VERSION and WARN) and every debug line to stdout: route them to stderr so that
     # stdout carries the one JSON line only
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -1059,7 +1093,7 @@ def main():
                            "parallelism": f"page-parallel replicas x{world}, NCCL weight broadcast at init only"},
                 "clocks": clocks, "e2e": {"value": e2e, "unit": wl["unit"], "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        emit_line(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

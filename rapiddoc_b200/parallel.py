@@ -77,11 +77,36 @@ def gpu_ideal_cores(local_world: int):
         return None
 
 
+def smt_order(cores):
+    """The allowed logical CPUs ordered so that hyper-thread siblings are adjacent (physical core by physical core, from
+    /sys/devices/system/cpu/cpuN/topology/thread_siblings_list): a contiguous split then hands WHOLE physical cores to a rank
+    instead of giving two ranks the two halves of the same cores (Linux numbers the second hardware threads after all the
+    first ones).  Falls back to numeric order."""
+    cores = sorted(cores)
+    allowed, groups, seen = set(cores), [], set()
+    try:
+        for c in cores:
+            if c in seen:
+                continue
+            with open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list") as f:
+                txt = f.read().strip()
+            sib = set()
+            for part in txt.split(","):
+                lo, _, hi = part.partition("-")
+                sib.update(range(int(lo), int(hi or lo) + 1))
+            g = sorted(sib & allowed) or [c]
+            seen.update(g)
+            groups.append(g)
+    except Exception:
+        return cores
+    return [c for g in sorted(groups, key=lambda g: g[0]) for c in g]
+
+
 def plan_rank_cores(cores, local_world: int, ideal=None):
     """Core lists for local ranks 0..local_world-1.  With `ideal` (per-GPU nearest-CPU sets) every rank gets an equal share of
     the allowed cores NEAR ITS GPU — ranks whose GPUs hang off the same NUMA node split that node's cores; ranks whose ideal set
     is empty after intersecting with the allowed cores, and the no-NVML case, fall back to contiguous equal shares."""
-    cores = sorted(cores)
+    cores = list(cores)                                   # caller's order (smt_order keeps hyper-thread siblings adjacent)
     per = len(cores) // max(1, local_world)
     if per < 1:
         return [list(cores) for _ in range(local_world)]
@@ -90,7 +115,8 @@ def plan_rank_cores(cores, local_world: int, ideal=None):
         return flat
     groups = {}
     for r in range(local_world):
-        key = tuple(sorted(set(ideal[r]) & set(cores)))
+        near = set(ideal[r])
+        key = tuple(c for c in cores if c in near)
         groups.setdefault(key, []).append(r)
     plan = [None] * local_world
     for key, ranks in groups.items():
@@ -113,7 +139,7 @@ def pin_rank_to_cores(local_rank: int, local_world: int, ideal="nvml"):
     oversubscribing the whole machine N times.  Returns the core list (or None where affinity is not supported)."""
     import os
     try:
-        cores = sorted(os.sched_getaffinity(0))
+        cores = smt_order(os.sched_getaffinity(0))
     except Exception:
         return None
     sets = gpu_ideal_cores(local_world) if ideal == "nvml" else ideal

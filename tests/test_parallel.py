@@ -86,3 +86,17 @@ def test_rank_core_plan_follows_gpu_numa_locality():
     # one GPU with every core near it: capped at twice the flat share is irrelevant for a single rank
     assert plan_rank_cores(cores, 1, [set(cores)]) == [cores]
     assert plan_rank_cores([0, 1], 4) == [[0, 1]] * 4                                # fewer cores than ranks: no pinning split
+
+
+def test_smt_order_keeps_siblings_adjacent():
+    import os
+    from rapiddoc_b200.parallel import plan_rank_cores, smt_order
+    if not hasattr(os, "sched_getaffinity"):
+        return
+    cores = sorted(os.sched_getaffinity(0))
+    order = smt_order(cores)
+    assert sorted(order) == cores
+    # a 16-core / 32-thread box numbered the Linux way: cpu c and c+16 share a core -> ranks get whole physical cores
+    fake = [c for pair in zip(range(16), range(16, 32)) for c in pair]
+    plan = plan_rank_cores(fake, 4)
+    assert plan[0] == [0, 16, 1, 17, 2, 18, 3, 19] and plan[3] == [12, 28, 13, 29, 14, 30, 15, 31]
