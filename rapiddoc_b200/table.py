@@ -1,16 +1,20 @@
-"""Table path: the numeric pre/post-processing around the table networks.
+"""Table path: the table-structure model RapidDoc ships and the numeric pre/post-processing
+around the table networks.
 
 Reference (under rapid_doc/model/):
   T2  PaddleCls / QanythingCls preprocessing + softmax vote      table/rapid_table_self/table_cls/main.py:46-187
   T3  TablePreprocess (488 pad)                                  table/rapid_table_self/table_structure/pp_structure/pre_process.py:10-60
-  T4/T6  SLANet_plus / UNET / cls networks                       ONNX files downloaded at first run — weights unavailable offline;
-                                                                 the classes below take the reference's InferSession-protocol object
+                                                                 (`device_batch`: normalise + pad + NHWC packing on the GPU, bit-identical)
+  T4  SLANet (`slanet-1m.onnx`, ModelType.SLANET1M)              `SlaNetSession` = OrtInferSession.__call__ for this file,
+                                                                 inference_engine/onnxruntime/main.py:70-76; `B200TableStructurer` =
+                                                                 PPTableStructurer, table_structure/pp_structure/main.py:25-51
+      SLANet_plus / UNET / cls networks                          ONNX files downloaded at first run — weights unavailable offline
   T5  TableLabelDecode                                           .../pp_structure/post_process.py:11-131
-  T8  RapidOrientationModel.predict's portrait / vertical-box rule   orientation/rapid_orientation_model.py:12-53
+  T8  RapidOrientationModel.predict's portrait / vertical-box rule   orientation/rapid_orientation_model.py:12-53 (classifier: orientation.py)
 
-T5's reduction over the structure vocabulary ([B,T,50] probabilities -> argmax id + its probability per step) runs on the GPU
+T5's reduction over the structure vocabulary ([B,T,V] probabilities -> argmax id + its probability per step) runs on the GPU
 (rdb_argmax_rows, first maximum wins as np.argmax) — with a device-resident `struct_probs` only 8 bytes per step come back
-instead of 200; the token walk (eos stop, <td> boxes, score mean) is short host code on those ids.
+instead of 4 V; the token walk (eos stop, <td> boxes, score mean) is short host code on those ids.
 """
 import cv2
 import numpy as np

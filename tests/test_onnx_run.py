@@ -201,6 +201,31 @@ def test_slanet_session_matches_the_oracle(batch):
 
 
 @pytest.mark.gpu
+def test_slanet_loop_edges_max_steps_and_split_batches():
+    """(1) a row that never emits the end token: the loop runs to max_steps and the outputs are the first max_steps rows of the
+    free-running decode; (2) batches larger than MAX_BATCH are decoded in pieces, each stopping at its own step, rows padded
+    with the untouched-row values."""
+    from rapiddoc_b200.table import SlaNetSession
+    _, x, _ = MG.table_inputs()
+    s = SlaNetSession(SLANET, 0)
+    loc, probs = s(x)                                   # 42 rows (longest table: 40 steps + eos + the untouched row)
+    ids = probs.argmax(-1)
+    s.max_steps, s.eos = 20, 3                          # token 3 ("</td>" of a spanning cell) never appears in these tables
+    loc20, probs20 = s(x)
+    assert s.last_steps == 20 and probs20.shape == (3, 20, 30) and loc20.shape == (3, 20, 4)
+    assert np.array_equal(probs20.argmax(-1), ids[:, :20]) and np.abs(probs20 - probs[:, :20]).max() < 1e-6
+    s.max_steps, s.eos = 501, 29
+    s.MAX_BATCH = 2                                     # instance override: 3 tables -> pieces of 2 + 1
+    loc_s, probs_s = s(x)
+    assert probs_s.shape[0] == 3 and probs_s.shape[1] == 42          # piece 1 = tables 0, 1 -> 42 rows; piece 2 = table 2 -> 18, padded
+    ids_s = probs_s.argmax(-1)
+    for b in range(3):
+        end = int(np.argmax(ids[b] == 29))
+        assert np.array_equal(ids_s[b, :end + 1], ids[b, :end + 1]) and np.abs(loc_s[b, :end + 1] - loc[b, :end + 1]).max() < 1e-6
+    assert np.allclose(probs_s[2, 18:], 1 / 30) and not loc_s[2, 18:].any()
+
+
+@pytest.mark.gpu
 def test_table_device_preprocess_is_bit_identical_to_the_host_class():
     import torch
     from rapiddoc_b200.table import TablePreprocess
