@@ -38,9 +38,17 @@ def _exec(g, env):
         elif n.op == "Constant":
             y = _t(np.asarray(a["value"]))
         elif n.op == "Conv":
-            p = a.get("pads", [0, 0, 0, 0])
-            assert p[0] == p[2] and p[1] == p[3]
-            y = F.conv2d(i[0], i[1], i[2] if len(i) > 2 else None, a.get("strides", [1, 1]), (p[0], p[1]), a.get("dilations", [1, 1]), a.get("group", 1))
+            x, st = i[0], a.get("strides", [1, 1])
+            if a.get("auto_pad", "NOTSET") == "SAME_UPPER":           # output = ceil(in / stride); the odd padding element goes at the end
+                k = i[1].shape[2:]
+                ph = max((-(-x.shape[2] // st[0]) - 1) * st[0] + k[0] - x.shape[2], 0)
+                pw = max((-(-x.shape[3] // st[1]) - 1) * st[1] + k[1] - x.shape[3], 0)
+                x = F.pad(x, (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2))
+                p = [0, 0, 0, 0]
+            else:
+                p = a.get("pads", [0, 0, 0, 0])
+                assert p[0] == p[2] and p[1] == p[3]
+            y = F.conv2d(x, i[1], i[2] if len(i) > 2 else None, st, (p[0], p[1]), a.get("dilations", [1, 1]), a.get("group", 1))
         elif n.op == "ConvTranspose":
             p = a.get("pads", [0, 0, 0, 0])
             y = F.conv_transpose2d(i[0], i[1], i[2] if len(i) > 2 else None, a.get("strides", [1, 1]), (p[0], p[1]), 0, a.get("group", 1))
@@ -62,6 +70,33 @@ def _exec(g, env):
             y = i[0] - i[1]
         elif n.op == "Mul":
             y = i[0] * i[1]
+        elif n.op == "Div":
+            y = i[0] / i[1]
+        elif n.op == "Pow":
+            y = torch.pow(i[0], i[1])
+        elif n.op == "Sqrt":
+            y = torch.sqrt(i[0])
+        elif n.op == "Erf":
+            y = torch.erf(i[0])
+        elif n.op == "ReduceMean":
+            axes = [int(v) - (1 << 64) if int(v) >= (1 << 63) else int(v) for v in a["axes"]]
+            y = i[0].mean(dim=axes, keepdim=bool(a.get("keepdims", 1)))
+        elif n.op in ("MaxPool", "AveragePool"):
+            k, st = a["kernel_shape"], a.get("strides", a["kernel_shape"])
+            x = i[0]
+            if a.get("auto_pad", "NOTSET") == "SAME_UPPER":
+                ph = max((-(-x.shape[2] // st[0]) - 1) * st[0] + k[0] - x.shape[2], 0)
+                pw = max((-(-x.shape[3] // st[1]) - 1) * st[1] + k[1] - x.shape[3], 0)
+                pads = (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2)                  # extra padding at the end (UPPER)
+            else:
+                p4 = a.get("pads", [0, 0, 0, 0])
+                pads = (p4[1], p4[3], p4[0], p4[2])
+            assert a.get("ceil_mode", 0) == 0
+            if n.op == "MaxPool":
+                y = F.max_pool2d(F.pad(x, pads, value=float("-inf")), k, st)
+            else:
+                assert a.get("count_include_pad", 0) == 0 and not any(pads)
+                y = F.avg_pool2d(x, k, st)
         elif n.op == "Min":
             y = torch.minimum(i[0], i[1])
         elif n.op == "Less":

@@ -252,3 +252,54 @@ def test_table_structurer_interface():
         assert tok == rtok and abs(score - rscore) < 1e-4
         assert tok.count("<tr>") == rows and tok.count("<td></td>") == rows * cols
         assert cb.shape == rcb.shape == (rows * cols, 4) and np.abs(cb - rcb).max() < 0.1        # pixels
+
+
+# ------------------------------------------------------------- the OCR oracles against the reference's own ONNX model files
+REF_RES = "/root/reference/rapid_doc/resources"
+
+
+def test_ocr_oracles_match_the_reference_onnx_files():
+    """RapidDoc's default engine is onnxruntime on ch_PP-OCRv6_{det,rec}_small.onnx; the repo's oracles are torch restatements on
+    the safetensors weights.  An independent runtime (OpenCV DNN) on the det file and the node-by-node interpreter on the rec file
+    agree with them."""
+    if not os.path.isdir(REF_RES):
+        pytest.skip("reference tree not mounted")
+    cv2 = pytest.importorskip("cv2")
+    import torch
+    from oracle import nets, ocr_post as P
+    from rapiddoc_b200 import synth
+    page = synth.det_pages(1, 256, 512, seed=4, lines=5)[0]
+    x = P.det_preprocess(page, limit_side_len=4096)
+    want = nets.det_forward(x)
+    net = cv2.dnn.readNetFromONNX(os.path.join(REF_RES, "ch_PP-OCRv6_det_small.onnx"))
+    net.setInput(x)
+    dnn = net.forward()
+    assert np.abs(dnn - want).max() < 2e-4 and ((dnn > 0.3) != (want > 0.3)).sum() == 0
+    assert np.abs(onnx_ref.run(os.path.join(REF_RES, "ch_PP-OCRv6_det_small.onnx"), x) - want).max() < 2e-5
+    assert np.abs(GOLD["ocr_det_onnx_prob"].astype(np.float32) - want[0, 0]).max() < 1e-3            # fp16 storage
+    xr = np.random.RandomState(0).randn(3, 3, 48, 160).astype(np.float32)
+    probs = onnx_ref.run(os.path.join(REF_RES, "ch_PP-OCRv6_rec_small.onnx"), xr)
+    mine = torch.softmax(torch.from_numpy(nets.rec_logits(xr)), -1).numpy()
+    assert probs.shape == mine.shape == (3, 20, 18710)
+    assert np.abs(probs - mine).max() < 2e-4 and np.array_equal(probs.argmax(-1), mine.argmax(-1))
+    assert np.array_equal(GOLD["ocr_rec_onnx_ids"], mine.argmax(-1))
+
+
+@pytest.mark.gpu
+def test_cuda_engines_match_the_reference_onnx_goldens():
+    """The CUDA det / rec engines (fp32 mode) against outputs of the reference's ONNX model files (fixtures made by cv2.dnn / the
+    interpreter in the build container)."""
+    from oracle import ocr_post as P
+    from rapiddoc_b200 import PREC_FP32, synth
+    from rapiddoc_b200.engine import DetEngine, RecEngine
+    page = synth.det_pages(1, 256, 512, seed=4, lines=5)[0]
+    det = DetEngine(device=0, precision=PREC_FP32)
+    prob, bitmap = det.infer_u8(page[None])
+    gold = GOLD["ocr_det_onnx_prob"].astype(np.float32)
+    assert prob.shape[1:] == gold.shape and np.abs(prob[0] - gold).max() < 1e-3               # fp16 storage of the fixture
+    far = np.abs(gold - 0.3) > 2e-3
+    assert np.array_equal((prob[0] > 0.3)[far], (gold > 0.3)[far])
+    xr = np.random.RandomState(0).randn(3, 3, 48, 160).astype(np.float32)
+    out = RecEngine(device=0, precision=PREC_FP32).infer_f32(xr)
+    assert np.array_equal(out["ids"], GOLD["ocr_rec_onnx_ids"])
+    assert np.abs(out["probs"] - GOLD["ocr_rec_onnx_pmax"]).max() < 2e-4
