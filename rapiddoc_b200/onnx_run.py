@@ -24,15 +24,29 @@ ACT_NONE = 0
 
 
 class _T:
-    """A device activation: buf [rows, ld] fp32 NHWC (rows = n*h*w) + a pending chain of per-element steps not yet applied."""
-    __slots__ = ("buf", "n", "h", "w", "c", "steps")
+    """A device activation: fp32 NHWC rows (rows = n*h*w) of `c` channels starting at column `off` of buf [rows, ld] — a plain
+    buffer (off 0, ld == c) or a channel slice of a wider one (a Concat output its producer wrote in place) — plus a pending chain
+    of per-element steps not yet applied."""
+    __slots__ = ("buf", "n", "h", "w", "c", "steps", "off")
 
-    def __init__(self, buf, n, h, w, c, steps=()):
-        self.buf, self.n, self.h, self.w, self.c, self.steps = buf, n, h, w, c, tuple(steps)
+    def __init__(self, buf, n, h, w, c, steps=(), off=0):
+        self.buf, self.n, self.h, self.w, self.c, self.steps, self.off = buf, n, h, w, c, tuple(steps), off
 
     @property
     def rows(self):
         return self.n * self.h * self.w
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr() + 4 * self.off
+
+    @property
+    def ld(self):
+        return self.buf.shape[1]
+
+    @property
+    def dense(self):
+        return self.off == 0 and self.buf.shape[1] == self.c
 
 
 class OnnxCnn:
@@ -56,6 +70,7 @@ class OnnxCnn:
             if n.op == "Constant":
                 self.consts[n.outputs[0]] = np.asarray(n.attrs["value"])
         self.nodes = self._rewrite(g)
+        self._place, self._cat = self._plan_concats(self.nodes), {}
         self.input_name, self.output_name = g.inputs[0], g.outputs[0]
 
     # ---------------------------------------------------------------- compile
@@ -157,20 +172,69 @@ class OnnxCnn:
         va = (ctypes.c_void_p * max(n, 1))(*[s[3].data_ptr() if s[3] is not None else None for s in t.steps])
         vb = (ctypes.c_void_p * max(n, 1))(*[s[4].data_ptr() if s[4] is not None else None for s in t.steps])
         self.launches += 1
-        _lib.check_op(self.lib.rdb_op_chain(self.device, t.buf.data_ptr(), t.rows, t.c, t.buf.shape[1], kinds, a, b, va, vb, n, out.data_ptr(), ld_out, c_off,
+        _lib.check_op(self.lib.rdb_op_chain(self.device, t.ptr, t.rows, t.c, t.ld, kinds, a, b, va, vb, n, out.data_ptr(), ld_out, c_off,
                                             self._st()))
         return out
 
-    def _mat(self, t):
-        """The activation with its pending steps applied (materialised)."""
-        if not t.steps:
+    def _mat(self, t, dense=False):
+        """The activation with its pending steps applied (materialised); dense: also as a plain [rows, c] buffer."""
+        if not t.steps and (t.dense or not dense):
             return t
         return _T(self._chain(t), t.n, t.h, t.w, t.c)
 
     def _push(self, t, step):
         if len(t.steps) >= MAX_STEPS:
             t = self._mat(t)
-        return _T(t.buf, t.n, t.h, t.w, t.c, t.steps + (step,))
+        return _T(t.buf, t.n, t.h, t.w, t.c, t.steps + (step,), t.off)
+
+    def _out(self, name, rows, c):
+        """Where a conv / resize writes: its own [rows, c] buffer, or — when the compile pass placed it — its channel slice of
+        the Concat output it feeds (allocated by the first producer).  -> (buffer, row pitch, column offset)"""
+        place = self._place.get(name)
+        if place is None:
+            return self._new(rows, c), c, 0
+        cat, off, ctot = place
+        buf = self._cat.get(cat)
+        if buf is None:
+            buf = self._cat[cat] = self._new(rows, ctot)
+        assert buf.shape == (rows, ctot)
+        return buf, ctot, off
+
+    def _plan_concats(self, nodes):
+        """Channel-count inference + placement: a Conv / Resize output that feeds a channel Concat is written straight into its
+        slice of the Concat buffer (every op reads pitched slices), so the Concat launches no copy for it."""
+        chan, prod = {self.graph.inputs[0]: 4}, {}
+        for n in nodes:
+            for o in n.outputs:
+                prod[o] = n
+            c = None
+            if n.op == "Conv":
+                c = int(self.consts[n.inputs[1]].shape[0])
+            elif n.op == "ConvTranspose":
+                c = int(self.consts[n.inputs[1]].shape[1])
+            elif n.op == "MatMul" and n.inputs[1] in self.consts:
+                c = int(self.consts[n.inputs[1]].shape[1])
+            elif n.op == "Concat" and n.attrs.get("axis") == 1:
+                cs = [chan.get(i) for i in n.inputs]
+                c = sum(cs) if all(v is not None for v in cs) else None
+            else:
+                c = next((chan[i] for i in n.inputs if i in chan and chan[i] is not None), None)
+            for o in n.outputs:
+                chan[o] = c
+        place = {}
+        for n in nodes:
+            if n.op != "Concat" or n.attrs.get("axis") != 1:
+                continue
+            cs = [chan.get(i) for i in n.inputs]
+            if any(v is None or v % 4 for v in cs):
+                continue
+            off = 0
+            for i, c in zip(n.inputs, cs):
+                p = prod.get(i)
+                if p is not None and p.op in ("Conv", "Resize") and i not in place:
+                    place[i] = (n.outputs[0], off, sum(cs))
+                off += c
+        return place
 
     def _gemm(self, A, lda, M, K, W, N, bias, out, ldc, c_off=0, act=ACT_NONE):
         self.launches += 1
@@ -211,40 +275,40 @@ class OnnxCnn:
         x = self._mat(x)
         oh, ow = (x.h + 2 * p - kh) // sh + 1, (x.w + 2 * p - kw) // sw + 1
         if group == 1:
-            if x.c % 4 or x.buf.shape[1] % 4:               # the GEMM reads 16-byte vectors: pad the channels to a multiple of 4
+            if x.c % 4 or x.ld % 4 or x.off % 4:  # the GEMM reads 16-byte vectors: pad the channels to a multiple of 4
                 cp = (x.c + 3) // 4 * 4
                 padded = self.torch.zeros((x.rows, cp), dtype=self.torch.float32, device=self.dev)
                 self._chain(x, padded, cp, 0)
                 x = _T(padded, x.n, x.h, x.w, cp)
             cin = x.c                                       # (the network input is stored padded the same way)
-            assert cig <= cin and cin % 4 == 0 and x.buf.shape[1] % 4 == 0
+            assert cig <= cin and cin % 4 == 0 and x.ld % 4 == 0
 
             def pack():
                 w = np.zeros((co, kh, kw, cin), np.float32)
                 w[..., :cig] = W.transpose(0, 2, 3, 1)
                 return w.reshape(co, kh * kw * cin)
             Wd = self._weight(("w", wname, cin), pack)
-            out = self._new(x.n * oh * ow, co)
             M = x.n * oh * ow
+            out, ldc, off = self._out(node.outputs[0], M, co)
             if kh == 1 and sh == 1 and p == 0:
-                self._gemm(x.buf.data_ptr(), x.buf.shape[1], M, cin, Wd, co, bias, out.data_ptr(), co, act=act)
+                self._gemm(x.ptr, x.ld, M, cin, Wd, co, bias, out.data_ptr(), ldc, off, act=act)
             else:
                 K = kh * kw * cin
                 col = self._new(M, K)
                 self.launches += 1
-                _lib.check_op(self.lib.rdb_op_im2col(self.device, _lib.PREC_FP32, x.buf.data_ptr(), x.n, x.h, x.w, cin, x.buf.shape[1], kh, kw, sh, sw, p, p, oh, ow,
+                _lib.check_op(self.lib.rdb_op_im2col(self.device, _lib.PREC_FP32, x.ptr, x.n, x.h, x.w, cin, x.ld, kh, kw, sh, sw, p, p, oh, ow,
                                                      col.data_ptr(), self._st()))
-                self._gemm(col.data_ptr(), K, M, K, Wd, co, bias, out.data_ptr(), co, act=act)
-            return _T(out, x.n, oh, ow, co)
+                self._gemm(col.data_ptr(), K, M, K, Wd, co, bias, out.data_ptr(), ldc, off, act=act)
+            return _T(out, x.n, oh, ow, co, off=off)
         assert group == x.c == co and cig == 1 and p == (kh - 1) // 2 and (kh & 1), f"only depthwise grouped convs are supported: {node}"
         Wd = self._weight(("dw", wname), lambda: W.reshape(co, kh * kw).T)
         if bias is None:
             bias = self._weight(("zeros", co), lambda: np.zeros(co, np.float32))
-        out = self._new(x.n * oh * ow, co)
+        out, ldc, off = self._out(node.outputs[0], x.n * oh * ow, co)
         self.launches += 1
-        _lib.check_op(self.lib.rdb_op_dwconv(self.device, _lib.PREC_FP32, x.buf.data_ptr(), x.n, x.h, x.w, co, x.buf.shape[1], kh, sh, Wd.data_ptr(), bias.data_ptr(),
-                                             act, out.data_ptr(), oh, ow, co, 0, self._st()))
-        return _T(out, x.n, oh, ow, co)
+        _lib.check_op(self.lib.rdb_op_dwconv(self.device, _lib.PREC_FP32, x.ptr, x.n, x.h, x.w, co, x.ld, kh, sh, Wd.data_ptr(), bias.data_ptr(),
+                                             act, out.data_ptr(), oh, ow, ldc, off, self._st()))
+        return _T(out, x.n, oh, ow, co, off=off)
 
     def _conv_transpose(self, node, x):
         g = self.graph
@@ -261,7 +325,7 @@ class OnnxCnn:
             bias = self._weight(("bt", node.inputs[2]), lambda: np.tile(self._const_of(node.inputs[2]).reshape(-1), k * k))
         M = x.rows
         tmp = self._new(M, k * k * co)
-        self._gemm(x.buf.data_ptr(), x.buf.shape[1], M, ci, Wd, k * k * co, bias, tmp.data_ptr(), k * k * co)
+        self._gemm(x.ptr, x.ld, M, ci, Wd, k * k * co, bias, tmp.data_ptr(), k * k * co)
         out = self._new(M * k * k, co)
         self.launches += 1
         _lib.check_op(self.lib.rdb_op_depth_to_space(self.device, tmp.data_ptr(), x.n, x.h, x.w, co, k, out.data_ptr(), self._st()))
@@ -295,18 +359,18 @@ class OnnxCnn:
         if mul:
             gate, x = (ta, tb) if ta.h * ta.w == 1 and tb.h * tb.w > 1 else (tb, ta)
             assert gate.h * gate.w == 1 and gate.c == x.c and gate.n == x.n, f"unsupported Mul of two activations: {node}"
-            gate, x = self._mat(gate), self._mat(x)
-            assert gate.buf.shape[1] == gate.c
+            gate, x = self._mat(gate, dense=True), self._mat(x)
+            assert gate.ld == gate.c
             out = self._new(x.rows, x.c)
             self.launches += 1
-            _lib.check_op(self.lib.rdb_op_mul_gate(self.device, x.buf.data_ptr(), gate.buf.data_ptr(), x.n, x.h * x.w, x.c, x.buf.shape[1], out.data_ptr(), x.c,
+            _lib.check_op(self.lib.rdb_op_mul_gate(self.device, x.ptr, gate.ptr, x.n, x.h * x.w, x.c, x.ld, out.data_ptr(), x.c,
                                                    self._st()))
             return _T(out, x.n, x.h, x.w, x.c)
-        ta, tb = self._mat(ta), self._mat(tb)
-        assert (ta.n, ta.h, ta.w, ta.c) == (tb.n, tb.h, tb.w, tb.c) and ta.buf.shape[1] == ta.c and tb.buf.shape[1] == tb.c, f"Add of unequal shapes: {node}"
+        ta, tb = self._mat(ta, dense=True), self._mat(tb, dense=True)
+        assert (ta.n, ta.h, ta.w, ta.c) == (tb.n, tb.h, tb.w, tb.c) and ta.ld == ta.c and tb.ld == tb.c, f"Add of unequal shapes: {node}"
         out = self._new(ta.rows, ta.c)
         self.launches += 1
-        _lib.check_op(self.lib.rdb_op_add(self.device, ta.buf.data_ptr(), tb.buf.data_ptr(), out.data_ptr(), ta.rows * ta.c, self._st()))
+        _lib.check_op(self.lib.rdb_op_add(self.device, ta.ptr, tb.ptr, out.data_ptr(), ta.rows * ta.c, self._st()))
         return _T(out, ta.n, ta.h, ta.w, ta.c)
 
     def _bn(self, node, x):
@@ -339,7 +403,7 @@ class OnnxCnn:
         with torch.cuda.device(self.dev):
             if nhwc4 is not None:
                 n, h, w = nhwc4
-                self._const, self._flat_out = {}, False
+                self._const, self._flat_out, self._cat = {}, False, {}
                 env = {self.input_name: _T(x.view(n * h * w, 4), n, h, w, 4)}
             else:
                 env = self._feed(x)
@@ -350,8 +414,8 @@ class OnnxCnn:
                 out = self._run_node(node, env)
                 if out is not None:
                     env[node.outputs[0]] = out
-            t = self._mat(env[self._alias.get(name, name)])
-            assert t.buf.shape[1] == t.c
+            t = self._mat(env[self._alias.get(name, name)], dense=True)
+            assert t.ld == t.c
             return t.buf, t.n, t.h, t.w, t.c
 
     def _feed(self, x):
@@ -362,7 +426,7 @@ class OnnxCnn:
         cp = (c + 3) // 4 * 4
         xin = torch.zeros((n, h, w, cp), dtype=torch.float32, device=self.dev)
         xin[..., :c] = x.permute(0, 2, 3, 1)
-        self._const, self._flat_out = {}, False
+        self._const, self._flat_out, self._cat = {}, False, {}
         return {self.input_name: _T(xin.view(n * h * w, cp), n, h, w, cp)}
 
     def __call__(self, x):
@@ -375,8 +439,8 @@ class OnnxCnn:
                 if out is not None:
                     env[node.outputs[0]] = out
             name = self._alias.get(self.output_name, self.output_name)
-            t = self._mat(env[name])
-            y = t.buf.view(t.n, t.h, t.w, t.buf.shape[1])[..., :t.c]
+            t = self._mat(env[name], dense=True)
+            y = t.buf.view(t.n, t.h, t.w, t.ld)[..., :t.c]
             y = y.permute(0, 3, 1, 2).contiguous().cpu().numpy()
             return y.reshape(t.n, t.c) if self._flat_out and t.h * t.w == 1 else y
 
@@ -443,7 +507,7 @@ class OnnxCnn:
             x = self._mat(env[node.inputs[0]])
             out = self._new(x.n, x.c)
             self.launches += 1
-            _lib.check_op(self.lib.rdb_op_global_avgpool(self.device, x.buf.data_ptr(), x.n, x.h * x.w, x.c, x.buf.shape[1], out.data_ptr(), self._st()))
+            _lib.check_op(self.lib.rdb_op_global_avgpool(self.device, x.ptr, x.n, x.h * x.w, x.c, x.ld, out.data_ptr(), self._st()))
             return _T(out, x.n, 1, 1, x.c)
         if op == "Resize":
             assert node.attrs.get("mode") == "nearest" and node.attrs.get("coordinate_transformation_mode") == "asymmetric" \
@@ -456,10 +520,10 @@ class OnnxCnn:
                 scales = np.asarray(self._const_of(node.inputs[2]), np.float32)
                 assert scales[0] == scales[1] == 1
                 oh, ow = int(x.h * scales[2]), int(x.w * scales[3])
-            out = self._new(x.n * oh * ow, x.c)
+            out, ldc, off = self._out(node.outputs[0], x.n * oh * ow, x.c)
             self.launches += 1
-            _lib.check_op(self.lib.rdb_op_resize_nearest(self.device, x.buf.data_ptr(), x.n, x.h, x.w, x.c, x.buf.shape[1], oh, ow, out.data_ptr(), x.c, 0, self._st()))
-            return _T(out, x.n, oh, ow, x.c)
+            _lib.check_op(self.lib.rdb_op_resize_nearest(self.device, x.ptr, x.n, x.h, x.w, x.c, x.ld, oh, ow, out.data_ptr(), ldc, off, self._st()))
+            return _T(out, x.n, oh, ow, x.c, off=off)
         if op == "Concat":
             if all(self._const_of(i) is not None for i in node.inputs):
                 self._const[node.outputs[0]] = np.concatenate([np.atleast_1d(self._const_of(i)) for i in node.inputs], axis=node.attrs.get("axis", 0))
@@ -468,11 +532,15 @@ class OnnxCnn:
             parts = [env[i] for i in node.inputs]
             ctot = sum(p.c for p in parts)
             p0 = parts[0]
-            out = self._new(p0.rows, ctot)
+            out = self._cat.get(node.outputs[0])             # already holds the slices its producers wrote in place
+            if out is None:
+                out = self._new(p0.rows, ctot)
+            assert out.shape == (p0.rows, ctot)
             off = 0
             for p in parts:
                 assert (p.n, p.h, p.w) == (p0.n, p0.h, p0.w)
-                self._chain(p, out, ctot, off)              # pending steps (or a plain copy) straight into the channel slice
+                if not (p.buf is out and p.off == off and not p.steps):
+                    self._chain(p, out, ctot, off)          # pending steps (or a plain copy) straight into the channel slice
                 off += p.c
             return _T(out, p0.n, p0.h, p0.w, ctot)
         if op == "Shape":
@@ -497,13 +565,13 @@ class OnnxCnn:
             assert t.h * t.w == 1 and W.shape[0] == t.c and t.c % 4 == 0
             Wd = self._weight(("mm", node.inputs[1]), lambda: W.T)
             out = self._new(t.n, W.shape[1])
-            self._gemm(t.buf.data_ptr(), t.buf.shape[1], t.n, t.c, Wd, W.shape[1], None, out.data_ptr(), W.shape[1])
+            self._gemm(t.ptr, t.ld, t.n, t.c, Wd, W.shape[1], None, out.data_ptr(), W.shape[1])
             return _T(out, t.n, 1, 1, W.shape[1])
         if op == "Softmax":
-            t = self._mat(env[node.inputs[0]])
-            assert t.h * t.w == 1 and node.attrs.get("axis", -1) in (-1, 1) and t.buf.shape[1] == t.c
+            t = self._mat(env[node.inputs[0]], dense=True)
+            assert t.h * t.w == 1 and node.attrs.get("axis", -1) in (-1, 1) and t.ld == t.c
             out = self._new(t.n, t.c)
             self.launches += 1
-            _lib.check_op(self.lib.rdb_op_softmax_rows(self.device, t.buf.data_ptr(), t.n, t.c, out.data_ptr(), self._st()))
+            _lib.check_op(self.lib.rdb_op_softmax_rows(self.device, t.ptr, t.n, t.c, out.data_ptr(), self._st()))
             return _T(out, t.n, 1, 1, t.c)
         raise NotImplementedError(f"ONNX op {op} is not supported by the B200 executor ({node})")
