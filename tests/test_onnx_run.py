@@ -303,3 +303,21 @@ def test_cuda_engines_match_the_reference_onnx_goldens():
     out = RecEngine(device=0, precision=PREC_FP32).infer_f32(xr)
     assert np.array_equal(out["ids"], GOLD["ocr_rec_onnx_ids"])
     assert np.abs(out["probs"] - GOLD["ocr_rec_onnx_pmax"]).max() < 2e-4
+
+
+@pytest.mark.gpu
+def test_table_and_orientation_on_a_second_device():
+    """Every op / the cluster decode kernel select their device themselves and put the caller's device back."""
+    import torch
+    from rapiddoc_b200 import _lib
+    if _lib.load().rdb_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from rapiddoc_b200.orientation import B200Orientation
+    from rapiddoc_b200.table import B200TableStructurer
+    imgs, x, shapes = MG.table_inputs()
+    a, b = B200TableStructurer(device=0), B200TableStructurer(device=1)
+    (sa, ca), (sb, cb) = a(imgs), b(imgs)
+    assert [s[0] for s in sa] == [s[0] for s in sb] and all(np.array_equal(u, v) for u, v in zip(ca, cb))
+    rots, _ = MG.orientation_inputs()
+    assert np.array_equal(B200Orientation(device=1).scores(rots), B200Orientation(device=0).scores(rots))
+    assert torch.cuda.current_device() == 0
