@@ -17,7 +17,6 @@ the Clipper offset is the library's native restatement (no pyclipper needed).
 
 Nothing here imports oracle/: this is product code.
 """
-import copy
 import ctypes as C
 import math
 import time

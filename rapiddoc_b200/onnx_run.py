@@ -243,7 +243,6 @@ class OnnxCnn:
 
     # ---------------------------------------------------------------- ops
     def _conv(self, node, x):
-        g = self.graph
         wname = node.inputs[1]
         W = self.consts[wname]
         co, cig, kh, kw = W.shape
@@ -311,7 +310,6 @@ class OnnxCnn:
         return _T(out, x.n, oh, ow, co, off=off)
 
     def _conv_transpose(self, node, x):
-        g = self.graph
         W = self._const_of(node.inputs[1])
         ci, co, kh, kw = W.shape
         s = node.attrs.get("strides", [1, 1])
@@ -374,7 +372,6 @@ class OnnxCnn:
         return _T(out, ta.n, ta.h, ta.w, ta.c)
 
     def _bn(self, node, x):
-        g = self.graph
         gamma, beta, mean, var = (self.consts[i].astype(np.float64) for i in node.inputs[1:5])
         eps = float(node.attrs.get("epsilon", 1e-5))
         key = ("bn", node.inputs[1])
