@@ -184,6 +184,10 @@ class FormulaEngine:
         self.sync_every = sync_every
         self.use_graph = use_graph
         self.implicit_conv = implicit_conv       # fp16: dense k x k convs through rdb_op_conv_tc instead of im2col + GEMM
+        import os
+        self.qkv_parallel = os.environ.get("RDB_FORMULA_QKV", "parallel") != "serial"
+        with torch.cuda.device(self.dev):
+            self._side = [torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev)]
         self._dec = {}
         self.launches = 0
         self.adt = torch.float16 if self.prec == _lib.PREC_FP16 else torch.float32
@@ -447,9 +451,23 @@ class FormulaEngine:
         for li, L in enumerate(self.layers):
             # self attention (pre-LN); k / v append to cache row `step`
             _lib.check_op(lib.rdb_op_layernorm(dv, h.data_ptr(), B, d, L["sln"][0].data_ptr(), L["sln"][1].data_ptr(), 1e-5, x.data_ptr(), stm))
+            # q / k / v read the same LayerNorm output and write three different buffers: k and v go to side streams, which the
+            # capture turns into parallel graph branches (three 13 us weight-streaming launches overlap instead of queueing)
+            if self.qkv_parallel:
+                main = self.torch.cuda.current_stream(self.dev)
+                for s_ in self._side:
+                    s_.wait_stream(main)
             self._gemm(f32, x.data_ptr(), d, B, d, L["sq"][0], d, L["sq"][1], ACT_NONE, None, 0, q.data_ptr(), d, 0)
-            self._gemm(f32, x.data_ptr(), d, B, d, L["sk"][0], d, L["sk"][1], ACT_NONE, None, 0, st["kc"][li].data_ptr(), cap * d, 0, sp, d)
-            self._gemm(f32, x.data_ptr(), d, B, d, L["sv"][0], d, L["sv"][1], ACT_NONE, None, 0, st["vc"][li].data_ptr(), cap * d, 0, sp, d)
+            if self.qkv_parallel:
+                with self.torch.cuda.stream(self._side[0]):
+                    self._gemm(f32, x.data_ptr(), d, B, d, L["sk"][0], d, L["sk"][1], ACT_NONE, None, 0, st["kc"][li].data_ptr(), cap * d, 0, sp, d)
+                with self.torch.cuda.stream(self._side[1]):
+                    self._gemm(f32, x.data_ptr(), d, B, d, L["sv"][0], d, L["sv"][1], ACT_NONE, None, 0, st["vc"][li].data_ptr(), cap * d, 0, sp, d)
+                for s_ in self._side:
+                    main.wait_stream(s_)
+            else:
+                self._gemm(f32, x.data_ptr(), d, B, d, L["sk"][0], d, L["sk"][1], ACT_NONE, None, 0, st["kc"][li].data_ptr(), cap * d, 0, sp, d)
+                self._gemm(f32, x.data_ptr(), d, B, d, L["sv"][0], d, L["sv"][1], ACT_NONE, None, 0, st["vc"][li].data_ptr(), cap * d, 0, sp, d)
             _lib.check_op(lib.rdb_op_attn_decode(dv, q.data_ptr(), st["kc"][li].data_ptr(), st["vc"][li].data_ptr(), B, 1, cap, H, hd, att.data_ptr(), stm, sp))
             self._gemm(f32, att.data_ptr(), d, B, d, L["so"][0], d, L["so"][1], ACT_NONE, h.data_ptr(), d, r1.data_ptr(), d, 0)
             # cross attention over the encoder tokens (K / V computed once per batch)
