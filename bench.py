@@ -511,7 +511,7 @@ def run_pipeline(args, wl):
 
 SKIPPED_CONFIGS = {
     "configs[0] single 960x960 page PP-DocLayout-S via onnxruntime CPU": "skipped: weights unavailable (PP-DocLayout-S is downloaded at first run; not on disk) and onnxruntime is not installed",
-    "configs[3] SLANet_plus + UNET table structure, batch=32 488x488": "skipped: weights unavailable (SLANet_plus / UNET model files are downloaded at first run; not on disk)",
+    "configs[3] SLANet_plus + UNET table structure, batch=32 488x488": "skipped: weights unavailable (SLANet_plus / UNET model files are downloaded at first run; not on disk) — the same shape runs on the SLANet RapidDoc ships (slanet-1m.onnx, ModelType.SLANET1M) as `bench.py --workload table`",
     "configs[4] full PP-DocLayoutV3 + OCRv5 det/rec + FormulaNet_plus-M, 1200 A4 pages": "skipped: weights unavailable for layout / formula / table (only the OCR det+rec part runs: this line)",
 }
 
