@@ -216,11 +216,32 @@ __global__ void attn_decode_kernel(const float* __restrict__ q, const float* __r
   const float* kp = k + (long long)b * Tcap * D + h * HD;
   const float* vp = v + (long long)b * Tcap * D + h * HD;
   float mx = -INFINITY;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    float s = 0.f;
-    for (int d = 0; d < HD; ++d) s = fmaf(qp[d], kp[(long long)t * D + d], s);
-    sc[t] = s;
-    mx = fmaxf(mx, s);
+  if (HD == 32 && (D & 3) == 0) {
+    // head_dim 32 (MBart d_model 512 / 16 heads): the query sits in registers and each key row is 8 x 128-bit loads (same
+    // summation order as the scalar loop)
+    float4 qv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) qv[j] = __ldg(reinterpret_cast<const float4*>(qp) + j);
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+      const float4* kr = reinterpret_cast<const float4*>(kp + (long long)t * D);
+      float4 kv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) kv[j] = __ldg(kr + j);
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s = fmaf(qv[j].x, kv[j].x, s); s = fmaf(qv[j].y, kv[j].y, s); s = fmaf(qv[j].z, kv[j].z, s); s = fmaf(qv[j].w, kv[j].w, s);
+      }
+      sc[t] = s;
+      mx = fmaxf(mx, s);
+    }
+  } else {
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+      float s = 0.f;
+      for (int d = 0; d < HD; ++d) s = fmaf(qp[d], kp[(long long)t * D + d], s);
+      sc[t] = s;
+      mx = fmaxf(mx, s);
+    }
   }
   __shared__ float red[32];
   for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
