@@ -7,7 +7,8 @@ class interfaces:
   B200OrientationModel     `RapidOrientationModel`   rapid_doc/model/orientation/rapid_orientation_model.py:7-53
   B200SealDetector         the `Det.*` half of `RapidOcrModel(is_seal=True)`  rapid_doc/model/ocr/rapid_ocr.py:122-143
                            (limit_side_len 736 / limit_type 'min', thresh 0.2; network pp-ocrv4_mobile_seal_det.onnx) up to the
-                           probability map and bitmap; `sort_poly_boxes` = SortPolyBoxes (model/ocr/seal_crop.py:26-39)
+                           text polygons (`detect`: probability map, bitmap, polygon-mode DB post-process); `sort_poly_boxes` =
+                           SortPolyBoxes (model/ocr/seal_crop.py:26-39)
 
 The networks run through `onnx_run.OnnxCnn` (CUDA, fp32).  No CPU path.
 """
@@ -67,6 +68,69 @@ class B200OrientationModel:
         return self.orientation_engine(input_img)[0]
 
 
+def polygons_from_bitmap(pred, bitmap, dest_width, dest_height, box_thresh=0.6, unclip_ratio=0.5, max_candidates=1000, min_size=3):
+    """DB post-process in polygon mode (`Det.box_type = 'poly'`, the seal configuration of rapid_ocr.py:122-131), restated from
+    the published PaddleOCR `DBPostProcess.polygons_from_bitmap` — the implementation RapidDoc calls lives in rapidocr (absent
+    here): **parity unpinned**.  contour -> approxPolyDP(0.002 * perimeter) -> mean probability inside the polygon ->
+    offset by area * unclip_ratio / perimeter (the library's Clipper restatement; pyclipper's final union of self-intersecting
+    offsets is not reproduced) -> min-area-rect size filter -> scale to the source image.  -> (list of [k,2] int arrays, scores)"""
+    import ctypes as C
+    from . import _lib
+    from .dbpost import cv2_score_fn
+    height, width = bitmap.shape
+    contours, _ = cv2.findContours((bitmap * 255).astype(np.uint8), cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
+    score_one = cv2_score_fn(None).score_one
+    lib = _lib.load()
+    boxes, scores = [], []
+    for contour in contours[:max_candidates]:
+        approx = cv2.approxPolyDP(contour, 0.002 * cv2.arcLength(contour, True), True)
+        points = approx.reshape((-1, 2))
+        if points.shape[0] < 4:
+            continue
+        score = score_one(pred, points.astype(np.float32))
+        if box_thresh > score:
+            continue
+        area, length = abs(cv2.contourArea(points.astype(np.float32))), cv2.arcLength(points.astype(np.float32), True)
+        if length <= 0:
+            continue
+        px, py = points[:, 0].astype(np.float64), points[:, 1].astype(np.float64)
+        if float(np.sum(px * np.roll(py, -1) - np.roll(px, -1) * py)) < 0:      # Clipper orients closed paths before offsetting
+            points = points[::-1]                                                # (same orientation as the ordered mini boxes)
+        xy = (C.c_double * (2 * len(points)))(*[float(v) for v in points.reshape(-1)])
+        cap = 4096
+        out = (C.c_int64 * (2 * cap))()
+        n = lib.rdb_clipper_offset(xy, len(points), float(area * unclip_ratio / length), out, cap)
+        if n <= 0:
+            continue
+        box = np.frombuffer(out, dtype=np.int64)[: 2 * n].reshape(-1, 2).astype(np.int32)
+        if not cv2.isContourConvex(points.reshape(-1, 1, 2).astype(np.int32)):
+            # the raw offset of a concave polygon carries a swallow-tail loop at every reflex vertex; pyclipper removes them with
+            # a polygon union.  Here the loops are dropped by re-tracing the outline of the filled offset path united with the
+            # source polygon (cv2 raster, so the vertices are pixel-chain corners rather than Clipper's arc points)
+            x0, y0 = box.min(axis=0) - 2
+            x1, y1 = box.max(axis=0) + 3
+            m = np.zeros((int(y1 - y0), int(x1 - x0)), np.uint8)
+            cv2.fillPoly(m, [(points.astype(np.int32) - [x0, y0]).reshape(-1, 1, 2)], 1)
+            cv2.polylines(m, [(box - [x0, y0]).reshape(-1, 1, 2)], True, 1, 1)
+            ff = m.copy()
+            mask = np.zeros((m.shape[0] + 2, m.shape[1] + 2), np.uint8)
+            cv2.floodFill(ff, mask, (0, 0), 2)                                   # outside of the outer boundary
+            outer, _ = cv2.findContours((ff != 2).astype(np.uint8), cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+            if len(outer) != 1:
+                continue
+            eps = 0.001 * cv2.arcLength(outer[0], True)
+            box = (cv2.approxPolyDP(outer[0], eps, True).reshape(-1, 2) + [x0, y0]).astype(np.int32)
+        rect = cv2.minAreaRect(box.reshape((-1, 1, 2)))
+        if min(rect[1]) < min_size + 2:
+            continue
+        box = box.astype(np.float64)
+        box[:, 0] = np.clip(np.round(box[:, 0] / width * dest_width), 0, dest_width)
+        box[:, 1] = np.clip(np.round(box[:, 1] / height * dest_height), 0, dest_height)
+        boxes.append(box.astype(np.int32))
+        scores.append(float(score))
+    return boxes, scores
+
+
 def sort_poly_boxes(dt_polys):
     """Seal polygons top to bottom by their smallest y (stable argsort)."""
     if len(dt_polys) == 0:
@@ -105,3 +169,11 @@ class B200SealDetector:
         """-> (probability map [rh, rw] float32, bitmap uint8) at the network resolution."""
         p = self.prob_map(img)
         return p, (p > self.thresh).astype(np.uint8)
+
+    def detect(self, img, box_thresh=0.6, unclip_ratio=0.5):
+        """Seal text polygons in image coordinates, top to bottom (the `dt_boxes` RapidOcrModel hands to SortPolyBoxes /
+        CropByPolys, rapid_ocr.py:266-268), with their scores."""
+        prob, bitmap = self(img)
+        polys, scores = polygons_from_bitmap(prob, bitmap, img.shape[1], img.shape[0], box_thresh, unclip_ratio)
+        order = np.argsort(np.array([p[:, 1].min() for p in polys])) if polys else []
+        return [polys[i] for i in order], [scores[i] for i in order]

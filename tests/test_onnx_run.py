@@ -74,6 +74,26 @@ def test_executor_plan_fuses_elementwise_runs():
     assert sum(n.op == "Conv" and "fold_bn" in n.attrs and n.attrs.get("fold_act") == 6 for n in sla) == 73
 
 
+def test_seal_polygons_from_the_oracle_probability_map():
+    """Polygon-mode DB post-process on the seal map (restated from the published algorithm, parity unpinned: rapidocr absent):
+    the curved text band and the straight line come out as two clean (loop-free) polygons around their text."""
+    cv2 = pytest.importorskip("cv2")
+    from rapiddoc_b200.orientation import polygons_from_bitmap, sort_poly_boxes
+    p = onnx_ref.run(SEAL, MG.seal_input())[0, 0]
+    polys, scores = polygons_from_bitmap(p, (p > 0.2).astype(np.uint8), 320, 320)
+    assert len(polys) == 2 and all(s > 0.6 for s in scores)
+    polys = sort_poly_boxes(polys)
+    arc, line = polys
+    assert arc[:, 1].min() < 40 and arc[:, 0].max() > 280 and cv2.contourArea(arc.astype(np.float32)) > 10000       # the band along the ring
+    assert 130 < line[:, 1].min() and line[:, 1].max() < 180 and line[:, 0].max() - line[:, 0].min() > 80           # "CONTRACT SEAL"
+    for q in polys:                                          # no self-intersection loops: filled area == shoelace area
+        m = np.zeros((320, 320), np.uint8)
+        cv2.fillPoly(m, [q.reshape(-1, 1, 2)], 1)
+        assert abs(int(m.sum()) - cv2.contourArea(q.astype(np.float32))) < 0.08 * m.sum() + 60
+    big, _ = polygons_from_bitmap(p, (p > 0.2).astype(np.uint8), 640, 960)        # scaled to the source image size
+    assert max(q[:, 0].max() for q in big) > 560 and max(q[:, 1].max() for q in big) > 780
+
+
 # ------------------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 def test_orientation_executor_matches_the_oracle():
@@ -135,6 +155,9 @@ def test_seal_detector_interface():
     assert ((prob > 0.2) != (ref > 0.2)).mean() < 1e-4
     polys = [np.array([[0, 30], [5, 40], [9, 31]]), np.array([[0, 3], [5, 4], [9, 9]]), np.array([[0, 13], [5, 14]])]
     assert [int(p[0, 1]) for p in sort_poly_boxes(polys)] == [3, 13, 30]
+    found, scores = det.detect(img)
+    assert len(found) == 2 and found[0][:, 1].min() < found[1][:, 1].min() and all(s > 0.6 for s in scores)
+    assert found[0][:, 0].max() <= 320 and found[0][:, 1].max() <= 320          # image coordinates of the 320-px source
 
 
 # ------------------------------------------------------------------------------------------------------- SLANet (T4)
