@@ -225,6 +225,25 @@ def test_slanet_session_matches_the_oracle(batch):
 
 
 @pytest.mark.gpu
+def test_slanet_batch_of_diverse_tables_matches_the_oracle():
+    """Six tables from 3x2 to 8x5 cells, ruled and borderless, decoded together: one common stop step, per-row tokens and boxes
+    equal to the node-by-node oracle run on the same batch."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from rapiddoc_b200.table import SlaNetSession, TablePreprocess
+    imgs = [bench.table_inputs(32)[i] for i in (0, 5, 11, 17, 22, 31)]
+    x, _ = TablePreprocess()(imgs)
+    x = np.asarray(x, np.float32)
+    s = SlaNetSession(SLANET, 0)
+    loc, probs = s(x)
+    rloc, rprobs = onnx_ref.run(SLANET, x)
+    assert probs.shape == rprobs.shape and np.array_equal(probs.argmax(-1), rprobs.argmax(-1))
+    assert np.abs(probs - rprobs).max() < 2e-4 and np.abs(loc - rloc).max() < 2e-4
+    lengths = [int(np.argmax(r == 29)) for r in probs.argmax(-1)]
+    assert len(set(lengths)) >= 4 and max(lengths) + 2 == probs.shape[1]
+
+
+@pytest.mark.gpu
 def test_slanet_loop_edges_max_steps_and_split_batches():
     """(1) a row that never emits the end token: the loop runs to max_steps and the outputs are the first max_steps rows of the
     free-running decode; (2) batches larger than MAX_BATCH are decoded in pieces, each stopping at its own step, rows padded
