@@ -60,7 +60,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("RDB_BENCH_WORKLOAD", "pipeline"), choices=list(WORKLOADS))
-    ap.add_argument("--precision", default=os.environ.get("RDB_BENCH_PRECISION", "fp16"), choices=["fp16", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("RDB_BENCH_PRECISION", "fp16"), choices=["fp16", "fp32", "tf32"],
+                    help="fp16 / fp32 for the OCR and formula workloads; the table workload computes in fp32 storage: fp32 (SIMT, default) or tf32 (tcgen05)")
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rec-batch", type=int, default=int(os.environ.get("RDB_BENCH_REC_BATCH", "256")), help="Rec.rec_batch_num of the pipeline workload (both arms)")
@@ -691,7 +692,8 @@ def run_table(args, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from rapiddoc_b200 import _lib, table as TB
-    ts = TB.B200TableStructurer(device=local)
+    tprec = "tf32" if args.precision == "tf32" else "fp32"
+    ts = TB.B200TableStructurer(device=local, precision=tprec)
     B = wl["batch"]
     imgs = table_inputs(B, seed=rank)
     x, shapes = ts.preprocess_op(imgs)
@@ -760,17 +762,17 @@ def run_table(args, wl):
             pass
         hbm = peaks.get("hbm_gbs_sustained", peaks.get("hbm_gbs", 6500.0))
         # the backbone's convolutions dominate: fp32 activations; a GEMM launch must read A [M,K] and W [N,K] and write [M,N] once
-        conv_ms = sum(v[0] for k, v in fam.items() if k in ("gemm_simt_op", "im2col", "im2col_op", "dwconv_op", "chain_op"))
+        conv_ms = sum(v[0] for k, v in fam.items() if k in ("gemm_simt_op", "gemm_tf32_op", "im2col", "im2col_op", "dwconv_op", "chain_op"))
         g_bytes = g_ms = 0.0
         g_launches = 0
         for k, v in prof.items():
             kind, a = _kv(k)
-            if kind == "gemm_simt_op":
+            if kind in ("gemm_simt_op", "gemm_tf32_op"):
                 g_bytes += 4.0 * (a["M"] * a["K"] + a["M"] * a["N"] + a["N"] * a["K"]) * v[1]
                 g_ms += v[0]
                 g_launches += v[1]
         ach = g_bytes / (g_ms * 1e-3) / 1e9 if g_ms else None
-        roofline = {"kernel": "gemm_simt_op (fp32 SIMT GEMM: the backbone's pointwise / im2col convolutions)", "bound": "hbm", "achieved": ach, "peak": hbm,
+        roofline = {"kernel": ("gemm_tf32_op (tcgen05 kind::tf32 GEMM on fp32 storage" if tprec == "tf32" else "gemm_simt_op (fp32 SIMT GEMM") + ": the backbone's pointwise / im2col convolutions)", "bound": "hbm", "achieved": ach, "peak": hbm,
                     "unit": "GB/s", "frac": (ach / hbm) if ach else None, "traffic": None, "launches_profiled": g_launches,
                     "avg_launch_us": (g_ms * 1e3 / g_launches) if g_launches else None,
                     "algorithmic_bytes_per_launch": (g_bytes / g_launches) if g_launches else None,
@@ -795,8 +797,8 @@ def run_table(args, wl):
                    "tokens_compared": int(rprobs[:, :n].shape[0] * n), "max_abs_dprob": float(np.abs(rprobs[:, :n] - got_probs[:, :n]).max()),
                    "max_abs_dbox": float(np.abs(rloc[:, :n] - got_loc[:, :n]).max())}
         line = {"metric": wl["metric"], "value": value, "unit": wl["unit"], "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": wl["name"], "batch_per_gpu": B, "h": 488, "w": 488, "precision": "fp32", "decode_steps": steps_decoded,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if tprec == "tf32" else "f32", "data": "synthetic",
+                "config": {"workload": wl["name"], "batch_per_gpu": B, "h": 488, "w": 488, "precision": tprec, "decode_steps": steps_decoded,
                            "weights": "slanet-1m.onnx (shipped with RapidDoc)", "tables": "synthetic ruled / borderless grids, 3-8 rows x 2-5 columns",
                            "l2": "activations per step exceed the 126 MB L2", "parallelism": f"crop-parallel replicas x{world}"},
                 "clocks": clocks, "e2e": {"value": e2e, "unit": wl["unit"], "h2d_bytes_per_step": int(x_host.numel() * 4),

@@ -33,6 +33,7 @@ extern "C" {
 /* arithmetic mode of the pointwise-conv / linear engine */
 #define RDB_PREC_FP32 0 /* fp32 storage + fp32 SIMT math: the exact-parity mode            */
 #define RDB_PREC_FP16 1 /* fp16 NHWC storage, tcgen05 (fp16 x fp16 -> fp32 TMEM) GEMMs      */
+#define RDB_PREC_TF32 2 /* rdb_op_gemm only: fp32 storage, tcgen05 kind::tf32 math          */
 
 typedef struct rdb_det rdb_det_t; /* PP-OCRv6-small DBNet detector on one GPU  */
 typedef struct rdb_rec rdb_rec_t; /* PP-OCRv6-small LightSVTR/CTC recogniser   */
@@ -191,7 +192,9 @@ int rdb_argmax_rows(int device, const float* x, long long rows, int vocab, int32
  * `InferSession.__call__` (rapid_formula_self/inference_engine/torch.py:25-131); here the host side
  * (rapiddoc_b200/formula.py) walks the network and enqueues these ops on DEVICE buffers (NHWC activations = [pixels, C]
  * matrices with a row pitch).  All pointers are device pointers; nothing synchronises; prec = RDB_PREC_FP32 (fp32 SIMT,
- * exact-parity mode) or RDB_PREC_FP16 (fp16 storage, tcgen05 GEMMs).  act: 0 none, 1 ReLU, 2 GELU(erf), 6 HardSwish (fp32 path). */
+ * exact-parity mode) or RDB_PREC_FP16 (fp16 storage, tcgen05 GEMMs).  act: 0 none, 1 ReLU, 2 GELU(erf), 6 HardSwish (fp32 path).
+ * rdb_op_gemm also takes RDB_PREC_TF32: fp32 buffers multiplied on the tensor cores as TF32 (10-bit mantissa inputs, fp32
+ * accumulation; act 0 / 1 / 6, no residual) — the fast mode of the ONNX CNN executor; rows <= 32 fall back to the fp32 path. */
 const char* rdb_ops_last_error(void);
 /* out[M, c_off : c_off+N] (row pitch ldc) = act(A[M,K] (pitch lda) * W[N,K]^T + bias) (+ res [M,N] pitch ldr): every conv1x1 /
  * nn.Linear, and every dense k x k conv after rdb_op_im2col.  W fp32 (prec 0) or fp16 (prec 1); bias fp32.

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "librapiddoc_b200.so")
 
 RDB_OK = 0
 RDB_ERR_INVALID, RDB_ERR_CUDA, RDB_ERR_NO_DEVICE = -1, -2, -3
-PREC_FP32, PREC_FP16 = 0, 1
+PREC_FP32, PREC_FP16, PREC_TF32 = 0, 1, 2
 
 # every symbol include/rapiddoc_b200.h declares: name -> (restype, argtypes)
 _vp, _i, _f = C.c_void_p, C.c_int, C.c_float

@@ -12,6 +12,7 @@
 #include "../../include/rapiddoc_b200.h"
 
 #include "engine.cuh"
+#include "gemm_tf32.cuh"
 
 namespace rdb {
 namespace ops {
@@ -518,6 +519,15 @@ int rdb_op_gemm(int device, int prec, const void* A, int lda, long long M, int K
     RDB_CHECK(A && W && out && M > 0 && K > 0 && N > 0, "gemm: bad argument");
     rdb::DeviceGuard g(device);
     cudaStream_t st = (cudaStream_t)stream;
+    if (prec == RDB_PREC_TF32 && M > 32 && res == nullptr && out_step == nullptr &&
+        (act == rdb::ACT_NONE || act == rdb::ACT_RELU || act == rdb::ACT_HSWISH)) {
+      RDB_CHECK(K % 4 == 0 && lda % 4 == 0, "gemm tf32: K and lda must be multiples of 4 (16-byte TMA rows)");
+      OpTimer tm("gemm_tf32_op[M=" + std::to_string(M) + ",K=" + std::to_string(K) + ",N=" + std::to_string(N) + "]", st);
+      rdb::tf32::launch_gemm_tf32(device, static_cast<const float*>(A), lda, M, K, static_cast<const float*>(W), N, bias, act, static_cast<float*>(out), ldc,
+                                  c_off, st);
+      return;
+    }
+    if (prec == RDB_PREC_TF32) prec = RDB_PREC_FP32;
     if (prec == RDB_PREC_FP32) {
       RDB_CHECK(K % 4 == 0 && lda % 4 == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "gemm fp32: K and lda must be multiples of 4, A and W 16-byte aligned (vector loads)");
       if (M <= 32 && (act == rdb::ACT_NONE || act == rdb::ACT_GELU || act == rdb::ACT_RELU)) {   // decode step: weight-streaming kernel

@@ -50,8 +50,13 @@ class _T:
 
 
 class OnnxCnn:
-    def __init__(self, path, device=0, compile_only=False):
-        """compile_only: read the file and build the launch plan without touching a device (plan inspection in CPU tests)."""
+    def __init__(self, path, device=0, compile_only=False, precision="fp32"):
+        """compile_only: read the file and build the launch plan without touching a device (plan inspection in CPU tests).
+        precision: "fp32" = fp32 SIMT GEMMs (exact mode); "tf32" = the same fp32 buffers multiplied on the tensor cores
+        (tcgen05 kind::tf32, RDB_PREC_TF32) for every GEMM with more than 32 rows."""
+        assert precision in ("fp32", "tf32")
+        self.precision = precision
+        self.gemm_prec = _lib.PREC_TF32 if precision == "tf32" else _lib.PREC_FP32
         import torch
         self.torch, self.device, self.lib = torch, int(device), _lib.load()
         if not compile_only:
@@ -238,7 +243,7 @@ class OnnxCnn:
 
     def _gemm(self, A, lda, M, K, W, N, bias, out, ldc, c_off=0, act=ACT_NONE):
         self.launches += 1
-        _lib.check_op(self.lib.rdb_op_gemm(self.device, _lib.PREC_FP32, A, lda, M, K, W.data_ptr(), N, bias.data_ptr() if bias is not None else None, act,
+        _lib.check_op(self.lib.rdb_op_gemm(self.device, self.gemm_prec, A, lda, M, K, W.data_ptr(), N, bias.data_ptr() if bias is not None else None, act,
                                            None, 0, out, ldc, c_off, self._st(), None, 0))
 
     # ---------------------------------------------------------------- ops

@@ -230,12 +230,12 @@ class SlaNetSession:
     (slanet-1m.onnx; SLANet_plus is exported by the same tool from the same head class)."""
     MAX_BATCH = 128          # one CTA per image, all co-resident (148 SMs)
 
-    def __init__(self, model_path, device=0):
+    def __init__(self, model_path, device=0, precision="fp32"):
         import ctypes
         import torch
         from .onnx_run import OnnxCnn
         self.torch, self.device = torch, int(device)
-        self.net = OnnxCnn(model_path, device)
+        self.net = OnnxCnn(model_path, device, precision=precision)
         self.lib = self.net.lib
         g, c = self.net.graph, self.net.consts
         loop = [n for n in g.nodes if n.op == "Loop"]
@@ -295,7 +295,7 @@ class SlaNetSession:
                 st = torch.cuda.current_stream(self.net.dev).cuda_stream or None
                 dev, hw, S, V, L = self.net.dev, h * w, self.max_steps, self.classes, self.loc_dim
                 proj = torch.empty((n * hw, self.hidden), dtype=torch.float32, device=dev)
-                _lib.check_op(self.lib.rdb_op_gemm(self.device, _lib.PREC_FP32, feat.data_ptr(), c, n * hw, c, self.Wi_t.data_ptr(), self.hidden, None, 0, None, 0,
+                _lib.check_op(self.lib.rdb_op_gemm(self.device, self.net.gemm_prec, feat.data_ptr(), c, n * hw, c, self.Wi_t.data_ptr(), self.hidden, None, 0, None, 0,
                                                    proj.data_ptr(), self.hidden, 0, st, None, 0))
                 logits = torch.zeros((n, S, V), dtype=torch.float32, device=dev)
                 probs = torch.empty((n, S, V), dtype=torch.float32, device=dev)
@@ -326,12 +326,12 @@ class B200TableStructurer:
     """Mirror of `PPTableStructurer` (table_structure/pp_structure/main.py:25-51) for ModelType.SLANET1M (the weights RapidDoc
     ships, rapid_table_self/main.py:38-40) — preprocess (T3) -> SLANet (T4) -> TableLabelDecode (T5)."""
 
-    def __init__(self, model_path=None, model_type="slanet_1m", device=0):
+    def __init__(self, model_path=None, model_type="slanet_1m", device=0, precision="fp32"):
         import os
         from .weights import WEIGHTS_DIR
         if model_path is None:
             model_path = os.path.join(WEIGHTS_DIR, "slanet-1m.onnx")
-        self.session = SlaNetSession(model_path, device)
+        self.session = SlaNetSession(model_path, device, precision=precision)
         self.preprocess_op = TablePreprocess()
         self.postprocess_op = TableLabelDecode(self.session.get_character_list(), slanet_plus=(model_type == "slanet_plus"), device=device)
 
