@@ -342,8 +342,15 @@ def aggregate_roofline(prof, esz, wl_det, wl_rec, hbm, peak_src):
     modelled = {k: v for k, v in fam.items() if v["bytes"] > 0}
     kind, f = max((modelled or fam).items(), key=lambda kv: kv[1]["ms"])
     ach = f["bytes"] / (f["modelled_ms"] / 1e3) / 1e9 if f["modelled_ms"] else None
-    return {"kernel": kind, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": (ach / hbm) if ach else None, "traffic": None,
-            "peak_source": peak_src, "launches_profiled": f["launches"], "avg_launch_us": f["ms"] / f["launches"] * 1e3,
+    traffic = traffic_src = None
+    try:        # DRAM bytes per launch of this family from the committed ncu --set full capture (recogniser chunk of the same step)
+        for row in json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))):
+            if row.get("kernel") == "family:" + kind:
+                traffic, traffic_src = row["dram_bytes"], row["source"]
+    except Exception:
+        pass
+    return {"kernel": kind, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": (ach / hbm) if ach else None, "traffic": traffic,
+            "traffic_source": traffic_src, "peak_source": peak_src, "launches_profiled": f["launches"], "avg_launch_us": f["ms"] / f["launches"] * 1e3,
             "algorithmic_bytes_per_launch": f["bytes"] / f["launches"], "share_of_step": f["ms"] / total,
             "top5": [{"kernel": k, "share": v["ms"] / total, "launches": v["launches"], "avg_us": v["ms"] / v["launches"] * 1e3,
                       "gbps": (v["bytes"] / (v["modelled_ms"] / 1e3) / 1e9) if v["modelled_ms"] else None}
