@@ -251,6 +251,11 @@ int rdb_op_softmax_rows(int device, const float* x, long long rows, int c, float
 /* Image normalisation of TablePreprocess (rapid_table_self/table_structure/pp_structure/pre_process.py) on the device:
  * img [n,h,w,3] uint8 canvases whose top-left valid_hw[i] = (rh, rw) region holds the resized image; out [n,h,w,4] fp32 NHWC
  * (4th channel and the padding = 0); lut [3][256] fp32 = the reference's numpy expression evaluated for every byte value. */
+/* First layer of the ONNX CNNs: dense 3x3 conv (stride, symmetric pad) on the 4-channel fp32 NHWC input (3 channels + a zero
+ * one, the layout rdb_op_lut_u8_nhwc4 writes), 16 output channels, wt [16][3][3][4]; direct form, bit-identical to
+ * rdb_op_im2col + rdb_op_gemm(RDB_PREC_FP32) in a ninth of the HBM traffic. */
+int rdb_op_conv3x3_c4(int device, const float* x, int n, int h, int w, const float* wt, int cout, const float* bias, int act, int stride, int pad,
+                      float* out, int oh, int ow, int ldc, int c_off, void* stream);
 int rdb_op_lut_u8_nhwc4(int device, const uint8_t* img, const int32_t* valid_hw, const float* lut, int n, int h, int w, float* out,
                         void* stream);
 

@@ -58,6 +58,7 @@ SYMBOLS = {
     "rdb_op_resize_nearest": (_i, [_i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "rdb_op_depth_to_space": (_i, [_i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "rdb_op_softmax_rows": (_i, [_i, _vp, C.c_longlong, _i, _vp, _vp]),
+    "rdb_op_conv3x3_c4": (_i, [_i, _vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),
     "rdb_op_lut_u8_nhwc4": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "rdb_sla_last_error": (C.c_char_p, []),
     "rdb_sla_decode": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -434,6 +434,19 @@ __global__ void resize_nearest_kernel(const float* __restrict__ x, int n, int H,
   }
 }
 
+// the same gather with 4 channels per thread and 32-bit index arithmetic (C, pitches, offsets multiples of 4; < 2^31 elements)
+__global__ void resize_nearest_vec4_kernel(const float* __restrict__ x, int n, int H, int W, int C4, int ld_in, int OH, int OW, float sy, float sx,
+                                           float* __restrict__ out, int ld_out, int c_off) {
+  const unsigned total = (unsigned)n * OH * OW * C4;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned c4 = i % C4, px = i / C4;
+    const unsigned ox = px % OW, t = px / OW, oy = t % OH, b = t / OH;
+    const int iy = min((int)floorf(__fdiv_rn((float)oy, sy)), H - 1), ix = min((int)floorf(__fdiv_rn((float)ox, sx)), W - 1);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + ((long long)(b * H + iy) * W + ix) * ld_in) + c4);
+    *(reinterpret_cast<float4*>(out + (long long)px * ld_out + c_off) + c4) = v;
+  }
+}
+
 // ConvTranspose(k = stride = s) after its GEMM: g [n*H*W, s*s*C] with columns (dy, dx, c) -> out [n, s*H, s*W, C]
 __global__ void depth_to_space_kernel(const float* __restrict__ g, int n, int H, int W, int C, int s, float* __restrict__ out) {
   const int OH = H * s, OW = W * s;
@@ -477,6 +490,53 @@ __global__ void lut_u8_nhwc4_kernel(const uint8_t* __restrict__ img, const int* 
       v = make_float4(t[p[0]], t[256 + p[1]], t[512 + p[2]], 0.f);
     }
     out[i] = v;
+  }
+}
+
+// First layer of the ONNX CNNs: dense 3x3 conv on the 4-channel (3 + zero pad) fp32 NHWC input, 16 output channels.  im2col +
+// GEMM moves the 9x-expanded input through HBM twice; here one thread owns one output pixel, reads its 9 input pixels as
+// float4 and keeps the 16 x 36 weights in shared memory.  The products are accumulated in the same (ky, kx, c) order, with
+// fmaf, as the GEMM path does, and the bias is added last: results are bit-identical to im2col + gemm_simt.
+template <int CO>
+__global__ void conv3x3_c4_kernel(const float4* __restrict__ x, int n, int H, int W, const float* __restrict__ w /*[CO][36]*/, const float* __restrict__ bias,
+                                  int act, int stride, int pad, float* __restrict__ out, int OH, int OW, int ldc, int c_off) {
+  __shared__ float sw[36][CO];
+  for (int i = threadIdx.x; i < 36 * CO; i += blockDim.x) sw[i % 36][i / 36] = w[i];
+  __syncthreads();
+  const long long total = (long long)n * OH * OW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % OW), oy = (int)((i / OW) % OH), b = (int)(i / ((long long)OW * OH));
+    float acc[CO];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * stride - pad + ky;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * stride - pad + kx;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + ((long long)(b * H + iy) * W + ix));
+        const int t = (ky * 3 + kx) * 4;
+#pragma unroll
+        for (int c = 0; c < CO; ++c) {
+          acc[c] = fmaf(v.x, sw[t][c], acc[c]);
+          acc[c] = fmaf(v.y, sw[t + 1][c], acc[c]);
+          acc[c] = fmaf(v.z, sw[t + 2][c], acc[c]);
+          acc[c] = fmaf(v.w, sw[t + 3][c], acc[c]);
+        }
+      }
+    }
+    float* o = out + i * ldc + c_off;
+#pragma unroll
+    for (int c = 0; c < CO; c += 4) {
+      float4 r;
+      r.x = rdb::apply_act_rt(acc[c] + (bias ? bias[c] : 0.f), act);
+      r.y = rdb::apply_act_rt(acc[c + 1] + (bias ? bias[c + 1] : 0.f), act);
+      r.z = rdb::apply_act_rt(acc[c + 2] + (bias ? bias[c + 2] : 0.f), act);
+      r.w = rdb::apply_act_rt(acc[c + 3] + (bias ? bias[c + 3] : 0.f), act);
+      *reinterpret_cast<float4*>(o + c) = r;
+    }
   }
 }
 
@@ -741,8 +801,13 @@ int rdb_op_resize_nearest(int device, const float* x, int n, int h, int w, int c
     RDB_CHECK(x && out && n > 0 && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0, "resize_nearest: bad argument");
     rdb::DeviceGuard g(device);
     OpTimer tm("resize_nearest_op", (cudaStream_t)stream);
-    rdb::ops::resize_nearest_kernel<<<rdb::ops::grid_for((long long)n * oh * ow * c), 256, 0, (cudaStream_t)stream>>>(x, n, h, w, c, ld_in, oh, ow, (float)oh / (float)h,
-                                                                                                                   (float)ow / (float)w, out, ld_out, c_off);
+    const long long total = (long long)n * oh * ow * c;
+    if (c % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0 && c_off % 4 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0 && total < (1ll << 31))
+      rdb::ops::resize_nearest_vec4_kernel<<<rdb::ops::grid_for(total / 4), 256, 0, (cudaStream_t)stream>>>(x, n, h, w, c / 4, ld_in, oh, ow, (float)oh / (float)h,
+                                                                                                           (float)ow / (float)w, out, ld_out, c_off);
+    else
+      rdb::ops::resize_nearest_kernel<<<rdb::ops::grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, n, h, w, c, ld_in, oh, ow, (float)oh / (float)h,
+                                                                                                  (float)ow / (float)w, out, ld_out, c_off);
     RDB_LAUNCH_CHECK();
   });
 }
@@ -773,6 +838,20 @@ int rdb_op_lut_u8_nhwc4(int device, const uint8_t* img, const int32_t* valid_hw,
     rdb::DeviceGuard g(device);
     OpTimer tm("lut_u8_nhwc4_op", (cudaStream_t)stream);
     rdb::ops::lut_u8_nhwc4_kernel<<<rdb::ops::grid_for((long long)n * h * w), 256, 0, (cudaStream_t)stream>>>(img, valid_hw, lut, n, h, w, reinterpret_cast<float4*>(out));
+    RDB_LAUNCH_CHECK();
+  });
+}
+
+int rdb_op_conv3x3_c4(int device, const float* x, int n, int h, int w, const float* wt, int cout, const float* bias, int act, int stride, int pad, float* out,
+                      int oh, int ow, int ldc, int c_off, void* stream) {
+  return op_guard([&] {
+    RDB_CHECK(x && wt && out && n > 0 && h > 0 && w > 0 && oh > 0 && ow > 0, "conv3x3_c4: bad argument");
+    RDB_CHECK(cout == 16, "conv3x3_c4: built for 16 output channels (the stem of the PP-LCNet family)");
+    RDB_CHECK(ldc % 4 == 0 && c_off % 4 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0, "conv3x3_c4: 16-byte alignment");
+    rdb::DeviceGuard g(device);
+    OpTimer tm("conv3x3_c4_op[P=" + std::to_string((long long)n * oh * ow) + "]", (cudaStream_t)stream);
+    rdb::ops::conv3x3_c4_kernel<16><<<rdb::ops::grid_for((long long)n * oh * ow), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(x), n, h, w, wt, bias, act, stride, pad, out, oh, ow, ldc, c_off);
     RDB_LAUNCH_CHECK();
   });
 }

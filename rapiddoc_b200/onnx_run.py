@@ -57,6 +57,7 @@ class OnnxCnn:
         assert precision in ("fp32", "tf32")
         self.precision = precision
         self.gemm_prec = _lib.PREC_TF32 if precision == "tf32" else _lib.PREC_FP32
+        self.direct_stem = True
         import torch
         self.torch, self.device, self.lib = torch, int(device), _lib.load()
         if not compile_only:
@@ -296,6 +297,10 @@ class OnnxCnn:
             out, ldc, off = self._out(node.outputs[0], M, co)
             if kh == 1 and sh == 1 and p == 0:
                 self._gemm(x.ptr, x.ld, M, cin, Wd, co, bias, out.data_ptr(), ldc, off, act=act)
+            elif kh == 3 and cin == 4 and x.ld == 4 and co == 16 and self.direct_stem:
+                self.launches += 1              # the network's first layer: direct conv, no 9x im2col buffer (bit-identical)
+                _lib.check_op(self.lib.rdb_op_conv3x3_c4(self.device, x.ptr, x.n, x.h, x.w, Wd.data_ptr(), co, bias.data_ptr() if bias is not None else None, act,
+                                                         sh, p, out.data_ptr(), oh, ow, ldc, off, self._st()))
             else:
                 K = kh * kw * cin
                 col = self._new(M, K)

@@ -111,6 +111,26 @@ def test_orientation_executor_matches_the_oracle():
 
 
 @pytest.mark.gpu
+def test_direct_stem_conv_is_bit_identical_to_im2col_gemm():
+    """rdb_op_conv3x3_c4 (first layer, direct form) against the im2col + fp32 GEMM path it replaces: same products, same order."""
+    import torch
+    from rapiddoc_b200.onnx_run import OnnxCnn
+    _, xs = MG.orientation_inputs()
+    a, b = OnnxCnn(ORI, 0), OnnxCnn(ORI, 0)
+    b.direct_stem = False
+    name = a.nodes[0].outputs[0]
+    fa = a.features(xs, name)[0].clone()
+    fb = b.features(xs, name)[0].clone()
+    assert fa.shape == fb.shape == (4 * 112 * 112, 16) and torch.equal(fa, fb)
+    assert a.launches < b.launches
+    assert np.array_equal(a(xs), b(xs))
+    _, x, _ = MG.table_inputs()
+    s, t = OnnxCnn(SLANET, 0), OnnxCnn(SLANET, 0)
+    t.direct_stem = False
+    assert torch.equal(s.features(x, "hardswish_72.tmp_0")[0], t.features(x, "hardswish_72.tmp_0")[0])
+
+
+@pytest.mark.gpu
 def test_orientation_model_interface():
     from rapiddoc_b200.orientation import B200Orientation, B200OrientationModel
     import cv2
