@@ -25,6 +25,7 @@ constexpr int kStagePitch = 36;                          // epilogue staging: 32
 
 struct Args {
   int M, N, K, BN, k_blocks, tmem_cols, stages;
+  int tiles_m, tiles_n, acc_stride;      // persistent kernel: tile grid, TMEM columns between the two accumulator stages
   uint32_t idesc;
   const float* bias;
   float* out;
@@ -144,6 +145,131 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(const __grid_consta
   if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols); }
 }
 
+// Persistent form (RDB_TF32=persistent; correct, currently the slower of the two — it needs the 16-warp epilogue of gemm_tc to
+// pay off): a CTA walks tiles t = blockIdx.x, + gridDim.x, ...; the TMA ring runs on across tile boundaries and the
+// accumulator has TWO TMEM stages, so the epilogue of tile i (TMEM -> shared tile -> 128-byte row segments) overlaps the loads
+// and MMAs of tile i + 1, and barrier setup / TMEM allocation are paid once per CTA instead of once per tile.
+__global__ void __launch_bounds__(kThreads) gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                                        const Args g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t span = 128u, a_bytes = 128u * span;
+  const uint32_t b_bytes = ((uint32_t)g.BN * span + 1023u) & ~1023u;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint8_t* smem = RDB_ALIGNED_SMEM(smem_raw);
+  const int kStages = g.stages;
+  float* stage_out = reinterpret_cast<float*>(smem + (size_t)kStages * stage_bytes);        // [4 warps][32][kStagePitch]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + 4 * 32 * kStagePitch);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kMaxStages;
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;        // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, (uint32_t)g.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total = g.tiles_m * g.tiles_n;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int m_row = (t / g.tiles_n) * 128, n_row = (t % g.tiles_n) * g.BN;
+        for (int kb = 0; kb < g.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          mbar_expect_tx(&full_bar[s], a_bytes + (uint32_t)g.BN * span);
+          tma_load_2d(sa, &tmA, &full_bar[s], kb * kBK, m_row);
+          tma_load_2d(sa + a_bytes, &tmB, &full_bar[s], kb * kBK, n_row);
+          if (++s == kStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * g.acc_stride);
+        for (int kb = 0; kb < g.k_blocks; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint64_t da = make_smem_desc(sa, span), db = make_smem_desc(sa + a_bytes, span);
+#pragma unroll
+          for (int kk = 0; kk < kBK / 8; ++kk)
+            umma_tf32(d_tmem, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), g.idesc, (kb | kk) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+          if (kb == g.k_blocks - 1) umma_commit(&tfull_bar[as]);
+          if (++s == kStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    float* tile = stage_out + warp * 32 * kStagePitch;
+    const int rr = lane >> 3, cc = (lane & 7) * 4;
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+      const int m_row = (t / g.tiles_n) * 128, n_row = (t % g.tiles_n) * g.BN;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const long long row0 = (long long)m_row + warp * 32;
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * g.acc_stride);
+      for (int c0 = 0; c0 < g.BN; c0 += 32) {
+        if (n_row + c0 >= g.N) break;
+        uint32_t r0[16], r1[16];
+        tmem_ld16(taddr + (uint32_t)c0, r0);
+        tmem_ld16(taddr + (uint32_t)(c0 + 16), r1);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int ca = n_row + c0 + j, cb = ca + 16;
+          v[j] = apply_act_rt(__uint_as_float(r0[j]) + ((g.bias != nullptr && ca < g.N) ? __ldg(g.bias + ca) : 0.f), g.act);
+          v[16 + j] = apply_act_rt(__uint_as_float(r1[j]) + ((g.bias != nullptr && cb < g.N) ? __ldg(g.bias + cb) : 0.f), g.act);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(tile + lane * kStagePitch + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const int cbase = n_row + c0 + cc;
+#pragma unroll
+        for (int r = 0; r < 32; r += 4) {
+          const long long row = row0 + r + rr;
+          if (row < g.M && cbase < g.N) {
+            const float4 q = *reinterpret_cast<const float4*>(tile + (r + rr) * kStagePitch + cc);
+            float* o = g.out + row * g.ldc + g.c_off + cbase;
+            if (cbase + 4 <= g.N) *reinterpret_cast<float4*>(o) = q;
+            else { o[0] = q.x; if (cbase + 1 < g.N) o[1] = q.y; if (cbase + 2 < g.N) o[2] = q.z; }
+          }
+        }
+        __syncwarp();
+      }
+      // this warp has drained its lanes of accumulator stage `as`: hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols); }
+}
+
 // 2-D fp32 row-major [rows, cols], row pitch ld (elements); box = [box_rows, 32] k-major, 128-byte swizzle
 inline CUtensorMap make_map_f32(const void* base, long long rows, int cols, int ld, int box_rows) {
   CUtensorMap m;
@@ -176,15 +302,45 @@ inline void launch_gemm_tf32(int device, const float* A, int lda, long long M, i
   const CUtensorMap mA = make_map_f32(A, M, K, lda, 128);
   const CUtensorMap mB = make_map_f32(W, N, K, K, a.BN);
   const uint32_t b_bytes = ((uint32_t)a.BN * 128u + 1023u) & ~1023u;
-  a.stages = a.k_blocks < kMaxStages ? a.k_blocks : kMaxStages;            // short K: fewer stages = more CTAs resident per SM
-  const size_t smem = (size_t)a.stages * (128 * 128 + b_bytes) + 4 * 32 * kStagePitch * sizeof(float) + 1024 + 256;
-  static bool attr[kMaxDevices] = {};
-  if (!attr[device]) {
-    RDB_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr[device] = true;
+  const char* mode = sw_get("RDB_TF32");
+  if (!(mode && std::string(mode) == "persistent")) {
+    // default: one short-lived CTA per tile.  Measured on the SLANet backbone (32 x 488^2): 1075 GB/s over its GEMMs against 986
+    // for the persistent kernel below — with 4 epilogue warps per CTA the store side is the bottleneck, and up to five small
+    // CTAs per SM give it more warps than two persistent ones.  RDB_TF32=persistent selects the other kernel (A/B).
+    a.stages = a.k_blocks < kMaxStages ? a.k_blocks : kMaxStages;          // short K: fewer stages = more CTAs resident per SM
+    const size_t smem = (size_t)a.stages * (128 * 128 + b_bytes) + 4 * 32 * kStagePitch * sizeof(float) + 1024 + 256;
+    static bool attr[kMaxDevices] = {};
+    if (!attr[device]) {
+      RDB_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      attr[device] = true;
+    }
+    dim3 grid((unsigned)((M + 127) / 128), (unsigned)tiles_n);
+    gemm_tf32_kernel<<<grid, kThreads, smem, st>>>(mA, mB, a);
+    RDB_LAUNCH_CHECK();
+    return;
   }
-  dim3 grid((unsigned)((M + 127) / 128), (unsigned)tiles_n);
-  gemm_tf32_kernel<<<grid, kThreads, smem, st>>>(mA, mB, a);
+  // persistent: two accumulator stages of acc_stride TMEM columns each; as many CTAs per SM as TMEM (512 columns) and shared
+  // memory allow, at most 2
+  a.tiles_m = (int)((M + 127) / 128);
+  a.tiles_n = tiles_n;
+  a.acc_stride = ((a.BN + 31) / 32) * 32;
+  a.tmem_cols = 32;
+  while (a.tmem_cols < 2 * a.acc_stride) a.tmem_cols *= 2;
+  const int per_sm = a.tmem_cols <= 256 ? 2 : 1;
+  const size_t budget = (per_sm == 2 ? 110 : 220) * 1024 - (4 * 32 * kStagePitch * sizeof(float) + 1024 + 256);
+  int stages = (int)(budget / (128 * 128 + b_bytes));
+  a.stages = stages > kMaxStages ? kMaxStages : (stages < 1 ? 1 : stages);
+  const size_t smem = (size_t)a.stages * (128 * 128 + b_bytes) + 4 * 32 * kStagePitch * sizeof(float) + 1024 + 256;
+  static bool attr_p[kMaxDevices] = {};
+  static int sms[kMaxDevices] = {};
+  if (!attr_p[device]) {
+    RDB_CUDA(cudaFuncSetAttribute(gemm_tf32_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    RDB_CUDA(cudaDeviceGetAttribute(&sms[device], cudaDevAttrMultiProcessorCount, device));
+    attr_p[device] = true;
+  }
+  const long long tiles = (long long)a.tiles_m * a.tiles_n;
+  const long long want = (long long)sms[device] * per_sm;
+  gemm_tf32_persistent_kernel<<<(unsigned)(tiles < want ? tiles : want), kThreads, smem, st>>>(mA, mB, a);
   RDB_LAUNCH_CHECK();
 }
 
