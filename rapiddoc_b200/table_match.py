@@ -5,15 +5,80 @@
                        (1 - IoU, distance) ordering of :75-117, get_pred_html, decode_logic_points)
   format_ocr_results   rapid_table_self/utils/utils.py:15-27
   B200RapidTable       RapidTable.__call__ for the PP-structure models, rapid_table_self/main.py:78-123
+  B200RapidTableModel  RapidTableModel.predict / batch_predict for model_type slanet_1m, rapid_doc/model/table/rapid_table.py:110-285
+                       (+ normalize_table_ocr_text / _cell_text / _html_cell_text of rapid_doc/model/table/utils.py:22-66)
 
 Host glue (a few hundred boxes per table); the structure model under it is `table.B200TableStructurer` (CUDA).
 tests/test_table_match.py runs it against the reference's own class imported by path.
 """
+import html as _html
+import re
 import time
 
 import numpy as np
 
 MIN_IOU = 0.1 ** 8
+
+# ---- OCR-text / cell-text normalisation of the table path (rapid_doc/model/table/utils.py:7-66) ---------------------------
+_SINGLE_CHAR = {"香": "否", "哦樂": "哦"}
+_REGEX_REPLACEMENTS = ((re.compile(r"^([0-9])號$"), r"\1"),)
+_CJK = re.compile(r"[\u3400-\u9fff]")
+_CJK_PUNCT = r"，。、“”‘’；：？！、：（）《》【】"
+
+
+def normalize_table_ocr_text(text):
+    """OCR text before table matching: strip, two known single-string repairs, `<digit>號` -> digit, HTML-escape."""
+    if text is None:
+        return ""
+    if not isinstance(text, str):
+        text = str(text)
+    text = text.strip()
+    text = _SINGLE_CHAR.get(text, text)
+    for pattern, repl in _REGEX_REPLACEMENTS:
+        m = pattern.fullmatch(text)
+        if m:
+            text = m.expand(repl)
+            break
+    return _html.escape(text)
+
+
+def normalize_table_cell_text(text):
+    """Spaces the recogniser puts inside Chinese cell text are removed (between CJK characters, around CJK punctuation, between
+    CJK and latin / digits)."""
+    if not text or not _CJK.search(text):
+        return text
+    text = re.sub(r"(?<=[\u3400-\u9fff])\s+(?=[\u3400-\u9fff])", "", text)
+    text = re.sub(rf"(?<=[\u3400-\u9fffA-Za-z0-9$])\s+(?=[{_CJK_PUNCT}])", "", text)
+    text = re.sub(rf"(?<=[{_CJK_PUNCT}])\s+(?=[\u3400-\u9fffA-Za-z0-9$])", "", text)
+    text = re.sub(r"(?<=[A-Za-z0-9$])\s+(?=[\u3400-\u9fff])", "", text)
+    text = re.sub(r"(?<=[\u3400-\u9fff])\s+(?=[A-Za-z0-9$])", "", text)
+    return text
+
+
+def normalize_table_html_cell_text(html_code):
+    """`normalize_table_cell_text` on the text nodes directly inside <td> / <th>.  The reference walks a BeautifulSoup tree
+    (bs4 is absent here: **parity unpinned**); the HTML this path produces is flat (`<td ...>text</td>`, optional <b>), so the
+    direct children are found with a tag tokenizer.  When nothing changes the input string is returned as it is, as upstream."""
+    if not html_code:
+        return html_code
+    out, depth_cell, changed = [], 0, False
+    for tok in re.split(r"(<[^<>]*>)", html_code):
+        if tok.startswith("<") and tok.endswith(">"):
+            name = re.match(r"</?\s*([a-zA-Z0-9]+)", tok)
+            tag = name.group(1).lower() if name else ""
+            if tag in ("td", "th"):
+                depth_cell = 0 if tok.startswith("</") else 1
+            elif depth_cell:
+                depth_cell += -1 if tok.startswith("</") else (0 if tok.endswith("/>") else 1)
+            out.append(tok)
+            continue
+        if depth_cell == 1 and tok:
+            new = _html.escape(normalize_table_cell_text(_html.unescape(tok)), quote=False)
+            if normalize_table_cell_text(_html.unescape(tok)) != _html.unescape(tok):
+                changed = True
+                tok = new
+        out.append(tok)
+    return "".join(out) if changed else html_code
 
 
 def format_ocr_results(ocr_results, img_h, img_w):
@@ -169,6 +234,16 @@ class TableMatch:
         return points
 
 
+def points_to_bbox(points):
+    (x0, y0), (x1, _), (_, y1) = points[0], points[1], points[2]
+    return [x0, y0, x1, y1]
+
+
+def bbox_to_points(bbox):
+    x0, y0, x1, y1 = bbox
+    return np.array([[x0, y0], [x1, y0], [x1, y1], [x0, y1]]).astype("float32")
+
+
 class RapidTableOutput:
     def __init__(self):
         self.imgs, self.pred_htmls, self.cell_bboxes, self.logic_points, self.elapse = [], [], [], [], 0.0
@@ -205,3 +280,64 @@ class B200RapidTable:
         res.logic_points.extend(self.table_matcher.decode_logic_points(structs))
         res.elapse = (time.perf_counter() - t0) / max(len(imgs), 1)
         return res
+
+
+class B200RapidTableModel:
+    """`RapidTableModel` for `model_type = slanet_1m` (rapid_doc/model/table/rapid_table.py:18-285): `predict(image RGB,
+    ocr_result)` -> html.  Flow of :120-285 for this model type: OCR results (given, or from the injected `ocr_engine` and then
+    text-normalised) -> white-out + placeholder boxes of embedded images (`fill_image_res`) -> formula / checkbox boxes
+    (`mfd_res`) appended as OCR entries -> SLANet structure + matching (`B200RapidTable`) -> cell-text normalisation.
+    The orientation pre-step (:131-162) runs when no OCR result is given and an `ocr_engine` is.  The wired / classifier branches
+    need weights that are not available and are not built."""
+
+    def __init__(self, ocr_engine=None, device=0, model_path=None, inline_delimiters=("$", "$")):
+        self.ocr_engine = ocr_engine
+        self.table_model = B200RapidTable(device=device, model_path=model_path, model_type="slanet_1m")
+        self.inline_left, self.inline_right = inline_delimiters
+
+    def batch_predict(self, images, ocr_result=None, fill_image_res=None, mfd_res=None, skip_text_in_image=True, use_img2table=False,
+                      skip_table_orientation=None):
+        return [self.predict(im, ocr_result, fill_image_res, mfd_res, skip_text_in_image, use_img2table, skip_table_orientation) for im in images]
+
+    def predict(self, image, ocr_result=None, fill_image_res=None, mfd_res=None, skip_text_in_image=True, use_img2table=False,
+                skip_table_orientation=None):
+        import cv2
+        from .table import needs_orientation_cls
+        bgr = cv2.cvtColor(np.asarray(image), cv2.COLOR_RGB2BGR)
+        if skip_table_orientation is None:
+            skip_table_orientation = ocr_result is not None
+        if not skip_table_orientation and self.ocr_engine is not None and bgr.shape[0] / max(bgr.shape[1], 1) > 1.2:
+            det_res = self.ocr_engine.ocr(bgr, rec=False)[0]
+            vertical = sum(1 for p1, _p2, p3, _p4 in (det_res or []) if ((p3[0] - p1[0]) / (p3[1] - p1[1]) if (p3[1] - p1[1]) > 0 else 1.0) < 0.8)
+            if det_res and vertical >= len(det_res) * 0.3:                       # (this caller's threshold is 0.3, without the >= 3 rule)
+                image = cv2.rotate(np.asarray(image), cv2.ROTATE_90_CLOCKWISE)
+                bgr = cv2.cvtColor(image, cv2.COLOR_RGB2BGR)
+        if not ocr_result:
+            res = self.ocr_engine.ocr(bgr, mfd_res=mfd_res)[0] if self.ocr_engine is not None else None
+            ocr_result = [list(x) for x in zip(*[[it[0], normalize_table_ocr_text(it[1][0]), it[1][1]] for it in res])] if res else None
+        if not ocr_result:
+            return None
+        ocr_result = [list(ocr_result[0]), list(ocr_result[1]), list(ocr_result[2])]
+        for fill in fill_image_res or []:
+            bb = points_to_bbox(fill["ocr_bbox"])
+            cv2.rectangle(bgr, (int(bb[0]), int(bb[1])), (int(bb[2]), int(bb[3])), (255, 255, 255), thickness=-1)
+            ocr_result[0].append(fill["ocr_bbox"])
+            ocr_result[1].append(fill["uuid"])
+            ocr_result[2].append(1)
+            if skip_text_in_image:
+                inside = [i for i, o in enumerate(ocr_result[0][:-1])
+                          if all(a >= b for a, b in zip(points_to_bbox(o)[:2], bb[:2])) and all(a <= b for a, b in zip(points_to_bbox(o)[2:], bb[2:]))]
+                for i in sorted(inside, reverse=True):
+                    for col in ocr_result:
+                        del col[i]
+        for mfd in mfd_res or []:
+            if mfd.get("latex"):
+                ocr_result[1].append(normalize_table_ocr_text(f"{self.inline_left}{mfd['latex']}{self.inline_right}"))
+            elif mfd.get("checkbox"):
+                ocr_result[1].append(normalize_table_ocr_text(mfd["checkbox"]))
+            else:
+                continue
+            ocr_result[0].append(bbox_to_points(mfd["bbox"]))
+            ocr_result[2].append(1)
+        html_code = self.table_model([bgr], [ocr_result]).pred_htmls[0]
+        return normalize_table_html_cell_text(html_code)

@@ -119,3 +119,60 @@ def test_rapid_table_end_to_end_on_synthetic_tables():
     for html, cells in zip(out.pred_htmls, out.cell_bboxes):
         got = [t.split("</td>")[0] for t in html.split("<td>")[1:]]
         assert got == [f"c{k}" for k in range(len(cells))]
+
+
+def _ref_table_utils(monkeypatch):
+    """rapid_doc/model/table/utils.py with its bs4 import satisfied by a stub (only the regex functions are used)."""
+    path = "/root/reference/rapid_doc/model/table/utils.py"
+    if not os.path.isfile(path):
+        pytest.skip("reference tree not mounted")
+    import types
+    bs4 = types.ModuleType("bs4")
+    bs4.BeautifulSoup = bs4.NavigableString = object
+    monkeypatch.setitem(sys.modules, "bs4", bs4)
+    spec = importlib.util.spec_from_file_location("ref_table_utils", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_table_text_normalisation_equals_the_reference(monkeypatch):
+    ref = _ref_table_utils(monkeypatch)
+    texts = [None, 5, "", " 5號 ", "10號", "第6號", "香", "香 ", "哦樂", "a<b & 'c' \"d\"", "  plain  ", "号", "7號x"]
+    for t in texts:
+        assert TM.normalize_table_ocr_text(t) == ref.normalize_table_ocr_text(t), t
+    cells = ["", None, "abc def", "中 文", "中 文 abc 测试 ， 好", "价格 $ 5 元", "（ 甲 ） 乙 ： 丙", "A 股 2024 年 报", "x ， y", "全角 ： 半角:", "中\t文\n换 行"]
+    for c in cells:
+        assert TM.normalize_table_cell_text(c) == ref.normalize_table_cell_text(c), c
+
+
+def test_table_html_cell_normalisation():
+    """The bs4-based upstream function cannot run here (parity unpinned): behaviour pinned by construction — only text nodes
+    directly inside <td> / <th> change, attributes and untouched htmls come back identical."""
+    h = '<html><body><table><tr><td>中 文 x</td><td colspan="2">a b</td><th>甲 ， 乙</th></tr><tr><td><b>粗 体</b></td><td>1 &lt; 2 中 文</td></tr></table></body></html>'
+    out = TM.normalize_table_html_cell_text(h)
+    assert out == '<html><body><table><tr><td>中文x</td><td colspan="2">a b</td><th>甲，乙</th></tr><tr><td><b>粗 体</b></td><td>1 &lt; 2中文</td></tr></table></body></html>'
+    plain = "<html><body><table><tr><td>a b</td><td></td></tr></table></body></html>"
+    assert TM.normalize_table_html_cell_text(plain) is plain and TM.normalize_table_html_cell_text("") == "" and TM.normalize_table_html_cell_text(None) is None
+    assert TM.points_to_bbox([[1, 2], [9, 2], [9, 7], [1, 7]]) == [1, 2, 9, 7] and TM.bbox_to_points([1, 2, 9, 7]).tolist() == [[1, 2], [9, 2], [9, 7], [1, 7]]
+
+
+@pytest.mark.gpu
+def test_rapid_table_model_predict_on_a_synthetic_table():
+    """RapidTableModel.predict for slanet_1m: RGB crop + OCR results (+ a formula box, + an embedded image) -> html."""
+    import cv2
+    from rapiddoc_b200 import synth
+    img = synth.table_image(0, 4, 3)
+    rgb = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+    m = TM.B200RapidTableModel(device=0)
+    cells = m.table_model([img]).cell_bboxes[0]
+    boxes = [[[c[0] + 4, c[1] + 4], [c[2] - 4, c[1] + 4], [c[2] - 4, c[3] - 4], [c[0] + 4, c[3] - 4]] for c in cells]
+    texts = [f"单 元 {k}" if k % 2 else f"c{k} <x>" for k in range(len(cells))]
+    ocr = [boxes[:-2], texts[:-2], [0.9] * (len(cells) - 2)]
+    mfd = [{"bbox": [cells[-2][0] + 4, cells[-2][1] + 4, cells[-2][2] - 4, cells[-2][3] - 4], "latex": "a^2"}]
+    fill = [{"ocr_bbox": boxes[-1], "uuid": "img-uuid-1"}]
+    html = m.predict(rgb, ocr_result=ocr, fill_image_res=fill, mfd_res=mfd)
+    got = [t.split("</td>")[0] for t in html.split("<td>")[1:]]
+    assert got[0] == "c0 <x>" and got[1] == "单元1" and got[-2] == "$a^2$" and got[-1] == "img-uuid-1" and len(got) == 12
+    assert m.predict(rgb, ocr_result=None) is None                                    # no OCR engine injected and no result given
+    assert m.batch_predict([rgb], ocr_result=ocr)[0].count("<td>") == 12
