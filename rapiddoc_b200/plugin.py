@@ -44,6 +44,24 @@ class B200OcrCustomModel(CustomBaseModel):
         return out
 
 
+class B200TableCustomModel(CustomBaseModel):
+    """Table plugin (seam 1): `table_config={"custom_model": B200TableCustomModel(device=0)}` — `BatchAnalyze._run_table_recognition`
+    then calls `batch_predict(table_imgs, fill_image_res_list=...)` (rapid_doc/backend/pipeline/batch_analyze.py:359-380) and stores
+    the returned html.  Inside: the OCR model the reference's `table_model_init` builds for tables (box_thresh 0.5, unclip 1.6, no
+    box merging; model_init.py:14-29) and `B200RapidTableModel` (SLANet-1m structure on the GPU + matching)."""
+
+    def __init__(self, device=0, precision=None, ocr_model=None):
+        from .table_match import B200RapidTableModel
+        if ocr_model is None:
+            from .ocr import B200OcrModel
+            ocr_model = B200OcrModel(det_db_box_thresh=0.5, det_db_unclip_ratio=1.6, enable_merge_det_boxes=False, device=device, precision=precision)
+        self.model = B200RapidTableModel(ocr_engine=ocr_model, device=device)
+
+    def batch_predict(self, image_list, fill_image_res_list=None, **kwargs):
+        fills = fill_image_res_list or [None] * len(image_list)
+        return [self.model.predict(img, fill_image_res=fill) for img, fill in zip(image_list, fills)]
+
+
 def make_ocr_model_init(device=0, precision=None, fallback=None, devices=None):
     """Factory with the signature of model_init.ocr_model_init (model_init.py:45-54).  devices=[0, 1, ...]: the model is a
     `B200OcrPool` that shards pages / text-line batches over those GPUs (rapiddoc_b200/multi.py)."""

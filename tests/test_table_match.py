@@ -176,3 +176,19 @@ def test_rapid_table_model_predict_on_a_synthetic_table():
     assert got[0] == "c0 <x>" and got[1] == "单元1" and got[-2] == "$a^2$" and got[-1] == "img-uuid-1" and len(got) == 12
     assert m.predict(rgb, ocr_result=None) is None                                    # no OCR engine injected and no result given
     assert m.batch_predict([rgb], ocr_result=ocr)[0].count("<td>") == 12
+
+
+@pytest.mark.gpu
+def test_table_custom_model_plugin_runs_ocr_and_structure():
+    """The CustomBaseModel table plugin: RGB table crops in, html with the recognised cell texts out (OCR + SLANet on the GPU)."""
+    import cv2
+    from rapiddoc_b200 import synth
+    from rapiddoc_b200.plugin import B200TableCustomModel, CustomBaseModel
+    m = B200TableCustomModel(device=0)
+    assert isinstance(m, CustomBaseModel)
+    imgs = [cv2.cvtColor(synth.table_image(s, 4, 3, 360, 560), cv2.COLOR_BGR2RGB) for s in (0, 1)]
+    htmls = m.batch_predict(imgs, fill_image_res_list=[[], []])
+    for h in htmls:
+        assert h.startswith("<html><body><table>") and h.count("<tr>") == 4 and h.count("<td>") == 12
+        filled = [t.split("</td>")[0] for t in h.split("<td>")[1:]]
+        assert sum(1 for t in filled if t.strip()) >= 9                      # the synthetic cell texts were recognised and matched
