@@ -192,3 +192,21 @@ def test_table_custom_model_plugin_runs_ocr_and_structure():
         assert h.startswith("<html><body><table>") and h.count("<tr>") == 4 and h.count("<td>") == 12
         filled = [t.split("</td>")[0] for t in h.split("<td>")[1:]]
         assert sum(1 for t in filled if t.strip()) >= 9                      # the synthetic cell texts were recognised and matched
+
+
+def test_match_result_fuzz_against_the_reference():
+    """Random cell grids and OCR boxes (overlapping, touching, degenerate, far away): same assignment as the reference."""
+    ref = _ref_matcher()
+    rng = np.random.RandomState(7)
+    mine = TM.TableMatch()
+    for trial in range(150):
+        k, m = rng.randint(1, 12), rng.randint(0, 15)
+        x0, y0 = rng.randint(0, 300, k), rng.randint(0, 200, k)
+        cells = np.stack([x0, y0, x0 + rng.randint(0, 120, k), y0 + rng.randint(0, 60, k)], 1).astype(np.float64)
+        if trial % 3 == 0:
+            cells[rng.randint(0, k)] = cells[rng.randint(0, k)]                      # duplicate cells: index tie-break
+        bx, by = rng.randint(-20, 320, m), rng.randint(-20, 220, m)
+        dt = np.stack([bx, by, bx + rng.randint(0, 90, m), by + rng.randint(0, 40, m)], 1).astype(np.float64)
+        if trial % 4 == 0 and m:
+            dt[0] = cells[0]                                                          # an exact hit
+        assert mine.match_result(cells, dt) == ref.match_result(cells, dt), (cells, dt)
